@@ -1,0 +1,23 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture
+def host_ops_on_cpu(monkeypatch):
+    """TEST-ONLY: let the host-side mirror run on CPU tensors through the library statements
+    (ops_lib) so its wiring can be checked against the reference goldens without a GPU.  The product
+    has no such switch: ops.require_cuda raises on CPU tensors."""
+    from gedepth_b200 import ops
+    monkeypatch.setattr(ops, "require_cuda", lambda *a, **k: None)
+    monkeypatch.setattr(ops, "use_native", lambda name: False)
+    yield
