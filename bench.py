@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py - frames/s (352x1120) fwd+bwd of the GEDepth path, BASELINE config 2:
+DepthFormer-Swin-T + GEDepth-Vanilla, batch 8 per GPU, synthetic KITTI-shape frames, random-init
+(deterministic synthetic) weights.  One "step" = forward + SiLog + backward (+ one NCCL all-reduce
+of the flat gradient arena when N>1) + clip + AdamW on one batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = the same metric through
+the public train-step call with HOST (pinned) buffers copied H2D every step and the loss read back;
+`roofline` = the dominant kernel of the step (by summed device time, measured with CUDA events around
+every C-ABI launch of one extra step); `ground_embed` = the HBM roofline of the kernel the metric
+names; `cpu_baseline` = the oracle port of the same step on this box's host cores.
+--impl reference times that CPU port alone (the reference's design cannot run here: mmcv is absent).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, B_PER_GPU = 352, 1120, 8
+WORKLOAD = "DepthFormer-Swin-T + GEDepth-Vanilla, batch 8/GPU, 352x1120 synthetic KITTI (BASELINE configs[1])"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def cpu_step_time(torch, n_frames=1, budget_s=200.0, steps=1, warmup=0):
+    """Oracle port (plain PyTorch CPU restatement of the reference path) fwd+bwd on `n_frames` frames."""
+    import gedepth_b200.models as M
+    from gedepth_b200.presets import model_cfg
+    from gedepth_b200.synth import synth_batch, synth_state_dict
+    from oracle import model as om
+    with torch.device("meta"):
+        tmpl = M.build_depther(model_cfg("v", "kitti", "swin_t", pretrained=None)).state_dict()
+    sd = synth_state_dict({k: torch.empty(v.shape, dtype=v.dtype) for k, v in tmpl.items()}, 0)
+    skip = ("running_mean", "running_var", "num_batches_tracked", "relative_position_index")
+    sd = {k: v.requires_grad_(not k.endswith(skip)) for k, v in sd.items()}
+    b = synth_batch(n_frames, H, W, seed=1234)
+    img, gt = torch.from_numpy(b["img"]), torch.from_numpy(b["depth_gt"])
+    cfg = om.PathConfig(train_bn=True)
+    times = []
+    t_begin = time.time()
+    for i in range(warmup + steps):
+        t0 = time.time()
+        r = om.forward_train(sd, cfg, img, gt)
+        r["loss"].backward()
+        for v in sd.values():
+            v.grad = None
+        dt = time.time() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.time() - t_begin > budget_s and times:
+            break
+    return times
+
+
+def ground_plane_numpy_rate():
+    import numpy as np
+    from oracle import ground as og
+    coef = og.plane_coefficients(og.kitti_projection(), og.KITTI_CAM_HEIGHT)
+    best = 1e9
+    for _ in range(5):
+        t0 = time.perf_counter()
+        og.ground_plane(coef, H, W, 61, 23)
+        best = min(best, time.perf_counter() - t0)
+    return H * W / best / 1e6
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    times = cpu_step_time(torch, 1, budget_s=200.0, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    ms = 1e3 * sum(times) / len(times)
+    val = 1.0 / (ms / 1e3)
+    sample = f"1 frame of the batch per step (352x1120 fwd+bwd), {len(times)} timed steps, torch-CPU {torch.get_num_threads()} threads"
+    line = dict(metric="frames/sec (352x1120) fwd+bwd", value=val, unit="frames/s", n_gpus=0, steps=len(times),
+                warmup=min(args.warmup, 1), ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD, note="oracle port of the reference path on host cores; the reference's "
+                            "own GPU path needs mmcv-full (absent, no network)"),
+                cpu_baseline=dict(value=val, unit="frames/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=val, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="v", choices=["v", "a"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import gedepth_b200.models as M
+    from gedepth_b200 import kernels, ops
+    from gedepth_b200.presets import model_cfg
+    from gedepth_b200.synth import synth_batch, synth_state_dict
+    from gedepth_b200.train import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    kernels.load()
+
+    Bn = args.batch
+    adaptive = args.variant == "a"
+    model = M.build_depther(model_cfg(args.variant, "kitti", "swin_t", pretrained=None))   # drop_path 0.3 as configured
+    model.load_state_dict(synth_state_dict(model.state_dict(), 0))
+    model.to(dev).train()
+    trainer = Trainer(model)
+
+    # synthetic host batches (pinned) - a few distinct ones so e2e copies are real
+    host = []
+    for i in range(2):
+        b = synth_batch(Bn, H, W, seed=1234 + rank * 17 + i, adaptive=adaptive)
+        host.append({k: torch.from_numpy(v).pin_memory() for k, v in b.items()})
+    metas = [dict(ori_shape=(H, W, 3), img_shape=(H, W, 3), pad_shape=(H, W, 3), flip=False)] * Bn
+    resident = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
+
+    def step_resident(i):
+        d = resident[i % len(resident)]
+        return trainer.step(dict(img=d["img"], img_metas=metas, depth_gt=d["depth_gt"],
+                                 **({"pe_k_gt": d["pe_k_gt"]} if adaptive else {})))
+
+    def step_e2e(i):
+        hb = host[i % len(host)]
+        d = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        loss, _ = trainer.step(dict(img=d["img"], img_metas=metas, depth_gt=d["depth_gt"],
+                                    **({"pe_k_gt": d["pe_k_gt"]} if adaptive else {})))
+        return float(loss)          # device->host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = kernels.LAUNCHES
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, kernels.LAUNCHES - n0
+
+    for i in range(max(3, args.warmup)):
+        step_resident(i)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_step, launches = timed(step_resident, args.steps)
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- per-kernel device time of ONE extra step (CUDA events around every C-ABI launch) ----------
+    prof = {}
+    if rank == 0:
+        orig_call = kernels._call
+        records = []
+
+        def prof_call(name, *a):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            orig_call(name, *a)
+            e.record()
+            flops = 0.0
+            if name == "ged_gemm_tf32":
+                flops = 2.0 * a[6] * a[7] * a[8]
+            elif name == "ged_conv3x3_tf32":
+                flops = 2.0 * a[4] * a[5] * a[6] * a[7] * a[8] * 9
+            records.append((name, s, e, flops))
+
+        kernels._call = prof_call
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        step_resident(0)
+        e1.record()
+        torch.cuda.synchronize()
+        kernels._call = orig_call
+        step_ms = e0.elapsed_time(e1)
+        for name, s, e, fl in records:
+            d = prof.setdefault(name, dict(ms=0.0, calls=0, flops=0.0))
+            d["ms"] += s.elapsed_time(e)
+            d["calls"] += 1
+            d["flops"] += fl
+        prof["_step_ms_profiled"] = step_ms
+    if world > 1:
+        dist.barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    frames = Bn * world
+    value = frames / (ms_step / 1e3)
+    e2e_val = frames / (ms_e2e / 1e3)
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    # dominant kernel of the step
+    kern = {k: v for k, v in prof.items() if not k.startswith("_")}
+    native_ms = sum(v["ms"] for v in kern.values())
+    dom = max(kern, key=lambda k: kern[k]["ms"])
+    tensor_names = ("ged_gemm_tf32", "ged_conv3x3_tf32")
+    if dom in tensor_names:
+        tf = kern[dom]["flops"] / (kern[dom]["ms"] / 1e3) / 1e12
+        peak = pk["bf16_sustained"] / 2.0
+        roof = dict(kernel=dom, bound="tensor", achieved=tf, peak=peak, unit="TFLOP/s", frac=tf / peak, traffic=None,
+                    peak_note=f"TF32 dense = 1/2 of the {pk['src']} sustained bf16 cuBLAS figure ({pk['bf16_sustained']})",
+                    calls_per_step=kern[dom]["calls"], share_of_step=kern[dom]["ms"] / prof["_step_ms_profiled"])
+    else:
+        roof = dict(kernel=dom, bound="hbm", achieved=None, peak=pk["hbm"], unit="GB/s", frac=None, traffic=None,
+                    calls_per_step=kern[dom]["calls"], share_of_step=kern[dom]["ms"] / prof["_step_ms_profiled"])
+
+    # ---- the kernel the metric names: ground embedding, HBM roofline ---------------------------------
+    def ge_bw(Bx, Hx, Wx, reps=20):
+        img = torch.randn(Bx, 5, Hx, Wx, device=dev)
+        yh = torch.rand(Bx, 1, Hx // 2, Wx // 2, device=dev)
+        flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+        with torch.no_grad():
+            for _ in range(3):
+                kernels.ge_vanilla(img, yh)
+            tot = 0.0
+            for _ in range(reps):
+                flush.zero_()                         # evict L2 (126 MB) between iterations
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                kernels.ge_vanilla(img, yh)
+                e.record()
+                torch.cuda.synchronize()
+                tot += s.elapsed_time(e)
+        t = tot / reps / 1e3
+        gb = 13.0 * Bx * Hx * Wx / 1e9                # 13 B per full-resolution pixel
+        return gb / t, t * 1e6
+    bw_work, us_work = ge_bw(Bn, H, W)
+    bw_big, us_big = ge_bw(32, 1024, 2048, reps=5)
+    ge = dict(kernel="ge_vanilla_fwd_kernel", bound="hbm", unit="GB/s", peak=pk["hbm"], peak_src=pk["src"],
+              bytes_per_pixel=13, at_workload=dict(shape=[Bn, H, W], achieved=bw_work, frac=bw_work / pk["hbm"], us=us_work,
+                                                   note="41 MB: launch-latency/L2 dominated"),
+              at_sweep_max=dict(shape=[32, 1024, 2048], achieved=bw_big, frac=bw_big / pk["hbm"], us=us_big),
+              l2_flushed_between_iterations=True)
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        t = cpu_step_time(torch, 1, budget_s=60.0, steps=1, warmup=0)
+        cpu = dict(value=1.0 / t[0], unit="frames/s", cores=cores, kind="port",
+                   sample="1 frame 352x1120 fwd+bwd through the oracle port (plain PyTorch CPU), all host threads",
+                   ground_plane_numpy_mpx_s=ground_plane_numpy_rate())
+
+    line = dict(metric="frames/sec (352x1120) fwd+bwd", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
+                warmup=max(3, args.warmup), ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="tf32", data="synthetic",
+                config=dict(workload=WORKLOAD, global_batch=frames, parallelism=f"dp{world}",
+                            step="fwd + SiLog + bwd + allreduce(N>1) + clip + AdamW", drop_path_rate=0.3,
+                            l2="inputs + activations per step (>2 GB) exceed the 126 MB L2"),
+                e2e=dict(value=e2e_val, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e),
+                gpu_launches=launches, clocks=clk, roofline=roof, ground_embed=ge, cpu_baseline=cpu,
+                native_ops=ops.native_table(),
+                kernel_ms={k: round(v["ms"], 3) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])},
+                native_ms_of_step=[round(native_ms, 2), round(prof["_step_ms_profiled"], 2)])
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,389 @@
+// TF32 tensor-core GEMM / implicit-GEMM 3x3 convolution for sm_100a: tcgen05.mma (kind::tf32) with
+// the accumulator in TMEM, operands staged by TMA into 128B-swizzled shared memory through an
+// mbarrier ring, warp-specialised (TMA producer / single-thread MMA issuer / 4 epilogue warps),
+// persistent over output tiles with a double-buffered TMEM accumulator so the epilogue of tile i
+// overlaps the main loop of tile i+1.
+//
+//   D[M,N] = epi( sum_t  A[m + tap_off[t], 0:Kt] . B[n, t*Kt : (t+1)*Kt]^T )
+//
+// * linear layers / 1x1 convs (a6, a8, a9, a11, a16 of SURVEY.md §8): one tap, tap_off = 0;
+//   A = activations (rows x K, K contiguous), B = the nn.Linear / 1x1 weight as stored ([N][K]).
+// * 3x3 convs (a11 fusion convs, a12/a13 PE necks, a16 decoder, a17 conv_depth): A is the
+//   zero-bordered NHWC input flattened to [(n,y,x) x C]; the nine taps are the same 2-D TMA box
+//   shifted by (dy-1)*(W+2) + (dx-1) rows, accumulated into one TMEM tile.  The epilogue maps the
+//   padded row index back to (n,y,x) and stores interior pixels only.
+// fp32 in HBM, tf32 multiply, fp32 accumulate: the reference's cuDNN convs run TF32 by default
+// (torch.backends.cudnn.allow_tf32) and its fp32 linears are the precision bar.
+//
+// Epilogue (fused, in order): + bias[n] -> activation -> * row_scale[batch(m)] -> + residual[m,n].
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include "common.cuh"
+
+namespace ged {
+
+constexpr int BM = 128;          // UMMA_M, rows per tile (TMEM lanes)
+constexpr int BK = 32;           // fp32 elements per 128-byte swizzle row
+constexpr int UK = 8;            // UMMA_K for tf32
+constexpr int GEMM_THREADS = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int MAX_TAPS = 9;
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_GELU = 3, ACT_SIGMOID = 4 };
+
+struct GemmParams {
+  int M, N, K;              // K = total contraction (ntaps * Kt)
+  int ntaps, kblocks_per_tap, Kt;  // Kt = contraction length of one tap
+  int tap_off[MAX_TAPS];    // row offset of each tap in A
+  const float* bias;        // [N] or null
+  const float* residual;    // [M_out, ldd] or null
+  const float* row_scale;   // [batch] or null (DropPath)
+  int rows_per_batch;       // for row_scale
+  float* D;
+  int ldd;                  // row pitch of D / residual in floats
+  int act;
+  float slope;
+  // conv epilogue: padded row -> (n, y, x); 0 disables
+  int conv_Hp, conv_Wp;     // padded extents (H+2, W+2)
+  int num_m_tiles, num_n_tiles;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart.
+// bits: [0,14) addr>>4 | [16,30) LBO>>4 (unused for one atom along K) | [32,46) SBO>>4 |
+//       [46,48) version=1 (sm_100) | [61,64) layout: 2 = SWIZZLE_128B   (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format TF32 (2) @7/@10, K-major both,
+// n_dim = N>>3 @17, m_dim = M>>4 @24
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float apply_act(float x, int act, float slope) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(x, 0.f);
+    case ACT_LEAKY: return x > 0.f ? x : x * slope;
+    case ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));   // exact GELU (nn.GELU default)
+    case ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+    default: return x;
+  }
+}
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 4;       // 16 KB
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;  // per-warp transpose tiles
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_kernel(
+    const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+    const GemmParams p) {
+  using S = GemmSmem<BN, STAGES>;
+  constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024B alignment
+  uint8_t* stage_base = smem;
+  float* epi_tiles = (float*)(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* full_bar = (uint64_t*)((uint8_t*)epi_tiles + S::EPI_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = p.ntaps * p.kblocks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&map_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int t = kb / p.kblocks_per_tap, kc = kb - t * p.kblocks_per_tap;
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* sa = stage_base + stage * S::STAGE_BYTES;
+          mbar_expect_tx(full_bar + stage, S::STAGE_BYTES);
+          tma_load_2d(sa, &map_a, full_bar + stage, kc * BK, m0 + p.tap_off[t]);
+          tma_load_2d(sa + S::A_BYTES, &map_b, full_bar + stage, t * p.Kt + kc * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_kmajor_sw128(sa), bdesc = umma_desc_kmajor_sw128(sa + S::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            // advance 8 tf32 = 32 bytes inside the 128B swizzle row: +2 in the (addr>>4) field
+            tc_mma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          tc_commit(empty_bar + stage);          // frees the smem slot when these MMAs retire
+          if (kb == num_kb - 1) tc_commit(tmem_full + acc);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> (smem transpose) -> coalesced global stores =====
+    const int ew = warp - 4;                       // TMEM lane quadrant = warp % 4
+    float (*tile_s)[33] = (float (*)[33])(epi_tiles + ew * 32 * 33);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
+      mbar_wait(tmem_full + acc, acc_phase);
+      tc_fence_after();
+      const int row_base = m0 + ew * 32;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) tile_s[lane][c] = __uint_as_float(v[c]);
+        __syncwarp();
+        const int col = n0 + c0 + lane;
+        const bool col_ok = col < p.N;
+        const float bias = (p.bias && col_ok) ? __ldg(p.bias + col) : 0.f;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const int row = row_base + r;
+          if (row >= p.M) break;
+          int64_t orow = row;
+          if (p.conv_Wp) {
+            // padded flattened pixel -> interior test and unpadded row
+            const int xp = row % p.conv_Wp, t2 = row / p.conv_Wp, yp = t2 % p.conv_Hp, n = t2 / p.conv_Hp;
+            if (xp == 0 || xp == p.conv_Wp - 1 || yp == 0 || yp == p.conv_Hp - 1) continue;
+            orow = ((int64_t)n * (p.conv_Hp - 2) + (yp - 1)) * (p.conv_Wp - 2) + (xp - 1);
+          }
+          if (!col_ok) continue;
+          float x = tile_s[r][lane] + bias;
+          x = apply_act(x, p.act, p.slope);
+          if (p.row_scale) x *= __ldg(p.row_scale + orow / p.rows_per_batch);
+          if (p.residual) x += __ldg(p.residual + orow * p.ldd + col);
+          p.D[orow * p.ldd + col] = x;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)ptr;
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: dims {inner=cols, outer=rows}, row pitch ld floats, box {32, box_rows}, 128B swizzle
+static int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  auto enc = get_encode();
+  if (!enc) return GED_ERR_LAUNCH;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? GED_OK : GED_ERR_ARG;
+}
+
+static int g_num_sms = 0;
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
+  using S = GemmSmem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return GED_ERR_LAUNCH;
+    attr_set = true;
+  }
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  p.num_m_tiles = cdiv(p.M, BM);
+  p.num_n_tiles = cdiv(p.N, BN);
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  gemm_tf32_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ma, mb, p);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+static int pick_bn(int N) {
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N % 128 != 0 && N % 96 == 0) return 96;
+  return 128;
+}
+
+static int run(const float* A, int64_t a_rows, int lda, const float* Bw, int ldb, GemmParams& p, cudaStream_t stream) {
+  if (!aligned16(A) || !aligned16(Bw) || (lda % 4) || (ldb % 4)) return GED_ERR_ALIGN;
+  const int bn = pick_bn(p.N);
+  CUtensorMap ma, mb;
+  const int Kt = p.K / p.ntaps;
+  if (int e = make_map_2d(&ma, A, a_rows, Kt, lda, BM)) return e;
+  if (int e = make_map_2d(&mb, Bw, p.N, p.K, ldb, bn)) return e;
+  p.kblocks_per_tap = cdiv(Kt, BK);
+  p.Kt = Kt;
+  switch (bn) {
+    case 32: return launch_gemm<32, 8>(ma, mb, p, stream);
+    case 64: return launch_gemm<64, 6>(ma, mb, p, stream);
+    case 96: return launch_gemm<96, 6>(ma, mb, p, stream);
+    default: return launch_gemm<128, 5>(ma, mb, p, stream);
+  }
+}
+
+}  // namespace ged
+using namespace ged;
+
+// D[M,N] = epi(A[M,K] @ W[N,K]^T).  A row pitch lda, W row pitch ldw, D/residual row pitch ldd (floats).
+// act: 0 none, 1 relu, 2 leaky(slope), 3 gelu(erf), 4 sigmoid.  row_scale[b] multiplies rows of batch b
+// (rows_per_batch rows each) before the residual is added.  Replaces F.linear / 1x1 Conv2d call sites
+// depthformer_swin.py:96,119,174-176,193,222 ; mmcv FFN ; hahi.py:122-165 (1x1) ; MSDA linears.
+GED_API int ged_gemm_tf32(const float* A, int lda, const float* W, int ldw, float* D, int ldd, int M,
+                          int N, int K, const float* bias, int act, float slope, const float* residual,
+                          const float* row_scale, int rows_per_batch, cudaStream_t stream) {
+  if (!A || !W || !D || M <= 0 || N <= 0 || K <= 0) return GED_ERR_ARG;
+  if (K % 4) return GED_ERR_SHAPE;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.ntaps = 1; p.tap_off[0] = 0;
+  p.bias = bias; p.residual = residual; p.row_scale = row_scale;
+  p.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
+  p.D = D; p.ldd = ldd; p.act = act; p.slope = slope; p.conv_Hp = 0; p.conv_Wp = 0;
+  return run(A, M, lda, W, ldw, p, stream);
+}
+
+// 3x3 / stride 1 / pad 1 convolution as nine shifted GEMMs.  Xpad: zero-bordered NHWC input
+// [B, H+2, W+2, Cin] (ged_pad_nhwc writes it); Wk: weights [Cout][ky][kx][Cin]; Y: NHWC [B,H,W,Cout]
+// with channel pitch ldy.  Replaces the nn.Conv2d(k=3,p=1) sites hahi.py:138-165, pemask_neck.py:36-42,
+// dynamicpe_neck.py:497-502, densedepth_head.py:21-22, decode_head.py:391.
+GED_API int ged_conv3x3_tf32(const float* Xpad, const float* Wk, float* Y, int ldy, int B, int H, int W,
+                             int Cin, int Cout, const float* bias, int act, float slope,
+                             cudaStream_t stream) {
+  if (!Xpad || !Wk || !Y || B <= 0 || H <= 0 || W <= 0) return GED_ERR_ARG;
+  if (Cin % 4) return GED_ERR_SHAPE;
+  const int Hp = H + 2, Wp = W + 2;
+  GemmParams p{};
+  p.M = B * Hp * Wp; p.N = Cout; p.K = 9 * Cin; p.ntaps = 9;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) p.tap_off[ky * 3 + kx] = (ky - 1) * Wp + (kx - 1);
+  p.bias = bias; p.residual = nullptr; p.row_scale = nullptr; p.rows_per_batch = 1;
+  p.D = Y; p.ldd = ldy; p.act = act; p.slope = slope; p.conv_Hp = Hp; p.conv_Wp = Wp;
+  // when Cin is not a multiple of 32 the K blocks of one tap would straddle into the next tap's
+  // weights; the A side reads zeros there (TMA out-of-bounds fill past column Cin), so it is exact.
+  return run(Xpad, (int64_t)p.M, Cin, Wk, 9 * Cin, p, stream);
+}

@@ -1,0 +1,565 @@
+// Ground-embedding kernels (the path BASELINE.json names), sm_100a.  HBM-bound per-pixel work:
+// float4-vectorised, coalesced, the half-resolution operands (attention map, slope logits) staged
+// through shared memory once per tile.
+//
+//   ged_ground_plane      a1   tools/preprocess_data_kitti.py:47-53 (+ loading.py:388-403, transforms.py:40-48)
+//   ged_pixel_grid        a1   the int64 (u,v) meshgrid of preprocess_data_kitti.py:52
+//   ged_ge_vanilla_*      a14  depth/models/depther/encoder_decoder.py:112-123
+//   ged_ge_adaptive_*     a15  depth/models/depther/encoder_decoder.py:79-102
+//   ged_fuse_head_*       a17  depth/models/decode_heads/decode_head.py:489-508
+//   ged_find_k            (f)1 tools/preprocess_data_kitti.py:59-63,86-89 / preprocess_data_ddad.py:47-51,77-82
+//
+// Algorithmic bytes per full-resolution pixel (fp32): ground_plane 8; vanilla fwd 13;
+// vanilla bwd 13; adaptive fwd 24 (+44 when the full-resolution logits are written); fuse_head ~9.
+#include "common.cuh"
+#include "tile.cuh"
+
+namespace ged {
+
+// ---------------------------------------------------------------------------------------------
+// a1: ground-plane generator.  fp64 on the integer grid, separate roundings (no FMA contraction)
+// so that the result equals numpy's `num / (cu*u + cv*v + c1)` bit for bit before the fp32 cast.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ground_plane_kernel(
+    float* __restrict__ ch3, float* __restrict__ ch4, int64_t batch_stride3, int64_t batch_stride4,
+    int B, int H, int W, double num, double cu, double cv, double c1, double u0, double v0, double su,
+    double sv, float depth_scale, float clamp_max) {
+  int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  int y = blockIdx.y;
+  if (x4 >= W) return;
+  double v = __dadd_rn(__dmul_rn((double)y, sv), v0);
+  double row = __dmul_rn(cv, v);
+  float raw[4], nrm[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double u = __dadd_rn(__dmul_rn((double)(x4 + i), su), u0);
+    double den = __dadd_rn(__dadd_rn(__dmul_rn(cu, u), row), c1);
+    float pe = (float)__ddiv_rn(num, den);
+    raw[i] = pe;
+    float c = pe;
+    if (c > clamp_max) c = 0.f;      // loading.py:400-401 (NaN compares false and stays, like numpy)
+    if (c < 0.f) c = 0.f;
+    if (c > 0.f) c = c / depth_scale;  // transforms.py:44
+    nrm[i] = c;
+  }
+  for (int b = 0; b < B; ++b) {
+    float* p3 = ch3 + b * batch_stride3 + (int64_t)y * W + x4;
+    float* p4 = ch4 + b * batch_stride4 + (int64_t)y * W + x4;
+    if (x4 + 3 < W && aligned16(p3) && aligned16(p4)) {
+      stg_stream((float4*)p3, make_float4(nrm[0], nrm[1], nrm[2], nrm[3]));
+      stg_stream((float4*)p4, make_float4(raw[0], raw[1], raw[2], raw[3]));
+    } else {
+      for (int i = 0; i < 4 && x4 + i < W; ++i) { p3[i] = nrm[i]; p4[i] = raw[i]; }
+    }
+  }
+}
+
+__global__ void pixel_grid_kernel(long long* __restrict__ u, long long* __restrict__ v, int H, int W,
+                                  int u0, int v0) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  u[(int64_t)y * W + x] = (long long)(u0 + x);
+  v[(int64_t)y * W + x] = (long long)(v0 + y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a14: Vanilla.  y = up(y_half) (align_corners=False); pe_mask = pe_norm * y * 200.
+// ---------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(TX * TILE_H) ge_vanilla_fwd_kernel(
+    const float* __restrict__ pe_norm, int64_t pe_bstride, const float* __restrict__ y_half,
+    float* __restrict__ y, float* __restrict__ pe_mask, int H, int W, int h2, int w2, float sy,
+    float sx) {
+  __shared__ float s_y[ST_H][ST_W];
+  const int b = blockIdx.z, oy0 = blockIdx.y * TILE_H, ox0 = blockIdx.x * TILE_W;
+  const SrcWindow sw = src_window(oy0, ox0, H, W, h2, w2, sy, sx, false);
+  const float* yh = y_half + (int64_t)b * h2 * w2;
+  for (int i = threadIdx.y * TX + threadIdx.x; i < sw.h * sw.w; i += TX * TILE_H) {
+    int r = i / sw.w, c = i - r * sw.w;
+    s_y[r][c] = __ldg(yh + (int64_t)(sw.y0 + r) * w2 + sw.x0 + c);
+  }
+  __syncthreads();
+  const int oy = oy0 + threadIdx.y, ox = ox0 + threadIdx.x * 4;
+  if (oy >= H || ox >= W) return;
+  const Tap ty = tap(oy, sy, false, h2);
+  const int r0 = ty.i0 - sw.y0, r1 = ty.i1 - sw.y0;
+  const int64_t o = ((int64_t)b * H + oy) * W + ox;
+  const float* pp = pe_norm + (int64_t)b * pe_bstride + (int64_t)oy * W + ox;
+  float pe[4], yo[4], mo[4];
+  const int n = min(4, W - ox);
+  if (VEC) { float4 t = ldg_stream((const float4*)pp); pe[0] = t.x; pe[1] = t.y; pe[2] = t.z; pe[3] = t.w; }
+  else { for (int i = 0; i < n; ++i) pe[i] = __ldg(pp + i); }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i < n) {
+      const Tap tx = tap(ox + i, sx, false, w2);
+      const int c0 = tx.i0 - sw.x0, c1 = tx.i1 - sw.x0;
+      float v = ty.l0 * (tx.l0 * s_y[r0][c0] + tx.l1 * s_y[r0][c1]) +
+                ty.l1 * (tx.l0 * s_y[r1][c0] + tx.l1 * s_y[r1][c1]);
+      yo[i] = v;
+      mo[i] = pe[i] * v * 200.f;    // literal 200, not depth_scale (encoder_decoder.py:122)
+    }
+  }
+  if (VEC) {
+    stg_stream((float4*)(y + o), make_float4(yo[0], yo[1], yo[2], yo[3]));
+    stg_stream((float4*)(pe_mask + o), make_float4(mo[0], mo[1], mo[2], mo[3]));
+  } else {
+    for (int i = 0; i < n; ++i) { y[o + i] = yo[i]; pe_mask[o + i] = mo[i]; }
+  }
+}
+
+// a14 backward: g_y_half += up^T( g_y + g_pe_mask * pe_norm * 200 ).  g_y_half must be zeroed.
+__global__ void __launch_bounds__(TX * TILE_H) ge_vanilla_bwd_kernel(
+    const float* __restrict__ pe_norm, int64_t pe_bstride, const float* __restrict__ g_y,
+    const float* __restrict__ g_pe_mask, float* __restrict__ g_y_half, int H, int W, int h2, int w2,
+    float sy, float sx) {
+  __shared__ float s_g[1][TILE_H][TILE_W + 1];
+  const int b = blockIdx.z, oy0 = blockIdx.y * TILE_H, ox0 = blockIdx.x * TILE_W;
+  const SrcWindow sw = src_window(oy0, ox0, H, W, h2, w2, sy, sx, false);
+  const int oy = oy0 + threadIdx.y;
+  if (oy < H) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int lx = i * TX + threadIdx.x, ox = ox0 + lx;   // lane-contiguous: coalesced, conflict-free
+      float g = 0.f;
+      if (ox < W) {
+        const int64_t o = ((int64_t)b * H + oy) * W + ox;
+        const float pe = __ldg(pe_norm + (int64_t)b * pe_bstride + (int64_t)oy * W + ox);
+        g = (g_y ? __ldg(g_y + o) : 0.f) + (g_pe_mask ? __ldg(g_pe_mask + o) * pe * 200.f : 0.f);
+      }
+      s_g[0][threadIdx.y][lx] = g;
+    }
+  }
+  __syncthreads();
+  tile_adjoint_upsample<1>(s_g, g_y_half + (int64_t)b * h2 * w2, 0, oy0, ox0, H, W, h2, w2, sy, sx,
+                           false, sw);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a15: Adaptive.  Per pixel: L = up(logits_half) (11 bins), theta = sum softmax(L) * (c-5),
+// k = tan(theta deg), a = -h/(pe+1e-8), off = -h/((a-k)+1e-8), m = [0 < off <= depth_scale],
+// pe_mask = off*m*y.
+// ---------------------------------------------------------------------------------------------
+struct SlopeEval {
+  float p[NSLOPE];
+  float theta, k, den, off, m;
+};
+
+__device__ __forceinline__ void slope_eval(const float* L, float pe, float h, float depth_scale,
+                                           SlopeEval& e) {
+  float mx = L[0];
+#pragma unroll
+  for (int c = 1; c < NSLOPE; ++c) mx = fmaxf(mx, L[c]);
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < NSLOPE; ++c) { e.p[c] = expf(L[c] - mx); sum += e.p[c]; }
+  const float inv = 1.f / sum;
+  float th = 0.f;
+#pragma unroll
+  for (int c = 0; c < NSLOPE; ++c) { e.p[c] *= inv; th += e.p[c] * (float)(c - 5); }
+  e.theta = th;
+  e.k = tanf(th * 0.017453292519943295f);
+  const float a = -h / (pe + 1e-8f);
+  e.den = (a - e.k) + 1e-8f;
+  e.off = -h / e.den;
+  // in-place thresholds of encoder_decoder.py:97-100: <0 -> 0, >depth_scale -> 0, >0 -> 1
+  // (a NaN offset survives all three and poisons the pixel exactly as in the reference)
+  float mm = e.off;
+  if (mm < 0.f) mm = 0.f;
+  if (mm > depth_scale) mm = 0.f;
+  if (mm > 0.f) mm = 1.f;
+  e.m = mm;
+}
+
+__global__ void __launch_bounds__(TX * TILE_H) ge_adaptive_fwd_kernel(
+    const float* __restrict__ pe_raw, int64_t pe_bstride, const float* __restrict__ y_half,
+    const float* __restrict__ logits_half, const float* __restrict__ height, float height_scalar,
+    float depth_scale, float* __restrict__ y, float* __restrict__ pe_mask,
+    float* __restrict__ logits_full, int H, int W, int h2, int w2, float sy, float sx) {
+  __shared__ float s_y[ST_H][ST_W];
+  __shared__ float s_l[NSLOPE][ST_H][ST_W];
+  const int b = blockIdx.z, oy0 = blockIdx.y * TILE_H, ox0 = blockIdx.x * TILE_W;
+  const SrcWindow sw = src_window(oy0, ox0, H, W, h2, w2, sy, sx, false);
+  const int64_t hw2 = (int64_t)h2 * w2;
+  for (int i = threadIdx.y * TX + threadIdx.x; i < sw.h * sw.w; i += TX * TILE_H) {
+    int r = i / sw.w, c = i - r * sw.w;
+    const int64_t so = (int64_t)(sw.y0 + r) * w2 + sw.x0 + c;
+    s_y[r][c] = __ldg(y_half + b * hw2 + so);
+#pragma unroll
+    for (int ch = 0; ch < NSLOPE; ++ch) s_l[ch][r][c] = __ldg(logits_half + ((int64_t)b * NSLOPE + ch) * hw2 + so);
+  }
+  __syncthreads();
+  const int oy = oy0 + threadIdx.y, ox = ox0 + threadIdx.x * 4;
+  if (oy >= H || ox >= W) return;
+  const float h = height ? __ldg(height + b) : height_scalar;
+  const Tap ty = tap(oy, sy, false, h2);
+  const int r0 = ty.i0 - sw.y0, r1 = ty.i1 - sw.y0;
+  const int64_t o = ((int64_t)b * H + oy) * W + ox;
+  const int64_t HW = (int64_t)H * W;
+  const int n = min(4, W - ox);
+  const bool vec = (n == 4) && ((W & 3) == 0);
+  float yo[4], mo[4], lo[NSLOPE][4], pev[4];
+  {
+    const float* pp = pe_raw + (int64_t)b * pe_bstride + (int64_t)oy * W + ox;
+    if (vec && aligned16(pp)) { float4 t = ldg_stream((const float4*)pp); pev[0] = t.x; pev[1] = t.y; pev[2] = t.z; pev[3] = t.w; }
+    else { for (int i = 0; i < n; ++i) pev[i] = __ldg(pp + i); }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i >= n) break;
+    const Tap tx = tap(ox + i, sx, false, w2);
+    const int c0 = tx.i0 - sw.x0, c1 = tx.i1 - sw.x0;
+    float L[NSLOPE];
+#pragma unroll
+    for (int ch = 0; ch < NSLOPE; ++ch) {
+      L[ch] = ty.l0 * (tx.l0 * s_l[ch][r0][c0] + tx.l1 * s_l[ch][r0][c1]) +
+              ty.l1 * (tx.l0 * s_l[ch][r1][c0] + tx.l1 * s_l[ch][r1][c1]);
+      lo[ch][i] = L[ch];
+    }
+    const float yv = ty.l0 * (tx.l0 * s_y[r0][c0] + tx.l1 * s_y[r0][c1]) +
+                     ty.l1 * (tx.l0 * s_y[r1][c0] + tx.l1 * s_y[r1][c1]);
+    SlopeEval e;
+    slope_eval(L, pev[i], h, depth_scale, e);
+    yo[i] = yv;
+    mo[i] = (e.off * e.m) * yv;
+  }
+  if (vec) {
+    stg_stream((float4*)(y + o), make_float4(yo[0], yo[1], yo[2], yo[3]));
+    stg_stream((float4*)(pe_mask + o), make_float4(mo[0], mo[1], mo[2], mo[3]));
+    if (logits_full) {
+#pragma unroll
+      for (int ch = 0; ch < NSLOPE; ++ch)
+        stg_stream((float4*)(logits_full + ((int64_t)b * NSLOPE + ch) * HW + (int64_t)oy * W + ox),
+                   make_float4(lo[ch][0], lo[ch][1], lo[ch][2], lo[ch][3]));
+    }
+  } else {
+    for (int i = 0; i < n; ++i) {
+      y[o + i] = yo[i];
+      pe_mask[o + i] = mo[i];
+      if (logits_full)
+        for (int ch = 0; ch < NSLOPE; ++ch)
+          logits_full[((int64_t)b * NSLOPE + ch) * HW + (int64_t)oy * W + ox + i] = lo[ch][i];
+    }
+  }
+}
+
+// a15 backward.  Recomputes L / softmax / offset from the half-resolution operands (11 B/px read
+// instead of 44), forms the 12 per-pixel gradients (11 logits + y) in shared memory and applies
+// the tile adjoint.  g_y_half and g_logits_half must be zeroed.
+__global__ void __launch_bounds__(TX * TILE_H) ge_adaptive_bwd_kernel(
+    const float* __restrict__ pe_raw, int64_t pe_bstride, const float* __restrict__ y_half,
+    const float* __restrict__ logits_half, const float* __restrict__ height, float height_scalar,
+    float depth_scale, const float* __restrict__ g_y, const float* __restrict__ g_pe_mask,
+    const float* __restrict__ g_logits_full, float* __restrict__ g_y_half,
+    float* __restrict__ g_logits_half, int H, int W, int h2, int w2, float sy, float sx) {
+  extern __shared__ float smem[];
+  float (*s_g)[TILE_H][TILE_W + 1] = (float (*)[TILE_H][TILE_W + 1])smem;            // 12 channels
+  float (*s_y)[ST_W] = (float (*)[ST_W])(smem + (NSLOPE + 1) * TILE_H * (TILE_W + 1));
+  float (*s_l)[ST_H][ST_W] = (float (*)[ST_H][ST_W])(smem + (NSLOPE + 1) * TILE_H * (TILE_W + 1) + ST_H * ST_W);
+  const int b = blockIdx.z, oy0 = blockIdx.y * TILE_H, ox0 = blockIdx.x * TILE_W;
+  const SrcWindow sw = src_window(oy0, ox0, H, W, h2, w2, sy, sx, false);
+  const int64_t hw2 = (int64_t)h2 * w2, HW = (int64_t)H * W;
+  for (int i = threadIdx.y * TX + threadIdx.x; i < sw.h * sw.w; i += TX * TILE_H) {
+    int r = i / sw.w, c = i - r * sw.w;
+    const int64_t so = (int64_t)(sw.y0 + r) * w2 + sw.x0 + c;
+    s_y[r][c] = __ldg(y_half + b * hw2 + so);
+#pragma unroll
+    for (int ch = 0; ch < NSLOPE; ++ch) s_l[ch][r][c] = __ldg(logits_half + ((int64_t)b * NSLOPE + ch) * hw2 + so);
+  }
+  __syncthreads();
+  const int oy = oy0 + threadIdx.y;
+  const float h = height ? __ldg(height + b) : height_scalar;
+  if (oy < H) {
+    const Tap ty = tap(oy, sy, false, h2);
+    const int r0 = ty.i0 - sw.y0, r1 = ty.i1 - sw.y0;
+    for (int i = 0; i < 4; ++i) {
+      const int lx = i * TX + threadIdx.x, ox = ox0 + lx;   // lane-contiguous: coalesced, conflict-free
+      if (ox >= W) {
+#pragma unroll
+        for (int ch = 0; ch <= NSLOPE; ++ch) s_g[ch][threadIdx.y][lx] = 0.f;
+        continue;
+      }
+      const Tap tx = tap(ox, sx, false, w2);
+      const int c0 = tx.i0 - sw.x0, c1 = tx.i1 - sw.x0;
+      float L[NSLOPE];
+#pragma unroll
+      for (int ch = 0; ch < NSLOPE; ++ch)
+        L[ch] = ty.l0 * (tx.l0 * s_l[ch][r0][c0] + tx.l1 * s_l[ch][r0][c1]) +
+                ty.l1 * (tx.l0 * s_l[ch][r1][c0] + tx.l1 * s_l[ch][r1][c1]);
+      const float yv = ty.l0 * (tx.l0 * s_y[r0][c0] + tx.l1 * s_y[r0][c1]) +
+                       ty.l1 * (tx.l0 * s_y[r1][c0] + tx.l1 * s_y[r1][c1]);
+      const int64_t po = (int64_t)oy * W + ox;
+      const float pe = __ldg(pe_raw + (int64_t)b * pe_bstride + po);
+      SlopeEval e;
+      slope_eval(L, pe, h, depth_scale, e);
+      const float gpm = g_pe_mask ? __ldg(g_pe_mask + b * HW + po) : 0.f;
+      // d pe_mask / d y = off*m ; d pe_mask / d off = m*y ; d off / d k = -h/den^2 ;
+      // d k / d theta = (pi/180)(1+k^2) ; d theta / d L_c = p_c (c-5 - theta).  m is a constant.
+      const float gy = (g_y ? __ldg(g_y + b * HW + po) : 0.f) + gpm * (e.off * e.m);
+      float G = gpm * e.m * yv * (-h / (e.den * e.den)) * (0.017453292519943295f * (1.f + e.k * e.k));
+      if (e.m == 0.f) G = 0.f;   // 0 * inf guards: the reference multiplies by an exact-zero mask
+      s_g[NSLOPE][threadIdx.y][lx] = gy;
+#pragma unroll
+      for (int ch = 0; ch < NSLOPE; ++ch) {
+        float gl = G * e.p[ch] * ((float)(ch - 5) - e.theta);
+        if (g_logits_full) gl += __ldg(g_logits_full + ((int64_t)b * NSLOPE + ch) * HW + po);
+        s_g[ch][threadIdx.y][lx] = gl;
+      }
+    }
+  }
+  __syncthreads();
+  // channels 0..10 -> g_logits_half, channel 11 -> g_y_half
+  const int tid = threadIdx.y * TX + threadIdx.x;
+  const int th = min(TILE_H, H - oy0), tw = min(TILE_W, W - ox0);
+  for (int i = tid; i < sw.h * sw.w; i += TX * TILE_H) {
+    const int r = i / sw.w, c = i - r * sw.w;
+    const int j = sw.y0 + r, k = sw.x0 + c;
+    int ylo, yhi, xlo, xhi;
+    adjoint_range(j, sy, false, h2, H, ylo, yhi);
+    adjoint_range(k, sx, false, w2, W, xlo, xhi);
+    ylo = max(ylo, oy0) - oy0; yhi = min(yhi, oy0 + th - 1) - oy0;
+    xlo = max(xlo, ox0) - ox0; xhi = min(xhi, ox0 + tw - 1) - ox0;
+    float acc[NSLOPE + 1];
+#pragma unroll
+    for (int ch = 0; ch <= NSLOPE; ++ch) acc[ch] = 0.f;
+    bool any = false;
+    for (int yy = ylo; yy <= yhi; ++yy) {
+      const Tap ty = tap(oy0 + yy, sy, false, h2);
+      const float wy = (ty.i0 == j ? ty.l0 : 0.f) + (ty.i1 == j ? ty.l1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int xx = xlo; xx <= xhi; ++xx) {
+        const Tap tx = tap(ox0 + xx, sx, false, w2);
+        const float wx = (tx.i0 == k ? tx.l0 : 0.f) + (tx.i1 == k ? tx.l1 : 0.f);
+        if (wx == 0.f) continue;
+        any = true;
+#pragma unroll
+        for (int ch = 0; ch <= NSLOPE; ++ch) acc[ch] += wy * wx * s_g[ch][yy][xx];
+      }
+    }
+    if (any) {
+      const int64_t so = (int64_t)j * w2 + k;
+#pragma unroll
+      for (int ch = 0; ch < NSLOPE; ++ch) atomicAdd(g_logits_half + ((int64_t)b * NSLOPE + ch) * hw2 + so, acc[ch]);
+      atomicAdd(g_y_half + b * hw2 + so, acc[NSLOPE]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a17: head fusion at half resolution.  pe_h, y_h = down(pe_mask), down(y) (align_corners=True);
+// out = d*(1-y_h) + pe_h + min_depth.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fuse_head_fwd_kernel(
+    const float* __restrict__ d, const float* __restrict__ pe_mask, const float* __restrict__ y,
+    float* __restrict__ out, float* __restrict__ y_h, int H, int W, int h2, int w2, float sy, float sx,
+    float min_depth) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, yy = blockIdx.y, b = blockIdx.z;
+  if (x >= w2) return;
+  const Tap ty = tap(yy, sy, true, H), tx = tap(x, sx, true, W);
+  const int64_t base = (int64_t)b * H * W;
+  const int64_t o00 = base + (int64_t)ty.i0 * W + tx.i0, o01 = base + (int64_t)ty.i0 * W + tx.i1;
+  const int64_t o10 = base + (int64_t)ty.i1 * W + tx.i0, o11 = base + (int64_t)ty.i1 * W + tx.i1;
+  const float pe_h = ty.l0 * (tx.l0 * __ldg(pe_mask + o00) + tx.l1 * __ldg(pe_mask + o01)) +
+                     ty.l1 * (tx.l0 * __ldg(pe_mask + o10) + tx.l1 * __ldg(pe_mask + o11));
+  const float yh = ty.l0 * (tx.l0 * __ldg(y + o00) + tx.l1 * __ldg(y + o01)) +
+                   ty.l1 * (tx.l0 * __ldg(y + o10) + tx.l1 * __ldg(y + o11));
+  const int64_t o = ((int64_t)b * h2 + yy) * w2 + x;
+  out[o] = ((__ldg(d + o) * (1.f - yh)) + pe_h) + min_depth;
+  y_h[o] = yh;
+}
+
+// backward at half resolution: g_d = g_out*(1-y_h); the full-resolution gradients are gathered
+// (deterministically) from the <=3x3 half-resolution pixels whose taps touch each pixel.
+__global__ void __launch_bounds__(256) fuse_head_bwd_half_kernel(
+    const float* __restrict__ g_out, const float* __restrict__ y_h, float* __restrict__ g_d, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) g_d[i] = __ldg(g_out + i) * (1.f - __ldg(y_h + i));
+}
+
+__global__ void __launch_bounds__(256) fuse_head_bwd_full_kernel(
+    const float* __restrict__ g_out, const float* __restrict__ d, const float* __restrict__ g_yh_extra,
+    float* __restrict__ g_pe_mask, float* __restrict__ g_y, int H, int W, int h2, int w2, float sy,
+    float sx) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, yy = blockIdx.y, b = blockIdx.z;
+  if (x >= W) return;
+  int jlo, jhi, klo, khi;
+  adjoint_range(yy, sy, true, H, h2, jlo, jhi);
+  adjoint_range(x, sx, true, W, w2, klo, khi);
+  float gp = 0.f, gy = 0.f;
+  for (int j = jlo; j <= jhi; ++j) {
+    const Tap ty = tap(j, sy, true, H);
+    const float wy = (ty.i0 == yy ? ty.l0 : 0.f) + (ty.i1 == yy ? ty.l1 : 0.f);
+    if (wy == 0.f) continue;
+    for (int k = klo; k <= khi; ++k) {
+      const Tap tx = tap(k, sx, true, W);
+      const float wx = (tx.i0 == x ? tx.l0 : 0.f) + (tx.i1 == x ? tx.l1 : 0.f);
+      if (wx == 0.f) continue;
+      const int64_t o = ((int64_t)b * h2 + j) * w2 + k;
+      const float go = __ldg(g_out + o);
+      gp += wy * wx * go;
+      gy += wy * wx * (-go * __ldg(d + o) + (g_yh_extra ? __ldg(g_yh_extra + o) : 0.f));
+    }
+  }
+  const int64_t o = ((int64_t)b * H + yy) * W + x;
+  g_pe_mask[o] = gp;
+  g_y[o] = gy;
+}
+
+// ---------------------------------------------------------------------------------------------
+// (f)1: slope labels.  k = deg(atan(h/gt - h/pe)); KITTI rounds half-to-even (np.around),
+// DDAD truncates (astype(int64)); clip to +-5; 255 where gt == 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) find_k_kernel(const float* __restrict__ gt,
+                                                      const float* __restrict__ pe, int64_t pe_bstride,
+                                                      float* __restrict__ k_out, int64_t HW, float h,
+                                                      int truncate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= HW) return;
+  const double g = (double)__ldg(gt + b * HW + i);
+  const double p = (double)__ldg(pe + b * pe_bstride + i);
+  double k = (double)h / g + (-(double)h) / p;
+  k = atan(k) * 57.29577951308232;
+  double r;
+  if (truncate) r = isfinite(k) ? trunc(k) : 0.0; else r = rint(k);
+  if (r > 5.0) r = 5.0;
+  if (r < -5.0) r = -5.0;
+  if (g == 0.0) r = 255.0;
+  k_out[b * HW + i] = (float)r;
+}
+
+}  // namespace ged
+
+using namespace ged;
+
+// ============================================================================================
+// C-ABI (include/gedepth.h)
+// ============================================================================================
+GED_API int ged_ground_plane(float* ch3, float* ch4, int64_t batch_stride3, int64_t batch_stride4,
+                             int B, int H, int W, const double* coef4, double u0, double v0,
+                             double su, double sv, float depth_scale, float clamp_max,
+                             cudaStream_t stream) {
+  if (!ch3 || !ch4 || !coef4 || B <= 0 || H <= 0 || W <= 0) return GED_ERR_ARG;
+  dim3 block(256), grid(cdiv(cdiv(W, 4), 256), H);
+  ground_plane_kernel<<<grid, block, 0, stream>>>(ch3, ch4, batch_stride3, batch_stride4, B, H, W,
+                                                 coef4[0], coef4[1], coef4[2], coef4[3], u0, v0, su, sv,
+                                                 depth_scale, clamp_max);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+GED_API int ged_pixel_grid(long long* u, long long* v, int H, int W, int u0, int v0,
+                           cudaStream_t stream) {
+  if (!u || !v || H <= 0 || W <= 0) return GED_ERR_ARG;
+  pixel_grid_kernel<<<dim3(cdiv(W, 256), H), 256, 0, stream>>>(u, v, H, W, u0, v0);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+static inline bool half_shape_ok(int H, int W, int h2, int w2) {
+  // the staged source window of one tile must fit the shared-memory tile (half map ~ H/2 x W/2)
+  if (h2 <= 0 || w2 <= 0 || H <= 0 || W <= 0) return false;
+  const float sy = resize_scale(h2, H, false), sx = resize_scale(w2, W, false);
+  const int th = H < TILE_H ? H : TILE_H, tw = W < TILE_W ? W : TILE_W;
+  return (float)th * sy + 3.f <= (float)ST_H && (float)tw * sx + 3.f <= (float)ST_W;
+}
+
+GED_API int ged_ge_vanilla_fwd(const float* pe_norm, int64_t pe_batch_stride, const float* y_half,
+                               float* y, float* pe_mask, int B, int H, int W, int h2, int w2,
+                               cudaStream_t stream) {
+  if (!pe_norm || !y_half || !y || !pe_mask || B <= 0) return GED_ERR_ARG;
+  if (!half_shape_ok(H, W, h2, w2)) return GED_ERR_SHAPE;
+  const float sy = resize_scale(h2, H, false), sx = resize_scale(w2, W, false);
+  dim3 block(TX, TILE_H), grid(cdiv(W, TILE_W), cdiv(H, TILE_H), B);
+  const bool vec = (W % 4 == 0) && aligned16(pe_norm) && aligned16(y) && aligned16(pe_mask) &&
+                   (pe_batch_stride % 4 == 0);
+  if (vec) ge_vanilla_fwd_kernel<true><<<grid, block, 0, stream>>>(pe_norm, pe_batch_stride, y_half, y, pe_mask, H, W, h2, w2, sy, sx);
+  else ge_vanilla_fwd_kernel<false><<<grid, block, 0, stream>>>(pe_norm, pe_batch_stride, y_half, y, pe_mask, H, W, h2, w2, sy, sx);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+GED_API int ged_ge_vanilla_bwd(const float* pe_norm, int64_t pe_batch_stride, const float* g_y,
+                               const float* g_pe_mask, float* g_y_half, int B, int H, int W, int h2,
+                               int w2, cudaStream_t stream) {
+  if (!pe_norm || !g_y_half || B <= 0) return GED_ERR_ARG;
+  if (!half_shape_ok(H, W, h2, w2)) return GED_ERR_SHAPE;
+  const float sy = resize_scale(h2, H, false), sx = resize_scale(w2, W, false);
+  if (cudaMemsetAsync(g_y_half, 0, sizeof(float) * (size_t)B * h2 * w2, stream) != cudaSuccess) return GED_ERR_LAUNCH;
+  dim3 block(TX, TILE_H), grid(cdiv(W, TILE_W), cdiv(H, TILE_H), B);
+  ge_vanilla_bwd_kernel<<<grid, block, 0, stream>>>(pe_norm, pe_batch_stride, g_y, g_pe_mask, g_y_half, H, W, h2, w2, sy, sx);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+GED_API int ged_ge_adaptive_fwd(const float* pe_raw, int64_t pe_batch_stride, const float* y_half,
+                                const float* logits_half, const float* height, float height_scalar,
+                                float depth_scale, float* y, float* pe_mask, float* logits_full, int B,
+                                int H, int W, int h2, int w2, cudaStream_t stream) {
+  if (!pe_raw || !y_half || !logits_half || !y || !pe_mask || B <= 0) return GED_ERR_ARG;
+  if (!half_shape_ok(H, W, h2, w2)) return GED_ERR_SHAPE;
+  if ((W % 4 == 0) && !(aligned16(y) && aligned16(pe_mask) && (!logits_full || aligned16(logits_full)))) return GED_ERR_ALIGN;
+  const float sy = resize_scale(h2, H, false), sx = resize_scale(w2, W, false);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(ge_adaptive_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    attr_set = true;
+  }
+  dim3 block(TX, TILE_H), grid(cdiv(W, TILE_W), cdiv(H, TILE_H), B);
+  ge_adaptive_fwd_kernel<<<grid, block, 0, stream>>>(pe_raw, pe_batch_stride, y_half, logits_half, height, height_scalar, depth_scale, y, pe_mask, logits_full, H, W, h2, w2, sy, sx);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+GED_API int ged_ge_adaptive_bwd(const float* pe_raw, int64_t pe_batch_stride, const float* y_half,
+                                const float* logits_half, const float* height, float height_scalar,
+                                float depth_scale, const float* g_y, const float* g_pe_mask,
+                                const float* g_logits_full, float* g_y_half, float* g_logits_half,
+                                int B, int H, int W, int h2, int w2, cudaStream_t stream) {
+  if (!pe_raw || !y_half || !logits_half || !g_y_half || !g_logits_half || B <= 0) return GED_ERR_ARG;
+  if (!half_shape_ok(H, W, h2, w2)) return GED_ERR_SHAPE;
+  const float sy = resize_scale(h2, H, false), sx = resize_scale(w2, W, false);
+  const size_t smem = sizeof(float) * ((NSLOPE + 1) * TILE_H * (TILE_W + 1) + ST_H * ST_W + NSLOPE * ST_H * ST_W);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(ge_adaptive_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return GED_ERR_LAUNCH;
+    attr_set = true;
+  }
+  if (cudaMemsetAsync(g_y_half, 0, sizeof(float) * (size_t)B * h2 * w2, stream) != cudaSuccess) return GED_ERR_LAUNCH;
+  if (cudaMemsetAsync(g_logits_half, 0, sizeof(float) * (size_t)B * NSLOPE * h2 * w2, stream) != cudaSuccess) return GED_ERR_LAUNCH;
+  dim3 block(TX, TILE_H), grid(cdiv(W, TILE_W), cdiv(H, TILE_H), B);
+  ge_adaptive_bwd_kernel<<<grid, block, smem, stream>>>(pe_raw, pe_batch_stride, y_half, logits_half, height, height_scalar, depth_scale, g_y, g_pe_mask, g_logits_full, g_y_half, g_logits_half, H, W, h2, w2, sy, sx);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+GED_API int ged_fuse_head_fwd(const float* d, const float* pe_mask, const float* y, float* out,
+                              float* y_h, float min_depth, int B, int H, int W, int h2, int w2,
+                              cudaStream_t stream) {
+  if (!d || !pe_mask || !y || !out || !y_h || B <= 0) return GED_ERR_ARG;
+  const float sy = resize_scale(H, h2, true), sx = resize_scale(W, w2, true);
+  fuse_head_fwd_kernel<<<dim3(cdiv(w2, 256), h2, B), 256, 0, stream>>>(d, pe_mask, y, out, y_h, H, W, h2, w2, sy, sx, min_depth);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+GED_API int ged_fuse_head_bwd(const float* g_out, const float* g_yh_extra, const float* d,
+                              const float* y_h, float* g_d, float* g_pe_mask, float* g_y, int B, int H,
+                              int W, int h2, int w2, cudaStream_t stream) {
+  if (!g_out || !d || !y_h || !g_d || !g_pe_mask || !g_y || B <= 0) return GED_ERR_ARG;
+  const float sy = resize_scale(H, h2, true), sx = resize_scale(W, w2, true);
+  const int64_t n = (int64_t)B * h2 * w2;
+  fuse_head_bwd_half_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(g_out, y_h, g_d, n);
+  fuse_head_bwd_full_kernel<<<dim3(cdiv(W, 256), H, B), 256, 0, stream>>>(g_out, d, g_yh_extra, g_pe_mask, g_y, H, W, h2, w2, sy, sx);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+GED_API int ged_find_k(const float* gt, const float* pe, int64_t pe_batch_stride, float* k_out, int B,
+                       int H, int W, float cam_height, int truncate, cudaStream_t stream) {
+  if (!gt || !pe || !k_out || B <= 0) return GED_ERR_ARG;
+  const int64_t HW = (int64_t)H * W;
+  find_k_kernel<<<dim3((unsigned)((HW + 255) / 256), B), 256, 0, stream>>>(gt, pe, pe_batch_stride, k_out, HW, cam_height, truncate);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}

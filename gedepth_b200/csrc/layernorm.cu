@@ -1,0 +1,128 @@
+// LayerNorm over the channel dimension of a token matrix (rows x C), sm_100a.
+// a5/a6/a9/a10: nn.LayerNorm(eps=1e-5) sites at embed.py:299-300, depthformer_swin.py:118,463,469,1178.
+// One warp per row, two-pass statistics (mean, then centred variance - same numerics class as ATen's
+// Welford), float4 accesses; mean / rstd are kept for the backward.  HBM-bound: 8 B/element fwd.
+#include "common.cuh"
+
+namespace ged {
+
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x,
+                                                             const float* __restrict__ w,
+                                                             const float* __restrict__ b,
+                                                             float* __restrict__ y, float* __restrict__ mean,
+                                                             float* __restrict__ rstd, int64_t rows, int C,
+                                                             float eps) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = (const float4*)(x + row * C);
+  const int C4 = C >> 2;
+  float s = 0.f;
+  for (int i = lane; i < C4; i += 32) { float4 v = __ldg(xr + i); s += (v.x + v.y) + (v.z + v.w); }
+  const float mu = warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int i = lane; i < C4; i += 32) {
+    float4 v = __ldg(xr + i);
+    float a = v.x - mu, b2 = v.y - mu, c = v.z - mu, d = v.w - mu;
+    q += (a * a + b2 * b2) + (c * c + d * d);
+  }
+  const float rs = rsqrtf(warp_sum(q) / (float)C + eps);
+  if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+  float4* yr = (float4*)(y + row * C);
+  for (int i = lane; i < C4; i += 32) {
+    float4 v = __ldg(xr + i), g = __ldg((const float4*)w + i), bb = __ldg((const float4*)b + i);
+    float4 o;
+    o.x = (v.x - mu) * rs * g.x + bb.x; o.y = (v.y - mu) * rs * g.y + bb.y;
+    o.z = (v.z - mu) * rs * g.z + bb.z; o.w = (v.w - mu) * rs * g.w + bb.w;
+    yr[i] = o;
+  }
+}
+
+// dx = rstd * (g*w - mean_c(g*w) - xhat * mean_c(g*w*xhat))
+__global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(
+    const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
+    const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx, int64_t rows,
+    int C) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = (const float4*)(x + row * C);
+  const float4* gr = (const float4*)(g + row * C);
+  const int C4 = C >> 2;
+  const float mu = mean[row], rs = rstd[row];
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < C4; i += 32) {
+    float4 v = __ldg(xr + i), gg = __ldg(gr + i), ww = __ldg((const float4*)w + i);
+    float a = gg.x * ww.x, b2 = gg.y * ww.y, c = gg.z * ww.z, d = gg.w * ww.w;
+    s1 += (a + b2) + (c + d);
+    s2 += (a * (v.x - mu) + b2 * (v.y - mu)) + (c * (v.z - mu) + d * (v.w - mu));
+  }
+  s1 = warp_sum(s1) / (float)C;
+  s2 = warp_sum(s2) * rs / (float)C;      // mean(g*w*xhat)
+  float4* dr = (float4*)(dx + row * C);
+  for (int i = lane; i < C4; i += 32) {
+    float4 v = __ldg(xr + i), gg = __ldg(gr + i), ww = __ldg((const float4*)w + i);
+    float4 o;
+    o.x = rs * (gg.x * ww.x - s1 - (v.x - mu) * rs * s2);
+    o.y = rs * (gg.y * ww.y - s1 - (v.y - mu) * rs * s2);
+    o.z = rs * (gg.z * ww.z - s1 - (v.z - mu) * rs * s2);
+    o.w = rs * (gg.w * ww.w - s1 - (v.w - mu) * rs * s2);
+    dr[i] = o;
+  }
+}
+
+// dw[c] += sum_rows g*xhat ; db[c] += sum_rows g.  grid (C/32, row chunks), block (32, 8).
+__global__ void __launch_bounds__(256) layernorm_bwd_wb_kernel(
+    const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ mean,
+    const float* __restrict__ rstd, float* __restrict__ dw, float* __restrict__ db, int64_t rows, int C,
+    int rows_per_block) {
+  __shared__ float s_w[8][33], s_b[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  float aw = 0.f, ab = 0.f;
+  if (c < C) {
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float gg = __ldg(g + r * C + c);
+      aw += gg * (__ldg(x + r * C + c) - __ldg(mean + r)) * __ldg(rstd + r);
+      ab += gg;
+    }
+  }
+  s_w[threadIdx.y][threadIdx.x] = aw; s_b[threadIdx.y][threadIdx.x] = ab;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) { aw += s_w[i][threadIdx.x]; ab += s_b[i][threadIdx.x]; }
+    atomicAdd(dw + c, aw);
+    atomicAdd(db + c, ab);
+  }
+}
+
+}  // namespace ged
+using namespace ged;
+
+GED_API int ged_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean,
+                              float* rstd, int64_t rows, int C, float eps, cudaStream_t stream) {
+  if (!x || !w || !b || !y || !mean || !rstd || rows <= 0) return GED_ERR_ARG;
+  if (C % 4 != 0) return GED_ERR_SHAPE;
+  if (!aligned16(x) || !aligned16(y) || !aligned16(w) || !aligned16(b)) return GED_ERR_ALIGN;
+  layernorm_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(x, w, b, y, mean, rstd, rows, C, eps);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+// dw / db are ACCUMULATED into (caller zeroes or passes the running .grad buffers).
+GED_API int ged_layernorm_bwd(const float* g, const float* x, const float* w, const float* mean,
+                              const float* rstd, float* dx, float* dw, float* db, int64_t rows, int C,
+                              cudaStream_t stream) {
+  if (!g || !x || !w || !mean || !rstd || !dx || rows <= 0) return GED_ERR_ARG;
+  if (C % 4 != 0) return GED_ERR_SHAPE;
+  if (!aligned16(x) || !aligned16(g) || !aligned16(dx) || !aligned16(w)) return GED_ERR_ALIGN;
+  layernorm_bwd_dx_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(g, x, w, mean, rstd, dx, rows, C);
+  if (dw && db) {
+    const int rpb = 256;
+    dim3 grid(cdiv(C, 32), (unsigned)((rows + rpb - 1) / rpb));
+    layernorm_bwd_wb_kernel<<<grid, dim3(32, 8), 0, stream>>>(g, x, mean, rstd, dw, db, rows, C, rpb);
+  }
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}

@@ -1,3 +1,642 @@
-"""placeholder - replaced below"""
-def has(name):
-    return False
+"""ctypes binding of libgedepth_sm100.so (include/gedepth.h) + the torch.autograd.Function wrappers
+that own tensors around it.  PyTorch is plumbing here: it allocates device memory and provides the
+current stream; every number is produced by the sm_100a kernels behind the C ABI.
+
+Fails loudly: a missing / unloadable library or a non-zero status raises RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+from torch.autograd import Function
+
+from . import ops_lib as L
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgedepth_sm100.so")
+
+_P, _I, _I64, _F, _D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+
+# name -> argtypes (mirrors include/gedepth.h; tests/test_cabi.py checks the header against this)
+SIGNATURES = {
+    "ged_ground_plane": [_P, _P, _I64, _I64, _I, _I, _I, _P, _D, _D, _D, _D, _F, _F, _P],
+    "ged_pixel_grid": [_P, _P, _I, _I, _I, _I, _P],
+    "ged_ge_vanilla_fwd": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "ged_ge_vanilla_bwd": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "ged_ge_adaptive_fwd": [_P, _I64, _P, _P, _P, _F, _F, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "ged_ge_adaptive_bwd": [_P, _I64, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "ged_fuse_head_fwd": [_P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P],
+    "ged_fuse_head_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "ged_find_k": [_P, _P, _I64, _P, _I, _I, _I, _F, _I, _P],
+    "ged_silog_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _I, _P],
+    "ged_silog_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _I, _P],
+    "ged_ce_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "ged_ce_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "ged_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I64, _I, _F, _P],
+    "ged_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P],
+    "ged_winattn_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    "ged_winattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    "ged_gemm_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _I, _P],
+    "ged_conv3x3_tf32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _F, _P],
+    "ged_msda_fwd": [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ged_msda_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ged_sumsq": [_P, _I64, _P, _P],
+    "ged_adamw_step": [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _F, _I, _P],
+}
+
+_lib = None
+_load_error: Optional[str] = None
+
+# ops whose sm_100a kernel is wired in (ops.py consults has()); everything else is a library call
+NATIVE_OPS = {"ground_plane", "ge_vanilla", "ge_adaptive", "fuse_head", "silog", "cross_entropy",
+              "layer_norm", "window_attention", "msda_sample", "linear", "conv2d", "conv_bn_act",
+              "find_k", "adamw"}
+
+
+def load():
+    """dlopen the extension once.  Raises RuntimeError when it is missing (no fallback)."""
+    global _lib, _load_error
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        _load_error = (f"{LIB_PATH} is missing: build it with `python -m gedepth_b200.build` "
+                       "(__graft_entry__.build()). gedepth_b200 has no fallback path.")
+        raise RuntimeError(_load_error)
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.ged_version.restype = C.c_int
+    lib.ged_arch.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def has(name: str) -> bool:
+    load()
+    return name in NATIVE_OPS
+
+
+_ERR = {-1: "GED_ERR_ARG", -2: "GED_ERR_SHAPE", -3: "GED_ERR_ALIGN", -4: "GED_ERR_LAUNCH", -5: "GED_ERR_WORKSPACE"}
+LAUNCHES = 0      # number of C-ABI calls issued (bench.py reports it as gpu_launches)
+
+
+def _call(name, *args):
+    global LAUNCHES
+    rc = getattr(load(), name)(*args)
+    LAUNCHES += 1
+    if rc != 0:
+        raise RuntimeError(f"{name} failed: {_ERR.get(rc, rc)}")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# =============================================================================================
+# ground embedding
+# =============================================================================================
+def ground_plane(coef, H, W, device, batch, u0, v0, depth_scale, clamp_max, su, sv):
+    out = torch.empty(batch, 2, H, W, dtype=torch.float32, device=device)
+    c = (C.c_double * 4)(*[float(x) for x in coef])
+    with torch.cuda.device(out.device):
+        _call("ged_ground_plane", _p(out[:, 0]), _p(out[:, 1]), 2 * H * W, 2 * H * W, batch, H, W, c,
+              float(u0), float(v0), float(su), float(sv), float(depth_scale), float(clamp_max), _stream())
+    return out
+
+
+def ground_plane_into(img: torch.Tensor, coef, u0=0, v0=0, depth_scale=200.0, clamp_max=200.0, su=1.0, sv=1.0):
+    """Write channels 3 and 4 of a (B,5,H,W) input batch in place (what the loader would attach)."""
+    B, Cc, H, W = img.shape
+    assert Cc == 5 and img.is_contiguous() and img.dtype == torch.float32
+    c = (C.c_double * 4)(*[float(x) for x in coef])
+    with torch.cuda.device(img.device):
+        _call("ged_ground_plane", _p(img[:, 3]), _p(img[:, 4]), 5 * H * W, 5 * H * W, B, H, W, c, float(u0),
+              float(v0), float(su), float(sv), float(depth_scale), float(clamp_max), _stream())
+    return img
+
+
+def pixel_grid(H, W, device, u0=0, v0=0):
+    u = torch.empty(H, W, dtype=torch.int64, device=device)
+    v = torch.empty(H, W, dtype=torch.int64, device=device)
+    with torch.cuda.device(u.device):
+        _call("ged_pixel_grid", _p(u), _p(v), H, W, int(u0), int(v0), _stream())
+    return u, v
+
+
+def _plane(img: torch.Tensor, ch: int):
+    """(pointer tensor, batch stride) of one channel plane of an NCHW batch without copying."""
+    B, Cc, H, W = img.shape
+    if img.dtype == torch.float32 and img.stride(3) == 1 and img.stride(2) == W:
+        return img[:, ch], img.stride(0)
+    pl = img[:, ch].float().contiguous()
+    return pl, H * W
+
+
+class _GEVanilla(Function):
+    @staticmethod
+    def forward(ctx, img, y_half):
+        B, _, H, W = img.shape
+        yh = _f32c(y_half)
+        h2, w2 = yh.shape[2], yh.shape[3]
+        pe, bs = _plane(img, 3)
+        y = torch.empty(B, 1, H, W, dtype=torch.float32, device=img.device)
+        pm = torch.empty_like(y)
+        _call("ged_ge_vanilla_fwd", _p(pe), bs, _p(yh), _p(y), _p(pm), B, H, W, h2, w2, _stream())
+        ctx.save_for_backward(img)
+        ctx.dims = (B, H, W, h2, w2)
+        return y, pm
+
+    @staticmethod
+    def backward(ctx, g_y, g_pm):
+        (img,) = ctx.saved_tensors
+        B, H, W, h2, w2 = ctx.dims
+        pe, bs = _plane(img, 3)
+        g_half = torch.empty(B, 1, h2, w2, dtype=torch.float32, device=img.device)
+        _call("ged_ge_vanilla_bwd", _p(pe), bs, _p(None if g_y is None else _f32c(g_y)),
+              _p(None if g_pm is None else _f32c(g_pm)), _p(g_half), B, H, W, h2, w2, _stream())
+        return None, g_half
+
+
+def ge_vanilla(img, y_half):
+    return _GEVanilla.apply(img, y_half)
+
+
+class _GEAdaptive(Function):
+    @staticmethod
+    def forward(ctx, img, y_half, logits_half, height, height_scalar, depth_scale, want_logits):
+        B, _, H, W = img.shape
+        yh, lh = _f32c(y_half), _f32c(logits_half)
+        h2, w2 = yh.shape[2], yh.shape[3]
+        pe, bs = _plane(img, 4)
+        y = torch.empty(B, 1, H, W, dtype=torch.float32, device=img.device)
+        pm = torch.empty_like(y)
+        lf = torch.empty(B, 11, H, W, dtype=torch.float32, device=img.device) if want_logits else None
+        ht = None if height is None else _f32c(height.to(img.device))
+        _call("ged_ge_adaptive_fwd", _p(pe), bs, _p(yh), _p(lh), _p(ht), float(height_scalar),
+              float(depth_scale), _p(y), _p(pm), _p(lf), B, H, W, h2, w2, _stream())
+        ctx.save_for_backward(img, yh, lh, ht if ht is not None else torch.empty(0, device=img.device))
+        ctx.cfg = (B, H, W, h2, w2, float(height_scalar), float(depth_scale), ht is not None)
+        if lf is None:
+            lf = torch.empty(0, device=img.device)
+        return y, pm, lf
+
+    @staticmethod
+    def backward(ctx, g_y, g_pm, g_lf):
+        img, yh, lh, ht = ctx.saved_tensors
+        B, H, W, h2, w2, hs, ds, has_h = ctx.cfg
+        pe, bs = _plane(img, 4)
+        g_yh = torch.empty_like(yh)
+        g_lh = torch.empty_like(lh)
+        if g_lf is not None and g_lf.numel() == 0:
+            g_lf = None
+        _call("ged_ge_adaptive_bwd", _p(pe), bs, _p(yh), _p(lh), _p(ht if has_h else None), hs, ds,
+              _p(None if g_y is None else _f32c(g_y)), _p(None if g_pm is None else _f32c(g_pm)),
+              _p(None if g_lf is None else _f32c(g_lf)), _p(g_yh), _p(g_lh), B, H, W, h2, w2, _stream())
+        return None, g_yh, g_lh, None, None, None, None
+
+
+def ge_adaptive(img, y_half, logits_half, height, depth_scale):
+    if torch.is_tensor(height):
+        ht, hs = height.reshape(-1), 0.0
+    else:
+        ht, hs = None, float(height)
+    want_logits = torch.is_grad_enabled()
+    y, pm, lf = _GEAdaptive.apply(img, y_half, logits_half, ht, hs, depth_scale, want_logits)
+    return y, pm, (lf if want_logits else None)
+
+
+class _FuseHead(Function):
+    @staticmethod
+    def forward(ctx, d, pe_mask, y, min_depth):
+        d, pe_mask, y = _f32c(d), _f32c(pe_mask), _f32c(y)
+        B, _, h2, w2 = d.shape
+        H, W = y.shape[2], y.shape[3]
+        out, y_h = torch.empty_like(d), torch.empty_like(d)
+        _call("ged_fuse_head_fwd", _p(d), _p(pe_mask), _p(y), _p(out), _p(y_h), float(min_depth), B, H, W, h2,
+              w2, _stream())
+        ctx.save_for_backward(d, y_h)
+        ctx.dims = (B, H, W, h2, w2)
+        return out, y_h
+
+    @staticmethod
+    def backward(ctx, g_out, g_yh):
+        d, y_h = ctx.saved_tensors
+        B, H, W, h2, w2 = ctx.dims
+        g_d = torch.empty_like(d)
+        g_pm = torch.empty(B, 1, H, W, dtype=torch.float32, device=d.device)
+        g_y = torch.empty_like(g_pm)
+        g_out = _f32c(g_out) if g_out is not None else torch.zeros_like(d)
+        _call("ged_fuse_head_bwd", _p(g_out), _p(None if g_yh is None else _f32c(g_yh)), _p(d), _p(y_h),
+              _p(g_d), _p(g_pm), _p(g_y), B, H, W, h2, w2, _stream())
+        return g_d, g_pm, g_y, None
+
+
+def fuse_head(d, pe_mask, y, min_depth):
+    return _FuseHead.apply(d, pe_mask, y, min_depth)
+
+
+def find_k(gt, pe, h, truncate=False):
+    gt = _f32c(gt)
+    B = gt.shape[0]
+    H, W = gt.shape[-2], gt.shape[-1]
+    pe = _f32c(pe)
+    bs = 0 if pe.numel() == H * W else H * W
+    out = torch.empty(B, H, W, dtype=torch.float32, device=gt.device)
+    _call("ged_find_k", _p(gt), _p(pe), bs, _p(out), B, H, W, float(h), int(bool(truncate)), _stream())
+    return out
+
+
+# =============================================================================================
+# losses
+# =============================================================================================
+class _SiLog(Function):
+    @staticmethod
+    def forward(ctx, pred, gt, eps, lam, max_depth, upsample):
+        pred, gt = _f32c(pred), _f32c(gt)
+        B, _, H, W = gt.shape
+        hp, wp = pred.shape[2], pred.shape[3]
+        stats = torch.empty(8, dtype=torch.float64, device=gt.device)
+        loss = torch.empty((), dtype=torch.float32, device=gt.device)
+        md = float(max_depth) if max_depth is not None else 0.0
+        _call("ged_silog_fwd", _p(pred), _p(gt), _p(stats), _p(loss), B, H, W, hp, wp, float(eps), float(lam),
+              md, int(upsample), _stream())
+        ctx.save_for_backward(pred, gt, stats)
+        ctx.cfg = (B, H, W, hp, wp, float(eps), float(lam), md, int(upsample))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, gt, stats = ctx.saved_tensors
+        B, H, W, hp, wp, eps, lam, md, up = ctx.cfg
+        g_pred = torch.empty_like(pred)
+        _call("ged_silog_bwd", _p(pred), _p(gt), _p(stats), _p(_f32c(g)), _p(g_pred), B, H, W, hp, wp, eps, lam,
+              md, up, _stream())
+        return g_pred, None, None, None, None, None
+
+
+def silog(pred, gt, eps, lam, max_depth, upsample):
+    return _SiLog.apply(pred, gt, eps, lam, max_depth, bool(upsample))
+
+
+class _CE(Function):
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        logits, target = _f32c(logits), _f32c(target)
+        B, Cc, H, W = logits.shape
+        stats = torch.empty(8, dtype=torch.float64, device=logits.device)
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        _call("ged_ce_fwd", _p(logits), _p(target), _p(stats), _p(loss), B, Cc, H, W, float(ignore_index), _stream())
+        ctx.save_for_backward(logits, target, stats)
+        ctx.ignore = float(ignore_index)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, target, stats = ctx.saved_tensors
+        B, Cc, H, W = logits.shape
+        gl = torch.empty_like(logits)
+        _call("ged_ce_bwd", _p(logits), _p(target), _p(stats), _p(_f32c(g)), _p(gl), B, Cc, H, W, ctx.ignore, _stream())
+        return gl, None, None
+
+
+def cross_entropy(logits, target, ignore_index=255):
+    if logits.shape[1] != 11:
+        return L.cross_entropy(logits, target, ignore_index)
+    return _CE.apply(logits, target, ignore_index)
+
+
+# =============================================================================================
+# Swin pieces
+# =============================================================================================
+class _LayerNorm(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        xc = _f32c(x)
+        Cc = xc.shape[-1]
+        rows = xc.numel() // Cc
+        y = torch.empty_like(xc)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        _call("ged_layernorm_fwd", _p(xc), _p(w), _p(b), _p(y), _p(mean), _p(rstd), rows, Cc, float(eps), _stream())
+        ctx.save_for_backward(xc, w, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, w, mean, rstd = ctx.saved_tensors
+        Cc = xc.shape[-1]
+        rows = xc.numel() // Cc
+        g = _f32c(g)
+        dx = torch.empty_like(xc)
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dw = torch.zeros(Cc, dtype=torch.float32, device=xc.device) if need_w else None
+        db = torch.zeros_like(dw) if need_w else None
+        _call("ged_layernorm_bwd", _p(g), _p(xc), _p(w), _p(mean), _p(rstd), _p(dx), _p(dw), _p(db), rows, Cc, _stream())
+        return dx, dw, db, None
+
+
+def layer_norm(x, w, b, eps):
+    if x.shape[-1] % 4:
+        return L.layer_norm(x, w, b, eps)
+    return _LayerNorm.apply(x, w, b, eps)
+
+
+class _WinAttn(Function):
+    @staticmethod
+    def forward(ctx, qkv, qkv_bias, table, index, H, W, nH, ws, shift, scale):
+        qkv = _f32c(qkv)
+        B, Lt, C3 = qkv.shape
+        Cc = C3 // 3
+        ctx_out = torch.empty(B, Lt, Cc, dtype=torch.float32, device=qkv.device)
+        idx = index if index.dtype == torch.int64 and index.is_contiguous() else index.long().contiguous()
+        table_c = _f32c(table)
+        _call("ged_winattn_fwd", _p(qkv), _p(qkv_bias), _p(table_c), _p(idx), _p(ctx_out), B, H, W, Cc, nH, ws,
+              shift, float(scale), _stream())
+        ctx.save_for_backward(qkv, qkv_bias if qkv_bias is not None else torch.empty(0, device=qkv.device),
+                              table_c, idx)
+        ctx.cfg = (B, H, W, Cc, nH, ws, shift, float(scale), qkv_bias is not None)
+        return ctx_out
+
+    @staticmethod
+    def backward(ctx, g):
+        qkv, bias, table, idx = ctx.saved_tensors
+        B, H, W, Cc, nH, ws, shift, scale, has_bias = ctx.cfg
+        g = _f32c(g)
+        g_qkv = torch.empty_like(qkv)
+        g_table = torch.zeros_like(table)
+        g_bias = torch.zeros(3 * Cc, dtype=torch.float32, device=qkv.device) if has_bias else None
+        _call("ged_winattn_bwd", _p(qkv), _p(bias if has_bias else None), _p(table), _p(idx), _p(g), _p(g_qkv),
+              _p(g_bias), _p(g_table), B, H, W, Cc, nH, ws, shift, scale, _stream())
+        return g_qkv, g_bias, g_table, None, None, None, None, None, None, None
+
+
+def window_attention(qkv, qkv_bias, table, index, hw, nH, ws, shift, scale):
+    return _WinAttn.apply(qkv, qkv_bias, table, index, int(hw[0]), int(hw[1]), nH, ws, shift, scale)
+
+
+# =============================================================================================
+# tcgen05 GEMM: linear / 1x1 conv
+# =============================================================================================
+_ACT = {None: 0, "relu": 1, "leaky_relu": 2, "gelu": 3, "sigmoid": 4}
+
+
+def gemm(a2d: torch.Tensor, w: torch.Tensor, bias=None, act=None, slope=0.01, residual=None,
+         row_scale=None, rows_per_batch=1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = epi(a2d[M,K] @ w[N,K]^T).  a2d / w: last dim contiguous, 16B-aligned pitches."""
+    M, K = a2d.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a2d.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a2d.device)
+    _call("ged_gemm_tf32", _p(a2d), a2d.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K,
+          _p(bias), _ACT[act], float(slope), _p(residual), _p(row_scale), int(rows_per_batch), _stream())
+    return out
+
+
+def _act_grad(gz, act, slope, pre, post):
+    """d act(z)/dz applied to gz; elementwise library ops (not on the GEMM critical path)."""
+    if act is None:
+        return gz
+    if act == "relu":
+        return gz * (post > 0)
+    if act == "leaky_relu":
+        return torch.where(post > 0, gz, gz * slope)
+    if act == "sigmoid":
+        return gz * post * (1 - post)
+    if act == "gelu":
+        z = pre
+        cdf = 0.5 * (1 + torch.erf(z * 0.7071067811865476))
+        pdf = torch.exp(-0.5 * z * z) * 0.3989422804014327
+        return gz * (cdf + z * pdf)
+    raise KeyError(act)
+
+
+def _gemm_ok(M, N, K, *tensors):
+    if K % 4 or N < 16 or K < 32:
+        return False
+    return all(t is None or (t.dtype == torch.float32 and t.data_ptr() % 16 == 0) for t in tensors)
+
+
+class _Linear(Function):
+    """y = [residual +] [row_scale *] act(x @ w^T + b).  Forward and dX on tcgen05; dW = gz^T @ x is a
+    cuBLAS TF32 GEMM for now (needs MN-major UMMA operands)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, residual, row_scale):
+        K = x.shape[-1]
+        x2 = _f32c(x).reshape(-1, K)
+        M, N = x2.shape[0], w.shape[0]
+        wc = _f32c(w)
+        res2 = None if residual is None else _f32c(residual).reshape(M, N)
+        rpb = M // x.shape[0] if row_scale is not None else 1
+        need_pre = act == "gelu" and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        if need_pre:
+            pre = gemm(x2, wc, b)
+            out = L._act(pre, act)           # elementwise; GELU'(z) needs z (saved instead of recomputed)
+            if row_scale is not None:
+                out = out * row_scale.repeat_interleave(rpb).unsqueeze(1)
+            if res2 is not None:
+                out = out + res2
+        else:
+            pre = None
+            out = gemm(x2, wc, b, act, 0.01, res2, row_scale, rpb)
+        ctx.act, ctx.rpb, ctx.has_res, ctx.has_bias = act, rpb, residual is not None, b is not None
+        ctx.save_for_backward(x2, wc, pre if pre is not None else torch.empty(0, device=x.device),
+                              out if act in ("relu", "leaky_relu", "sigmoid") else torch.empty(0, device=x.device),
+                              row_scale if row_scale is not None else torch.empty(0, device=x.device))
+        ctx.xshape = x.shape
+        return out.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, w, pre, post, row_scale = ctx.saved_tensors
+        N, K = w.shape
+        g2 = _f32c(g).reshape(-1, N)
+        gz = g2
+        if row_scale.numel():
+            gz = gz * row_scale.repeat_interleave(ctx.rpb).unsqueeze(1)
+        gz = _act_grad(gz, ctx.act, 0.01, pre, post)
+        gz = gz if gz.is_contiguous() else gz.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wt = w.t().contiguous()                      # [K, N]: the [N'][K'] operand of dX = gz @ w
+            if _gemm_ok(gz.shape[0], K, N, gz, wt):
+                dx = gemm(gz, wt).reshape(ctx.xshape)
+            else:
+                dx = (gz @ w).reshape(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            dw = gz.t() @ x2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = gz.sum(0)
+        dres = g if ctx.has_res else None
+        return dx, dw, db, None, dres, None
+
+
+def linear(x, w, b=None, act=None, residual=None, row_scale=None):
+    K, N = x.shape[-1], w.shape[0]
+    M = x.numel() // K
+    if not _gemm_ok(M, N, K, x, w, b, residual) or act not in _ACT:
+        return L.linear(x, w, b, act, residual, row_scale)
+    return _Linear.apply(x, w, b, act, residual, row_scale)
+
+
+# =============================================================================================
+# tcgen05 implicit-GEMM 3x3 conv (NHWC) and 1x1 conv
+# =============================================================================================
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    """logical NCHW -> contiguous (B,H,W,C) tensor (a view when x is channels_last)."""
+    return _f32c(x.permute(0, 2, 3, 1))
+
+
+def conv2d_supported(x, w, stride, padding) -> bool:
+    Cout, Cin, kh, kw = w.shape
+    if stride != 1 or Cin % 32 or x.dtype != torch.float32:
+        return False
+    if kh == 1 and kw == 1 and padding == 0:
+        return Cout >= 16
+    return kh == 3 and kw == 3 and padding == 1
+
+
+def conv3x3_raw(x_nhwc: torch.Tensor, wk: torch.Tensor, bias, act, slope) -> torch.Tensor:
+    """x (B,H,W,Cin) contiguous, wk [Cout,3,3,Cin] contiguous -> (B,H,W,Cout)."""
+    B, H, W, Cin = x_nhwc.shape
+    Cout = wk.shape[0]
+    xp = torch.nn.functional.pad(x_nhwc, (0, 0, 1, 1, 1, 1))       # zero border (data movement only)
+    y = torch.empty(B, H, W, Cout, dtype=torch.float32, device=x_nhwc.device)
+    _call("ged_conv3x3_tf32", _p(xp), _p(wk), _p(y), Cout, B, H, W, Cin, Cout, _p(bias), _ACT[act], float(slope),
+          _stream())
+    return y
+
+
+class _Conv(Function):
+    """3x3/s1/p1 or 1x1 conv + bias + activation.  Forward and dX on tcgen05 (dX of a 3x3 conv is the
+    3x3 conv of dY with the flipped, transposed kernel); dW/db via cuDNN for now."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, slope):
+        Cout, Cin, kh, kw = w.shape
+        xh = _nhwc(x)
+        B, H, W, _ = xh.shape
+        if kh == 3:
+            y = conv3x3_raw(xh, w.permute(0, 2, 3, 1).contiguous(), b, act, slope)
+        else:
+            y = gemm(xh.reshape(-1, Cin), w.reshape(Cout, Cin), b, act, slope).reshape(B, H, W, Cout)
+        ctx.save_for_backward(xh, w, y if act is not None else torch.empty(0, device=x.device))
+        ctx.cfg = (act, slope, kh, b is not None)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        xh, w, y = ctx.saved_tensors
+        act, slope, kh, has_bias = ctx.cfg
+        Cout, Cin = w.shape[0], w.shape[1]
+        B, H, W, _ = xh.shape
+        gz = _act_grad(_nhwc(g), act, slope, None, y)
+        gz = gz if gz.is_contiguous() else gz.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            if kh == 3 and Cout % 32 == 0:
+                wt = w.flip(2, 3).permute(1, 2, 3, 0).contiguous()          # [Cin,3,3,Cout]
+                dx = conv3x3_raw(gz, wt, None, None, 0.0).permute(0, 3, 1, 2)
+            elif kh == 1 and _gemm_ok(B * H * W, Cin, Cout, gz):
+                dx = gemm(gz.reshape(-1, Cout), w.reshape(Cout, Cin).t().contiguous()).reshape(B, H, W, Cin).permute(0, 3, 1, 2)
+        mask = [ctx.needs_input_grad[0] and dx is None, ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]]
+        if any(mask):
+            pad = 1 if kh == 3 else 0
+            r = torch.ops.aten.convolution_backward(gz.permute(0, 3, 1, 2), xh.permute(0, 3, 1, 2), w,
+                                                    [Cout] if has_bias else None, [1, 1], [pad, pad], [1, 1],
+                                                    False, [0, 0], 1, mask)
+            dx = r[0] if mask[0] else dx
+            dw = r[1] if mask[1] else None
+            db = r[2] if mask[2] else None
+        return dx, dw, db, None, None
+
+
+def conv2d(x, w, b=None, stride=1, padding=0, act=None, slope=0.01):
+    return _Conv.apply(x, w, b, act, slope)
+
+
+def conv_bn_act(x, w, b, bn, stride=1, padding=0, act=None):
+    """ConvModule(conv -> BN -> act).  Eval mode: BN folds into the conv's weight/bias and the
+    activation into its epilogue.  Train mode needs batch statistics between conv and activation:
+    conv (tcgen05) -> BatchNorm (library, per-GPU statistics as in the reference) -> act."""
+    if bn is None:
+        return _Conv.apply(x, w, b, act, 0.01)
+    if not bn.training:
+        s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+        wf = w * s.view(-1, 1, 1, 1)
+        bf = bn.bias - bn.running_mean * s + (b * s if b is not None else 0)
+        return _Conv.apply(x, wf, bf, act, 0.01)
+    y = bn(_Conv.apply(x, w, b, None, 0.0))
+    return L._act(y, act)
+
+
+# =============================================================================================
+# deformable attention sampling
+# =============================================================================================
+class _MSDA(Function):
+    @staticmethod
+    def forward(ctx, v, ref, off, logit, shapes, nH, P):
+        v, ref, off, logit = _f32c(v), _f32c(ref), _f32c(off), _f32c(logit)
+        B, S, E = v.shape
+        Q = off.shape[1]
+        hw = (C.c_int * (2 * len(shapes)))(*[int(a) for s in shapes for a in s])
+        out = torch.empty(B, Q, E, dtype=torch.float32, device=v.device)
+        _call("ged_msda_fwd", _p(v), _p(ref), ref.shape[0], _p(off), _p(logit), _p(out), hw, len(shapes), B, S, Q,
+              nH, E // nH, P, _stream())
+        ctx.save_for_backward(v, ref, off, logit)
+        ctx.cfg = (tuple(tuple(s) for s in shapes), nH, P)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        v, ref, off, logit = ctx.saved_tensors
+        shapes, nH, P = ctx.cfg
+        B, S, E = v.shape
+        Q = off.shape[1]
+        hw = (C.c_int * (2 * len(shapes)))(*[int(a) for s in shapes for a in s])
+        g = _f32c(g)
+        g_v = torch.zeros_like(v)
+        need_ref = ctx.needs_input_grad[1] and ref.shape[0] == B
+        g_ref = torch.zeros_like(ref) if need_ref else None
+        g_off, g_logit = torch.empty_like(off), torch.empty_like(logit)
+        _call("ged_msda_bwd", _p(v), _p(ref), ref.shape[0], _p(off), _p(logit), _p(g), _p(g_v), _p(g_ref),
+              _p(g_off), _p(g_logit), hw, len(shapes), B, S, Q, nH, E // nH, P, _stream())
+        return g_v, g_ref, g_off, g_logit, None, None, None
+
+
+def msda_sample(v, shapes, ref, off, logit, nH, P):
+    B = v.shape[0]
+    if ref.shape[0] not in (1, B):
+        raise ValueError("reference_points batch must be 1 or B")
+    if ref.shape[0] == 1 and ref.requires_grad and B > 1:
+        ref = ref.expand(B, -1, -1)        # learnable reference points shared over the batch
+    return _MSDA.apply(v, ref, off, logit, shapes, nH, P)
+
+
+# =============================================================================================
+# optimizer
+# =============================================================================================
+def sumsq(flat_grad: torch.Tensor, out: torch.Tensor):
+    _call("ged_sumsq", _p(flat_grad), flat_grad.numel(), _p(out), _stream())
+    return out
+
+
+def adamw_step(p, g, m, v, wd_mask, sumsq_buf, max_norm, grad_scale, lr, beta1, beta2, eps, wd, step):
+    _call("ged_adamw_step", _p(p), _p(g), _p(m), _p(v), _p(wd_mask), p.numel(), _p(sumsq_buf), float(max_norm),
+          float(grad_scale), float(lr), float(beta1), float(beta2), float(eps), float(wd), int(step), _stream())

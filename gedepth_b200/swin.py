@@ -218,7 +218,7 @@ class DepthFormerSwin(BaseModule):
                                           pad_to_patch_size=True,
                                           norm_cfg=norm_cfg if patch_norm else None)
         total_depth = sum(depths)
-        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, total_depth)]
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, total_depth, device="cpu")]
         self.stages = ModuleList()
         c = embed_dims
         for i in range(len(depths)):

@@ -1,0 +1,76 @@
+"""Training step of the path: forward + SiLog(/CE) + backward + ONE NCCL all-reduce over a flat fp32
+gradient arena + fused clip/AdamW.
+
+Replaces, for this path, the reference's runner plumbing around ``train_step``:
+MMDistributedDataParallel bucketed all-reduce (depth/apis/train.py:58-67), OptimizerHook grad-clip
+(configs/depthformer/depthformer_v.py:148) and AdamW with paramwise decay_mult
+(depthformer_v.py:128-139, mmcv DefaultOptimizerConstructor: custom_keys match as substrings).
+One process per GPU; batch sharded only (no collective in the forward; BatchNorm statistics stay
+per-GPU exactly as in the reference).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import kernels
+
+NO_DECAY_KEYS = ("absolute_pos_embed", "relative_position_bias_table", "norm")
+
+
+class FlatArena:
+    """All parameters (and their gradients) of a model as views into two contiguous fp32 buffers."""
+
+    def __init__(self, model: torch.nn.Module):
+        params = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        self.names = [n for n, _ in params]
+        self.params = [p for _, p in params]
+        dev = self.params[0].device
+        sizes = [((p.numel() + 3) // 4) * 4 for p in self.params]        # 16-byte aligned segments
+        self.total = sum(sizes)
+        self.flat_p = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.wd_mask = torch.ones(self.total, dtype=torch.uint8, device=dev)
+        off = 0
+        for (n, p), sz in zip(params, sizes):
+            view = self.flat_p[off:off + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.flat_g[off:off + p.numel()].view_as(p)
+            if any(k in n for k in NO_DECAY_KEYS):
+                self.wd_mask[off:off + sz] = 0
+            off += sz
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+
+class Trainer:
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_norm=35.0,
+                 native_optimizer: bool = True):
+        self.model = model
+        self.arena = FlatArena(model)
+        self.m = torch.zeros_like(self.arena.flat_p)
+        self.v = torch.zeros_like(self.arena.flat_p)
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.arena.flat_p.device)
+        self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_norm
+        self.step_idx = 0
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def step(self, data_batch: Dict, sync_logs: bool = False):
+        """One optimisation step.  Returns the loss tensor (device) and, if ``sync_logs``, the
+        rank-averaged log_vars of the reference's ``_parse_losses`` (one device->host copy)."""
+        self.arena.zero_grad()
+        losses = self.model(**data_batch)
+        loss, log_vars = self.model._parse_losses(losses, sync=sync_logs)
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.arena.flat_g)            # ONE collective per step, NCCL over NVLink
+        self.step_idx += 1
+        kernels.sumsq(self.arena.flat_g, self.sumsq)
+        kernels.adamw_step(self.arena.flat_p, self.arena.flat_g, self.m, self.v, self.arena.wd_mask, self.sumsq,
+                           self.max_norm, 1.0 / self.world, self.lr, self.betas[0], self.betas[1], self.eps,
+                           self.wd, self.step_idx)
+        return loss, log_vars

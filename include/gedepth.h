@@ -1,0 +1,146 @@
+/* gedepth.h - C ABI of libgedepth_sm100.so: the sm_100a kernels of the GEDepth hot path.
+ *
+ * The reference (qcraftai/gedepth) is pure Python on PyTorch + mmcv; it has no FFI of its own for
+ * this path (its only native code, depth/models/_cdht, is dead and used pybind:
+ * depth/models/_cdht/deep_hough_cuda.cpp:99-102).  Each entry point below therefore cites the
+ * reference call site whose arithmetic it replaces.  A maintainer binds them with ctypes inside
+ * the corresponding module's forward (INTEGRATION.md shows the stubs).
+ *
+ * Conventions: plain device pointers and sizes, no framework types; every function enqueues work
+ * on `stream` and returns immediately with 0 (GED_OK) or a negative error code; nothing here
+ * allocates, synchronises or throws.  All tensors are fp32 and contiguous in the stated layout
+ * unless a stride argument says otherwise.  "accumulated" outputs must be zeroed by the caller.
+ */
+#ifndef GEDEPTH_H_
+#define GEDEPTH_H_
+
+#include <stdint.h>
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GED_OK 0
+#define GED_ERR_ARG (-1)       /* null pointer / non-positive size */
+#define GED_ERR_SHAPE (-2)     /* shape outside what the kernel is built for */
+#define GED_ERR_ALIGN (-3)     /* pointer or pitch not 16-byte aligned */
+#define GED_ERR_LAUNCH (-4)    /* CUDA launch / runtime error */
+#define GED_ERR_WORKSPACE (-5)
+
+int ged_version(void);                 /* 10000*major + 100*minor + patch */
+const char* ged_arch(void);            /* "sm_100a" */
+
+/* ---- ground embedding ------------------------------------------------------------------------ */
+/* tools/preprocess_data_kitti.py:47-53 (+ loading.py:388-403, transforms.py:40-48).
+ * pe[v,u] = coef[0] / (coef[1]*(u0+su*x) + coef[2]*(v0+sv*y) + coef[3]) in fp64 on the integer grid;
+ * ch4 <- (float)pe; ch3 <- pe with >clamp_max -> 0, <0 -> 0, then /depth_scale where >0.
+ * ch3/ch4: first pixel of the channel plane of batch 0; batch_stride in floats (5*H*W inside img). */
+int ged_ground_plane(float* ch3, float* ch4, int64_t batch_stride3, int64_t batch_stride4, int B, int H,
+                     int W, const double* coef4, double u0, double v0, double su, double sv,
+                     float depth_scale, float clamp_max, cudaStream_t stream);
+/* the int64 meshgrid of preprocess_data_kitti.py:52 (u[y,x] = u0+x, v[y,x] = v0+y) */
+int ged_pixel_grid(long long* u, long long* v, int H, int W, int u0, int v0, cudaStream_t stream);
+
+/* depth/models/depther/encoder_decoder.py:112-123 (Vanilla).  pe_norm = img[:,3] (batch stride in
+ * floats), y_half (B,1,h2,w2) -> y (B,1,H,W) = bilinear(align_corners=False), pe_mask = pe_norm*y*200. */
+int ged_ge_vanilla_fwd(const float* pe_norm, int64_t pe_batch_stride, const float* y_half, float* y,
+                       float* pe_mask, int B, int H, int W, int h2, int w2, cudaStream_t stream);
+/* g_y / g_pe_mask may be NULL; g_y_half is overwritten. */
+int ged_ge_vanilla_bwd(const float* pe_norm, int64_t pe_batch_stride, const float* g_y,
+                       const float* g_pe_mask, float* g_y_half, int B, int H, int W, int h2, int w2,
+                       cudaStream_t stream);
+
+/* depth/models/depther/encoder_decoder.py:79-102 (Adaptive).  pe_raw = img[:,4]; logits_half
+ * (B,11,h2,w2) planar; height (B) per-sample camera height or NULL -> height_scalar;
+ * logits_full (B,11,H,W) may be NULL (inference). */
+int ged_ge_adaptive_fwd(const float* pe_raw, int64_t pe_batch_stride, const float* y_half,
+                        const float* logits_half, const float* height, float height_scalar,
+                        float depth_scale, float* y, float* pe_mask, float* logits_full, int B, int H,
+                        int W, int h2, int w2, cudaStream_t stream);
+int ged_ge_adaptive_bwd(const float* pe_raw, int64_t pe_batch_stride, const float* y_half,
+                        const float* logits_half, const float* height, float height_scalar,
+                        float depth_scale, const float* g_y, const float* g_pe_mask,
+                        const float* g_logits_full, float* g_y_half, float* g_logits_half, int B, int H,
+                        int W, int h2, int w2, cudaStream_t stream);
+
+/* depth/models/decode_heads/decode_head.py:489-508.  d = relu(conv_depth(feat)) (B,1,h2,w2);
+ * out = d*(1-y_h) + pe_h + min_depth with y_h, pe_h = bilinear(align_corners=True) of y, pe_mask. */
+int ged_fuse_head_fwd(const float* d, const float* pe_mask, const float* y, float* out, float* y_h,
+                      float min_depth, int B, int H, int W, int h2, int w2, cudaStream_t stream);
+/* g_yh_extra: gradient arriving on the returned y_h (may be NULL). */
+int ged_fuse_head_bwd(const float* g_out, const float* g_yh_extra, const float* d, const float* y_h,
+                      float* g_d, float* g_pe_mask, float* g_y, int B, int H, int W, int h2, int w2,
+                      cudaStream_t stream);
+
+/* tools/preprocess_data_kitti.py:59-63,86-89 (truncate=0: round half even) and
+ * tools/preprocess_data_ddad.py:47-51,77-82 (truncate=1).  k_out in {-5..5} or 255 where gt==0. */
+int ged_find_k(const float* gt, const float* pe, int64_t pe_batch_stride, float* k_out, int B, int H,
+               int W, float cam_height, int truncate, cudaStream_t stream);
+
+/* ---- losses ---------------------------------------------------------------------------------- */
+/* decode_head.py:586-599 + losses/sigloss.py:36-53.  upsample=1: pred is (B,1,hp,wp) and is
+ * bilinearly resized (align_corners=True) to the gt size on the fly.  stats: double[8] scratch kept
+ * for the backward.  max_depth <= 0 disables the upper bound. */
+int ged_silog_fwd(const float* pred, const float* gt, double* stats, float* loss, int B, int H, int W,
+                  int hp, int wp, float eps, float lam, float max_depth, int upsample, cudaStream_t stream);
+int ged_silog_bwd(const float* pred, const float* gt, const double* stats, const float* g_loss,
+                  float* g_pred, int B, int H, int W, int hp, int wp, float eps, float lam,
+                  float max_depth, int upsample, cudaStream_t stream);
+/* losses/celoss.py:355-413 with decode_head.py:523-525: logits (B,C=11,H,W) planar, float labels. */
+int ged_ce_fwd(const float* logits, const float* target, double* stats, float* loss, int B, int C, int H,
+               int W, float ignore_index, cudaStream_t stream);
+int ged_ce_bwd(const float* logits, const float* target, const double* stats, const float* g_loss,
+               float* g_logits, int B, int C, int H, int W, float ignore_index, cudaStream_t stream);
+
+/* ---- Swin ------------------------------------------------------------------------------------ */
+/* nn.LayerNorm sites: embed.py:299-300, depthformer_swin.py:118,463,469,1178. */
+int ged_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd,
+                      int64_t rows, int C, float eps, cudaStream_t stream);
+/* dw / db accumulated (may both be NULL). */
+int ged_layernorm_bwd(const float* g, const float* x, const float* w, const float* mean,
+                      const float* rstd, float* dx, float* dw, float* db, int64_t rows, int C,
+                      cudaStream_t stream);
+/* depthformer_swin.py:285-360 + :184-224 minus the two linears.  qkv (B,H*W,3C) image order. */
+int ged_winattn_fwd(const float* qkv, const float* qkv_bias, const float* table, const long long* index,
+                    float* ctx, int B, int H, int W, int C, int nH, int window, int shift, float scale,
+                    cudaStream_t stream);
+/* g_qkv overwritten; g_bias (3C, may be NULL) and g_table (169,nH) accumulated. */
+int ged_winattn_bwd(const float* qkv, const float* qkv_bias, const float* table, const long long* index,
+                    const float* g_ctx, float* g_qkv, float* g_bias, float* g_table, int B, int H, int W,
+                    int C, int nH, int window, int shift, float scale, cudaStream_t stream);
+
+/* ---- tensor-core GEMM / conv (tcgen05, TF32) --------------------------------------------------- */
+/* D[M,N] = epi(A[M,K] @ W[N,K]^T): F.linear / 1x1 Conv2d sites depthformer_swin.py:96,119,174-176,
+ * 193,222; mmcv FFN; hahi.py:122-165; MSDA linears.  act: 0 none 1 relu 2 leaky 3 gelu 4 sigmoid. */
+int ged_gemm_tf32(const float* A, int lda, const float* W, int ldw, float* D, int ldd, int M, int N,
+                  int K, const float* bias, int act, float slope, const float* residual,
+                  const float* row_scale, int rows_per_batch, cudaStream_t stream);
+/* 3x3/s1/p1 conv, NHWC: hahi.py:138-165, pemask_neck.py:36-42, dynamicpe_neck.py:497-502,
+ * densedepth_head.py:21-22, decode_head.py:391.  Xpad [B,H+2,W+2,Cin] zero-bordered;
+ * Wk [Cout][3][3][Cin]; Y [B,H,W,*] with channel pitch ldy. */
+int ged_conv3x3_tf32(const float* Xpad, const float* Wk, float* Y, int ldy, int B, int H, int W, int Cin,
+                     int Cout, const float* bias, int act, float slope, cudaStream_t stream);
+
+/* ---- deformable attention sampling ----------------------------------------------------------- */
+/* mmcv.ops.MultiScaleDeformableAttention core (hahi.py:280-289,316-325).  value (B,S,nH,64);
+ * ref (ref_batch,Q,2); off (B,Q,nH,4,8,2); logit (B,Q,nH,32); out (B,Q,nH*64); level_hw = {h0,w0,...}. */
+int ged_msda_fwd(const float* value, const float* ref, int ref_batch, const float* off,
+                 const float* logit, float* out, const int* level_hw, int num_levels, int B, int S, int Q,
+                 int nH, int head_dim, int num_points, cudaStream_t stream);
+/* g_value accumulated; g_ref accumulated or NULL; g_off, g_logit overwritten. */
+int ged_msda_bwd(const float* value, const float* ref, int ref_batch, const float* off,
+                 const float* logit, const float* g_out, float* g_value, float* g_ref, float* g_off,
+                 float* g_logit, const int* level_hw, int num_levels, int B, int S, int Q, int nH,
+                 int head_dim, int num_points, cudaStream_t stream);
+
+/* ---- optimizer (configs/depthformer/depthformer_v.py:128-148) ---------------------------------- */
+int ged_sumsq(const float* g, int64_t n, double* out, cudaStream_t stream);
+int ged_adamw_step(float* p, const float* g, float* m, float* v, const uint8_t* wd_mask, int64_t n,
+                   const double* sumsq, float max_norm, float grad_scale, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEDEPTH_H_ */

@@ -1,0 +1,389 @@
+"""Per-kernel parity on the B200: every sm_100a kernel, called through the C-ABI (kernels.py ->
+ctypes -> libgedepth_sm100.so), against (i) the oracle's numpy/torch-CPU restatement and (ii) the
+plain PyTorch fp32 statement of the same op (ops_lib) on the GPU.  Tolerances are stated per test:
+bit-exact for integer work, ~1e-5 for fp32 SIMT kernels, 2e-3 relative for TF32 tensor-core GEMMs.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    from gedepth_b200 import kernels
+    kernels.load()
+    yield
+    torch.cuda.synchronize()
+
+
+def _close(a, b, rtol, atol, msg=""):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = int((err > tol).sum())
+    assert bad == 0, f"{msg}: {bad}/{a.numel()} mismatches, max abs err {float(err.max()):.3e}, max ref {float(b.abs().max()):.3e}"
+
+
+# ------------------------------------------------------------------------------------------------
+# a1: ground plane + integer grid
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H,W,u0,v0", [(375, 1242, 0, 0), (352, 1120, 61, 23), (37, 53, 5, 3)])
+def test_ground_plane_bit_exact_vs_numpy(H, W, u0, v0):
+    from gedepth_b200 import kernels as K
+    from oracle import ground as og
+    coef = og.plane_coefficients(og.kitti_projection(), og.KITTI_CAM_HEIGHT)
+    pe = og.ground_plane(coef, H, W, u0, v0)
+    ch3, ch4 = og.load_channels(pe, 200.0)
+    ch3 = og.normalize_pe(ch3, 200.0)
+    out = K.ground_plane(coef, H, W, DEV, 3, u0, v0, 200.0, 200.0, 1.0, 1.0).cpu().numpy()
+    for b in range(3):
+        assert np.array_equal(out[b, 1], ch4), "raw ground depth must equal float32(numpy float64 result) bit for bit"
+        assert np.array_equal(out[b, 0], ch3)
+    u, v = K.pixel_grid(H, W, DEV, u0, v0)
+    ur, vr = og.pixel_grid(H, W, u0, v0)
+    assert u.dtype == torch.int64 and np.array_equal(u.cpu().numpy(), ur) and np.array_equal(v.cpu().numpy(), vr)
+
+
+def test_find_k_matches_numpy():
+    from gedepth_b200 import kernels as K
+    from oracle import ground as og
+    coef = og.plane_coefficients(og.kitti_projection(), og.KITTI_CAM_HEIGHT)
+    pe = og.ground_plane(coef, 96, 320, 400, 150).astype(np.float32)
+    rng = np.random.default_rng(1)
+    gt = np.where(rng.random((2, 96, 320)) < 0.3, np.abs(pe) * (1 + 0.2 * rng.standard_normal((2, 96, 320))), 0).astype(np.float32)
+    got = K.find_k(torch.from_numpy(gt).to(DEV), torch.from_numpy(pe).to(DEV), 1.65, False).cpu().numpy()
+    ref = np.stack([og.find_k_kitti(gt[b].astype(np.float64), pe) for b in range(2)])
+    assert (got != ref).mean() < 1e-4          # rounding ties of atan in fp64 vs numpy's libm
+    assert np.all(got[gt == 0] == 255)
+    got_t = K.find_k(torch.from_numpy(gt).to(DEV), torch.from_numpy(pe).to(DEV), 1.56, True).cpu().numpy()
+    ref_t = np.stack([og.find_k_ddad(gt[b].astype(np.float64), pe.astype(np.float64), 1.56) for b in range(2)])
+    assert (got_t != ref_t).mean() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# a14 / a15 / a17: ground embedding, forward and backward, vs the library statement and the oracle
+# ------------------------------------------------------------------------------------------------
+def _ge_inputs(B, H, W, adaptive, seed=0):
+    from gedepth_b200.synth import synth_batch
+    b = synth_batch(B, H, W, seed=seed, adaptive=adaptive)
+    g = torch.Generator().manual_seed(seed)
+    h2, w2 = (H + 1) // 2, (W + 1) // 2
+    y_half = torch.rand(B, 1, h2, w2, generator=g)
+    logits_half = torch.randn(B, 11, h2, w2, generator=g) * 2
+    return torch.from_numpy(b["img"]), y_half, logits_half
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 160), (1, 70, 166), (3, 35, 83), (2, 352, 1120)])
+def test_ge_vanilla_fwd_bwd(B, H, W):
+    from gedepth_b200 import kernels as K, ops_lib as L
+    from oracle import model as om
+    img, y_half, _ = _ge_inputs(B, H, W, False)
+    y_o, pm_o = om.ground_embed_vanilla(img, y_half)                       # oracle (CPU)
+    img_d = img.to(DEV)
+    yh1 = y_half.to(DEV).requires_grad_(True)
+    yh2 = y_half.to(DEV).requires_grad_(True)
+    y, pm = K.ge_vanilla(img_d, yh1)
+    y_l, pm_l = L.ge_vanilla(img_d, yh2)
+    _close(y, y_o, 1e-6, 1e-6, "y vs oracle")
+    _close(pm, pm_o, 1e-5, 1e-5, "pe_mask vs oracle")
+    _close(y, y_l, 1e-6, 1e-6, "y vs torch")
+    gy, gpm = torch.randn_like(y), torch.randn_like(pm) * 0.1
+    (y * gy + pm * gpm).sum().backward()
+    (y_l * gy + pm_l * gpm).sum().backward()
+    _close(yh1.grad, yh2.grad, 1e-4, 1e-4 * float(yh2.grad.abs().max()), "g_y_half")
+
+
+@pytest.mark.parametrize("B,H,W,per_sample_h", [(2, 64, 160, False), (1, 70, 166, True), (2, 352, 1120, False)])
+def test_ge_adaptive_fwd_bwd(B, H, W, per_sample_h):
+    from gedepth_b200 import kernels as K, ops_lib as L
+    from oracle import model as om
+    img, y_half, logits_half = _ge_inputs(B, H, W, True)
+    height = torch.tensor([1.56, 1.57, 1.53][:B]) if per_sample_h else 1.65
+    y_o, pm_o, lf_o = om.ground_embed_adaptive(img, y_half, logits_half, 200.0, height)
+    img_d = img.to(DEV)
+    hd = height.to(DEV) if per_sample_h else height
+    a1 = [t.to(DEV).requires_grad_(True) for t in (y_half, logits_half)]
+    a2 = [t.to(DEV).requires_grad_(True) for t in (y_half, logits_half)]
+    y, pm, lf = K.ge_adaptive(img_d, a1[0], a1[1], hd, 200.0)
+    y_l, pm_l, lf_l = L.ge_adaptive(img_d, a2[0], a2[1], hd, 200.0)
+    _close(y, y_o, 1e-6, 1e-6, "y vs oracle")
+    _close(lf, lf_o, 1e-5, 1e-5, "logits vs oracle")
+    # the range mask is a hard threshold: exclude pixels whose offset sits within 1e-3 of a threshold
+    ok = ((pm_o - pm_l.cpu()).abs() <= 1e-3 + 1e-3 * pm_o.abs())
+    assert ok.float().mean() > 0.9999
+    err = ((pm.cpu() - pm_o).abs() > 2e-3 + 2e-4 * pm_o.abs()) & ok
+    assert err.float().mean() < 1e-5, f"pe_mask mismatch fraction {err.float().mean():.2e}"
+    gy, gpm, glf = torch.randn_like(y), torch.randn_like(pm) * 0.1, torch.randn_like(lf) * 0.01
+    (y * gy + pm * gpm).sum().backward(retain_graph=True)
+    (lf * glf).sum().backward()
+    (y_l * gy + pm_l * gpm + lf_l * glf).sum().backward()
+    for n, p, q in (("g_y_half", a1[0], a2[0]), ("g_logits_half", a1[1], a2[1])):
+        d = (p.grad - q.grad).abs()
+        tol = 2e-3 * float(q.grad.abs().max()) + 1e-3 * q.grad.abs()
+        assert float((d > tol).float().mean()) < 1e-4, (n, float(d.max()), float(q.grad.abs().max()))
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 160), (1, 70, 166), (2, 352, 1120)])
+def test_fuse_head_fwd_bwd(B, H, W):
+    from gedepth_b200 import kernels as K, ops_lib as L
+    g = torch.Generator().manual_seed(3)
+    h2, w2 = (H + 1) // 2, (W + 1) // 2
+    d0, pm0, y0 = torch.rand(B, 1, h2, w2, generator=g) * 20, torch.rand(B, 1, H, W, generator=g) * 80, torch.rand(B, 1, H, W, generator=g)
+    a1 = [t.to(DEV).requires_grad_(True) for t in (d0, pm0, y0)]
+    a2 = [t.to(DEV).requires_grad_(True) for t in (d0, pm0, y0)]
+    o1, yh1 = K.fuse_head(*a1, 1e-3)
+    o2, yh2 = L.fuse_head(*a2, 1e-3)
+    _close(o1, o2, 1e-5, 1e-5, "fused depth")
+    _close(yh1, yh2, 1e-6, 1e-6, "y_h")
+    go = torch.randn_like(o1)
+    (o1 * go).sum().backward()
+    (o2 * go).sum().backward()
+    for n, p, q in zip(("g_d", "g_pe_mask", "g_y"), a1, a2):
+        _close(p.grad, q.grad, 1e-4, 1e-5 * float(q.grad.abs().max()) + 1e-6, n)
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,up", [(2, 64, 160, True), (1, 70, 166, True), (2, 352, 1120, True), (2, 64, 160, False)])
+def test_silog_fwd_bwd(B, H, W, up):
+    from gedepth_b200 import kernels as K, ops_lib as L
+    from gedepth_b200.synth import synth_batch
+    gt = torch.from_numpy(synth_batch(B, H, W, seed=5)["depth_gt"]).to(DEV)
+    g = torch.Generator().manual_seed(4)
+    shape = (B, 1, (H + 1) // 2, (W + 1) // 2) if up else (B, 1, H, W)
+    p0 = (torch.rand(shape, generator=g) * 30 + 0.5)
+    p1, p2 = p0.to(DEV).requires_grad_(True), p0.to(DEV).requires_grad_(True)
+    l1 = K.silog(p1, gt, 1e-3, 0.15, None, up)
+    l2 = L.silog(p2, gt, 1e-3, 0.15, None, up)
+    assert abs(float(l1) - float(l2)) < 2e-5 * float(l2)
+    (l1 * 1.7).backward()
+    (l2 * 1.7).backward()
+    _close(p1.grad, p2.grad, 1e-3, 1e-4 * float(p2.grad.abs().max()), "g_pred")
+
+
+def test_cross_entropy_fwd_bwd():
+    from gedepth_b200 import kernels as K, ops_lib as L
+    g = torch.Generator().manual_seed(6)
+    l0 = torch.randn(2, 11, 64, 160, generator=g) * 2
+    t = torch.randint(0, 11, (2, 64, 160), generator=g).float()
+    t[torch.rand(2, 64, 160, generator=g) < 0.9] = 255
+    t = t.to(DEV)
+    l1, l2 = l0.to(DEV).requires_grad_(True), l0.to(DEV).requires_grad_(True)
+    a, b = K.cross_entropy(l1, t, 255), L.cross_entropy(l2, t, 255)
+    assert abs(float(a) - float(b)) < 1e-5 * abs(float(b)) + 1e-6
+    (a * 0.08).backward()
+    (b * 0.08).backward()
+    _close(l1.grad, l2.grad, 1e-4, 1e-6 * float(l2.grad.abs().max()) + 1e-9, "g_logits")
+
+
+# ------------------------------------------------------------------------------------------------
+# Swin pieces
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,C", [(640, 96), (333, 384), (70, 1536), (50, 3072)])
+def test_layernorm_fwd_bwd(rows, C):
+    from gedepth_b200 import kernels as K
+    g = torch.Generator().manual_seed(7)
+    x0 = torch.randn(2, rows, C, generator=g) * 3 + 1
+    w0, b0 = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    a1 = [t.to(DEV).requires_grad_(True) for t in (x0, w0, b0)]
+    a2 = [t.to(DEV).requires_grad_(True) for t in (x0, w0, b0)]
+    y1 = K.layer_norm(*a1, 1e-5)
+    y2 = F.layer_norm(a2[0], (C,), a2[1], a2[2], 1e-5)
+    _close(y1, y2, 1e-5, 1e-5, "layernorm")
+    go = torch.randn_like(y1)
+    (y1 * go).sum().backward()
+    (y2 * go).sum().backward()
+    for n, p, q in zip(("dx", "dw", "db"), a1, a2):
+        _close(p.grad, q.grad, 1e-4, 2e-5 * float(q.grad.abs().max()), n)
+
+
+@pytest.mark.parametrize("B,H,W,nH,shift", [(2, 16, 40, 3, 0), (2, 16, 40, 3, 3), (1, 9, 21, 6, 3), (2, 7, 7, 12, 0), (1, 18, 42, 3, 3)])
+def test_window_attention_fwd_bwd(B, H, W, nH, shift):
+    from gedepth_b200 import kernels as K, ops_lib as L
+    from oracle import model as om
+    C = nH * 32
+    g = torch.Generator().manual_seed(8)
+    qkv0 = torch.randn(B, H * W, 3 * C, generator=g)
+    bias0 = torch.randn(3 * C, generator=g) * 0.5
+    table0 = torch.randn(169, nH, generator=g) * 0.5
+    index = om.relative_position_index(7).to(DEV)
+    a1 = [t.to(DEV).requires_grad_(True) for t in (qkv0, bias0, table0)]
+    a2 = [t.to(DEV).requires_grad_(True) for t in (qkv0, bias0, table0)]
+    o1 = K.window_attention(a1[0], a1[1], a1[2], index, (H, W), nH, 7, shift, 32 ** -0.5)
+    o2 = L.window_attention(a2[0], a2[1], a2[2], index, (H, W), nH, 7, shift, 32 ** -0.5)
+    _close(o1, o2, 1e-4, 1e-5, "context")
+    go = torch.randn_like(o1)
+    (o1 * go).sum().backward()
+    (o2 * go).sum().backward()
+    for n, p, q in zip(("g_qkv", "g_bias", "g_table"), a1, a2):
+        _close(p.grad, q.grad, 1e-3, 2e-5 * float(q.grad.abs().max()) + 1e-6, n)
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 GEMM / conv (TF32: 10-bit mantissa products, fp32 accumulate)
+# ------------------------------------------------------------------------------------------------
+def _tf32_tol(ref, K):
+    return 2e-3 * float(ref.abs().max()) * max(1.0, (K / 512) ** 0.5) * 0.25 + 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 96, 96), (1000, 288, 96), (24640, 384, 96), (777, 512, 512),
+                                   (3000, 1536, 384), (130, 64, 2304), (500, 256, 512), (260, 2, 512), (128, 32, 64)])
+def test_gemm_plain(M, N, K):
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    if N < 16:
+        pytest.skip("N<16 goes to the library by design")
+    out = Kn.gemm(a, w)
+    ref = (a.double() @ w.double().t()).float()
+    _close(out, ref, 0, _tf32_tol(ref, K), f"gemm {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("act", [None, "relu", "gelu", "leaky_relu", "sigmoid"])
+def test_gemm_epilogue(act):
+    from gedepth_b200 import kernels as Kn, ops_lib as L
+    g = torch.Generator().manual_seed(10)
+    B, T, K, N = 3, 215, 192, 160
+    a = torch.randn(B * T, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(B * T, N, generator=g).to(DEV)
+    rs = torch.tensor([0.0, 1.0 / 0.7, 1.0 / 0.7]).to(DEV)
+    out = Kn.gemm(a, w, bias, act, 0.01, res, rs, T)
+    ref = L._act((a.double() @ w.double().t() + bias.double()).float(), act)
+    ref = ref * rs.repeat_interleave(T).unsqueeze(1) + res
+    _close(out, ref, 0, 3e-3 * float(ref.abs().max()) * 0.25 + 1e-5, f"epilogue {act}")
+    assert torch.equal(out[:T], res[:T])          # dropped sample: exactly the residual
+
+
+@pytest.mark.parametrize("act", [None, "gelu"])
+def test_linear_autograd(act):
+    from gedepth_b200 import kernels as Kn, ops_lib as L
+    g = torch.Generator().manual_seed(11)
+    x0, w0, b0 = torch.randn(2, 300, 96, generator=g), torch.randn(384, 96, generator=g) / 10, torch.randn(384, generator=g)
+    r0 = torch.randn(2, 300, 384, generator=g)
+    a1 = [t.to(DEV).requires_grad_(True) for t in (x0, w0, b0, r0)]
+    a2 = [t.to(DEV).double().requires_grad_(True) for t in (x0, w0, b0, r0)]
+    y1 = Kn.linear(a1[0], a1[1], a1[2], act, a1[3], None)
+    y2 = L.linear(a2[0], a2[1], a2[2], act, a2[3], None)
+    _close(y1, y2, 0, 2e-3 * float(y2.abs().max()), "linear fwd")
+    go = torch.randn_like(y1)
+    (y1 * go).sum().backward()
+    (y2 * go.double()).sum().backward()
+    for n, p, q in zip(("dx", "dw", "db", "dres"), a1, a2):
+        _close(p.grad, q.grad, 0, 3e-3 * float(q.grad.abs().max()), n)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,act", [(2, 11, 35, 64, 64, "leaky_relu"), (1, 22, 70, 576, 192, "relu"),
+                                                (2, 16, 40, 96, 11, None), (1, 9, 12, 2304, 768, "leaky_relu"),
+                                                (2, 32, 80, 64, 1, "sigmoid")])
+def test_conv3x3(B, H, W, Cin, Cout, act):
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(12)
+    x0 = torch.randn(B, Cin, H, W, generator=g)
+    w0 = torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5
+    b0 = torch.randn(Cout, generator=g)
+    a1 = [t.to(DEV).requires_grad_(True) for t in (x0, w0, b0)]
+    a1[0] = x0.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    a2 = [t.to(DEV).double().requires_grad_(True) for t in (x0, w0, b0)]
+    y1 = Kn.conv2d(a1[0], a1[1], a1[2], 1, 1, act, 0.01)
+    from gedepth_b200 import ops_lib as L
+    y2 = L.conv2d(a2[0], a2[1], a2[2], 1, 1, act, 0.01)
+    assert y1.shape == y2.shape
+    _close(y1, y2, 0, 2e-3 * float(y2.abs().max()) + 1e-5, "conv fwd")
+    go = torch.randn_like(y2).float()
+    (y1 * go).sum().backward()
+    (y2 * go.double()).sum().backward()
+    for n, p, q in zip(("dx", "dw", "db"), a1, a2):
+        _close(p.grad, q.grad, 0, 3e-3 * float(q.grad.abs().max()) + 1e-6, n)
+
+
+def test_conv1x1_and_folded_bn():
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(2, 96, 16, 40, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(192, 96, 1, 1, generator=g) / 10).to(DEV)
+    bn = torch.nn.BatchNorm2d(192).to(DEV)
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.1, generator=None)
+        bn.running_var.uniform_(0.5, 1.5)
+        bn.weight.normal_(1, 0.1)
+        bn.bias.normal_(0, 0.1)
+    bn.eval()
+    y = Kn.conv_bn_act(x, w, None, bn, 1, 0, "relu")
+    ref = F.relu(bn(F.conv2d(x.double(), w.double()).float()))
+    _close(y, ref, 0, 2e-3 * float(ref.abs().max()), "1x1 conv + folded BN + relu")
+    bn.train()
+    y = Kn.conv_bn_act(x, w, None, bn, 1, 0, "relu")
+    bn2 = torch.nn.BatchNorm2d(192).to(DEV)
+    bn2.load_state_dict(bn.state_dict())
+    bn2.train()
+    ref = F.relu(bn2(F.conv2d(x.double(), w.double()).float()))
+    _close(y, ref, 0, 3e-3 * float(ref.abs().max()), "1x1 conv + train BN + relu")
+
+
+# ------------------------------------------------------------------------------------------------
+# deformable attention sampling
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,shapes,Q,ref_b", [(2, [(16, 40), (8, 20), (4, 10), (2, 5)], 850, 1),
+                                               (1, [(18, 42), (9, 21), (5, 11), (3, 6)], 333, 1),
+                                               (2, [(16, 40), (8, 20), (4, 10), (2, 5)], 1280, 2)])
+def test_msda_fwd_bwd(B, shapes, Q, ref_b):
+    from gedepth_b200 import kernels as Kn, ops_lib as L
+    g = torch.Generator().manual_seed(14)
+    S = sum(h * w for h, w in shapes)
+    v0 = torch.randn(B, S, 512, generator=g)
+    ref0 = torch.rand(ref_b, Q, 2, generator=g) * 1.1 - 0.05
+    off0 = torch.randn(B, Q, 8 * 4 * 8 * 2, generator=g) * 2.5
+    lg0 = torch.randn(B, Q, 8 * 32, generator=g)
+    a1 = [t.to(DEV).requires_grad_(True) for t in (v0, ref0, off0, lg0)]
+    a2 = [t.to(DEV).requires_grad_(True) for t in (v0, ref0, off0, lg0)]
+    o1 = Kn.msda_sample(a1[0], shapes, a1[1], a1[2], a1[3], 8, 8)
+    o2 = L.msda_sample(a2[0], shapes, a2[1], a2[2], a2[3], 8, 8)
+    _close(o1, o2, 1e-4, 2e-5 * float(o2.abs().max()), "sampled")
+    go = torch.randn_like(o1)
+    (o1 * go).sum().backward()
+    (o2 * go).sum().backward()
+    names = ["g_value", "g_ref", "g_off", "g_logit"]
+    for n, p, q in zip(names, a1, a2):
+        if n == "g_ref" and ref_b == 1 and B > 1:
+            continue
+        d = (p.grad - q.grad).abs()
+        tol = 1e-3 * q.grad.abs() + 5e-5 * float(q.grad.abs().max())
+        # bilinear kinks: a sample landing within fp32 round-off of a pixel boundary may pick the other cell
+        assert float((d > tol).float().mean()) < 2e-4, (n, float(d.max()), float(q.grad.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer
+# ------------------------------------------------------------------------------------------------
+def test_adamw_and_clip_match_torch():
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(15)
+    n = 100003
+    p0, g0 = torch.randn(n, generator=g), torch.randn(n, generator=g) * 3
+    p_ref = torch.nn.Parameter(p0.clone().to(DEV))
+    opt = torch.optim.AdamW([p_ref], lr=1e-4, betas=(0.9, 0.999), weight_decay=0.01)
+    p = p0.clone().to(DEV)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    ss = torch.zeros(1, dtype=torch.float64, device=DEV)
+    for step in range(1, 4):
+        grad = (g0 * step).to(DEV)
+        p_ref.grad = grad.clone()
+        torch.nn.utils.clip_grad_norm_([p_ref], 35.0)
+        opt.step()
+        Kn.sumsq(grad, ss)
+        Kn.adamw_step(p, grad, m, v, None, ss, 35.0, 1.0, 1e-4, 0.9, 0.999, 1e-8, 0.01, step)
+        assert abs(float(ss.sqrt()) - float(grad.double().norm())) < 1e-6 * float(grad.norm())
+    _close(p, p_ref.data, 1e-6, 1e-6, "adamw")
