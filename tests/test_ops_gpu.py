@@ -123,9 +123,8 @@ def test_ge_adaptive_fwd_bwd(B, H, W, per_sample_h):
     err = ((pm.cpu() - pm_o).abs() > 2e-3 + 2e-4 * pm_o.abs()) & ok
     assert err.float().mean() < 1e-5, f"pe_mask mismatch fraction {err.float().mean():.2e}"
     gy, gpm, glf = torch.randn_like(y), torch.randn_like(pm) * 0.1, torch.randn_like(lf) * 0.01
-    (y * gy + pm * gpm).sum().backward(retain_graph=True)
-    (lf * glf).sum().backward()
-    (y_l * gy + pm_l * gpm + lf_l * glf).sum().backward()
+    ((y * gy).sum() + (pm * gpm).sum() + (lf * glf).sum()).backward()
+    ((y_l * gy).sum() + (pm_l * gpm).sum() + (lf_l * glf).sum()).backward()
     for n, p, q in (("g_y_half", a1[0], a2[0]), ("g_logits_half", a1[1], a2[1])):
         d = (p.grad - q.grad).abs()
         tol = 2e-3 * float(q.grad.abs().max()) + 1e-3 * q.grad.abs()
@@ -226,14 +225,17 @@ def test_window_attention_fwd_bwd(B, H, W, nH, shift):
     (o1 * go).sum().backward()
     (o2 * go).sum().backward()
     for n, p, q in zip(("g_qkv", "g_bias", "g_table"), a1, a2):
-        _close(p.grad, q.grad, 1e-3, 2e-5 * float(q.grad.abs().max()) + 1e-6, n)
+        qg = q.grad if q.grad is not None else torch.zeros_like(q)      # no padded tokens -> bias unused
+        _close(p.grad, qg, 1e-3, 2e-5 * float(qg.abs().max()) + 1e-6, n)
 
 
 # ------------------------------------------------------------------------------------------------
 # tcgen05 GEMM / conv (TF32: 10-bit mantissa products, fp32 accumulate)
 # ------------------------------------------------------------------------------------------------
 def _tf32_tol(ref, K):
-    return 2e-3 * float(ref.abs().max()) * max(1.0, (K / 512) ** 0.5) * 0.25 + 1e-5
+    # tcgen05 kind::tf32 reads fp32 operands and drops the low 13 mantissa bits (truncation):
+    # per-product relative error <= 2^-9, random-walk over K terms -> ~1e-3 of the output scale
+    return 1.5e-3 * float(ref.abs().max()) + 1e-5
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 96, 96), (1000, 288, 96), (24640, 384, 96), (777, 512, 512),
@@ -263,7 +265,7 @@ def test_gemm_epilogue(act):
     out = Kn.gemm(a, w, bias, act, 0.01, res, rs, T)
     ref = L._act((a.double() @ w.double().t() + bias.double()).float(), act)
     ref = ref * rs.repeat_interleave(T).unsqueeze(1) + res
-    _close(out, ref, 0, 3e-3 * float(ref.abs().max()) * 0.25 + 1e-5, f"epilogue {act}")
+    _close(out, ref, 0, 1.5e-3 * float(ref.abs().max()) + 1e-5, f"epilogue {act}")
     assert torch.equal(out[:T], res[:T])          # dropped sample: exactly the residual
 
 
@@ -299,9 +301,17 @@ def test_conv3x3(B, H, W, Cin, Cout, act):
     a2 = [t.to(DEV).double().requires_grad_(True) for t in (x0, w0, b0)]
     y1 = Kn.conv2d(a1[0], a1[1], a1[2], 1, 1, act, 0.01)
     from gedepth_b200 import ops_lib as L
-    y2 = L.conv2d(a2[0], a2[1], a2[2], 1, 1, act, 0.01)
+    pre2 = F.conv2d(a2[0], a2[1], a2[2], padding=1)
+    if act in ("relu", "leaky_relu"):
+        # piecewise-linear activations: take the branch the kernel took (pre-activations within TF32
+        # round-off of 0 would otherwise flip the derivative and dominate the gradient comparison)
+        pos = (y1.detach() > 0)
+        y2 = torch.where(pos, pre2, pre2 * (0.01 if act == "leaky_relu" else 0.0))
+        _close(y1, L._act(pre2, act, 0.01), 0, 2e-3 * float(pre2.abs().max()) + 1e-5, "conv fwd")
+    else:
+        y2 = L._act(pre2, act, 0.01)
+        _close(y1, y2, 0, 2e-3 * float(y2.abs().max()) + 1e-5, "conv fwd")
     assert y1.shape == y2.shape
-    _close(y1, y2, 0, 2e-3 * float(y2.abs().max()) + 1e-5, "conv fwd")
     go = torch.randn_like(y2).float()
     (y1 * go).sum().backward()
     (y2 * go.double()).sum().backward()
