@@ -25,7 +25,7 @@ namespace ged {
 constexpr int BM = 128;          // UMMA_M, rows per tile (TMEM lanes)
 constexpr int BK = 32;           // fp32 elements per 128-byte swizzle row
 constexpr int UK = 8;            // UMMA_K for tf32
-constexpr int GEMM_THREADS = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+// warp0 TMA producer, warp1 MMA issuer, warp2 TMEM allocator, warp3 idle, warps 4-11 epilogue, warps 12-15 splitter
 constexpr int MAX_TAPS = 9;
 
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_GELU = 3, ACT_SIGMOID = 4 };
@@ -126,21 +126,40 @@ __device__ __forceinline__ float apply_act(float x, int act, float slope) {
   }
 }
 
-template <int BN, int STAGES>
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+constexpr int EPI_WARPS = 8;       // two warps per TMEM lane quadrant, each owning half of the columns
+constexpr int EPI_PITCH = 20;      // floats; 32 rows x 16 columns staging tile per warp, conflict-free for float4
+constexpr int SPLIT_WARPS = 4;
+
+// SPLIT = error-compensated "3xTF32": every fp32 operand x is used as hi = tf32(x) (the tensor core's own
+// truncation) plus lo = x - hi (exact in fp32), and each k-step issues hi*hi + lo*hi + hi*lo.  The dropped
+// lo*lo term is 2^-22 relative: the product is fp32-accurate while still running on tcgen05.
+template <int BN, int STAGES, bool SPLIT>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 4;       // 16 KB
   static constexpr int B_BYTES = BN * BK * 4;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;  // per-warp transpose tiles
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int HI_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = HI_BYTES * (SPLIT ? 2 : 1);
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
+  static constexpr int BAR_BYTES = (3 * STAGES + 4) * 8 + 16;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+  static constexpr int THREADS = 128 + EPI_WARPS * 32 + (SPLIT ? SPLIT_WARPS * 32 : 0);
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_kernel(
+template <int BN, int STAGES, bool SPLIT>
+__global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_tf32_kernel(
     const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
     const GemmParams p) {
-  using S = GemmSmem<BN, STAGES>;
+  using S = GemmSmem<BN, STAGES, SPLIT>;
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024B alignment
@@ -148,7 +167,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_kernel(
   float* epi_tiles = (float*)(smem + STAGES * S::STAGE_BYTES);
   uint64_t* full_bar = (uint64_t*)((uint8_t*)epi_tiles + S::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;      // [2]
+  uint64_t* split_bar = empty_bar + STAGES;
+  uint64_t* tmem_full = split_bar + STAGES;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
 
@@ -161,8 +181,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_kernel(
     asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&map_b) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 4); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); mbar_init(split_bar + i, SPLIT_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -184,7 +204,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_kernel(
           const int t = kb / p.kblocks_per_tap, kc = kb - t * p.kblocks_per_tap;
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = stage_base + stage * S::STAGE_BYTES;
-          mbar_expect_tx(full_bar + stage, S::STAGE_BYTES);
+          mbar_expect_tx(full_bar + stage, S::HI_BYTES);
           tma_load_2d(sa, &map_a, full_bar + stage, kc * BK, m0 + p.tap_off[t]);
           tma_load_2d(sa + S::A_BYTES, &map_b, full_bar + stage, t * p.Kt + kc * BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -202,7 +222,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_kernel(
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar + stage, phase);
+          mbar_wait((SPLIT ? split_bar : full_bar) + stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
           const uint64_t adesc = umma_desc_kmajor_sw128(sa), bdesc = umma_desc_kmajor_sw128(sa + S::A_BYTES);
@@ -210,6 +230,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_kernel(
           for (int k = 0; k < BK / UK; ++k) {
             // advance 8 tf32 = 32 bytes inside the 128B swizzle row: +2 in the (addr>>4) field
             tc_mma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (SPLIT) {
+              const uint64_t alo = umma_desc_kmajor_sw128(sa + S::HI_BYTES), blo = umma_desc_kmajor_sw128(sa + S::HI_BYTES + S::A_BYTES);
+              tc_mma_tf32(tmem_d, alo + 2 * k, bdesc + 2 * k, idesc, 1u);   // lo(A) * hi(B)
+              tc_mma_tf32(tmem_d, adesc + 2 * k, blo + 2 * k, idesc, 1u);   // hi(A) * lo(B)
+            }
           }
           tc_commit(empty_bar + stage);          // frees the smem slot when these MMAs retire
           if (kb == num_kb - 1) tc_commit(tmem_full + acc);
@@ -218,43 +243,70 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_kernel(
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> (smem transpose) -> coalesced global stores =====
-    const int ew = warp - 4;                       // TMEM lane quadrant = warp % 4
-    float (*tile_s)[33] = (float (*)[33])(epi_tiles + ew * 32 * 33);
+  } else if (warp >= 4 && warp < 4 + EPI_WARPS) {
+    // ===== epilogue: TMEM -> registers -> smem transpose -> 128-bit coalesced global accesses =====
+    const int ew = warp - 4, q = ew & 3, half = ew >> 2;   // TMEM lane quadrant = warp % 4
+    float* tile_s = epi_tiles + ew * 32 * EPI_PITCH;
+    const bool vec = ((p.ldd & 3) == 0) && ((p.N & 3) == 0) && aligned16(p.D) && (!p.residual || aligned16(p.residual));
+    const int lr = lane >> 2, lc = (lane & 3) * 4;          // store phase: lane -> (row lr + 8 i, 4 columns from lc)
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
+      // the four output rows this lane stores (fixed for the whole tile)
+      int64_t orow[4];
+      float rscale[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = m0 + q * 32 + lr + 8 * i;
+        orow[i] = -1; rscale[i] = 1.f;
+        if (row < p.M) {
+          orow[i] = row;
+          if (p.conv_Wp) {   // padded flattened pixel -> interior test and unpadded row
+            const int xp = row % p.conv_Wp, t2 = row / p.conv_Wp, yp = t2 % p.conv_Hp, n = t2 / p.conv_Hp;
+            orow[i] = (xp == 0 || xp == p.conv_Wp - 1 || yp == 0 || yp == p.conv_Hp - 1)
+                          ? -1 : ((int64_t)n * (p.conv_Hp - 2) + (yp - 1)) * (p.conv_Wp - 2) + (xp - 1);
+          }
+          if (p.row_scale && orow[i] >= 0) rscale[i] = __ldg(p.row_scale + orow[i] / p.rows_per_batch);
+        }
+      }
       mbar_wait(tmem_full + acc, acc_phase);
       tc_fence_after();
-      const int row_base = m0 + ew * 32;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
+        uint32_t v[16];
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) tile_s[lane][c] = __uint_as_float(v[c]);
+        for (int j = 0; j < 4; ++j)
+          *(float4*)(tile_s + lane * EPI_PITCH + 4 * j) =
+              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         __syncwarp();
-        const int col = n0 + c0 + lane;
-        const bool col_ok = col < p.N;
-        const float bias = (p.bias && col_ok) ? __ldg(p.bias + col) : 0.f;
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          const int row = row_base + r;
-          if (row >= p.M) break;
-          int64_t orow = row;
-          if (p.conv_Wp) {
-            // padded flattened pixel -> interior test and unpadded row
-            const int xp = row % p.conv_Wp, t2 = row / p.conv_Wp, yp = t2 % p.conv_Hp, n = t2 / p.conv_Hp;
-            if (xp == 0 || xp == p.conv_Wp - 1 || yp == 0 || yp == p.conv_Hp - 1) continue;
-            orow = ((int64_t)n * (p.conv_Hp - 2) + (yp - 1)) * (p.conv_Wp - 2) + (xp - 1);
+        const int col = n0 + c0 + lc;
+        if (col < p.N) {
+          float bias[4] = {0.f, 0.f, 0.f, 0.f};
+          if (p.bias) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (col + e < p.N) bias[e] = __ldg(p.bias + col + e);
           }
-          if (!col_ok) continue;
-          float x = tile_s[r][lane] + bias;
-          x = apply_act(x, p.act, p.slope);
-          if (p.row_scale) x *= __ldg(p.row_scale + orow / p.rows_per_batch);
-          if (p.residual) x += __ldg(p.residual + orow * p.ldd + col);
-          p.D[orow * p.ldd + col] = x;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (orow[i] < 0) continue;
+            const float4 t = *(const float4*)(tile_s + (lr + 8 * i) * EPI_PITCH + lc);
+            float x[4] = {t.x + bias[0], t.y + bias[1], t.z + bias[2], t.w + bias[3]};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = apply_act(x[e], p.act, p.slope) * rscale[i];
+            float* dst = p.D + orow[i] * p.ldd + col;
+            if (vec) {
+              if (p.residual) {
+                const float4 r = __ldg((const float4*)(p.residual + orow[i] * p.ldd + col));
+                x[0] += r.x; x[1] += r.y; x[2] += r.z; x[3] += r.w;
+              }
+              *(float4*)dst = make_float4(x[0], x[1], x[2], x[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (col + e < p.N) dst[e] = x[e] + (p.residual ? __ldg(p.residual + orow[i] * p.ldd + col + e) : 0.f);
+            }
+          }
         }
         __syncwarp();
       }
@@ -262,6 +314,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32_kernel(
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (SPLIT && warp >= 4 + EPI_WARPS) {
+    // ===== splitter: lo = x - tf32(x) for both operand tiles of every stage =====
+    const int st = threadIdx.x - (4 + EPI_WARPS) * 32;
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar + stage, phase);
+        const float4* hi = (const float4*)(stage_base + stage * S::STAGE_BYTES);
+        float4* lo = (float4*)(stage_base + stage * S::STAGE_BYTES + S::HI_BYTES);
+#pragma unroll 4
+        for (int i = st; i < S::HI_BYTES / 16; i += SPLIT_WARPS * 32) {
+          const float4 x = hi[i];
+          float4 l;
+          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          lo[i] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_bar + stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
     }
   }
   tc_fence_before();
@@ -300,13 +377,15 @@ static int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_
 }
 
 static int g_num_sms = 0;
+static int g_precision = 3;   // 1 = single-pass TF32, 3 = error-compensated 3xTF32 (fp32-accurate)
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool SPLIT>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
-  using S = GemmSmem<BN, STAGES>;
+  using S = GemmSmem<BN, STAGES, SPLIT>;
+  static_assert(S::TOTAL <= 232448, "shared memory budget (227 KB)");
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return GED_ERR_LAUNCH;
+    if (cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return GED_ERR_LAUNCH;
     attr_set = true;
   }
   if (!g_num_sms) {
@@ -318,7 +397,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams&
   p.num_n_tiles = cdiv(p.N, BN);
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tf32_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ma, mb, p);
+  gemm_tf32_kernel<BN, STAGES, SPLIT><<<grid, S::THREADS, S::TOTAL, stream>>>(ma, mb, p);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }
@@ -339,16 +418,32 @@ static int run(const float* A, int64_t a_rows, int lda, const float* Bw, int ldb
   if (int e = make_map_2d(&mb, Bw, p.N, p.K, ldb, bn)) return e;
   p.kblocks_per_tap = cdiv(Kt, BK);
   p.Kt = Kt;
+  if (g_precision == 3) {
+    switch (bn) {
+      case 32: return launch_gemm<32, 4, true>(ma, mb, p, stream);
+      case 64: return launch_gemm<64, 4, true>(ma, mb, p, stream);
+      case 96: return launch_gemm<96, 3, true>(ma, mb, p, stream);
+      default: return launch_gemm<128, 3, true>(ma, mb, p, stream);
+    }
+  }
   switch (bn) {
-    case 32: return launch_gemm<32, 8>(ma, mb, p, stream);
-    case 64: return launch_gemm<64, 6>(ma, mb, p, stream);
-    case 96: return launch_gemm<96, 6>(ma, mb, p, stream);
-    default: return launch_gemm<128, 5>(ma, mb, p, stream);
+    case 32: return launch_gemm<32, 8, false>(ma, mb, p, stream);
+    case 64: return launch_gemm<64, 6, false>(ma, mb, p, stream);
+    case 96: return launch_gemm<96, 6, false>(ma, mb, p, stream);
+    default: return launch_gemm<128, 5, false>(ma, mb, p, stream);
   }
 }
 
 }  // namespace ged
 using namespace ged;
+
+// precision: 1 = TF32 (10-bit mantissa products), 3 = 3xTF32 split (fp32-accurate; default).  Returns the
+// previous setting.  Process-wide; not a per-call argument so call sites stay those of F.linear / conv2d.
+GED_API int ged_set_gemm_precision(int passes) {
+  const int prev = g_precision;
+  if (passes == 1 || passes == 3) g_precision = passes;
+  return prev;
+}
 
 // D[M,N] = epi(A[M,K] @ W[N,K]^T).  A row pitch lda, W row pitch ldw, D/residual row pitch ldd (floats).
 // act: 0 none, 1 relu, 2 leaky(slope), 3 gelu(erf), 4 sigmoid.  row_scale[b] multiplies rows of batch b

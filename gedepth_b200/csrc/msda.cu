@@ -18,73 +18,84 @@ struct MsdaShapes {
   int h[MS_L], w[MS_L], start[MS_L];
 };
 
-struct PointGeom {
-  int64_t o00, o01, o10, o11;   // element offsets of the four corners (pos * nH*HD), -1 when outside
-  float w00, w01, w10, w11;     // bilinear weights
-  float lx, ly;                 // fractional parts (for the location gradient)
+// Per-point geometry, computed ONCE by the lane that owns the point and shared through smem:
+// four corner element offsets (0 with the valid bit cleared when outside), fractional parts,
+// softmax weight and the valid mask.
+struct __align__(16) PointRec {
+  int o00, o01, o10, o11;
+  float lx, ly, a;
+  int valid;            // bit0..3 = corner 00,01,10,11 inside the map
 };
 
-__device__ __forceinline__ PointGeom point_geom(float x, float y, int H, int W, int start, int rowpitch) {
-  PointGeom g;
+__device__ __forceinline__ PointRec make_point(float x, float y, float a, int H, int W, int start, int rowpitch) {
+  PointRec g;
   const float xf = floorf(x), yf = floorf(y);
   const int x0 = (int)xf, y0 = (int)yf;
-  g.lx = x - xf; g.ly = y - yf;
+  g.lx = x - xf; g.ly = y - yf; g.a = a;
   const bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W;
   const bool vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H;
-  g.w00 = (1.f - g.ly) * (1.f - g.lx); g.w01 = (1.f - g.ly) * g.lx;
-  g.w10 = g.ly * (1.f - g.lx);         g.w11 = g.ly * g.lx;
-  const int64_t base = (int64_t)start + (int64_t)y0 * W + x0;
-  g.o00 = (vy0 && vx0) ? base * rowpitch : -1;
-  g.o01 = (vy0 && vx1) ? (base + 1) * rowpitch : -1;
-  g.o10 = (vy1 && vx0) ? (base + W) * rowpitch : -1;
-  g.o11 = (vy1 && vx1) ? (base + W + 1) * rowpitch : -1;
+  const int base = start + y0 * W + x0;
+  g.valid = (vy0 && vx0 ? 1 : 0) | (vy0 && vx1 ? 2 : 0) | (vy1 && vx0 ? 4 : 0) | (vy1 && vx1 ? 8 : 0);
+  g.o00 = (g.valid & 1) ? base * rowpitch : 0;
+  g.o01 = (g.valid & 2) ? (base + 1) * rowpitch : 0;
+  g.o10 = (g.valid & 4) ? (base + W) * rowpitch : 0;
+  g.o11 = (g.valid & 8) ? (base + W + 1) * rowpitch : 0;
   return g;
 }
 
-// lane = (level, point): load the lane's logit/offset, softmax across the warp, pixel coordinates
-__device__ __forceinline__ void lane_point(const float* __restrict__ off, const float* __restrict__ logit,
-                                           float rx, float ry, const MsdaShapes& sh, int lane, float& aw,
-                                           float& px, float& py) {
+// lane = (level, point): softmax over the warp's 32 logits, pixel coordinates, record into smem
+__device__ __forceinline__ float lane_point(const float* __restrict__ off, const float* __restrict__ logit,
+                                            float rx, float ry, const MsdaShapes& sh, int lane, int rowpitch,
+                                            PointRec* rec) {
   const float lg = __ldg(logit + lane);
   const float mx = warp_max(lg);
   const float e = __expf(lg - mx);
-  aw = e / warp_sum(e);
+  const float aw = e / warp_sum(e);
   const float2 o = __ldg((const float2*)off + lane);
   const int l = lane >> 3;
   const float Wl = (float)sh.w[l], Hl = (float)sh.h[l];
-  px = (rx + o.x / Wl) * Wl - 0.5f;
-  py = (ry + o.y / Hl) * Hl - 0.5f;
+  const float px = (rx + o.x / Wl) * Wl - 0.5f, py = (ry + o.y / Hl) * Hl - 0.5f;
+  rec[lane] = make_point(px, py, aw, sh.h[l], sh.w[l], sh.start[l], rowpitch);
+  return aw;
 }
 
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg((const float4*)p); }
+
+// One warp per (batch, query, head).  Half-warps take alternate points; a lane owns 4 of the 64 channels.
 __global__ void __launch_bounds__(MS_WARPS * 32) msda_fwd_kernel(
     const float* __restrict__ value, const float* __restrict__ ref, const float* __restrict__ off,
     const float* __restrict__ logit, float* __restrict__ out, MsdaShapes sh, int B, int S, int Q, int nH,
     int ref_bstride) {
+  __shared__ PointRec s_rec[MS_WARPS][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * MS_WARPS + warp, h = blockIdx.y, b = blockIdx.z;
   if (q >= Q) return;
   const int64_t bq = (int64_t)b * Q + q;
   const float rx = __ldg(ref + (int64_t)b * ref_bstride + q * 2), ry = __ldg(ref + (int64_t)b * ref_bstride + q * 2 + 1);
-  float aw, px, py;
-  lane_point(off + (bq * nH + h) * (MS_L * MS_P * 2), logit + (bq * nH + h) * (MS_L * MS_P), rx, ry, sh, lane, aw, px, py);
   const int rowpitch = nH * MS_HD;
-  const float* vb = value + (int64_t)b * S * rowpitch + h * MS_HD + lane * 2;
-  float2 acc = make_float2(0.f, 0.f);
+  lane_point(off + (bq * nH + h) * (MS_L * MS_P * 2), logit + (bq * nH + h) * (MS_L * MS_P), rx, ry, sh, lane, rowpitch, s_rec[warp]);
+  __syncwarp();
+  const int half = lane >> 4, cl = (lane & 15) * 4;
+  const float* vb = value + (int64_t)b * S * rowpitch + h * MS_HD + cl;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-  for (int j = 0; j < MS_L * MS_P; ++j) {
-    const float x = __shfl_sync(0xffffffffu, px, j), y = __shfl_sync(0xffffffffu, py, j);
-    const float a = __shfl_sync(0xffffffffu, aw, j);
-    const int l = j >> 3;
-    const PointGeom g = point_geom(x, y, sh.h[l], sh.w[l], sh.start[l], rowpitch);
-    float2 v00 = make_float2(0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
-    if (g.o00 >= 0) v00 = __ldg((const float2*)(vb + g.o00));
-    if (g.o01 >= 0) v01 = __ldg((const float2*)(vb + g.o01));
-    if (g.o10 >= 0) v10 = __ldg((const float2*)(vb + g.o10));
-    if (g.o11 >= 0) v11 = __ldg((const float2*)(vb + g.o11));
-    acc.x += a * (g.w00 * v00.x + g.w01 * v01.x + g.w10 * v10.x + g.w11 * v11.x);
-    acc.y += a * (g.w00 * v00.y + g.w01 * v01.y + g.w10 * v10.y + g.w11 * v11.y);
+  for (int j = 0; j < MS_L * MS_P / 2; ++j) {
+    const PointRec g = s_rec[warp][2 * j + half];
+    const float w00 = g.a * (1.f - g.ly) * (1.f - g.lx) * (float)(g.valid & 1);
+    const float w01 = g.a * (1.f - g.ly) * g.lx * (float)((g.valid >> 1) & 1);
+    const float w10 = g.a * g.ly * (1.f - g.lx) * (float)((g.valid >> 2) & 1);
+    const float w11 = g.a * g.ly * g.lx * (float)((g.valid >> 3) & 1);
+    const float4 v00 = ld4(vb + g.o00), v01 = ld4(vb + g.o01), v10 = ld4(vb + g.o10), v11 = ld4(vb + g.o11);
+    acc.x += w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x;
+    acc.y += w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y;
+    acc.z += w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z;
+    acc.w += w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w;
   }
-  *(float2*)(out + bq * rowpitch + h * MS_HD + lane * 2) = acc;
+  acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+  acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+  acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
+  acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+  if (half == 0) *(float4*)(out + bq * rowpitch + h * MS_HD + cl) = acc;
 }
 
 // butterfly reduce-scatter: every lane enters with N partial sums, leaves with N/2
@@ -103,49 +114,50 @@ __global__ void __launch_bounds__(MS_WARPS * 32) msda_bwd_kernel(
     const float* __restrict__ logit, const float* __restrict__ g_out, float* __restrict__ g_value,
     float* __restrict__ g_ref, float* __restrict__ g_off, float* __restrict__ g_logit, MsdaShapes sh,
     int B, int S, int Q, int nH, int ref_bstride) {
+  __shared__ PointRec s_rec[MS_WARPS][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * MS_WARPS + warp, h = blockIdx.y, b = blockIdx.z;
   if (q >= Q) return;
   const int64_t bq = (int64_t)b * Q + q;
   const float rx = __ldg(ref + (int64_t)b * ref_bstride + q * 2), ry = __ldg(ref + (int64_t)b * ref_bstride + q * 2 + 1);
-  float aw, px, py;
-  lane_point(off + (bq * nH + h) * (MS_L * MS_P * 2), logit + (bq * nH + h) * (MS_L * MS_P), rx, ry, sh, lane, aw, px, py);
   const int rowpitch = nH * MS_HD;
-  const int64_t voff = (int64_t)b * S * rowpitch + h * MS_HD + lane * 2;
+  const float aw = lane_point(off + (bq * nH + h) * (MS_L * MS_P * 2), logit + (bq * nH + h) * (MS_L * MS_P), rx, ry, sh, lane, rowpitch, s_rec[warp]);
+  __syncwarp();
+  const int half = lane >> 4, cl = (lane & 15) * 4;
+  const int64_t voff = (int64_t)b * S * rowpitch + h * MS_HD + cl;
   const float* vb = value + voff;
   float* gvb = g_value + voff;
-  const float2 go = __ldg((const float2*)(g_out + bq * rowpitch + h * MS_HD + lane * 2));
-  float part[96];   // [point][gw, gx, gy] partial sums over this lane's two channels
+  const float4 go = ld4(g_out + bq * rowpitch + h * MS_HD + cl);
+  float part[48];   // [j][gw, gx, gy] partial sums over this lane's four channels, point 2j+half
 #pragma unroll
-  for (int j = 0; j < MS_L * MS_P; ++j) {
-    const float x = __shfl_sync(0xffffffffu, px, j), y = __shfl_sync(0xffffffffu, py, j);
-    const float a = __shfl_sync(0xffffffffu, aw, j);
-    const int l = j >> 3;
-    const PointGeom g = point_geom(x, y, sh.h[l], sh.w[l], sh.start[l], rowpitch);
-    float2 v00 = make_float2(0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
-    if (g.o00 >= 0) { v00 = __ldg((const float2*)(vb + g.o00)); atomicAdd((float2*)(gvb + g.o00), make_float2(go.x * a * g.w00, go.y * a * g.w00)); }
-    if (g.o01 >= 0) { v01 = __ldg((const float2*)(vb + g.o01)); atomicAdd((float2*)(gvb + g.o01), make_float2(go.x * a * g.w01, go.y * a * g.w01)); }
-    if (g.o10 >= 0) { v10 = __ldg((const float2*)(vb + g.o10)); atomicAdd((float2*)(gvb + g.o10), make_float2(go.x * a * g.w10, go.y * a * g.w10)); }
-    if (g.o11 >= 0) { v11 = __ldg((const float2*)(vb + g.o11)); atomicAdd((float2*)(gvb + g.o11), make_float2(go.x * a * g.w11, go.y * a * g.w11)); }
-    // sample and its derivatives w.r.t. the pixel coordinates, dotted with g_out over channels
-    const float sx_ = g.w00 * v00.x + g.w01 * v01.x + g.w10 * v10.x + g.w11 * v11.x;
-    const float sy_ = g.w00 * v00.y + g.w01 * v01.y + g.w10 * v10.y + g.w11 * v11.y;
-    const float dxx = (1.f - g.ly) * (v01.x - v00.x) + g.ly * (v11.x - v10.x);
-    const float dxy = (1.f - g.ly) * (v01.y - v00.y) + g.ly * (v11.y - v10.y);
-    const float dyx = (1.f - g.lx) * (v10.x - v00.x) + g.lx * (v11.x - v01.x);
-    const float dyy = (1.f - g.lx) * (v10.y - v00.y) + g.lx * (v11.y - v01.y);
-    part[j * 3 + 0] = go.x * sx_ + go.y * sy_;
-    part[j * 3 + 1] = a * (go.x * dxx + go.y * dxy);
-    part[j * 3 + 2] = a * (go.x * dyx + go.y * dyy);
+  for (int j = 0; j < MS_L * MS_P / 2; ++j) {
+    const PointRec g = s_rec[warp][2 * j + half];
+    const float u00 = (1.f - g.ly) * (1.f - g.lx), u01 = (1.f - g.ly) * g.lx, u10 = g.ly * (1.f - g.lx), u11 = g.ly * g.lx;
+    float4 v00 = make_float4(0.f, 0.f, 0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
+    if (g.valid & 1) { v00 = ld4(vb + g.o00); const float w = g.a * u00; atomicAdd((float4*)(gvb + g.o00), make_float4(go.x * w, go.y * w, go.z * w, go.w * w)); }
+    if (g.valid & 2) { v01 = ld4(vb + g.o01); const float w = g.a * u01; atomicAdd((float4*)(gvb + g.o01), make_float4(go.x * w, go.y * w, go.z * w, go.w * w)); }
+    if (g.valid & 4) { v10 = ld4(vb + g.o10); const float w = g.a * u10; atomicAdd((float4*)(gvb + g.o10), make_float4(go.x * w, go.y * w, go.z * w, go.w * w)); }
+    if (g.valid & 8) { v11 = ld4(vb + g.o11); const float w = g.a * u11; atomicAdd((float4*)(gvb + g.o11), make_float4(go.x * w, go.y * w, go.z * w, go.w * w)); }
+    // <g_out, corner> over this lane's channels
+    const float d00 = go.x * v00.x + go.y * v00.y + go.z * v00.z + go.w * v00.w;
+    const float d01 = go.x * v01.x + go.y * v01.y + go.z * v01.z + go.w * v01.w;
+    const float d10 = go.x * v10.x + go.y * v10.y + go.z * v10.z + go.w * v10.w;
+    const float d11 = go.x * v11.x + go.y * v11.y + go.z * v11.z + go.w * v11.w;
+    part[j * 3 + 0] = u00 * d00 + u01 * d01 + u10 * d10 + u11 * d11;                          // d/d a
+    part[j * 3 + 1] = g.a * ((1.f - g.ly) * (d01 - d00) + g.ly * (d11 - d10));               // d/d x_pix
+    part[j * 3 + 2] = g.a * ((1.f - g.lx) * (d10 - d00) + g.lx * (d11 - d01));               // d/d y_pix
   }
-  float p48[48], p24[24], p12[12], p6[6], p3[3];
-  halve<96>(part, p48, 16, (lane & 16) != 0);
-  halve<48>(p48, p24, 8, (lane & 8) != 0);
+  float p24[24], p12[12], p6[6], p3[3];
+  halve<48>(part, p24, 8, (lane & 8) != 0);
   halve<24>(p24, p12, 4, (lane & 4) != 0);
   halve<12>(p12, p6, 2, (lane & 2) != 0);
   halve<6>(p6, p3, 1, (lane & 1) != 0);
-  // lane now holds (gw, g_xpix, g_ypix) of point `lane`
-  const float gw = p3[0], gx = p3[1], gy = p3[2];
+  // lane (half, i) now holds (gw, g_xpix, g_ypix) of local point j = i, i.e. global point 2*i + half;
+  // move them to the lane that owns that point (lane index == point index)
+  const int src = ((lane & 1) << 4) | (lane >> 1);
+  const float gw = __shfl_sync(0xffffffffu, p3[0], src);
+  const float gx = __shfl_sync(0xffffffffu, p3[1], src);
+  const float gy = __shfl_sync(0xffffffffu, p3[2], src);
   const float dot = warp_sum(aw * gw);
   g_logit[(bq * nH + h) * (MS_L * MS_P) + lane] = aw * (gw - dot);
   // x_pix = (ref + off/W)*W - 0.5  ->  d/d off = 1, d/d ref = W_l

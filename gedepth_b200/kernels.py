@@ -43,6 +43,7 @@ SIGNATURES = {
     "ged_conv3x3_tf32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _F, _P],
     "ged_msda_fwd": [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_msda_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ged_set_gemm_precision": [_I],
     "ged_sumsq": [_P, _I64, _P, _P],
     "ged_adamw_step": [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _F, _I, _P],
 }
@@ -73,7 +74,14 @@ def load():
     lib.ged_version.restype = C.c_int
     lib.ged_arch.restype = C.c_char_p
     _lib = lib
+    if os.environ.get("GEDEPTH_GEMM_PASSES"):
+        lib.ged_set_gemm_precision(int(os.environ["GEDEPTH_GEMM_PASSES"]))
     return lib
+
+
+def set_gemm_precision(passes: int) -> int:
+    """3 = error-compensated 3xTF32 (fp32-accurate, default), 1 = single-pass TF32.  Returns the previous mode."""
+    return load().ged_set_gemm_precision(int(passes))
 
 
 def has(name: str) -> bool:

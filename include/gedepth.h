@@ -116,6 +116,10 @@ int ged_winattn_bwd(const float* qkv, const float* qkv_bias, const float* table,
 int ged_gemm_tf32(const float* A, int lda, const float* W, int ldw, float* D, int ldd, int M, int N,
                   int K, const float* bias, int act, float slope, const float* residual,
                   const float* row_scale, int rows_per_batch, cudaStream_t stream);
+/* Process-wide GEMM/conv arithmetic: 3 (default) = error-compensated 3xTF32 (each fp32 operand split into
+ * tf32 hi + lo, three tcgen05 MMAs per k-step: fp32-accurate, the parity mode); 1 = single-pass TF32 (what
+ * PyTorch 1.8 / cuDNN run by default on Ampere+ for the reference).  Returns the previous value. */
+int ged_set_gemm_precision(int passes);
 /* 3x3/s1/p1 conv, NHWC: hahi.py:138-165, pemask_neck.py:36-42, dynamicpe_neck.py:497-502,
  * densedepth_head.py:21-22, decode_head.py:391.  Xpad [B,H+2,W+2,Cin] zero-bordered;
  * Wk [Cout][3][3][Cin]; Y [B,H,W,*] with channel pitch ldy. */
