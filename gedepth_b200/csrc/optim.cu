@@ -36,7 +36,13 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
                                                      const uint8_t* __restrict__ wd_mask, int64_t n,
                                                      const double* __restrict__ sumsq, float max_norm,
                                                      float grad_scale, float lr, float beta1, float beta2,
-                                                     float eps, float wd, float bc1, float bc2) {
+                                                     float eps, float wd, float bc1, float bc2,
+                                                     const int* __restrict__ step_dev) {
+  if (step_dev) {   // step count lives on the device (CUDA-graph replays must not bake it in)
+    const float t = (float)(*step_dev);
+    bc1 = 1.f - powf(beta1, t);
+    bc2 = 1.f - powf(beta2, t);
+  }
   // clip coefficient: max_norm / (norm + 1e-6), clamped to 1 (torch.nn.utils.clip_grad_norm_)
   float coef = grad_scale;
   if (sumsq && max_norm > 0.f) {
@@ -69,14 +75,16 @@ GED_API int ged_sumsq(const float* g, int64_t n, double* out, cudaStream_t strea
   return GED_OK;
 }
 
-// step >= 1.  sumsq may be NULL (no clipping).  grad_scale folds the 1/world_size average.
+// step >= 1, or step_dev != NULL: the 1-based step count is read from device memory at run time (for
+// CUDA-graph replay).  sumsq may be NULL (no clipping).  grad_scale folds the 1/world_size average.
 GED_API int ged_adamw_step(float* p, const float* g, float* m, float* v, const uint8_t* wd_mask, int64_t n,
                            const double* sumsq, float max_norm, float grad_scale, float lr, float beta1,
-                           float beta2, float eps, float weight_decay, int step, cudaStream_t stream) {
-  if (!p || !g || !m || !v || n <= 0 || step < 1) return GED_ERR_ARG;
+                           float beta2, float eps, float weight_decay, int step, const int* step_dev,
+                           cudaStream_t stream) {
+  if (!p || !g || !m || !v || n <= 0 || (step < 1 && !step_dev)) return GED_ERR_ARG;
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   const unsigned grid = (unsigned)(n / 256 + 1 < 2368 ? n / 256 + 1 : 2368);
-  adamw_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, wd_mask, n, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, weight_decay, bc1, bc2);
+  adamw_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, wd_mask, n, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, weight_decay, bc1, bc2, step_dev);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }

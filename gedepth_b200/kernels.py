@@ -45,7 +45,7 @@ SIGNATURES = {
     "ged_msda_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_set_gemm_precision": [_I],
     "ged_sumsq": [_P, _I64, _P, _P],
-    "ged_adamw_step": [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _F, _I, _P],
+    "ged_adamw_step": [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _F, _I, _P, _P],
 }
 
 _lib = None
@@ -645,6 +645,8 @@ def sumsq(flat_grad: torch.Tensor, out: torch.Tensor):
     return out
 
 
-def adamw_step(p, g, m, v, wd_mask, sumsq_buf, max_norm, grad_scale, lr, beta1, beta2, eps, wd, step):
+def adamw_step(p, g, m, v, wd_mask, sumsq_buf, max_norm, grad_scale, lr, beta1, beta2, eps, wd, step, step_dev=None):
+    """step: host-side 1-based count, or step_dev: int32 device tensor holding it (CUDA-graph replay)."""
     _call("ged_adamw_step", _p(p), _p(g), _p(m), _p(v), _p(wd_mask), p.numel(), _p(sumsq_buf), float(max_norm),
-          float(grad_scale), float(lr), float(beta1), float(beta2), float(eps), float(wd), int(step), _stream())
+          float(grad_scale), float(lr), float(beta1), float(beta2), float(eps), float(wd), int(step), _p(step_dev),
+          _stream())

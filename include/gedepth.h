@@ -142,7 +142,8 @@ int ged_msda_bwd(const float* value, const float* ref, int ref_batch, const floa
 int ged_sumsq(const float* g, int64_t n, double* out, cudaStream_t stream);
 int ged_adamw_step(float* p, const float* g, float* m, float* v, const uint8_t* wd_mask, int64_t n,
                    const double* sumsq, float max_norm, float grad_scale, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, int step, cudaStream_t stream);
+                   float beta2, float eps, float weight_decay, int step, const int* step_dev,
+                   cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ def _inject_cpu_ops():
         out.copy_(flat_g.double().pow(2).sum().reshape(1))
         return out
 
-    def adamw_step(p, g, m, v, wd_mask, ss, max_norm, grad_scale, lr, b1, b2, eps, wd, step):
+    def adamw_step(p, g, m, v, wd_mask, ss, max_norm, grad_scale, lr, b1, b2, eps, wd, step, step_dev=None):
         coef = grad_scale * min(max_norm / (float(ss.sqrt()) * grad_scale + 1e-6), 1.0)
         gi = g * coef
         p.mul_(torch.where(wd_mask.bool(), 1 - lr * wd, 1.0))
@@ -50,7 +50,7 @@ def _build(seed_data):
         if isinstance(getattr(m, "dropout", None), torch.nn.Dropout):
             m.dropout.p = 0.0
     model.train()
-    b = synth_batch(1, 32, 64, seed=seed_data)
+    b = synth_batch(1, 64, 160, seed=seed_data)
     data = dict(img=torch.from_numpy(b["img"]), img_metas=[{}], depth_gt=torch.from_numpy(b["depth_gt"]))
     return model, data
 
@@ -70,6 +70,7 @@ def _worker(rank, world, port, out):
     if rank == 0:
         out["same_params"] = bool(torch.equal(gathered[0], gathered[1]))
         out["flat_p"] = flat
+        out["flat_g"] = tr.arena.flat_g.clone()
         out["loss_logged"] = logs["loss"]
         out["loss_local"] = float(loss)
         out["wd_frac"] = float(tr.arena.wd_mask.float().mean())
@@ -84,7 +85,10 @@ def test_two_rank_step_equals_averaged_gradients():
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert out["same_params"], "ranks diverged after the all-reduced step"
     assert 0.9 < out["wd_frac"] < 1.0        # LayerNorm / rel-pos-bias tensors are exempt from decay
-    # single-process reference: average the two shards' gradients, same update
+    # single-process reference: average the two shards' gradients, same update.  Same CPU thread count as
+    # the workers: with B=1 the train-mode BatchNorms see <= 10 values per channel at the deepest level, so
+    # even reduction-order round-off is visibly amplified in the gradients.
+    torch.set_num_threads(2)
     _inject_cpu_ops()
     from gedepth_b200 import kernels
     from gedepth_b200.train import FlatArena
@@ -103,6 +107,12 @@ def test_two_rank_step_equals_averaged_gradients():
     ss = torch.zeros(1, dtype=torch.float64)
     kernels.sumsq(g, ss)
     kernels.adamw_step(p, g, m, v, arena.wd_mask, ss, 35.0, 0.5, 1e-4, 0.9, 0.999, 1e-8, 0.01, 1)
-    assert torch.allclose(p, out["flat_p"], rtol=1e-5, atol=1e-7)
+    # the all-reduced arena holds the SUM of the two shards' gradients (1/world is folded into AdamW)
+    assert torch.allclose(out["flat_g"], g, rtol=1e-4, atol=1e-6 * float(g.abs().max()))
+    # Adam's first step is lr*sign(g): compare parameters where the gradient is above round-off
+    # (CPU thread count changes reduction order, and sign(noise) flips)
+    solid = g.abs() > 1e-4 * float(g.abs().max())
+    diff = (p - out["flat_p"]).abs()
+    assert float(diff.max()) <= 2.1e-4 and float(diff[solid].max()) < 2e-6 and float(solid.float().mean()) > 0.2
     assert abs(out["loss_logged"] - sum(losses) / 2) < 1e-5      # log_vars are rank means (base.py:197-202)
     assert abs(out["loss_local"] - losses[0]) < 1e-5

@@ -405,6 +405,7 @@ def test_adamw_and_clip_match_torch():
         torch.nn.utils.clip_grad_norm_([p_ref], 35.0)
         opt.step()
         Kn.sumsq(grad, ss)
-        Kn.adamw_step(p, grad, m, v, None, ss, 35.0, 1.0, 1e-4, 0.9, 0.999, 1e-8, 0.01, step)
+        Kn.adamw_step(p, grad, m, v, None, ss, 35.0, 1.0, 1e-4, 0.9, 0.999, 1e-8, 0.01, step,
+                      torch.tensor([step], dtype=torch.int32, device=DEV) if step == 2 else None)
         assert abs(float(ss.sqrt()) - float(grad.double().norm())) < 1e-6 * float(grad.norm())
     _close(p, p_ref.data, 1e-6, 1e-6, "adamw")
