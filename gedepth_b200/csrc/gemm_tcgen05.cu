@@ -39,6 +39,7 @@ struct GemmParams {
   const float* row_scale;   // [batch] or null (DropPath)
   int rows_per_batch;       // for row_scale
   float* D;
+  float* D_pre;             // optional: pre-activation (x + bias) copy, same pitch as D (saved for GELU')
   int ldd;                  // row pitch of D / residual in floats
   int act;
   float slope;
@@ -292,6 +293,10 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
             if (orow[i] < 0) continue;
             const float4 t = *(const float4*)(tile_s + (lr + 8 * i) * EPI_PITCH + lc);
             float x[4] = {t.x + bias[0], t.y + bias[1], t.z + bias[2], t.w + bias[3]};
+            if (p.D_pre) {
+              if (vec) *(float4*)(p.D_pre + orow[i] * p.ldd + col) = make_float4(x[0], x[1], x[2], x[3]);
+              else for (int e = 0; e < 4; ++e) if (col + e < p.N) p.D_pre[orow[i] * p.ldd + col + e] = x[e];
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = apply_act(x[e], p.act, p.slope) * rscale[i];
             float* dst = p.D + orow[i] * p.ldd + col;
@@ -451,14 +456,14 @@ GED_API int ged_set_gemm_precision(int passes) {
 // depthformer_swin.py:96,119,174-176,193,222 ; mmcv FFN ; hahi.py:122-165 (1x1) ; MSDA linears.
 GED_API int ged_gemm_tf32(const float* A, int lda, const float* W, int ldw, float* D, int ldd, int M,
                           int N, int K, const float* bias, int act, float slope, const float* residual,
-                          const float* row_scale, int rows_per_batch, cudaStream_t stream) {
+                          const float* row_scale, int rows_per_batch, float* D_pre, cudaStream_t stream) {
   if (!A || !W || !D || M <= 0 || N <= 0 || K <= 0) return GED_ERR_ARG;
   if (K % 4) return GED_ERR_SHAPE;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.ntaps = 1; p.tap_off[0] = 0;
   p.bias = bias; p.residual = residual; p.row_scale = row_scale;
   p.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
-  p.D = D; p.ldd = ldd; p.act = act; p.slope = slope; p.conv_Hp = 0; p.conv_Wp = 0;
+  p.D = D; p.D_pre = D_pre; p.ldd = ldd; p.act = act; p.slope = slope; p.conv_Hp = 0; p.conv_Wp = 0;
   return run(A, M, lda, W, ldw, p, stream);
 }
 
@@ -477,7 +482,7 @@ GED_API int ged_conv3x3_tf32(const float* Xpad, const float* Wk, float* Y, int l
   for (int ky = 0; ky < 3; ++ky)
     for (int kx = 0; kx < 3; ++kx) p.tap_off[ky * 3 + kx] = (ky - 1) * Wp + (kx - 1);
   p.bias = bias; p.residual = nullptr; p.row_scale = nullptr; p.rows_per_batch = 1;
-  p.D = Y; p.ldd = ldy; p.act = act; p.slope = slope; p.conv_Hp = Hp; p.conv_Wp = Wp;
+  p.D = Y; p.D_pre = nullptr; p.ldd = ldy; p.act = act; p.slope = slope; p.conv_Hp = Hp; p.conv_Wp = Wp;
   // when Cin is not a multiple of 32 the K blocks of one tap would straddle into the next tap's
   // weights; the A side reads zeros there (TMA out-of-bounds fill past column Cin), so it is exact.
   return run(Xpad, (int64_t)p.M, Cin, Wk, 9 * Cin, p, stream);

@@ -1,0 +1,216 @@
+// Data-movement kernels around the tensor-core convs, NHWC fp32, sm_100a.  All HBM-bound, 128-bit accesses.
+//
+//   ged_prep_conv_input   ONE pass that builds the zero-bordered input of a 3x3 conv from up to two sources:
+//                         [ bilinear(src0 -> HxW, align_corners=True) | src1 ] along channels.  Replaces
+//                         F.interpolate + torch.cat + zero padding (three full-tensor passes) of
+//                         densedepth_head.py:24-27 (UpSample) and the cat of hahi.py:329-353.
+//   ged_upsample_nhwc_bwd adjoint of that bilinear resize for the first C0 channels of dX.
+//   ged_act_bwd           gz = g * act'(.) * row_scale  and  db += column sums of gz, one pass
+//                         (ReLU / LeakyReLU / sigmoid from the output, exact GELU from the pre-activation).
+//   ged_resize_add_nhwc   acc += bilinear(t -> HxW, align_corners=True)   (pemask_neck.py:52-63)
+#include "common.cuh"
+
+namespace ged {
+
+__global__ void __launch_bounds__(256) prep_conv_input_kernel(
+    const float* __restrict__ src0, int C0, int h0, int w0, const float* __restrict__ src1, int C1,
+    float* __restrict__ dst, int B, int H, int W, float sy, float sx) {
+  const int C = C0 + C1, C4 = C >> 2;
+  const int64_t total = (int64_t)B * (H + 2) * (W + 2) * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    int64_t p = i / C4;
+    const int xp = (int)(p % (W + 2)); p /= (W + 2);
+    const int yp = (int)(p % (H + 2));
+    const int b = (int)(p / (H + 2));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (xp > 0 && xp <= W && yp > 0 && yp <= H) {
+      const int x = xp - 1, y = yp - 1;
+      if (c < C0) {
+        if (h0 == H && w0 == W) {
+          v = __ldg((const float4*)(src0 + (((int64_t)b * H + y) * W + x) * C0 + c));
+        } else {
+          const Tap ty = tap(y, sy, true, h0), tx = tap(x, sx, true, w0);
+          const float* base = src0 + (int64_t)b * h0 * w0 * C0 + c;
+          const float4 v00 = __ldg((const float4*)(base + ((int64_t)ty.i0 * w0 + tx.i0) * C0));
+          const float4 v01 = __ldg((const float4*)(base + ((int64_t)ty.i0 * w0 + tx.i1) * C0));
+          const float4 v10 = __ldg((const float4*)(base + ((int64_t)ty.i1 * w0 + tx.i0) * C0));
+          const float4 v11 = __ldg((const float4*)(base + ((int64_t)ty.i1 * w0 + tx.i1) * C0));
+          v.x = ty.l0 * (tx.l0 * v00.x + tx.l1 * v01.x) + ty.l1 * (tx.l0 * v10.x + tx.l1 * v11.x);
+          v.y = ty.l0 * (tx.l0 * v00.y + tx.l1 * v01.y) + ty.l1 * (tx.l0 * v10.y + tx.l1 * v11.y);
+          v.z = ty.l0 * (tx.l0 * v00.z + tx.l1 * v01.z) + ty.l1 * (tx.l0 * v10.z + tx.l1 * v11.z);
+          v.w = ty.l0 * (tx.l0 * v00.w + tx.l1 * v01.w) + ty.l1 * (tx.l0 * v10.w + tx.l1 * v11.w);
+        }
+      } else {
+        v = __ldg((const float4*)(src1 + (((int64_t)b * H + y) * W + x) * C1 + (c - C0)));
+      }
+    }
+    *((float4*)dst + i) = v;
+  }
+}
+
+// g: (B,H,W,ldg) - uses channels [0,C0); out (B,h0,w0,C0) = resize^T(g[..., :C0])
+__global__ void __launch_bounds__(256) upsample_nhwc_bwd_kernel(
+    const float* __restrict__ g, int ldg, float* __restrict__ out, int C0, int B, int H, int W, int h0, int w0,
+    float sy, float sx) {
+  const int C4 = C0 >> 2;
+  const int64_t total = (int64_t)B * h0 * w0 * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    int64_t p = i / C4;
+    const int k = (int)(p % w0); p /= w0;
+    const int j = (int)(p % h0);
+    const int b = (int)(p / h0);
+    int ylo, yhi, xlo, xhi;
+    adjoint_range(j, sy, true, h0, H, ylo, yhi);
+    adjoint_range(k, sx, true, w0, W, xlo, xhi);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int y = ylo; y <= yhi; ++y) {
+      const Tap ty = tap(y, sy, true, h0);
+      const float wy = (ty.i0 == j ? ty.l0 : 0.f) + (ty.i1 == j ? ty.l1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int x = xlo; x <= xhi; ++x) {
+        const Tap tx = tap(x, sx, true, w0);
+        const float wgt = wy * ((tx.i0 == k ? tx.l0 : 0.f) + (tx.i1 == k ? tx.l1 : 0.f));
+        if (wgt == 0.f) continue;
+        const float4 v = __ldg((const float4*)(g + (((int64_t)b * H + y) * W + x) * ldg + c));
+        acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
+      }
+    }
+    *((float4*)out + i) = acc;
+  }
+}
+
+// acc (B,H,W,C) += bilinear(t (B,h0,w0,C) -> HxW, align_corners=True)
+__global__ void __launch_bounds__(256) resize_add_nhwc_kernel(
+    const float* __restrict__ t, float* __restrict__ acc, int C, int B, int H, int W, int h0, int w0, float sy,
+    float sx) {
+  const int C4 = C >> 2;
+  const int64_t total = (int64_t)B * H * W * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    int64_t p = i / C4;
+    const int x = (int)(p % W); p /= W;
+    const int y = (int)(p % H);
+    const int b = (int)(p / H);
+    const Tap ty = tap(y, sy, true, h0), tx = tap(x, sx, true, w0);
+    const float* base = t + (int64_t)b * h0 * w0 * C + c;
+    const float4 v00 = __ldg((const float4*)(base + ((int64_t)ty.i0 * w0 + tx.i0) * C));
+    const float4 v01 = __ldg((const float4*)(base + ((int64_t)ty.i0 * w0 + tx.i1) * C));
+    const float4 v10 = __ldg((const float4*)(base + ((int64_t)ty.i1 * w0 + tx.i0) * C));
+    const float4 v11 = __ldg((const float4*)(base + ((int64_t)ty.i1 * w0 + tx.i1) * C));
+    float4 a = *((float4*)acc + i);
+    a.x += ty.l0 * (tx.l0 * v00.x + tx.l1 * v01.x) + ty.l1 * (tx.l0 * v10.x + tx.l1 * v11.x);
+    a.y += ty.l0 * (tx.l0 * v00.y + tx.l1 * v01.y) + ty.l1 * (tx.l0 * v10.y + tx.l1 * v11.y);
+    a.z += ty.l0 * (tx.l0 * v00.z + tx.l1 * v01.z) + ty.l1 * (tx.l0 * v10.z + tx.l1 * v11.z);
+    a.w += ty.l0 * (tx.l0 * v00.w + tx.l1 * v01.w) + ty.l1 * (tx.l0 * v10.w + tx.l1 * v11.w);
+    *((float4*)acc + i) = a;
+  }
+}
+
+// gz[r, c] = g[r, c] * act'(ref[r, c]) * row_scale[r / rows_per_batch];  db[c] += sum_r gz[r, c]
+// act: 1 relu, 2 leaky (ref = output), 3 gelu (ref = pre-activation), 4 sigmoid (ref = output), 0 none.
+// grid (ceil(N/128), row chunks), block (32, 8): a thread owns 4 consecutive columns.
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ ref,
+                                                       float* __restrict__ gz, float* __restrict__ db,
+                                                       const float* __restrict__ row_scale, int rows_per_batch,
+                                                       int64_t rows, int N, int act, float slope,
+                                                       int rows_per_block) {
+  __shared__ float4 s_red[8][32];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < N) {
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      float4 v = __ldg((const float4*)(g + r * N + c));
+      if (act) {
+        const float4 y = __ldg((const float4*)(ref + r * N + c));
+        float d[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float t = d[e];
+          if (act == 1) d[e] = t > 0.f ? 1.f : 0.f;
+          else if (act == 2) d[e] = t > 0.f ? 1.f : slope;
+          else if (act == 4) d[e] = t * (1.f - t);
+          else d[e] = 0.5f * (1.f + erff(t * 0.70710678118654752f)) + t * 0.3989422804014327f * __expf(-0.5f * t * t);
+        }
+        v.x *= d[0]; v.y *= d[1]; v.z *= d[2]; v.w *= d[3];
+      }
+      if (row_scale) {
+        const float s = __ldg(row_scale + r / rows_per_batch);
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+      }
+      if (gz) *(float4*)(gz + r * N + c) = v;
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  if (db == nullptr) return;
+  s_red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < N) {
+    for (int i = 1; i < 8; ++i) {
+      const float4 t = s_red[i][threadIdx.x];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    atomicAdd(db + c, acc.x); atomicAdd(db + c + 1, acc.y); atomicAdd(db + c + 2, acc.z); atomicAdd(db + c + 3, acc.w);
+  }
+}
+
+}  // namespace ged
+using namespace ged;
+
+static inline unsigned grid_for(int64_t total) {
+  const int64_t b = (total + 255) / 256;
+  return (unsigned)(b < 148 * 16 ? b : 148 * 16);
+}
+
+// dst [B,H+2,W+2,C0+C1] <- zero border | [resize(src0 (B,h0,w0,C0)) , src1 (B,H,W,C1)].  src1 may be NULL (C1=0).
+GED_API int ged_prep_conv_input(const float* src0, int C0, int h0, int w0, const float* src1, int C1, float* dst,
+                                int B, int H, int W, cudaStream_t stream) {
+  if (!src0 || !dst || B <= 0 || H <= 0 || W <= 0 || C0 <= 0 || (C1 > 0 && !src1)) return GED_ERR_ARG;
+  if ((C0 % 4) || (C1 % 4)) return GED_ERR_SHAPE;
+  if (!aligned16(src0) || !aligned16(dst) || (src1 && !aligned16(src1))) return GED_ERR_ALIGN;
+  const int64_t total = (int64_t)B * (H + 2) * (W + 2) * ((C0 + C1) / 4);
+  prep_conv_input_kernel<<<grid_for(total), 256, 0, stream>>>(src0, C0, h0, w0, src1, C1, dst, B, H, W,
+                                                             resize_scale(h0, H, true), resize_scale(w0, W, true));
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+GED_API int ged_upsample_nhwc_bwd(const float* g, int ldg, float* out, int C0, int B, int H, int W, int h0, int w0,
+                                  cudaStream_t stream) {
+  if (!g || !out || B <= 0 || C0 <= 0) return GED_ERR_ARG;
+  if ((C0 % 4) || (ldg % 4)) return GED_ERR_SHAPE;
+  if (!aligned16(g) || !aligned16(out)) return GED_ERR_ALIGN;
+  const int64_t total = (int64_t)B * h0 * w0 * (C0 / 4);
+  upsample_nhwc_bwd_kernel<<<grid_for(total), 256, 0, stream>>>(g, ldg, out, C0, B, H, W, h0, w0,
+                                                               resize_scale(h0, H, true), resize_scale(w0, W, true));
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+GED_API int ged_resize_add_nhwc(const float* t, float* acc, int C, int B, int H, int W, int h0, int w0,
+                                cudaStream_t stream) {
+  if (!t || !acc || B <= 0 || C <= 0) return GED_ERR_ARG;
+  if (C % 4) return GED_ERR_SHAPE;
+  if (!aligned16(t) || !aligned16(acc)) return GED_ERR_ALIGN;
+  const int64_t total = (int64_t)B * H * W * (C / 4);
+  resize_add_nhwc_kernel<<<grid_for(total), 256, 0, stream>>>(t, acc, C, B, H, W, h0, w0, resize_scale(h0, H, true),
+                                                             resize_scale(w0, W, true));
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+// db (N floats) is ACCUMULATED into when non-NULL.  ref: output (relu/leaky/sigmoid) or pre-activation (gelu).
+GED_API int ged_act_bwd(const float* g, const float* ref, float* gz, float* db, const float* row_scale,
+                        int rows_per_batch, int64_t rows, int N, int act, float slope, cudaStream_t stream) {
+  if (!g || (!gz && !db) || rows <= 0 || N <= 0 || (act && !ref)) return GED_ERR_ARG;
+  if (N % 4) return GED_ERR_SHAPE;
+  if (!aligned16(g) || (gz && !aligned16(gz)) || (ref && !aligned16(ref))) return GED_ERR_ALIGN;
+  const int rpb = 128;
+  dim3 grid(cdiv(N, 128), (unsigned)((rows + rpb - 1) / rpb));
+  act_bwd_kernel<<<grid, dim3(32, 8), 0, stream>>>(g, ref, gz, db, row_scale, rows_per_batch > 0 ? rows_per_batch : 1,
+                                                  rows, N, act, slope, rpb);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}

@@ -210,11 +210,13 @@ class HAHIHeteroNeck(BaseModule):
         else:
             fused = query
         fused = ops.tokens_to_map(fused, (h, w))
-        outs = [self._cm(self.conv_fusion[0], ops.cat_channels([fused, feat_conv]), padding=1)]
+        cf = self.conv_fusion[0]
+        outs = [ops.conv_bn_act_cat(fused, feat_conv, cf.conv.weight, cf.conv.bias, cf.norm, act="relu")]
         start = 0
         for i, t in enumerate(feats_trans):
             hh, ww = shapes[i]
             f = ops.tokens_to_map(src[:, start:start + hh * ww], (hh, ww))
             start += hh * ww
-            outs.append(self._cm(self.trans_fusion[i], ops.cat_channels([t, f]), padding=1))
+            tf = self.trans_fusion[i]
+            outs.append(ops.conv_bn_act_cat(t, f, tf.conv.weight, tf.conv.bias, tf.norm, act="relu"))
         return tuple(outs)

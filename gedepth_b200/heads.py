@@ -204,10 +204,8 @@ class UpSample(nn.Sequential):
                                 conv_cfg=conv_cfg, norm_cfg=norm_cfg, act_cfg=act_cfg)
 
     def forward(self, x, concat_with):
-        up = ops.resize(x, (concat_with.shape[2], concat_with.shape[3]), align_corners=True)
         a, b = self.convA, self.convB
-        t = ops.conv2d(ops.cat_channels([up, concat_with]), a.conv.weight, a.conv.bias, padding=1,
-                       act=_act_name(a), slope=a.act_slope)
+        t = ops.conv2d_cat(x, concat_with, a.conv.weight, a.conv.bias, act=_act_name(a), slope=a.act_slope)
         return ops.conv2d(t, b.conv.weight, b.conv.bias, padding=1, act=_act_name(b), slope=b.act_slope)
 
 

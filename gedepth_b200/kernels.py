@@ -39,7 +39,11 @@ SIGNATURES = {
     "ged_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P],
     "ged_winattn_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "ged_winattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
-    "ged_gemm_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _I, _P],
+    "ged_gemm_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _I, _P, _P],
+    "ged_prep_conv_input": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P],
+    "ged_upsample_nhwc_bwd": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ged_resize_add_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ged_act_bwd": [_P, _P, _P, _P, _P, _I, _I64, _I, _I, _F, _P],
     "ged_conv3x3_tf32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _F, _P],
     "ged_msda_fwd": [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_msda_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -54,7 +58,7 @@ _load_error: Optional[str] = None
 # ops whose sm_100a kernel is wired in (ops.py consults has()); everything else is a library call
 NATIVE_OPS = {"ground_plane", "ge_vanilla", "ge_adaptive", "fuse_head", "silog", "cross_entropy",
               "layer_norm", "window_attention", "msda_sample", "linear", "conv2d", "conv_bn_act",
-              "find_k", "adamw"}
+              "conv2d_cat", "resize_add", "find_k", "adamw"}
 
 
 def load():
@@ -82,6 +86,20 @@ def load():
 def set_gemm_precision(passes: int) -> int:
     """3 = error-compensated 3xTF32 (fp32-accurate, default), 1 = single-pass TF32.  Returns the previous mode."""
     return load().ged_set_gemm_precision(int(passes))
+
+
+# GEMM arithmetic of the backward (dX) kernels.  The forward default (3xTF32) is what the depth-map parity bar
+# needs; gradients are computed in single-pass TF32 exactly as the reference's PyTorch 1.8 does on Ampere+
+# (torch.backends.{cuda.matmul,cudnn}.allow_tf32 default True there).  Set to 3 for fp32-accurate gradients.
+BACKWARD_PASSES = int(os.environ.get("GEDEPTH_BWD_GEMM_PASSES", "1"))
+
+
+class _bwd_precision:
+    def __enter__(self):
+        self.prev = load().ged_set_gemm_precision(BACKWARD_PASSES)
+
+    def __exit__(self, *a):
+        load().ged_set_gemm_precision(self.prev)
 
 
 def has(name: str) -> bool:
@@ -404,7 +422,8 @@ _ACT = {None: 0, "relu": 1, "leaky_relu": 2, "gelu": 3, "sigmoid": 4}
 
 
 def gemm(a2d: torch.Tensor, w: torch.Tensor, bias=None, act=None, slope=0.01, residual=None,
-         row_scale=None, rows_per_batch=1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         row_scale=None, rows_per_batch=1, out: Optional[torch.Tensor] = None,
+         pre_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = epi(a2d[M,K] @ w[N,K]^T).  a2d / w: last dim contiguous, 16B-aligned pitches."""
     M, K = a2d.shape
     N = w.shape[0]
@@ -412,8 +431,23 @@ def gemm(a2d: torch.Tensor, w: torch.Tensor, bias=None, act=None, slope=0.01, re
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=a2d.device)
     _call("ged_gemm_tf32", _p(a2d), a2d.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K,
-          _p(bias), _ACT[act], float(slope), _p(residual), _p(row_scale), int(rows_per_batch), _stream())
+          _p(bias), _ACT[act], float(slope), _p(residual), _p(row_scale), int(rows_per_batch), _p(pre_out), _stream())
     return out
+
+
+def act_bwd(g2d: torch.Tensor, ref: Optional[torch.Tensor], act, slope=0.01, row_scale=None, rows_per_batch=1,
+            want_db=False):
+    """gz = g * act'(ref) * row_scale and (optionally) db = column sums of gz, in ONE pass.  With no
+    activation and no scale gz is g itself and only the column sums are computed."""
+    rows, N = g2d.shape
+    ident = act is None and row_scale is None
+    if ident and not want_db:
+        return g2d, None
+    gz = g2d if ident else torch.empty_like(g2d)
+    db = torch.zeros(N, dtype=torch.float32, device=g2d.device) if want_db else None
+    _call("ged_act_bwd", _p(g2d), _p(ref), _p(None if ident else gz), _p(db), _p(row_scale), int(rows_per_batch), rows,
+          N, _ACT[act], float(slope), _stream())
+    return gz, db
 
 
 def _act_grad(gz, act, slope, pre, post):
@@ -441,8 +475,9 @@ def _gemm_ok(M, N, K, *tensors):
 
 
 class _Linear(Function):
-    """y = [residual +] [row_scale *] act(x @ w^T + b).  Forward and dX on tcgen05; dW = gz^T @ x is a
-    cuBLAS TF32 GEMM for now (needs MN-major UMMA operands)."""
+    """y = [residual +] [row_scale *] act(x @ w^T + b).  Forward and dX on tcgen05 (GELU keeps its
+    pre-activation through the epilogue's second store); the activation derivative, DropPath scale and
+    the bias gradient are one fused pass; dW = gz^T @ x is a cuBLAS TF32 GEMM for now."""
 
     @staticmethod
     def forward(ctx, x, w, b, act, residual, row_scale):
@@ -453,20 +488,16 @@ class _Linear(Function):
         res2 = None if residual is None else _f32c(residual).reshape(M, N)
         rpb = M // x.shape[0] if row_scale is not None else 1
         need_pre = act == "gelu" and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
-        if need_pre:
-            pre = gemm(x2, wc, b)
-            out = L._act(pre, act)           # elementwise; GELU'(z) needs z (saved instead of recomputed)
-            if row_scale is not None:
-                out = out * row_scale.repeat_interleave(rpb).unsqueeze(1)
-            if res2 is not None:
-                out = out + res2
-        else:
-            pre = None
-            out = gemm(x2, wc, b, act, 0.01, res2, row_scale, rpb)
+        pre = torch.empty(M, N, dtype=torch.float32, device=x.device) if need_pre else None
+        out = gemm(x2, wc, b, act, 0.01, res2, row_scale, rpb, pre_out=pre)
         ctx.act, ctx.rpb, ctx.has_res, ctx.has_bias = act, rpb, residual is not None, b is not None
-        ctx.save_for_backward(x2, wc, pre if pre is not None else torch.empty(0, device=x.device),
-                              out if act in ("relu", "leaky_relu", "sigmoid") else torch.empty(0, device=x.device),
-                              row_scale if row_scale is not None else torch.empty(0, device=x.device))
+        empty = torch.empty(0, device=x.device)
+        # relu/leaky/sigmoid derive from the output - only valid when nothing was added after the activation
+        post = out if (act in ("relu", "leaky_relu", "sigmoid") and residual is None and row_scale is None) else empty
+        if act in ("relu", "leaky_relu", "sigmoid") and post is empty:
+            raise NotImplementedError("activation + residual/row_scale in one linear is only wired for GELU/none")
+        ctx.save_for_backward(x2, wc, pre if pre is not None else empty, post,
+                              row_scale if row_scale is not None else empty)
         ctx.xshape = x.shape
         return out.reshape(*x.shape[:-1], N)
 
@@ -475,22 +506,24 @@ class _Linear(Function):
         x2, w, pre, post, row_scale = ctx.saved_tensors
         N, K = w.shape
         g2 = _f32c(g).reshape(-1, N)
-        gz = g2
-        if row_scale.numel():
-            gz = gz * row_scale.repeat_interleave(ctx.rpb).unsqueeze(1)
-        gz = _act_grad(gz, ctx.act, 0.01, pre, post)
-        gz = gz if gz.is_contiguous() else gz.contiguous()
-        dx = dw = db = None
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        ref = pre if ctx.act == "gelu" else (post if ctx.act is not None else None)
+        if N % 4 == 0:
+            gz, db = act_bwd(g2, ref, ctx.act, 0.01, row_scale if row_scale.numel() else None, ctx.rpb, want_db)
+        else:
+            gz = g2 if not row_scale.numel() else g2 * row_scale.repeat_interleave(ctx.rpb).unsqueeze(1)
+            gz = _act_grad(gz, ctx.act, 0.01, pre, post).contiguous()
+            db = gz.sum(0) if want_db else None
+        dx = dw = None
         if ctx.needs_input_grad[0]:
             wt = w.t().contiguous()                      # [K, N]: the [N'][K'] operand of dX = gz @ w
             if _gemm_ok(gz.shape[0], K, N, gz, wt):
-                dx = gemm(gz, wt).reshape(ctx.xshape)
+                with _bwd_precision():
+                    dx = gemm(gz, wt).reshape(ctx.xshape)
             else:
                 dx = (gz @ w).reshape(ctx.xshape)
         if ctx.needs_input_grad[1]:
             dw = gz.t() @ x2
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = gz.sum(0)
         dres = g if ctx.has_res else None
         return dx, dw, db, None, dres, None
 
@@ -520,78 +553,165 @@ def conv2d_supported(x, w, stride, padding) -> bool:
     return kh == 3 and kw == 3 and padding == 1
 
 
-def conv3x3_raw(x_nhwc: torch.Tensor, wk: torch.Tensor, bias, act, slope) -> torch.Tensor:
-    """x (B,H,W,Cin) contiguous, wk [Cout,3,3,Cin] contiguous -> (B,H,W,Cout)."""
-    B, H, W, Cin = x_nhwc.shape
-    Cout = wk.shape[0]
-    xp = torch.nn.functional.pad(x_nhwc, (0, 0, 1, 1, 1, 1))       # zero border (data movement only)
-    y = torch.empty(B, H, W, Cout, dtype=torch.float32, device=x_nhwc.device)
+def prep_conv_input(x0: torch.Tensor, x1: Optional[torch.Tensor], H: int, W: int) -> torch.Tensor:
+    """Zero-bordered NHWC input [B,H+2,W+2,C0+C1] = [bilinear(x0 -> HxW, align_corners=True) | x1] in one pass."""
+    B, h0, w0, C0 = x0.shape
+    C1 = 0 if x1 is None else x1.shape[3]
+    xp = torch.empty(B, H + 2, W + 2, C0 + C1, dtype=torch.float32, device=x0.device)
+    _call("ged_prep_conv_input", _p(x0), C0, h0, w0, _p(x1), C1, _p(xp), B, H, W, _stream())
+    return xp
+
+
+def conv3x3_padded(xp: torch.Tensor, wk: torch.Tensor, bias, act, slope) -> torch.Tensor:
+    """xp (B,H+2,W+2,Cin) zero-bordered, wk [Cout,3,3,Cin] -> (B,H,W,Cout)."""
+    B, Hp, Wp, Cin = xp.shape
+    H, W, Cout = Hp - 2, Wp - 2, wk.shape[0]
+    y = torch.empty(B, H, W, Cout, dtype=torch.float32, device=xp.device)
     _call("ged_conv3x3_tf32", _p(xp), _p(wk), _p(y), Cout, B, H, W, Cin, Cout, _p(bias), _ACT[act], float(slope),
           _stream())
     return y
 
 
+def conv3x3_raw(x_nhwc: torch.Tensor, wk: torch.Tensor, bias, act, slope) -> torch.Tensor:
+    """x (B,H,W,Cin) contiguous, wk [Cout,3,3,Cin] contiguous -> (B,H,W,Cout)."""
+    return conv3x3_padded(prep_conv_input(x_nhwc, None, x_nhwc.shape[1], x_nhwc.shape[2]), wk, bias, act, slope)
+
+
 class _Conv(Function):
-    """3x3/s1/p1 or 1x1 conv + bias + activation.  Forward and dX on tcgen05 (dX of a 3x3 conv is the
-    3x3 conv of dY with the flipped, transposed kernel); dW/db via cuDNN for now."""
+    """3x3/s1/p1 or 1x1 conv + bias + activation over [resize(x0) | x1] (x1 optional, resize only when
+    x0 is smaller).  Forward and dX on tcgen05 (dX of a 3x3 conv is the 3x3 conv of dY with the flipped,
+    transposed kernel); activation derivative + bias gradient one fused pass; dW via cuDNN for now."""
 
     @staticmethod
-    def forward(ctx, x, w, b, act, slope):
+    def forward(ctx, x0, x1, w, b, act, slope):
         Cout, Cin, kh, kw = w.shape
-        xh = _nhwc(x)
-        B, H, W, _ = xh.shape
+        a0 = _nhwc(x0)
+        a1 = None if x1 is None else _nhwc(x1)
+        B = a0.shape[0]
+        H, W = (a0.shape[1], a0.shape[2]) if a1 is None else (a1.shape[1], a1.shape[2])
         if kh == 3:
-            y = conv3x3_raw(xh, w.permute(0, 2, 3, 1).contiguous(), b, act, slope)
+            xin = prep_conv_input(a0, a1, H, W)                          # padded, concatenated
+            y = conv3x3_padded(xin, w.permute(0, 2, 3, 1).contiguous(), b, act, slope)
         else:
-            y = gemm(xh.reshape(-1, Cin), w.reshape(Cout, Cin), b, act, slope).reshape(B, H, W, Cout)
-        ctx.save_for_backward(xh, w, y if act is not None else torch.empty(0, device=x.device))
-        ctx.cfg = (act, slope, kh, b is not None)
+            assert a1 is None
+            xin = a0
+            y = gemm(a0.reshape(-1, Cin), w.reshape(Cout, Cin), b, act, slope).reshape(B, H, W, Cout)
+        ctx.save_for_backward(xin, w, y if act is not None else torch.empty(0, device=x0.device))
+        ctx.cfg = (act, slope, kh, b is not None, a0.shape, None if a1 is None else a1.shape[3])
         return y.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, g):
-        xh, w, y = ctx.saved_tensors
-        act, slope, kh, has_bias = ctx.cfg
+        xin, w, y = ctx.saved_tensors
+        act, slope, kh, has_bias, shape0, C1 = ctx.cfg
         Cout, Cin = w.shape[0], w.shape[1]
-        B, H, W, _ = xh.shape
-        gz = _act_grad(_nhwc(g), act, slope, None, y)
-        gz = gz if gz.is_contiguous() else gz.contiguous()
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
+        B, h0, w0, C0 = shape0
+        gh = _nhwc(g)
+        H, W = gh.shape[1], gh.shape[2]
+        want_db = has_bias and ctx.needs_input_grad[3]
+        need_dx = ctx.needs_input_grad[0] or (C1 is not None and ctx.needs_input_grad[1])
+        db = None
+        if Cout % 4 == 0:
+            gz2, db = act_bwd(gh.reshape(-1, Cout), y.reshape(-1, Cout) if act is not None else None, act, slope,
+                              None, 1, want_db)
+            gz = gz2.reshape(B, H, W, Cout)
+        else:
+            gz = _act_grad(gh, act, slope, None, y)
+            gz = gz if gz.is_contiguous() else gz.contiguous()
+            if want_db:
+                db = gz.sum((0, 1, 2))
+        dxc = dw = None
+        if need_dx:
             if kh == 3 and Cout % 32 == 0:
                 wt = w.flip(2, 3).permute(1, 2, 3, 0).contiguous()          # [Cin,3,3,Cout]
-                dx = conv3x3_raw(gz, wt, None, None, 0.0).permute(0, 3, 1, 2)
+                with _bwd_precision():
+                    dxc = conv3x3_raw(gz, wt, None, None, 0.0)                # (B,H,W,Cin)
             elif kh == 1 and _gemm_ok(B * H * W, Cin, Cout, gz):
-                dx = gemm(gz.reshape(-1, Cout), w.reshape(Cout, Cin).t().contiguous()).reshape(B, H, W, Cin).permute(0, 3, 1, 2)
-        mask = [ctx.needs_input_grad[0] and dx is None, ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]]
+                with _bwd_precision():
+                    dxc = gemm(gz.reshape(-1, Cout), w.reshape(Cout, Cin).t().contiguous()).reshape(B, H, W, Cin)
+        pad = 0                                     # xin already carries the zero border for 3x3
+        xin_nchw = xin.permute(0, 3, 1, 2)
+        mask = [need_dx and dxc is None, ctx.needs_input_grad[2], False]
         if any(mask):
-            pad = 1 if kh == 3 else 0
-            r = torch.ops.aten.convolution_backward(gz.permute(0, 3, 1, 2), xh.permute(0, 3, 1, 2), w,
-                                                    [Cout] if has_bias else None, [1, 1], [pad, pad], [1, 1],
-                                                    False, [0, 0], 1, mask)
-            dx = r[0] if mask[0] else dx
+            r = torch.ops.aten.convolution_backward(gz.permute(0, 3, 1, 2), xin_nchw, w, None, [1, 1], [pad, pad],
+                                                    [1, 1], False, [0, 0], 1, mask)
+            if mask[0]:
+                dxc = r[0].permute(0, 2, 3, 1)
+                if kh == 3:
+                    dxc = dxc[:, 1:-1, 1:-1, :]
             dw = r[1] if mask[1] else None
-            db = r[2] if mask[2] else None
-        return dx, dw, db, None, None
+        dx0 = dx1 = None
+        if need_dx:
+            if C1 is not None and ctx.needs_input_grad[1]:
+                dx1 = dxc[..., C0:].permute(0, 3, 1, 2)
+            if ctx.needs_input_grad[0]:
+                if (h0, w0) != (H, W):
+                    d0 = torch.empty(B, h0, w0, C0, dtype=torch.float32, device=gz.device)
+                    dcc = dxc if dxc.is_contiguous() else dxc.contiguous()
+                    _call("ged_upsample_nhwc_bwd", _p(dcc), dcc.shape[3], _p(d0), C0, B, H, W, h0, w0, _stream())
+                    dx0 = d0.permute(0, 3, 1, 2)
+                else:
+                    dx0 = (dxc[..., :C0] if C1 is not None else dxc).permute(0, 3, 1, 2)
+        return dx0, dx1, dw, db, None, None
 
 
 def conv2d(x, w, b=None, stride=1, padding=0, act=None, slope=0.01):
-    return _Conv.apply(x, w, b, act, slope)
+    return _Conv.apply(x, None, w, b, act, slope)
+
+
+def conv2d_cat(x0, x1, w, b=None, act=None, slope=0.01):
+    """3x3 conv over cat([bilinear(x0 -> size of x1, align_corners=True), x1], channels)."""
+    return _Conv.apply(x0, x1, w, b, act, slope)
+
+
+def conv2d_cat_supported(x0, x1, w) -> bool:
+    Cout, Cin, kh, kw = w.shape
+    return (kh == 3 and kw == 3 and x0.shape[1] % 4 == 0 and x1.shape[1] % 4 == 0 and Cin % 32 == 0
+            and x0.dtype == torch.float32 and x1.dtype == torch.float32)
 
 
 def conv_bn_act(x, w, b, bn, stride=1, padding=0, act=None):
     """ConvModule(conv -> BN -> act).  Eval mode: BN folds into the conv's weight/bias and the
     activation into its epilogue.  Train mode needs batch statistics between conv and activation:
     conv (tcgen05) -> BatchNorm (library, per-GPU statistics as in the reference) -> act."""
+    return conv_bn_act_cat(x, None, w, b, bn, act)
+
+
+def conv_bn_act_cat(x0, x1, w, b, bn, act=None):
     if bn is None:
-        return _Conv.apply(x, w, b, act, 0.01)
+        return _Conv.apply(x0, x1, w, b, act, 0.01)
     if not bn.training:
         s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
         wf = w * s.view(-1, 1, 1, 1)
         bf = bn.bias - bn.running_mean * s + (b * s if b is not None else 0)
-        return _Conv.apply(x, wf, bf, act, 0.01)
-    y = bn(_Conv.apply(x, w, b, None, 0.0))
+        return _Conv.apply(x0, x1, wf, bf, act, 0.01)
+    y = bn(_Conv.apply(x0, x1, w, b, None, 0.0))
     return L._act(y, act)
+
+
+class _ResizeAdd(Function):
+    """acc + bilinear(t -> size of acc, align_corners=True), NHWC, in place on a fresh copy of acc."""
+
+    @staticmethod
+    def forward(ctx, t, acc):
+        th, ah = _nhwc(t), _nhwc(acc)
+        out = ah.clone()
+        B, H, W, Cc = out.shape
+        _call("ged_resize_add_nhwc", _p(th), _p(out), Cc, B, H, W, th.shape[1], th.shape[2], _stream())
+        ctx.shape = th.shape
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        gh = _nhwc(g)
+        B, h0, w0, Cc = ctx.shape
+        gt = torch.empty(B, h0, w0, Cc, dtype=torch.float32, device=g.device)
+        _call("ged_upsample_nhwc_bwd", _p(gh), Cc, _p(gt), Cc, B, gh.shape[1], gh.shape[2], h0, w0, _stream())
+        return gt.permute(0, 3, 1, 2), g
+
+
+def resize_add(t, size, acc):
+    return _ResizeAdd.apply(t, acc)
 
 
 # =============================================================================================

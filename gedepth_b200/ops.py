@@ -43,7 +43,7 @@ def native_table():
 
 
 OPS = ["linear", "layer_norm", "patch_embed", "merge_patches", "window_attention", "conv2d",
-       "conv_bn_act", "resize", "resize_add", "msda_sample", "ground_plane", "ge_vanilla",
+       "conv_bn_act", "conv2d_cat", "resize", "resize_add", "msda_sample", "ground_plane", "ge_vanilla",
        "ge_adaptive", "fuse_head", "silog", "cross_entropy", "clamp_resize", "find_k", "adamw"]
 
 
@@ -67,6 +67,24 @@ def conv_bn_act(x, w, b, bn, stride=1, padding=0, act=None):
     if use_native("conv_bn_act") and _k().conv2d_supported(x, w, stride, padding):
         return _k().conv_bn_act(x, w, b, bn, stride, padding, act)
     return L.conv_bn_act(x, w, b, bn, stride, padding, act)
+
+
+def conv2d_cat(x_low, x_skip, w, b=None, act=None, slope=0.01):
+    """3x3 conv (+bias, +act) over cat([bilinear(x_low -> skip size, align_corners=True), x_skip], 1):
+    the UpSample block of densedepth_head.py:24-27 without materialising the resize or the concat."""
+    require_cuda(x_low, x_skip, w)
+    if use_native("conv2d_cat") and _k().conv2d_cat_supported(x_low, x_skip, w):
+        return _k().conv2d_cat(x_low, x_skip, w, b, act, slope)
+    up = L.resize(x_low, (x_skip.shape[2], x_skip.shape[3]), True) if x_low.shape[2:] != x_skip.shape[2:] else x_low
+    return L.conv2d(L.cat_channels([up, x_skip]), w, b, 1, 1, act, slope)
+
+
+def conv_bn_act_cat(x0, x1, w, b, bn, act=None):
+    """ConvModule(3x3, BN, act) over cat([x0, x1], 1) (hahi.py:329-353) without the concat copy."""
+    require_cuda(x0, x1, w)
+    if use_native("conv2d_cat") and _k().conv2d_cat_supported(x0, x1, w) and x0.shape[2:] == x1.shape[2:]:
+        return _k().conv_bn_act_cat(x0, x1, w, b, bn, act)
+    return L.conv_bn_act(L.cat_channels([x0, x1]), w, b, bn, 1, 1, act)
 
 
 def patch_embed(x, w, b, patch):
@@ -136,7 +154,7 @@ def resize(x, size, align_corners=True):
 
 def resize_add(t, size, acc):
     require_cuda(t)
-    if use_native("resize_add"):
+    if use_native("resize_add") and t.shape[1] % 4 == 0:
         return _k().resize_add(t, size, acc)
     return L.resize_add(t, size, acc)
 

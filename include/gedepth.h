@@ -112,10 +112,11 @@ int ged_winattn_bwd(const float* qkv, const float* qkv_bias, const float* table,
 
 /* ---- tensor-core GEMM / conv (tcgen05, TF32) --------------------------------------------------- */
 /* D[M,N] = epi(A[M,K] @ W[N,K]^T): F.linear / 1x1 Conv2d sites depthformer_swin.py:96,119,174-176,
- * 193,222; mmcv FFN; hahi.py:122-165; MSDA linears.  act: 0 none 1 relu 2 leaky 3 gelu 4 sigmoid. */
+ * 193,222; mmcv FFN; hahi.py:122-165; MSDA linears.  act: 0 none 1 relu 2 leaky 3 gelu 4 sigmoid.
+ * D_pre (optional, pitch ldd): copy of the pre-activation x+bias, kept for the GELU derivative. */
 int ged_gemm_tf32(const float* A, int lda, const float* W, int ldw, float* D, int ldd, int M, int N,
                   int K, const float* bias, int act, float slope, const float* residual,
-                  const float* row_scale, int rows_per_batch, cudaStream_t stream);
+                  const float* row_scale, int rows_per_batch, float* D_pre, cudaStream_t stream);
 /* Process-wide GEMM/conv arithmetic: 3 (default) = error-compensated 3xTF32 (each fp32 operand split into
  * tf32 hi + lo, three tcgen05 MMAs per k-step: fp32-accurate, the parity mode); 1 = single-pass TF32 (what
  * PyTorch 1.8 / cuDNN run by default on Ampere+ for the reference).  Returns the previous value. */
@@ -125,6 +126,21 @@ int ged_set_gemm_precision(int passes);
  * Wk [Cout][3][3][Cin]; Y [B,H,W,*] with channel pitch ldy. */
 int ged_conv3x3_tf32(const float* Xpad, const float* Wk, float* Y, int ldy, int B, int H, int W, int Cin,
                      int Cout, const float* bias, int act, float slope, cudaStream_t stream);
+
+/* ---- data movement around the convs (NHWC fp32) ------------------------------------------------ */
+/* dst [B,H+2,W+2,C0+C1] = zero border | [bilinear(src0 (B,h0,w0,C0) -> HxW, align_corners=True), src1 (B,H,W,C1)]:
+ * F.interpolate + torch.cat + padding of densedepth_head.py:24-27 / hahi.py:329-353 in one pass. */
+int ged_prep_conv_input(const float* src0, int C0, int h0, int w0, const float* src1, int C1, float* dst, int B,
+                        int H, int W, cudaStream_t stream);
+/* out (B,h0,w0,C0) = resize^T of channels [0,C0) of g (B,H,W,ldg). */
+int ged_upsample_nhwc_bwd(const float* g, int ldg, float* out, int C0, int B, int H, int W, int h0, int w0,
+                          cudaStream_t stream);
+/* acc (B,H,W,C) += bilinear(t (B,h0,w0,C) -> HxW, align_corners=True): pemask_neck.py:52-63. */
+int ged_resize_add_nhwc(const float* t, float* acc, int C, int B, int H, int W, int h0, int w0, cudaStream_t stream);
+/* gz = g * act'(ref) * row_scale[row / rows_per_batch]; db[c] += column sums (db may be NULL).
+ * ref = layer output for relu(1)/leaky(2)/sigmoid(4), pre-activation for gelu(3); act 0: copy/scale only. */
+int ged_act_bwd(const float* g, const float* ref, float* gz, float* db, const float* row_scale, int rows_per_batch,
+                int64_t rows, int N, int act, float slope, cudaStream_t stream);
 
 /* ---- deformable attention sampling ----------------------------------------------------------- */
 /* mmcv.ops.MultiScaleDeformableAttention core (hahi.py:280-289,316-325).  value (B,S,nH,64);

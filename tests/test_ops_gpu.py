@@ -233,10 +233,12 @@ def test_window_attention_fwd_bwd(B, H, W, nH, shift):
 # tcgen05 GEMM / conv (TF32: 10-bit mantissa products, fp32 accumulate)
 # ------------------------------------------------------------------------------------------------
 @pytest.fixture(params=[3, 1], ids=["3xtf32", "tf32"])
-def passes(request):
-    """GEMM arithmetic: 3 = error-compensated 3xTF32 (default, fp32-accurate), 1 = single-pass TF32."""
+def passes(request, monkeypatch):
+    """GEMM arithmetic: 3 = error-compensated 3xTF32 (default, fp32-accurate), 1 = single-pass TF32.
+    The backward (dX) kernels follow the same setting in these tests."""
     from gedepth_b200 import kernels as Kn
     prev = Kn.set_gemm_precision(request.param)
+    monkeypatch.setattr(Kn, "BACKWARD_PASSES", request.param)
     yield request.param
     Kn.set_gemm_precision(prev)
 
@@ -409,3 +411,82 @@ def test_adamw_and_clip_match_torch():
                       torch.tensor([step], dtype=torch.int32, device=DEV) if step == 2 else None)
         assert abs(float(ss.sqrt()) - float(grad.double().norm())) < 1e-6 * float(grad.norm())
     _close(p, p_ref.data, 1e-6, 1e-6, "adamw")
+
+
+# ------------------------------------------------------------------------------------------------
+# data-movement kernels around the convs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,h0,w0,H,W,C0,C1", [(2, 11, 35, 22, 70, 64, 32), (1, 9, 12, 9, 12, 32, 96), (2, 22, 70, 44, 139, 96, 0)])
+def test_prep_conv_input_and_adjoint(B, h0, w0, H, W, C0, C1):
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(20)
+    x0 = torch.randn(B, h0, w0, C0, generator=g).to(DEV)
+    x1 = torch.randn(B, H, W, C1, generator=g).to(DEV) if C1 else None
+    xp = Kn.prep_conv_input(x0, x1, H, W)
+    up = F.interpolate(x0.permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True) if (h0, w0) != (H, W) else x0.permute(0, 3, 1, 2)
+    ref = torch.cat([up] + ([x1.permute(0, 3, 1, 2)] if C1 else []), 1)
+    ref = F.pad(ref, (1, 1, 1, 1)).permute(0, 2, 3, 1)
+    _close(xp, ref, 1e-5, 1e-5, "prep")
+    # adjoint of the resize on the first C0 channels
+    gfull = torch.randn(B, H, W, C0 + C1, generator=g).to(DEV)
+    out = torch.empty(B, h0, w0, C0, device=DEV)
+    Kn._call("ged_upsample_nhwc_bwd", Kn._p(gfull), C0 + C1, Kn._p(out), C0, B, H, W, h0, w0, Kn._stream())
+    x0r = x0.clone().requires_grad_(True)
+    upr = F.interpolate(x0r.permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True)
+    (upr * gfull[..., :C0].permute(0, 3, 1, 2)).sum().backward()
+    _close(out, x0r.grad, 1e-4, 1e-5, "resize adjoint")
+
+
+@pytest.mark.parametrize("act", [None, "relu", "leaky_relu", "gelu", "sigmoid"])
+def test_act_bwd(act):
+    from gedepth_b200 import kernels as Kn, ops_lib as L
+    g = torch.Generator().manual_seed(21)
+    rows, N, T = 3 * 217, 96, 217
+    pre = torch.randn(rows, N, generator=g).to(DEV).requires_grad_(True)
+    go = torch.randn(rows, N, generator=g).to(DEV)
+    rs = torch.tensor([0.0, 1.4, 1.4]).to(DEV)
+    y = L._act(pre, act, 0.01)
+    (y * rs.repeat_interleave(T).unsqueeze(1) * go).sum().backward()
+    ref = pre.detach() if act == "gelu" else (y.detach() if act else None)
+    gz, db = Kn.act_bwd(go, ref, act, 0.01, rs, T, True)
+    _close(gz, pre.grad, 1e-5, 1e-6, "gz")
+    _close(db, pre.grad.sum(0), 1e-4, 1e-4, "db")
+    gz2, db2 = Kn.act_bwd(go, None, None, 0.01, None, 1, True)
+    assert gz2 is go
+    _close(db2, go.sum(0), 1e-4, 1e-4, "db only")
+
+
+def test_resize_add_fwd_bwd():
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(22)
+    t0, a0 = torch.randn(2, 64, 11, 35, generator=g), torch.randn(2, 64, 44, 140, generator=g)
+    a1 = [x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for x in (t0, a0)]
+    a2 = [x.to(DEV).requires_grad_(True) for x in (t0, a0)]
+    o1 = Kn.resize_add(a1[0], (44, 140), a1[1])
+    o2 = a2[1] + F.interpolate(a2[0], size=(44, 140), mode="bilinear", align_corners=True)
+    _close(o1, o2, 1e-5, 1e-5, "resize_add")
+    go = torch.randn_like(o2)
+    (o1 * go).sum().backward()
+    (o2 * go).sum().backward()
+    _close(a1[0].grad, a2[0].grad, 1e-4, 1e-5, "g_t")
+    _close(a1[1].grad, a2[1].grad, 0, 0, "g_acc")
+
+
+def test_conv2d_cat_upsample_fwd_bwd(passes):
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(23)
+    B, h0, w0, H, W, C0, C1, Co = 2, 11, 35, 22, 70, 64, 32, 64
+    x0, x1 = torch.randn(B, C0, h0, w0, generator=g), torch.randn(B, C1, H, W, generator=g)
+    w0_, b0 = torch.randn(Co, C0 + C1, 3, 3, generator=g) / (9 * (C0 + C1)) ** 0.5, torch.randn(Co, generator=g)
+    a1 = [t.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for t in (x0, x1)] + \
+         [t.to(DEV).requires_grad_(True) for t in (w0_, b0)]
+    a2 = [t.to(DEV).double().requires_grad_(True) for t in (x0, x1, w0_, b0)]
+    y1 = Kn.conv2d_cat(a1[0], a1[1], a1[2], a1[3], None, 0.0)
+    up = F.interpolate(a2[0], size=(H, W), mode="bilinear", align_corners=True)
+    y2 = F.conv2d(torch.cat([up, a2[1]], 1), a2[2], a2[3], padding=1)
+    _close(y1, y2, 0, _gemm_tol(y2, passes, 9 * (C0 + C1)), "fwd")
+    go = torch.randn_like(y2).float()
+    (y1 * go).sum().backward()
+    (y2 * go.double()).sum().backward()
+    for n, p, q in zip(("dx_low", "dx_skip", "dw", "db"), a1, a2):
+        _close(p.grad, q.grad, 0, 2 * _gemm_tol(q.grad, passes, 9 * (C0 + C1)), n)

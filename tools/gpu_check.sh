@@ -9,8 +9,8 @@ T="timeout 600 python -m pytest -q -m gpu -p no:cacheprovider"
 $T tests/test_ops_gpu.py -k "not gemm and not conv and not linear" > gpurun_out/t_ops_simt.log 2>&1
 $T tests/test_ops_gpu.py -k "gemm or linear" > gpurun_out/t_ops_gemm.log 2>&1
 $T tests/test_ops_gpu.py -k "conv" > gpurun_out/t_ops_conv.log 2>&1
-GEDEPTH_FORCE_LIB=linear,conv2d,conv_bn_act $T tests/test_model_gpu.py -s -k "train_step or inference" > gpurun_out/t_model_libgemm.log 2>&1
+
 $T tests/test_model_gpu.py -s > gpurun_out/t_model.log 2>&1
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 timeout 900 python bench.py --steps 5 --warmup 3 ${BENCH_ARGS:---no-cpu-baseline} > gpurun_out/bench.log 2>&1
-tail -n 5 gpurun_out/t_ops_simt.log gpurun_out/t_ops_gemm.log gpurun_out/t_ops_conv.log gpurun_out/t_model_libgemm.log gpurun_out/t_model.log gpurun_out/smoke.log gpurun_out/bench.log
+tail -n 5 gpurun_out/t_ops_simt.log gpurun_out/t_ops_gemm.log gpurun_out/t_ops_conv.log gpurun_out/t_model.log gpurun_out/smoke.log gpurun_out/bench.log
