@@ -76,9 +76,8 @@ def cpu_step_time(torch, n_frames=1, budget_s=200.0, steps=1, warmup=0):
     from gedepth_b200.presets import model_cfg
     from gedepth_b200.synth import synth_batch, synth_state_dict
     from oracle import model as om
-    with torch.device("meta"):
-        tmpl = M.build_depther(model_cfg("v", "kitti", "swin_t", pretrained=None)).state_dict()
-    sd = synth_state_dict({k: torch.empty(v.shape, dtype=v.dtype) for k, v in tmpl.items()}, 0)
+    tmpl = M.build_depther(model_cfg("v", "kitti", "swin_t", pretrained=None)).state_dict()
+    sd = synth_state_dict(tmpl, 0)
     skip = ("running_mean", "running_var", "num_batches_tracked", "relative_position_index")
     sd = {k: v.requires_grad_(not k.endswith(skip)) for k, v in sd.items()}
     b = synth_batch(n_frames, H, W, seed=1234)
@@ -123,7 +122,7 @@ def run_reference(args):
     ms = 1e3 * sum(times) / len(times)
     val = 1.0 / (ms / 1e3)
     sample = f"1 frame of the batch per step (352x1120 fwd+bwd), {len(times)} timed steps, torch-CPU {torch.get_num_threads()} threads"
-    line = dict(metric="frames/sec (352x1120) fwd+bwd", value=val, unit="frames/s", n_gpus=0, steps=len(times),
+    line = dict(metric="frames/sec (352x1120) fwd+bwd", value=val, unit="frames/s", n_gpus=args.gpus, steps=len(times),
                 warmup=min(args.warmup, 1), ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", impl="reference",
                 config=dict(workload=WORKLOAD, note="oracle port of the reference path on host cores; the reference's "
@@ -142,6 +141,8 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", default="v", choices=["v", "a"])
+    ap.add_argument("--backbone", default="swin_t", choices=["swin_t", "swin_l"])
+    ap.add_argument("--dataset", default="kitti", choices=["kitti", "ddad"], help="ddad: 384x640, depth_scale 250 (BASELINE configs[3])")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
     ap.add_argument("--passes", type=int, default=3, choices=[1, 3], help="GEMM arithmetic: 3 = 3xTF32 (fp32-accurate), 1 = TF32")
     args = ap.parse_args()
@@ -169,9 +170,16 @@ def main():
     kernels.load()
     kernels.set_gemm_precision(args.passes)
 
+    global H, W
+    if args.dataset == "ddad":
+        H, W = 384, 640
     Bn = args.batch
     adaptive = args.variant == "a"
-    model = M.build_depther(model_cfg(args.variant, "kitti", "swin_t", pretrained=None))   # drop_path 0.3 as configured
+    workload = WORKLOAD
+    if (args.variant, args.backbone, args.dataset, Bn) != ("v", "swin_t", "kitti", B_PER_GPU):
+        workload = (f"DepthFormer-{args.backbone} + GEDepth-{'Adaptive' if adaptive else 'Vanilla'}, batch {Bn}/GPU, "
+                    f"{H}x{W} synthetic {args.dataset.upper()} (not the headline configuration)")
+    model = M.build_depther(model_cfg(args.variant, args.dataset, args.backbone, pretrained=None))   # drop_path 0.3 as configured
     model.load_state_dict(synth_state_dict(model.state_dict(), 0))
     model.to(dev).train()
     trainer = Trainer(model)
@@ -179,14 +187,18 @@ def main():
     # synthetic host batches (pinned) - a few distinct ones so e2e copies are real
     host = []
     for i in range(2):
-        b = synth_batch(Bn, H, W, seed=1234 + rank * 17 + i, adaptive=adaptive)
+        b = synth_batch(Bn, H, W, seed=1234 + rank * 17 + i, adaptive=adaptive,
+                        depth_scale=250.0 if args.dataset == "ddad" else 200.0,
+                        max_depth=200.0 if args.dataset == "ddad" else 80.0)
+        if args.dataset == "ddad" and adaptive:
+            b["height"] = np.array(([1.56, 1.57, 1.53, 1.53] * Bn)[:Bn], dtype=np.float32)
         host.append({k: torch.from_numpy(v).pin_memory() for k, v in b.items()})
     metas = [dict(ori_shape=(H, W, 3), img_shape=(H, W, 3), pad_shape=(H, W, 3), flip=False)] * Bn
     resident = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
 
     def as_batch(d):
-        return dict(img=d["img"], img_metas=metas, depth_gt=d["depth_gt"],
-                    **({"pe_k_gt": d["pe_k_gt"]} if adaptive else {}))
+        extra = {k: d[k] for k in ("pe_k_gt", "height") if k in d}
+        return dict(img=d["img"], img_metas=metas, depth_gt=d["depth_gt"], **extra)
 
     use_graph = not args.no_graph
     if use_graph:
@@ -253,11 +265,17 @@ def main():
             s.record()
             orig_call(name, *a)
             e.record()
-            flops = 0.0
+            flops = 0.0          # algorithmic flops (tensor kernels) or compulsory HBM bytes (the rest)
             if name == "ged_gemm_tf32":
                 flops = 2.0 * a[6] * a[7] * a[8]
             elif name == "ged_conv3x3_tf32":
                 flops = 2.0 * a[4] * a[5] * a[6] * a[7] * a[8] * 9
+            elif name == "ged_msda_fwd":       # value + offsets + logits read once, output written once
+                Bq, Sq, Qq, nHq = a[8], a[9], a[10], a[11]
+                flops = 4.0 * (Bq * Sq * nHq * 64 + Bq * Qq * nHq * 96 + Bq * Qq * nHq * 64)
+            elif name == "ged_msda_bwd":       # + g_out read, g_value read-modify-write, g_off / g_logit written
+                Bq, Sq, Qq, nHq = a[12], a[13], a[14], a[15]
+                flops = 4.0 * (3 * Bq * Sq * nHq * 64 + 2 * Bq * Qq * nHq * 96 + Bq * Qq * nHq * 64)
             records.append((name, s, e, flops))
 
         step_eager(1)                      # re-warm the eager path (allocator pools differ from the graph's)
@@ -279,12 +297,24 @@ def main():
     if world > 1:
         dist.barrier()
 
-    if rank != 0:
+    def finish():
+        """Leave without tearing NCCL down: communicators captured in CUDA graphs can block
+        destroy_process_group(); every rank meets at one last barrier, flushes and exits."""
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
-        return
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        return finish()
 
     pk = peaks()
+    ncu_traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")     # dram bytes per launch from ncu --set full captures
+    if os.path.exists(tpath):
+        ncu_traffic = json.load(open(tpath))
     frames = Bn * world
     value = frames / (ms_step / 1e3)
     e2e_val = frames / (ms_e2e / 1e3)
@@ -306,9 +336,22 @@ def main():
     else:
         # gather/atomics-bound kernel (MSDA): algorithmic bytes = 32 points x 4 corners x 256 B per (query, head),
         # served by L1/L2, not HBM - reported against the HBM peak for scale only
-        roof = dict(kernel=dom, bound="hbm", achieved=None, peak=pk["hbm"], unit="GB/s", frac=None, traffic=None,
+        gbs = kern[dom]["flops"] / (kern[dom]["ms"] / 1e3) / 1e9 if kern[dom]["flops"] else None
+        roof = dict(kernel=dom, bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s",
+                    frac=(gbs / pk["hbm"]) if gbs else None, traffic=ncu_traffic.get(dom),
                     calls_per_step=kern[dom]["calls"], share_of_step=kern[dom]["ms"] / ms_step,
-                    note="L1/L2 gather + L2 atomics bound (ncu: l1tex 73 %, DRAM 2 %); see profiles/")
+                    note="achieved = COMPULSORY HBM bytes (each operand once) / time. The deformable-attention "
+                         "kernels are bound by the L1 gather of 32x4 corner segments per (query, head) and by L2 "
+                         "atomics, not by HBM (ncu: l1tex 73 %, lts 61 %, DRAM 2 %; profiles/r01_ncu_msda_v2.csv)")
+    # second view: all tcgen05 launches of the step together (the tensor-bound share)
+    tens = [kern[k] for k in tensor_names if k in kern]
+    tens_ms = sum(t["ms"] for t in tens)
+    tens_tf = sum(t["flops"] for t in tens) / (tens_ms / 1e3) / 1e12 if tens_ms else None
+    roof_tensor = dict(kernels=list(tensor_names), bound="tensor", achieved=tens_tf, peak=pk["bf16_sustained"] / 2.0,
+                       unit="TFLOP/s", frac=(tens_tf / (pk["bf16_sustained"] / 2.0)) if tens_tf else None,
+                       share_of_step=tens_ms / ms_step, mma_passes_forward=args.passes, mma_passes_backward=kernels.BACKWARD_PASSES,
+                       note="ALGORITHMIC flops (2MNK) over the summed device time of every GEMM/conv launch; the forward "
+                            "issues 3 tcgen05.mma per k-step (3xTF32), so the tensor pipe does ~2x this figure")
 
     # ---- the kernel the metric names: ground embedding, HBM roofline ---------------------------------
     def ge_bw(Bx, Hx, Wx, reps=20):
@@ -336,10 +379,10 @@ def main():
               bytes_per_pixel=13, at_workload=dict(shape=[Bn, H, W], achieved=bw_work, frac=bw_work / pk["hbm"], us=us_work,
                                                    note="41 MB: launch-latency/L2 dominated"),
               at_sweep_max=dict(shape=[32, 1024, 2048], achieved=bw_big, frac=bw_big / pk["hbm"], us=us_big),
-              l2_flushed_between_iterations=True)
+              traffic=ncu_traffic.get("ge_vanilla_fwd_kernel"), l2_flushed_between_iterations=True)
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         t = cpu_step_time(torch, 1, budget_s=60.0, steps=1, warmup=0)
@@ -350,18 +393,18 @@ def main():
     line = dict(metric="frames/sec (352x1120) fwd+bwd", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
                 warmup=max(3, args.warmup), ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32 (3xTF32 split on tcgen05, fp32 accumulate)" if args.passes == 3 else "tf32", data="synthetic",
-                config=dict(workload=WORKLOAD, global_batch=frames, parallelism=f"dp{world}",
+                config=dict(workload=workload, global_batch=frames, parallelism=f"dp{world}",
                             step="fwd + SiLog + bwd + allreduce(N>1) + clip + AdamW", drop_path_rate=0.3,
                             launch="one captured CUDA graph per step" if use_graph else "eager",
                             l2="inputs + activations per step (>2 GB) exceed the 126 MB L2"),
                 e2e=dict(value=e2e_val, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e),
-                gpu_launches=launches, clocks=clk, roofline=roof, ground_embed=ge, cpu_baseline=cpu,
+                gpu_launches=launches, clocks=clk, roofline=roof, roofline_tensor=roof_tensor, ground_embed=ge,
+                cpu_baseline=cpu,
                 native_ops=ops.native_table(),
                 kernel_ms={k: round(v["ms"], 3) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])},
                 native_ms_of_step=[round(native_ms, 2), round(prof["_step_ms_profiled"], 2)])
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

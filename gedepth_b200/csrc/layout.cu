@@ -156,6 +156,57 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
   }
 }
 
+// img (B, Cimg, H, W) NCHW, channels [0,Cin) -> tokens (B, DH*DW, Cin*P*P) in Conv2d weight order (c, ky, kx);
+// bottom/right zero padding to a multiple of P (embed.py:286-294).  The 4x4/s4 patch-embedding conv is then a GEMM.
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, int64_t bstride,
+                                                        float* __restrict__ tok, int Cin, int H, int W, int P,
+                                                        int DH, int DW, int64_t total) {
+  const int K = Cin * P * P;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    int64_t t = i / K;
+    const int px = (int)(t % DW); t /= DW;
+    const int py = (int)(t % DH);
+    const int b = (int)(t / DH);
+    const int c = k / (P * P), r = k - c * P * P, ky = r / P, kx = r - ky * P;
+    const int y = py * P + ky, x = px * P + kx;
+    tok[i] = (y < H && x < W) ? __ldg(img + b * bstride + ((int64_t)c * H + y) * W + x) : 0.f;
+  }
+}
+
+// x (B, H, W, C) tokens -> (B, ceil(H/2)*ceil(W/2), 4C) in nn.Unfold(2,2) order: feature = c*4 + ky*2 + kx
+// (depthformer_swin.py:86,115; zero padding bottom/right for odd sizes :110-111).  dir=1: backward (scatter = gather).
+__global__ void __launch_bounds__(256) merge_patches_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                             int H, int W, int C, int H2, int W2, int64_t total, int dir) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // i indexes the UNMERGED tensor (b, y, x, c): coalesced on that side; the merged side is a 16-byte-strided gather
+    const int c = (int)(i % C);
+    int64_t t = i / C;
+    const int x = (int)(t % W); t /= W;
+    const int y = (int)(t % H);
+    const int b = (int)(t / H);
+    const int64_t m = (((int64_t)b * H2 + (y >> 1)) * W2 + (x >> 1)) * (4 * C) + c * 4 + (y & 1) * 2 + (x & 1);
+    if (dir == 0) dst[m] = __ldg(src + i); else dst[i] = __ldg(src + m);
+  }
+}
+
+// out (B,1,H,W) = bilinear(clamp(x (B,1,h0,w0), lo, hi) -> HxW, align_corners=True)  (encoder_decoder.py:132-138)
+__global__ void __launch_bounds__(256) clamp_resize_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                            int h0, int w0, int H, int W, float sy, float sx, float lo,
+                                                            float hi, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % W);
+    int64_t t = i / W;
+    const int yy = (int)(t % H);
+    const int b = (int)(t / H);
+    const Tap ty = tap(yy, sy, true, h0), tx = tap(xx, sx, true, w0);
+    const float* base = x + (int64_t)b * h0 * w0;
+    const float v00 = fminf(fmaxf(__ldg(base + ty.i0 * w0 + tx.i0), lo), hi), v01 = fminf(fmaxf(__ldg(base + ty.i0 * w0 + tx.i1), lo), hi);
+    const float v10 = fminf(fmaxf(__ldg(base + ty.i1 * w0 + tx.i0), lo), hi), v11 = fminf(fmaxf(__ldg(base + ty.i1 * w0 + tx.i1), lo), hi);
+    out[i] = ty.l0 * (tx.l0 * v00 + tx.l1 * v01) + ty.l1 * (tx.l0 * v10 + tx.l1 * v11);
+  }
+}
+
 }  // namespace ged
 using namespace ged;
 
@@ -211,6 +262,40 @@ GED_API int ged_act_bwd(const float* g, const float* ref, float* gz, float* db, 
   dim3 grid(cdiv(N, 128), (unsigned)((rows + rpb - 1) / rpb));
   act_bwd_kernel<<<grid, dim3(32, 8), 0, stream>>>(g, ref, gz, db, row_scale, rows_per_batch > 0 ? rows_per_batch : 1,
                                                   rows, N, act, slope, rpb);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+// tokens (B, DH*DW, Cin*P*P) from channels [0,Cin) of an NCHW image batch (batch stride in floats): embed.py:282-297.
+GED_API int ged_patchify(const float* img, int64_t batch_stride, float* tok, int B, int Cin, int H, int W, int P,
+                         cudaStream_t stream) {
+  if (!img || !tok || B <= 0 || Cin <= 0 || P <= 0) return GED_ERR_ARG;
+  const int DH = cdiv(H, P), DW = cdiv(W, P);
+  const int64_t total = (int64_t)B * DH * DW * Cin * P * P;
+  patchify_kernel<<<grid_for(total), 256, 0, stream>>>(img, batch_stride, tok, Cin, H, W, P, DH, DW, total);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+// backward=0: x (B,H,W,C) -> merged (B,H2*W2,4C) (zero-filled first when H or W is odd); backward=1: g_merged -> g_x.
+GED_API int ged_merge_patches(const float* src, float* dst, int B, int H, int W, int C, int backward,
+                              cudaStream_t stream) {
+  if (!src || !dst || B <= 0 || C <= 0) return GED_ERR_ARG;
+  const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+  if (!backward && ((H | W) & 1))
+    if (cudaMemsetAsync(dst, 0, sizeof(float) * (size_t)B * H2 * W2 * 4 * C, stream) != cudaSuccess) return GED_ERR_LAUNCH;
+  const int64_t total = (int64_t)B * H * W * C;
+  merge_patches_kernel<<<grid_for(total), 256, 0, stream>>>(src, dst, H, W, C, H2, W2, total, backward);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+GED_API int ged_clamp_resize(const float* x, float* out, int B, int h0, int w0, int H, int W, float lo, float hi,
+                             cudaStream_t stream) {
+  if (!x || !out || B <= 0) return GED_ERR_ARG;
+  const int64_t total = (int64_t)B * H * W;
+  clamp_resize_kernel<<<grid_for(total), 256, 0, stream>>>(x, out, h0, w0, H, W, resize_scale(h0, H, true),
+                                                          resize_scale(w0, W, true), lo, hi, total);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }

@@ -44,6 +44,11 @@ SIGNATURES = {
     "ged_upsample_nhwc_bwd": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "ged_resize_add_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ged_act_bwd": [_P, _P, _P, _P, _P, _I, _I64, _I, _I, _F, _P],
+    "ged_bn_train_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _F, _F, _I, _P],
+    "ged_bn_train_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
+    "ged_patchify": [_P, _I64, _P, _I, _I, _I, _I, _I, _P],
+    "ged_merge_patches": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "ged_clamp_resize": [_P, _P, _I, _I, _I, _I, _I, _F, _F, _P],
     "ged_conv3x3_tf32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _F, _P],
     "ged_msda_fwd": [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_msda_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -58,7 +63,7 @@ _load_error: Optional[str] = None
 # ops whose sm_100a kernel is wired in (ops.py consults has()); everything else is a library call
 NATIVE_OPS = {"ground_plane", "ge_vanilla", "ge_adaptive", "fuse_head", "silog", "cross_entropy",
               "layer_norm", "window_attention", "msda_sample", "linear", "conv2d", "conv_bn_act",
-              "conv2d_cat", "resize_add", "find_k", "adamw"}
+              "conv2d_cat", "resize_add", "batch_norm", "patch_embed", "merge_patches", "clamp_resize", "find_k", "adamw"}
 
 
 def load():
@@ -685,8 +690,49 @@ def conv_bn_act_cat(x0, x1, w, b, bn, act=None):
         wf = w * s.view(-1, 1, 1, 1)
         bf = bn.bias - bn.running_mean * s + (b * s if b is not None else 0)
         return _Conv.apply(x0, x1, wf, bf, act, 0.01)
-    y = bn(_Conv.apply(x0, x1, w, b, None, 0.0))
-    return L._act(y, act)
+    y = _Conv.apply(x0, x1, w, b, None, 0.0)
+    if act in (None, "relu") and y.shape[1] % 4 == 0 and bn.momentum is not None and bn.track_running_stats:
+        return bn_act_train(y, bn, relu=act == "relu")
+    return L._act(bn(y), act)
+
+
+class _BNTrain(Function):
+    """Train-mode BatchNorm2d (+ReLU) on a channels-last map; batch statistics per GPU."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, running_mean, running_var, eps, momentum, relu):
+        xh = _nhwc(x)
+        B, H, W, Cc = xh.shape
+        rows = B * H * W
+        y = torch.empty_like(xh)
+        mean = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        sums = torch.empty(2 * Cc, dtype=torch.float64, device=x.device)
+        _call("ged_bn_train_fwd", _p(xh), _p(w), _p(b), _p(running_mean), _p(running_var), _p(y), _p(mean), _p(rstd),
+              _p(sums), rows, Cc, float(eps), float(momentum), int(relu), _stream())
+        ctx.save_for_backward(xh, y if relu else torch.empty(0, device=x.device), w, mean, rstd)
+        ctx.relu = relu
+        ctx.mark_non_differentiable(running_mean, running_var)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        xh, y, w, mean, rstd = ctx.saved_tensors
+        B, H, W, Cc = xh.shape
+        gh = _nhwc(g)
+        dx = torch.empty_like(xh)
+        dw = torch.empty(Cc, dtype=torch.float32, device=g.device)
+        db = torch.empty_like(dw)
+        sums = torch.empty(2 * Cc, dtype=torch.float64, device=g.device)
+        _call("ged_bn_train_bwd", _p(gh), _p(xh), _p(y if ctx.relu else None), _p(w), _p(mean), _p(rstd), _p(dx), _p(dw),
+              _p(db), _p(sums), B * H * W, Cc, int(ctx.relu), _stream())
+        return dx.permute(0, 3, 1, 2), dw, db, None, None, None, None, None
+
+
+def bn_act_train(x, bn, relu: bool):
+    y = _BNTrain.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, relu)
+    bn.num_batches_tracked.add_(1)
+    return y
 
 
 class _ResizeAdd(Function):
@@ -712,6 +758,55 @@ class _ResizeAdd(Function):
 
 def resize_add(t, size, acc):
     return _ResizeAdd.apply(t, acc)
+
+
+# =============================================================================================
+# patch embedding / patch merging / inference resize
+# =============================================================================================
+def patch_embed(x, w, b, patch):
+    """4x4/s4 conv of embed.py:282-297 as patchify (gather) + tcgen05 GEMM.  x: NCHW view of the input batch."""
+    B, Cin, H, W = x.shape
+    assert x.stride(3) == 1 and x.stride(2) == W and x.stride(1) == H * W and x.dtype == torch.float32
+    DH, DW = -(-H // patch), -(-W // patch)
+    K = Cin * patch * patch
+    tok = torch.empty(B, DH * DW, K, dtype=torch.float32, device=x.device)
+    _call("ged_patchify", _p(x), x.stride(0), _p(tok), B, Cin, H, W, patch, _stream())
+    return linear(tok, w.reshape(w.shape[0], K), b), (DH, DW)
+
+
+class _MergePatches(Function):
+    @staticmethod
+    def forward(ctx, x, H, W):
+        xc = _f32c(x)
+        B, Lt, Cc = xc.shape
+        H2, W2 = (H + 1) // 2, (W + 1) // 2
+        out = torch.empty(B, H2 * W2, 4 * Cc, dtype=torch.float32, device=x.device)
+        _call("ged_merge_patches", _p(xc), _p(out), B, H, W, Cc, 0, _stream())
+        ctx.dims = (B, H, W, Cc)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, H, W, Cc = ctx.dims
+        g = _f32c(g)
+        gx = torch.empty(B, H * W, Cc, dtype=torch.float32, device=g.device)
+        _call("ged_merge_patches", _p(g), _p(gx), B, H, W, Cc, 1, _stream())
+        return gx, None, None
+
+
+def merge_patches(x, H, W):
+    return _MergePatches.apply(x, int(H), int(W))
+
+
+def clamp_resize(x, lo, hi, size):
+    x = _f32c(x)
+    B, Cc, h0, w0 = x.shape
+    assert Cc == 1
+    if size is None:
+        return torch.clamp(x, min=lo, max=hi)
+    out = torch.empty(B, 1, int(size[0]), int(size[1]), dtype=torch.float32, device=x.device)
+    _call("ged_clamp_resize", _p(x), _p(out), B, h0, w0, int(size[0]), int(size[1]), float(lo), float(hi), _stream())
+    return out
 
 
 # =============================================================================================

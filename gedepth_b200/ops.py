@@ -43,7 +43,7 @@ def native_table():
 
 
 OPS = ["linear", "layer_norm", "patch_embed", "merge_patches", "window_attention", "conv2d",
-       "conv_bn_act", "conv2d_cat", "resize", "resize_add", "msda_sample", "ground_plane", "ge_vanilla",
+       "conv_bn_act", "conv2d_cat", "batch_norm", "resize", "resize_add", "msda_sample", "ground_plane", "ge_vanilla",
        "ge_adaptive", "fuse_head", "silog", "cross_entropy", "clamp_resize", "find_k", "adamw"]
 
 
@@ -66,6 +66,10 @@ def conv_bn_act(x, w, b, bn, stride=1, padding=0, act=None):
     require_cuda(x, w)
     if use_native("conv_bn_act") and _k().conv2d_supported(x, w, stride, padding):
         return _k().conv_bn_act(x, w, b, bn, stride, padding, act)
+    if (bn is not None and bn.training and use_native("batch_norm") and w.shape[0] % 4 == 0 and act in (None, "relu")
+            and bn.momentum is not None and bn.track_running_stats):
+        # stem 7x7/s2 conv (K = 147): library conv, native train-mode BN + ReLU
+        return _k().bn_act_train(L.conv2d(x, w, b, stride, padding), bn, relu=act == "relu")
     return L.conv_bn_act(x, w, b, bn, stride, padding, act)
 
 
@@ -89,7 +93,8 @@ def conv_bn_act_cat(x0, x1, w, b, bn, act=None):
 
 def patch_embed(x, w, b, patch):
     require_cuda(x, w)
-    if use_native("patch_embed"):
+    if use_native("patch_embed") and x.dtype == torch.float32 and x.stride(3) == 1 and x.stride(2) == x.shape[3] \
+            and x.stride(1) == x.shape[2] * x.shape[3] and (x.shape[1] * patch * patch) % 32 == 0:
         return _k().patch_embed(x, w, b, patch)
     return L.patch_embed(x, w, b, patch)
 
@@ -161,7 +166,7 @@ def resize_add(t, size, acc):
 
 def clamp_resize(x, lo, hi, size, align_corners=True):
     require_cuda(x)
-    if use_native("clamp_resize") and align_corners:
+    if use_native("clamp_resize") and align_corners and x.shape[1] == 1 and not torch.is_grad_enabled():
         return _k().clamp_resize(x, lo, hi, size)
     return L.clamp_resize(x, lo, hi, size, align_corners)
 

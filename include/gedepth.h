@@ -110,6 +110,16 @@ int ged_winattn_bwd(const float* qkv, const float* qkv_bias, const float* table,
                     const float* g_ctx, float* g_qkv, float* g_bias, float* g_table, int B, int H, int W,
                     int C, int nH, int window, int shift, float scale, cudaStream_t stream);
 
+/* Train-mode BatchNorm2d (+ReLU) over channels-last maps as (rows=B*H*W, C): stem bn1 (depthformer_swin.py:1040-1041)
+ * and the ConvModule BNs of hahi.py:122-165.  Per-GPU batch statistics, biased variance for normalisation, unbiased
+ * for running_var, momentum 0.1.  sums: double[2C] scratch.  save_mean / save_rstd (float[C]) feed the backward. */
+int ged_bn_train_fwd(const float* x, const float* w, const float* b, float* running_mean, float* running_var, float* y,
+                     float* save_mean, float* save_rstd, double* sums, int64_t rows, int C, float eps, float momentum,
+                     int relu, cudaStream_t stream);
+int ged_bn_train_bwd(const float* g, const float* x, const float* y, const float* w, const float* save_mean,
+                     const float* save_rstd, float* dx, float* dw, float* db, double* sums, int64_t rows, int C, int relu,
+                     cudaStream_t stream);
+
 /* ---- tensor-core GEMM / conv (tcgen05, TF32) --------------------------------------------------- */
 /* D[M,N] = epi(A[M,K] @ W[N,K]^T): F.linear / 1x1 Conv2d sites depthformer_swin.py:96,119,174-176,
  * 193,222; mmcv FFN; hahi.py:122-165; MSDA linears.  act: 0 none 1 relu 2 leaky 3 gelu 4 sigmoid.
@@ -141,6 +151,17 @@ int ged_resize_add_nhwc(const float* t, float* acc, int C, int B, int H, int W, 
  * ref = layer output for relu(1)/leaky(2)/sigmoid(4), pre-activation for gelu(3); act 0: copy/scale only. */
 int ged_act_bwd(const float* g, const float* ref, float* gz, float* db, const float* row_scale, int rows_per_batch,
                 int64_t rows, int N, int act, float slope, cudaStream_t stream);
+
+/* tokens (B, ceil(H/P)*ceil(W/P), Cin*P*P) in Conv2d weight order from channels [0,Cin) of an NCHW batch, zero
+ * padded bottom/right (embed.py:282-297): the patch-embedding conv becomes ged_gemm_tf32. */
+int ged_patchify(const float* img, int64_t batch_stride, float* tok, int B, int Cin, int H, int W, int P,
+                 cudaStream_t stream);
+/* nn.Unfold(2,2) gather of PatchMerging (depthformer_swin.py:98-117): (B,H,W,C) -> (B,ceil(H/2)*ceil(W/2),4C),
+ * feature = c*4 + ky*2 + kx; backward=1 applies the adjoint. */
+int ged_merge_patches(const float* src, float* dst, int B, int H, int W, int C, int backward, cudaStream_t stream);
+/* encoder_decoder.py:132-138: clamp to [lo,hi] then bilinear (align_corners=True) to HxW; x (B,1,h0,w0). */
+int ged_clamp_resize(const float* x, float* out, int B, int h0, int w0, int H, int W, float lo, float hi,
+                     cudaStream_t stream);
 
 /* ---- deformable attention sampling ----------------------------------------------------------- */
 /* mmcv.ops.MultiScaleDeformableAttention core (hahi.py:280-289,316-325).  value (B,S,nH,64);

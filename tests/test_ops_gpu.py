@@ -490,3 +490,71 @@ def test_conv2d_cat_upsample_fwd_bwd(passes):
     (y2 * go.double()).sum().backward()
     for n, p, q in zip(("dx_low", "dx_skip", "dw", "db"), a1, a2):
         _close(p.grad, q.grad, 0, 2 * _gemm_tol(q.grad, passes, 9 * (C0 + C1)), n)
+
+
+@pytest.mark.parametrize("H,W", [(64, 160), (70, 166)])
+def test_patch_embed_as_gemm(H, W, passes):
+    from gedepth_b200 import kernels as Kn, ops_lib as L
+    g = torch.Generator().manual_seed(24)
+    img = torch.randn(2, 5, H, W, generator=g).to(DEV)
+    w = (torch.randn(96, 4, 4, 4, generator=g) / 8).to(DEV).requires_grad_(True)
+    b = torch.randn(96, generator=g).to(DEV).requires_grad_(True)
+    t1, hw1 = Kn.patch_embed(img[:, 0:4], w, b, 4)
+    w2, b2 = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    t2, hw2 = L.patch_embed(img[:, 0:4], w2, b2, 4)
+    assert tuple(hw1) == tuple(hw2)
+    _close(t1, t2, 0, _gemm_tol(t2, passes, 64) + 1e-5, "tokens")
+    go = torch.randn_like(t2)
+    (t1 * go).sum().backward()
+    (t2 * go).sum().backward()
+    _close(w.grad, w2.grad, 0, 2e-3 * float(w2.grad.abs().max()), "dw")     # dW: library GEMM in both
+    _close(b.grad, b2.grad, 1e-4, 1e-3, "db")
+
+
+@pytest.mark.parametrize("H,W,C", [(16, 40, 96), (9, 21, 192), (5, 11, 384)])
+def test_merge_patches_fwd_bwd(H, W, C):
+    from gedepth_b200 import kernels as Kn, ops_lib as L
+    g = torch.Generator().manual_seed(25)
+    x0 = torch.randn(2, H * W, C, generator=g)
+    a, c = x0.to(DEV).requires_grad_(True), x0.to(DEV).requires_grad_(True)
+    m1, m2 = Kn.merge_patches(a, H, W), L.merge_patches(c, H, W)
+    assert torch.equal(m1, m2)
+    go = torch.randn_like(m2)
+    (m1 * go).sum().backward()
+    (m2 * go).sum().backward()
+    assert torch.equal(a.grad, c.grad)
+
+
+def test_clamp_resize():
+    from gedepth_b200 import kernels as Kn, ops_lib as L
+    g = torch.Generator().manual_seed(26)
+    x = (torch.rand(2, 1, 35, 83, generator=g) * 120 - 10).to(DEV)
+    with torch.no_grad():
+        _close(Kn.clamp_resize(x, 1e-3, 80.0, (70, 166)), L.clamp_resize(x, 1e-3, 80.0, (70, 166), True), 1e-5, 1e-5, "clamp_resize")
+
+
+@pytest.mark.parametrize("B,C,H,W,relu", [(2, 64, 32, 80, True), (3, 192, 9, 21, False), (2, 1536, 2, 5, True)])
+def test_batchnorm_train_fwd_bwd(B, C, H, W, relu):
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(27)
+    x0 = torch.randn(B, C, H, W, generator=g) * 2 + 0.5
+    bn1, bn2 = torch.nn.BatchNorm2d(C).to(DEV), torch.nn.BatchNorm2d(C).to(DEV)
+    with torch.no_grad():
+        bn1.weight.normal_(1, 0.2); bn1.bias.normal_(0, 0.2)
+        bn2.load_state_dict(bn1.state_dict())
+    bn1.train(); bn2.train()
+    a = x0.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    c = x0.to(DEV).requires_grad_(True)
+    y1 = Kn.bn_act_train(a, bn1, relu)
+    y2 = bn2(c)
+    y2 = F.relu(y2) if relu else y2
+    _close(y1, y2, 1e-4, 1e-5, "bn fwd")
+    _close(bn1.running_mean, bn2.running_mean, 1e-5, 1e-6, "running_mean")
+    _close(bn1.running_var, bn2.running_var, 1e-4, 1e-6, "running_var")
+    assert int(bn1.num_batches_tracked) == 1
+    go = torch.randn_like(y2)
+    (y1 * go).sum().backward()
+    (y2 * go).sum().backward()
+    _close(a.grad, c.grad, 1e-3, 2e-5 * float(c.grad.abs().max()), "dx")
+    _close(bn1.weight.grad, bn2.weight.grad, 1e-3, 1e-4 * float(bn2.weight.grad.abs().max()), "dw")
+    _close(bn1.bias.grad, bn2.bias.grad, 1e-3, 1e-4 * float(bn2.bias.grad.abs().max()), "db")
