@@ -19,7 +19,13 @@ def _free_port():
 
 
 def _inject_cpu_ops():
+    """Returns an undo callable (the pytest process must not leak the injection into other tests)."""
     from gedepth_b200 import kernels, ops
+    saved = (ops.require_cuda, ops.use_native, kernels.sumsq, kernels.adamw_step)
+
+    def undo():
+        ops.require_cuda, ops.use_native, kernels.sumsq, kernels.adamw_step = saved
+
     ops.require_cuda = lambda *a, **k: None
     ops.use_native = lambda name: False
 
@@ -37,6 +43,7 @@ def _inject_cpu_ops():
         p.addcdiv_(m, denom, value=-lr / (1 - b1 ** step))
 
     kernels.sumsq, kernels.adamw_step = sumsq, adamw_step
+    return undo
 
 
 def _build(seed_data):
@@ -88,8 +95,17 @@ def test_two_rank_step_equals_averaged_gradients():
     # single-process reference: average the two shards' gradients, same update.  Same CPU thread count as
     # the workers: with B=1 the train-mode BatchNorms see <= 10 values per channel at the deepest level, so
     # even reduction-order round-off is visibly amplified in the gradients.
+    threads = torch.get_num_threads()
     torch.set_num_threads(2)
-    _inject_cpu_ops()
+    undo = _inject_cpu_ops()
+    try:
+        _check_against_single_process(world, out)
+    finally:
+        undo()
+        torch.set_num_threads(threads)
+
+
+def _check_against_single_process(world, out):
     from gedepth_b200 import kernels
     from gedepth_b200.train import FlatArena
     grads, losses = [], []
