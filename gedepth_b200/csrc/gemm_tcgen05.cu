@@ -46,6 +46,19 @@ struct GemmParams {
   // conv epilogue: padded row -> (n, y, x); 0 disables
   int conv_Hp, conv_Wp;     // padded extents (H+2, W+2)
   int num_m_tiles, num_n_tiles;
+  // weight-gradient modes (dW = G^T X, contraction over the rows/pixels P): the work unit is
+  // (output tile, output tap, K split); partial tiles are added to D with vector atomics.
+  //   mode 0: forward/dX GEMM as documented above (one unit per output tile, plain stores)
+  //   mode 1: both operands MN-major as stored ([P][features]); TMA 32x32 panels with the
+  //           128B/32B-atom swizzle, UMMA LayoutType SWIZZLE_128B_BASE32B (the only MN-major tf32 layout)
+  int mode;
+  int out_taps;             // 1 (linear / 1x1) or 9 (3x3): tap t reads B rows shifted by tap_off[t]
+  int tap_dstride;          // element offset of tap t's output block in D
+  int total_kb, kb_per_split, splits;
+};
+
+struct Unit {
+  int m0, n0, kb0, kb1, tap;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -111,10 +124,36 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format TF32 (2) @7/@10, K-major both,
-// n_dim = N>>3 @17, m_dim = M>>4 @24
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major tf32 operand tile (cute::UMMA::Layout_MN_SW128_32B_Atom): 32-float (128 B) rows along MN, four
+// consecutive K rows form one 512-byte swizzle atom (Swizzle<2,5,2>: 32-byte chunks XOR (row & 3)), which is
+// what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B for a {32 features, BK rows} box.  One panel of
+// 32 features x BK rows is BK*128 bytes; LBO = distance between MN panels, SBO = distance between K atoms.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128_32b(uint32_t smem_addr, uint32_t panel_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((panel_bytes >> 4) & 0x3FFF) << 16;   // LBO
+  d |= (uint64_t)(512 >> 4) << 32;                      // SBO
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                               // SWIZZLE_128B_BASE32B
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format TF32 (2) @7/@10, a/b major @15/@16
+// (0 = K-major, 1 = MN-major), n_dim = N>>3 @17, m_dim = M>>4 @24
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, bool mn_major = false) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ Unit decode_unit(const GemmParams& p, int u, int BN_) {
+  const int tiles = p.num_m_tiles * p.num_n_tiles, per = tiles * p.out_taps;
+  const int split = u / per, r = u - split * per;
+  Unit t;
+  t.tap = r / tiles;
+  const int tile = r - t.tap * tiles;
+  t.m0 = (tile / p.num_n_tiles) * 128;
+  t.n0 = (tile % p.num_n_tiles) * BN_;
+  t.kb0 = split * p.kb_per_split;
+  t.kb1 = min(t.kb0 + p.kb_per_split, p.total_kb);
+  return t;
 }
 
 __device__ __forceinline__ float apply_act(float x, int act, float slope) {
@@ -174,8 +213,7 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
   uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int num_kb = p.ntaps * p.kblocks_per_tap;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.out_taps * p.splits;   // work units
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&map_a) : "memory");
@@ -200,14 +238,25 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int t = kb / p.kblocks_per_tap, kc = kb - t * p.kblocks_per_tap;
+        const Unit u = decode_unit(p, tile, BN);
+        for (int kb = u.kb0; kb < u.kb1; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = stage_base + stage * S::STAGE_BYTES;
           mbar_expect_tx(full_bar + stage, S::HI_BYTES);
-          tma_load_2d(sa, &map_a, full_bar + stage, kc * BK, m0 + p.tap_off[t]);
-          tma_load_2d(sa + S::A_BYTES, &map_b, full_bar + stage, t * p.Kt + kc * BK, n0);
+          if (p.mode == 0) {
+            const int t = kb / p.kblocks_per_tap, kc = kb - t * p.kblocks_per_tap;
+            tma_load_2d(sa, &map_a, full_bar + stage, kc * BK, u.m0 + p.tap_off[t]);
+            tma_load_2d(sa + S::A_BYTES, &map_b, full_bar + stage, t * p.Kt + kc * BK, u.n0);
+          } else {
+            // operands as stored: rows = contraction index (pixels), 32-feature panels side by side
+#pragma unroll
+            for (int pnl = 0; pnl < BM / 32; ++pnl)
+              tma_load_2d(sa + pnl * (BK * 128), &map_a, full_bar + stage, u.m0 + 32 * pnl, kb * BK);
+#pragma unroll
+            for (int pnl = 0; pnl < BN / 32; ++pnl)
+              tma_load_2d(sa + S::A_BYTES + pnl * (BK * 128), &map_b, full_bar + stage, u.n0 + 32 * pnl,
+                          kb * BK + p.tap_off[u.tap]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -215,30 +264,35 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+      const bool mn = p.mode == 1;
+      const uint32_t idesc = umma_idesc_tf32(BM, BN, mn);
+      // K-major: 8 tf32 = 32 bytes inside the 128B swizzle row, +2 in the (addr>>4) field per k-step;
+      // MN-major: 8 K rows = two 512-byte atoms = 1024 bytes, +64 per k-step
+      const uint32_t kstep = mn ? 64u : 2u;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const Unit u = decode_unit(p, tile, BN);
         mbar_wait(tmem_empty + acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = u.kb0; kb < u.kb1; ++kb) {
           mbar_wait((SPLIT ? split_bar : full_bar) + stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
-          const uint64_t adesc = umma_desc_kmajor_sw128(sa), bdesc = umma_desc_kmajor_sw128(sa + S::A_BYTES);
+          const uint64_t adesc = mn ? umma_desc_mnmajor_sw128_32b(sa, BK * 128) : umma_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = mn ? umma_desc_mnmajor_sw128_32b(sa + S::A_BYTES, BK * 128) : umma_desc_kmajor_sw128(sa + S::A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
-            // advance 8 tf32 = 32 bytes inside the 128B swizzle row: +2 in the (addr>>4) field
-            tc_mma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            tc_mma_tf32(tmem_d, adesc + kstep * k, bdesc + kstep * k, idesc, ((kb - u.kb0) | k) != 0);
             if (SPLIT) {
-              const uint64_t alo = umma_desc_kmajor_sw128(sa + S::HI_BYTES), blo = umma_desc_kmajor_sw128(sa + S::HI_BYTES + S::A_BYTES);
-              tc_mma_tf32(tmem_d, alo + 2 * k, bdesc + 2 * k, idesc, 1u);   // lo(A) * hi(B)
-              tc_mma_tf32(tmem_d, adesc + 2 * k, blo + 2 * k, idesc, 1u);   // hi(A) * lo(B)
+              const uint64_t alo = adesc + (S::HI_BYTES >> 4), blo = bdesc + (S::HI_BYTES >> 4);
+              tc_mma_tf32(tmem_d, alo + kstep * k, bdesc + kstep * k, idesc, 1u);   // lo(A) * hi(B)
+              tc_mma_tf32(tmem_d, adesc + kstep * k, blo + kstep * k, idesc, 1u);   // hi(A) * lo(B)
             }
           }
           tc_commit(empty_bar + stage);          // frees the smem slot when these MMAs retire
-          if (kb == num_kb - 1) tc_commit(tmem_full + acc);
+          if (kb == u.kb1 - 1) tc_commit(tmem_full + acc);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -252,7 +306,9 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
     const int lr = lane >> 2, lc = (lane & 3) * 4;          // store phase: lane -> (row lr + 8 i, 4 columns from lc)
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.num_n_tiles) * BM, n0 = (tile % p.num_n_tiles) * BN;
+      const Unit u = decode_unit(p, tile, BN);
+      const int m0 = u.m0, n0 = u.n0;
+      float* const Dt = p.D + (int64_t)u.tap * p.tap_dstride;
       // the four output rows this lane stores (fixed for the whole tile)
       int64_t orow[4];
       float rscale[4];
@@ -299,8 +355,11 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = apply_act(x[e], p.act, p.slope) * rscale[i];
-            float* dst = p.D + orow[i] * p.ldd + col;
-            if (vec) {
+            float* dst = Dt + orow[i] * p.ldd + col;
+            if (p.mode != 0) {          // split-K partial: accumulate (D is zero-initialised / holds the running gradient)
+              if (vec && ((p.tap_dstride & 3) == 0)) atomicAdd((float4*)dst, make_float4(x[0], x[1], x[2], x[3]));
+              else for (int e = 0; e < 4; ++e) if (col + e < p.N) atomicAdd(dst + e, x[e]);
+            } else if (vec) {
               if (p.residual) {
                 const float4 r = __ldg((const float4*)(p.residual + orow[i] * p.ldd + col));
                 x[0] += r.x; x[1] += r.y; x[2] += r.z; x[3] += r.w;
@@ -325,7 +384,8 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
     const int st = threadIdx.x - (4 + EPI_WARPS) * 32;
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const Unit u = decode_unit(p, tile, BN);
+      for (int kb = u.kb0; kb < u.kb1; ++kb) {
         mbar_wait(full_bar + stage, phase);
         const float4* hi = (const float4*)(stage_base + stage * S::STAGE_BYTES);
         float4* lo = (float4*)(stage_base + stage * S::STAGE_BYTES + S::HI_BYTES);
@@ -368,7 +428,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 // 2-D fp32 tensor map: dims {inner=cols, outer=rows}, row pitch ld floats, box {32, box_rows}, 128B swizzle
-static int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                       CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   auto enc = get_encode();
   if (!enc) return GED_ERR_LAUNCH;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -376,12 +437,13 @@ static int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? GED_OK : GED_ERR_ARG;
 }
 
 static int g_num_sms = 0;
+static int g_wide_tiles = 1;   // allow BN = 192 / 256 (fewer re-reads of the A operand through L2)
 static int g_precision = 3;   // 1 = single-pass TF32, 3 = error-compensated 3xTF32 (fp32-accurate)
 
 template <int BN, int STAGES, bool SPLIT>
@@ -400,34 +462,60 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams&
   }
   p.num_m_tiles = cdiv(p.M, BM);
   p.num_n_tiles = cdiv(p.N, BN);
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  if (p.mode == 0) {
+    p.out_taps = 1; p.tap_dstride = 0; p.splits = 1;
+    p.total_kb = p.ntaps * p.kblocks_per_tap; p.kb_per_split = p.total_kb;
+  } else {
+    // split the contraction so that every SM gets ~2 units, but keep >= 8 k-blocks (256 rows) per unit
+    const int base_units = p.num_m_tiles * p.num_n_tiles * p.out_taps;
+    int splits = cdiv(2 * g_num_sms, base_units);
+    const int max_splits = p.total_kb / 8 > 0 ? p.total_kb / 8 : 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.kb_per_split = cdiv(p.total_kb, splits);
+    p.splits = cdiv(p.total_kb, p.kb_per_split);
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles * p.out_taps * p.splits;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   gemm_tf32_kernel<BN, STAGES, SPLIT><<<grid, S::THREADS, S::TOTAL, stream>>>(ma, mb, p);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }
 
-static int pick_bn(int N) {
+// Output-tile width.  Both arithmetic modes are bound by bytes moved per k-block, which scale with (128 + BN) rows of
+// 128 bytes (TMA in, splitter, operand reads), while the work scales with BN: wider tiles re-read the A operand less.
+// Against that stand wave quantisation over the SMs and, for the 3xTF32 kernel, a 2-stage ring at BN > 128 (measured
+// ~1.25x per k-block: tools/ab_gemm.py).  Pick the candidate with the lowest waves x (128 + BN) estimate.
+static int pick_bn(int M, int N, bool split) {
   if (N <= 32) return 32;
   if (N <= 64) return 64;
-  if (N % 128 != 0 && N % 96 == 0) return 96;
-  return 128;
+  if (N <= 96) return 96;
+  if (N <= 128) return 128;
+  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  const int m_tiles = cdiv(M, BM);
+  const int cands[4] = {128, 96, 192, 256};
+  int best = 128;
+  double best_cost = 1e30;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (bn > 128 && !g_wide_tiles) continue;
+    if (bn > 128 && (int64_t)cdiv(N, bn) * bn * 100 > (int64_t)N * 115) continue;   // > 15 % padded columns: not worth it
+    const int64_t tiles = (int64_t)m_tiles * cdiv(N, bn);
+    const double waves = (double)((tiles + sms - 1) / sms);
+    const double cost = waves * (128 + bn) * ((split && bn > 128) ? 1.25 : 1.0);
+    if (cost < best_cost * 0.999) { best_cost = cost; best = bn; }
+  }
+  return best;
 }
 
-static int run(const float* A, int64_t a_rows, int lda, const float* Bw, int ldb, GemmParams& p, cudaStream_t stream) {
-  if (!aligned16(A) || !aligned16(Bw) || (lda % 4) || (ldb % 4)) return GED_ERR_ALIGN;
-  const int bn = pick_bn(p.N);
-  CUtensorMap ma, mb;
-  const int Kt = p.K / p.ntaps;
-  if (int e = make_map_2d(&ma, A, a_rows, Kt, lda, BM)) return e;
-  if (int e = make_map_2d(&mb, Bw, p.N, p.K, ldb, bn)) return e;
-  p.kblocks_per_tap = cdiv(Kt, BK);
-  p.Kt = Kt;
+static int dispatch(int bn, const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
   if (g_precision == 3) {
     switch (bn) {
       case 32: return launch_gemm<32, 4, true>(ma, mb, p, stream);
       case 64: return launch_gemm<64, 4, true>(ma, mb, p, stream);
       case 96: return launch_gemm<96, 3, true>(ma, mb, p, stream);
+      case 192: return launch_gemm<192, 2, true>(ma, mb, p, stream);
+      case 256: return launch_gemm<256, 2, true>(ma, mb, p, stream);
       default: return launch_gemm<128, 3, true>(ma, mb, p, stream);
     }
   }
@@ -435,8 +523,45 @@ static int run(const float* A, int64_t a_rows, int lda, const float* Bw, int ldb
     case 32: return launch_gemm<32, 8, false>(ma, mb, p, stream);
     case 64: return launch_gemm<64, 6, false>(ma, mb, p, stream);
     case 96: return launch_gemm<96, 6, false>(ma, mb, p, stream);
+    case 192: return launch_gemm<192, 5, false>(ma, mb, p, stream);
+    case 256: return launch_gemm<256, 4, false>(ma, mb, p, stream);
     default: return launch_gemm<128, 5, false>(ma, mb, p, stream);
   }
+}
+
+static int run(const float* A, int64_t a_rows, int lda, const float* Bw, int ldb, GemmParams& p, cudaStream_t stream) {
+  if (!aligned16(A) || !aligned16(Bw) || (lda % 4) || (ldb % 4)) return GED_ERR_ALIGN;
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int bn = pick_bn(p.M, p.N, g_precision == 3);
+  CUtensorMap ma, mb;
+  const int Kt = p.K / p.ntaps;
+  if (int e = make_map_2d(&ma, A, a_rows, Kt, lda, BM)) return e;
+  if (int e = make_map_2d(&mb, Bw, p.N, p.K, ldb, bn)) return e;
+  p.kblocks_per_tap = cdiv(Kt, BK);
+  p.Kt = Kt;
+  return dispatch(bn, ma, mb, p, stream);
+}
+
+// dW[N][tap][K] += sum_p G[p][n] * X[p + tap_off[tap]][k]  (weight gradients).
+// G = [P][N], X = [Px][K] as the forward stored them (MN-major UMMA operands, no copies).
+static int run_dw(const float* G, int ldg, const float* X, int ldx, int64_t P, int64_t Px, GemmParams& p, cudaStream_t stream) {
+  if (!aligned16(G) || !aligned16(X) || (ldg % 4) || (ldx % 4)) return GED_ERR_ALIGN;
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  // panels of 32 features: at most four boxes per operand and stage
+  const int bn = p.N <= 32 ? 32 : p.N <= 64 ? 64 : p.N <= 96 ? 96 : (p.N % 128 != 0 && p.N % 96 == 0) ? 96 : 128;
+  CUtensorMap ma, mb;
+  if (int e = make_map_2d(&ma, G, P, p.M, ldg, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
+  if (int e = make_map_2d(&mb, X, Px, p.N, ldx, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
+  p.ntaps = 1; p.Kt = (int)P; p.kblocks_per_tap = cdiv((int)P, BK); p.total_kb = p.kblocks_per_tap;
+  return dispatch(bn, ma, mb, p, stream);
 }
 
 }  // namespace ged
@@ -448,6 +573,33 @@ GED_API int ged_set_gemm_precision(int passes) {
   const int prev = g_precision;
   if (passes == 1 || passes == 3) g_precision = passes;
   return prev;
+}
+
+// 1 = allow 192/256-wide output tiles (default), 0 = at most 128.  Returns the previous setting.
+GED_API int ged_set_gemm_wide_tiles(int on) {
+  const int prev = g_wide_tiles;
+  g_wide_tiles = on ? 1 : 0;
+  return prev;
+}
+
+// Weight gradient of a linear / 1x1 conv (ntaps = 1) or a 3x3 conv (ntaps = 9) on tcgen05:
+//   D[n][t][k] += sum_p G[p][n] * X[p + tap_off[t]][k],   n < N, k < K, p < P  (rows of X outside [0, Px) read as 0)
+// D element (n, t, k) lives at D[n * ldd + t * tap_dstride + k]; D must hold the running gradient (or zeros): the
+// contraction over P is split across SMs and partial tiles are added with vector atomics.
+// G is [P][N] (pitch ldg) and X is [Px][K] (pitch ldx) exactly as the forward stored them (MN-major UMMA operands,
+// TMA panels of 32 features, no transposed copies).
+// Replaces the autograd weight-gradient GEMMs / cuDNN wgrad of every nn.Linear / Conv2d on the path.
+GED_API int ged_gemm_dw_tf32(const float* G, int ldg, const float* X, int ldx, float* D, int ldd, int N, int K,
+                             int64_t P, int64_t Px, int ntaps, const int* tap_off, int tap_dstride,
+                             cudaStream_t stream) {
+  if (!G || !X || !D || N <= 0 || K <= 0 || P <= 0 || Px <= 0 || ntaps < 1 || ntaps > MAX_TAPS) return GED_ERR_ARG;
+  if ((N % 4) || (K % 4) || P > 0x7fffffff || Px > 0x7fffffff) return GED_ERR_SHAPE;
+  GemmParams p{};
+  p.M = N; p.N = K; p.K = (int)P; p.mode = 1; p.out_taps = ntaps; p.tap_dstride = tap_dstride;
+  for (int t = 0; t < ntaps; ++t) p.tap_off[t] = tap_off ? tap_off[t] : 0;
+  p.bias = nullptr; p.residual = nullptr; p.row_scale = nullptr; p.rows_per_batch = 1;
+  p.D = D; p.D_pre = nullptr; p.ldd = ldd; p.act = 0; p.slope = 0.f; p.conv_Hp = 0; p.conv_Wp = 0;
+  return run_dw(G, ldg, X, ldx, P, Px, p, stream);
 }
 
 // D[M,N] = epi(A[M,K] @ W[N,K]^T).  A row pitch lda, W row pitch ldw, D/residual row pitch ldd (floats).

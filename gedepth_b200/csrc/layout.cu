@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(256) clamp_resize_kernel(const float* __restri
   }
 }
 
+
 }  // namespace ged
 using namespace ged;
 

@@ -53,6 +53,9 @@ SIGNATURES = {
     "ged_msda_fwd": [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_msda_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_set_gemm_precision": [_I],
+    "ged_set_gemm_wide_tiles": [_I],
+    "ged_set_msda_variant": [_I],
+    "ged_gemm_dw_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I64, _I64, _I, _P, _I, _P],
     "ged_sumsq": [_P, _I64, _P, _P],
     "ged_adamw_step": [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _F, _I, _P, _P],
 }
@@ -85,6 +88,8 @@ def load():
     _lib = lib
     if os.environ.get("GEDEPTH_GEMM_PASSES"):
         lib.ged_set_gemm_precision(int(os.environ["GEDEPTH_GEMM_PASSES"]))
+    if os.environ.get("GEDEPTH_MSDA_VARIANT"):
+        lib.ged_set_msda_variant(int(os.environ["GEDEPTH_MSDA_VARIANT"]))
     return lib
 
 
@@ -440,6 +445,35 @@ def gemm(a2d: torch.Tensor, w: torch.Tensor, bias=None, act=None, slope=0.01, re
     return out
 
 
+# Weight gradients: 1 = tcgen05 on the operands as stored (MN-major UMMA descriptors, split-K partials accumulated
+# with vector atomics), 0 = library (cuBLAS / cuDNN wgrad; kept as an A/B switch for the tests).
+DW_MODE = int(os.environ.get("GEDEPTH_DW_MODE", "1"))
+
+
+def set_gemm_wide_tiles(on: bool) -> int:
+    return load().ged_set_gemm_wide_tiles(int(bool(on)))
+
+
+def gemm_dw(g2d: torch.Tensor, x2d: torch.Tensor, out: Optional[torch.Tensor] = None, tap_off=None) -> torch.Tensor:
+    """out[n, t, k] += sum_p g2d[p, n] * x2d[p + tap_off[t], k]  (rows of x2d outside the tensor count as zero).
+    g2d [P, N], x2d [Px, K] with unit inner stride.  out: [N, K] (no taps) or [N, T, K]; allocated zeroed if None."""
+    P, N = g2d.shape
+    Px, K = x2d.shape
+    T = 1 if tap_off is None else len(tap_off)
+    if out is None:
+        out = torch.zeros((N, K) if tap_off is None else (N, T, K), dtype=torch.float32, device=g2d.device)
+    taps = None if tap_off is None else (C.c_int * T)(*[int(t) for t in tap_off])
+    assert g2d.stride(1) == 1 and x2d.stride(1) == 1
+    _call("ged_gemm_dw_tf32", _p(g2d), g2d.stride(0), _p(x2d), x2d.stride(0), _p(out), T * K, N, K, P, Px, T, taps, K,
+          _stream())
+    return out
+
+
+def _dw_ok(N, K, *tensors):
+    return DW_MODE == 1 and N % 4 == 0 and K % 4 == 0 and N >= 16 and K >= 16 and all(
+        t.dtype == torch.float32 and t.data_ptr() % 16 == 0 for t in tensors)
+
+
 def act_bwd(g2d: torch.Tensor, ref: Optional[torch.Tensor], act, slope=0.01, row_scale=None, rows_per_batch=1,
             want_db=False):
     """gz = g * act'(ref) * row_scale and (optionally) db = column sums of gz, in ONE pass.  With no
@@ -528,7 +562,11 @@ class _Linear(Function):
             else:
                 dx = (gz @ w).reshape(ctx.xshape)
         if ctx.needs_input_grad[1]:
-            dw = gz.t() @ x2
+            if _dw_ok(N, K, gz, x2):
+                with _bwd_precision():
+                    dw = gemm_dw(gz, x2)
+            else:
+                dw = gz.t() @ x2
         dres = g if ctx.has_res else None
         return dx, dw, db, None, dres, None
 
@@ -626,17 +664,31 @@ class _Conv(Function):
             if want_db:
                 db = gz.sum((0, 1, 2))
         dxc = dw = None
+        need_dw = ctx.needs_input_grad[2]
+        dw_native = need_dw and _dw_ok(Cout, Cin, gz, xin)
+        gzp = None
+        if kh == 3 and Cout % 4 == 0 and ((need_dx and Cout % 32 == 0) or dw_native):
+            gzp = prep_conv_input(gz, None, H, W)                            # zero-bordered dY, shared by dX and dW
         if need_dx:
             if kh == 3 and Cout % 32 == 0:
                 wt = w.flip(2, 3).permute(1, 2, 3, 0).contiguous()          # [Cin,3,3,Cout]
                 with _bwd_precision():
-                    dxc = conv3x3_raw(gz, wt, None, None, 0.0)                # (B,H,W,Cin)
+                    dxc = conv3x3_padded(gzp, wt, None, None, 0.0)            # (B,H,W,Cin)
             elif kh == 1 and _gemm_ok(B * H * W, Cin, Cout, gz):
                 with _bwd_precision():
                     dxc = gemm(gz.reshape(-1, Cout), w.reshape(Cout, Cin).t().contiguous()).reshape(B, H, W, Cin)
+        if dw_native:
+            with _bwd_precision():
+                if kh == 3:
+                    Wp = W + 2
+                    taps = [(ky - 1) * Wp + (kx - 1) for ky in range(3) for kx in range(3)]
+                    dwk = gemm_dw(gzp.reshape(-1, Cout), xin.reshape(-1, Cin), None, taps)    # [Cout, 9, Cin]
+                    dw = dwk.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+                else:
+                    dw = gemm_dw(gz.reshape(-1, Cout), xin.reshape(-1, Cin)).reshape(Cout, Cin, 1, 1)
         pad = 0                                     # xin already carries the zero border for 3x3
         xin_nchw = xin.permute(0, 3, 1, 2)
-        mask = [need_dx and dxc is None, ctx.needs_input_grad[2], False]
+        mask = [need_dx and dxc is None, need_dw and dw is None, False]
         if any(mask):
             r = torch.ops.aten.convolution_backward(gz.permute(0, 3, 1, 2), xin_nchw, w, None, [1, 1], [pad, pad],
                                                     [1, 1], False, [0, 0], 1, mask)
@@ -644,7 +696,7 @@ class _Conv(Function):
                 dxc = r[0].permute(0, 2, 3, 1)
                 if kh == 3:
                     dxc = dxc[:, 1:-1, 1:-1, :]
-            dw = r[1] if mask[1] else None
+            dw = r[1] if mask[1] else dw
         dx0 = dx1 = None
         if need_dx:
             if C1 is not None and ctx.needs_input_grad[1]:
@@ -841,6 +893,10 @@ class _MSDA(Function):
         _call("ged_msda_bwd", _p(v), _p(ref), ref.shape[0], _p(off), _p(logit), _p(g), _p(g_v), _p(g_ref),
               _p(g_off), _p(g_logit), hw, len(shapes), B, S, Q, nH, E // nH, P, _stream())
         return g_v, g_ref, g_off, g_logit, None, None, None
+
+
+def set_msda_variant(v: int) -> int:
+    return load().ged_set_msda_variant(int(v))
 
 
 def msda_sample(v, shapes, ref, off, logit, nH, P):

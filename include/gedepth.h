@@ -131,6 +131,17 @@ int ged_gemm_tf32(const float* A, int lda, const float* W, int ldw, float* D, in
  * tf32 hi + lo, three tcgen05 MMAs per k-step: fp32-accurate, the parity mode); 1 = single-pass TF32 (what
  * PyTorch 1.8 / cuDNN run by default on Ampere+ for the reference).  Returns the previous value. */
 int ged_set_gemm_precision(int passes);
+/* 1 (default) = allow 192/256-column output tiles, 0 = at most 128.  Returns the previous value. */
+int ged_set_gemm_wide_tiles(int on);
+/* Weight gradients (autograd of every nn.Linear / Conv2d on the path; the reference gets them from cuBLAS /
+ * cuDNN wgrad through torch.autograd):  D[n*ldd + t*tap_dstride + k] += sum_p G[p][n] * X[p + tap_off[t]][k]
+ * for n < N, k < K, t < ntaps (1: linear / 1x1, 9: 3x3 with tap_off = (ky-1)*(W+2) + (kx-1) over zero-bordered
+ * NHWC operands); rows of X outside [0,Px) read as zero.  D holds the running gradient (or zeros): the
+ * contraction over P is split across SMs and partial tiles are added with vector atomics.
+ * G [P][N] pitch ldg, X [Px][K] pitch ldx exactly as the forward stored them: MN-major UMMA operands
+ * (SWIZZLE_128B_BASE32B, TMA panels of 32 features), no transposed copies. */
+int ged_gemm_dw_tf32(const float* G, int ldg, const float* X, int ldx, float* D, int ldd, int N, int K,
+                     int64_t P, int64_t Px, int ntaps, const int* tap_off, int tap_dstride, cudaStream_t stream);
 /* 3x3/s1/p1 conv, NHWC: hahi.py:138-165, pemask_neck.py:36-42, dynamicpe_neck.py:497-502,
  * densedepth_head.py:21-22, decode_head.py:391.  Xpad [B,H+2,W+2,Cin] zero-bordered;
  * Wk [Cout][3][3][Cin]; Y [B,H,W,*] with channel pitch ldy. */
@@ -174,6 +185,11 @@ int ged_msda_bwd(const float* value, const float* ref, int ref_batch, const floa
                  const float* logit, const float* g_out, float* g_value, float* g_ref, float* g_off,
                  float* g_logit, const int* level_hw, int num_levels, int B, int S, int Q, int nH,
                  int head_dim, int num_points, cudaStream_t stream);
+
+/* Work mapping of the two kernels above.  bit0: a CTA takes one query x 8 heads (default: 8 queries x one head);
+ * bit1: backward as two kernels (g_value scatter, then offset/weight gradients); -1 (default) = pick bit0 per call
+ * (one query x 8 heads when Q >= 2 S).  Returns the previous value. */
+int ged_set_msda_variant(int v);
 
 /* ---- optimizer (configs/depthformer/depthformer_v.py:128-148) ---------------------------------- */
 int ged_sumsq(const float* g, int64_t n, double* out, cudaStream_t stream);

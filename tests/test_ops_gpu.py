@@ -264,6 +264,41 @@ def test_gemm_plain(M, N, K, passes):
     _close(out, ref, 0, _gemm_tol(ref, passes, K), f"gemm {M}x{N}x{K}")
 
 
+@pytest.mark.parametrize("P,N,K", [(64, 32, 32), (600, 384, 96), (1000, 96, 288), (5000, 128, 128), (20011, 512, 64),
+                                   (70000, 64, 256), (3000, 1536, 384), (777, 16, 2304)])
+def test_gemm_dw(P, N, K, passes):
+    """dW[n,k] = sum_p G[p,n] X[p,k] on tcgen05 with MN-major operands as stored; contraction split across SMs
+    with atomic accumulation."""
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(21)
+    G = torch.randn(P, N, generator=g).to(DEV)
+    X = torch.randn(P, K, generator=g).to(DEV)
+    out = Kn.gemm_dw(G, X)
+    ref = (G.double().t() @ X.double()).float()
+    _close(out, ref, 0, _gemm_tol(ref, passes, P), f"dW {P}x{N}x{K}")
+    # accumulation into a running gradient
+    out2 = Kn.gemm_dw(G, X, out=ref.clone())
+    _close(out2, 2 * ref, 0, 2 * _gemm_tol(ref, passes, P), "dW accumulate")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 11, 35, 64, 64), (1, 22, 70, 576, 192), (3, 9, 12, 96, 32)])
+def test_conv3x3_dw_taps(B, H, W, Cin, Cout, passes):
+    """3x3 weight gradient as nine row-shifted contractions over the zero-bordered NHWC operands."""
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(B, H, W, Cin, generator=g).to(DEV)
+    gy = torch.randn(B, H, W, Cout, generator=g).to(DEV)
+    xp, gp = Kn.prep_conv_input(x, None, H, W), Kn.prep_conv_input(gy, None, H, W)
+    taps = [(ky - 1) * (W + 2) + (kx - 1) for ky in range(3) for kx in range(3)]
+    dwk = Kn.gemm_dw(gp.reshape(-1, Cout), xp.reshape(-1, Cin), None, taps)        # [Cout, 9, Cin]
+    dw = dwk.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+    xd = x.permute(0, 3, 1, 2).double().requires_grad_(False)
+    wd = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float64, device=DEV, requires_grad=True)
+    (F.conv2d(xd, wd, padding=1) * gy.permute(0, 3, 1, 2).double()).sum().backward()
+    ref = wd.grad.float()
+    _close(dw, ref, 0, _gemm_tol(ref, passes, B * H * W) * (3.0 if passes == 1 else 1.0), "conv dW")
+
+
 @pytest.mark.parametrize("act", [None, "relu", "gelu", "leaky_relu", "sigmoid"])
 def test_gemm_epilogue(act, passes):
     from gedepth_b200 import kernels as Kn, ops_lib as L
@@ -362,7 +397,17 @@ def test_conv1x1_and_folded_bn():
 @pytest.mark.parametrize("B,shapes,Q,ref_b", [(2, [(16, 40), (8, 20), (4, 10), (2, 5)], 850, 1),
                                                (1, [(18, 42), (9, 21), (5, 11), (3, 6)], 333, 1),
                                                (2, [(16, 40), (8, 20), (4, 10), (2, 5)], 1280, 2)])
-def test_msda_fwd_bwd(B, shapes, Q, ref_b):
+@pytest.mark.parametrize("variant", [0, 1, 2, 3], ids=["q8xh1", "q1xh8", "q8xh1-split", "q1xh8-split"])
+def test_msda_fwd_bwd(B, shapes, Q, ref_b, variant):
+    from gedepth_b200 import kernels as Kn, ops_lib as L
+    prev = Kn.set_msda_variant(variant)
+    try:
+        _msda_case(B, shapes, Q, ref_b)
+    finally:
+        Kn.set_msda_variant(prev)
+
+
+def _msda_case(B, shapes, Q, ref_b):
     from gedepth_b200 import kernels as Kn, ops_lib as L
     g = torch.Generator().manual_seed(14)
     S = sum(h * w for h, w in shapes)
