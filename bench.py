@@ -253,6 +253,8 @@ def main():
 
     # ---- per-kernel device time of ONE extra step (CUDA events around every C-ABI launch) ----------
     prof = {}
+    if use_graph:
+        trainer.release_graph()         # timing is done: give the graph's activation pool back before the eager passes
     if rank != 0:
         step_eager(1)          # same collectives as rank 0's two eager steps below
         step_eager(0)

@@ -52,6 +52,10 @@ struct GemmParams {
   //   mode 1: both operands MN-major as stored ([P][features]); TMA 32x32 panels with the
   //           128B/32B-atom swizzle, UMMA LayoutType SWIZZLE_128B_BASE32B (the only MN-major tf32 layout)
   int mode;
+  // mode 0 only: B operand stored [K rows][N cols] (row pitch in the tensor map), i.e. MN-major - the forward's
+  // weight matrix used untransposed by the dX GEMMs: dX = dY @ W with W [N_out][K_in], and the 3x3 dX conv reading
+  // tap t's slab W[:, t*b_tap_cols : (t+1)*b_tap_cols] of the forward layout [Cout][9][Cin].
+  int b_mn, b_tap_cols;
   int out_taps;             // 1 (linear / 1x1) or 9 (3x3): tap t reads B rows shifted by tap_off[t]
   int tap_dstride;          // element offset of tap t's output block in D
   int total_kb, kb_per_split, splits;
@@ -139,9 +143,9 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128_32b(uint32_t smem_ad
 }
 // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format TF32 (2) @7/@10, a/b major @15/@16
 // (0 = K-major, 1 = MN-major), n_dim = N>>3 @17, m_dim = M>>4 @24
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, bool mn_major = false) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ Unit decode_unit(const GemmParams& p, int u, int BN_) {
   const int tiles = p.num_m_tiles * p.num_n_tiles, per = tiles * p.out_taps;
@@ -179,6 +183,81 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
 constexpr int EPI_WARPS = 8;       // two warps per TMEM lane quadrant, each owning half of the columns
 constexpr int EPI_PITCH = 20;      // floats; 32 rows x 16 columns staging tile per warp, conflict-free for float4
 constexpr int SPLIT_WARPS = 4;
+
+// One output tile of the epilogue for one warp: TMEM quadrant q (32 accumulator rows), column half `half` of the
+// BN-wide tile.  Waits for the accumulator (full_bar, phase), then bias -> activation -> row scale -> residual and
+// 128-bit coalesced stores (or vector-atomic accumulation for the split-K weight-gradient modes).
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* tile_s, uint32_t tmem_acc, uint64_t* full_bar,
+                                          uint32_t full_phase, int m0, int n0, float* Dt, int q, int half, int lane) {
+  const bool vec = ((p.ldd & 3) == 0) && ((p.N & 3) == 0) && aligned16(p.D) && (!p.residual || aligned16(p.residual));
+  const int lr = lane >> 2, lc = (lane & 3) * 4;          // store phase: lane -> (row lr + 8 i, 4 columns from lc)
+  // the four output rows this lane stores (fixed for the whole tile)
+  int64_t orow[4];
+  float rscale[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + q * 32 + lr + 8 * i;
+    orow[i] = -1; rscale[i] = 1.f;
+    if (row < p.M) {
+      orow[i] = row;
+      if (p.conv_Wp) {   // padded flattened pixel -> interior test and unpadded row
+        const int xp = row % p.conv_Wp, t2 = row / p.conv_Wp, yp = t2 % p.conv_Hp, n = t2 / p.conv_Hp;
+        orow[i] = (xp == 0 || xp == p.conv_Wp - 1 || yp == 0 || yp == p.conv_Hp - 1)
+                      ? -1 : ((int64_t)n * (p.conv_Hp - 2) + (yp - 1)) * (p.conv_Wp - 2) + (xp - 1);
+      }
+      if (p.row_scale && orow[i] >= 0) rscale[i] = __ldg(p.row_scale + orow[i] / p.rows_per_batch);
+    }
+  }
+  mbar_wait(full_bar, full_phase);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
+    uint32_t v[16];
+    tc_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *(float4*)(tile_s + lane * EPI_PITCH + 4 * j) =
+          make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+    __syncwarp();
+    const int col = n0 + c0 + lc;
+    if (col < p.N) {
+      float bias[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.bias) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (col + e < p.N) bias[e] = __ldg(p.bias + col + e);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (orow[i] < 0) continue;
+        const float4 t = *(const float4*)(tile_s + (lr + 8 * i) * EPI_PITCH + lc);
+        float x[4] = {t.x + bias[0], t.y + bias[1], t.z + bias[2], t.w + bias[3]};
+        if (p.D_pre) {
+          if (vec) *(float4*)(p.D_pre + orow[i] * p.ldd + col) = make_float4(x[0], x[1], x[2], x[3]);
+          else for (int e = 0; e < 4; ++e) if (col + e < p.N) p.D_pre[orow[i] * p.ldd + col + e] = x[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[e] = apply_act(x[e], p.act, p.slope) * rscale[i];
+        float* dst = Dt + orow[i] * p.ldd + col;
+        if (p.mode != 0) {          // split-K partial: accumulate (D is zero-initialised / holds the running gradient)
+          if (vec && ((p.tap_dstride & 3) == 0)) atomicAdd((float4*)dst, make_float4(x[0], x[1], x[2], x[3]));
+          else for (int e = 0; e < 4; ++e) if (col + e < p.N) atomicAdd(dst + e, x[e]);
+        } else if (vec) {
+          if (p.residual) {
+            const float4 r = __ldg((const float4*)(p.residual + orow[i] * p.ldd + col));
+            x[0] += r.x; x[1] += r.y; x[2] += r.z; x[3] += r.w;
+          }
+          *(float4*)dst = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (col + e < p.N) dst[e] = x[e] + (p.residual ? __ldg(p.residual + orow[i] * p.ldd + col + e) : 0.f);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
 
 // SPLIT = error-compensated "3xTF32": every fp32 operand x is used as hi = tf32(x) (the tensor core's own
 // truncation) plus lo = x - hi (exact in fp32), and each k-step issues hi*hi + lo*hi + hi*lo.  The dropped
@@ -246,7 +325,14 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
           if (p.mode == 0) {
             const int t = kb / p.kblocks_per_tap, kc = kb - t * p.kblocks_per_tap;
             tma_load_2d(sa, &map_a, full_bar + stage, kc * BK, u.m0 + p.tap_off[t]);
-            tma_load_2d(sa + S::A_BYTES, &map_b, full_bar + stage, t * p.Kt + kc * BK, u.n0);
+            if (!p.b_mn) {
+              tma_load_2d(sa + S::A_BYTES, &map_b, full_bar + stage, t * p.Kt + kc * BK, u.n0);
+            } else {
+#pragma unroll
+              for (int pnl = 0; pnl < BN / 32; ++pnl)
+                tma_load_2d(sa + S::A_BYTES + pnl * (BK * 128), &map_b, full_bar + stage,
+                            t * p.b_tap_cols + u.n0 + 32 * pnl, kc * BK);
+            }
           } else {
             // operands as stored: rows = contraction index (pixels), 32-feature panels side by side
 #pragma unroll
@@ -264,11 +350,11 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      const bool mn = p.mode == 1;
-      const uint32_t idesc = umma_idesc_tf32(BM, BN, mn);
+      const bool a_mn = p.mode == 1, b_mn = p.mode == 1 || p.b_mn;
+      const uint32_t idesc = umma_idesc_tf32(BM, BN, a_mn, b_mn);
       // K-major: 8 tf32 = 32 bytes inside the 128B swizzle row, +2 in the (addr>>4) field per k-step;
       // MN-major: 8 K rows = two 512-byte atoms = 1024 bytes, +64 per k-step
-      const uint32_t kstep = mn ? 64u : 2u;
+      const uint32_t kstep_a = a_mn ? 64u : 2u, kstep_b = b_mn ? 64u : 2u;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -280,15 +366,15 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
           mbar_wait((SPLIT ? split_bar : full_bar) + stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
-          const uint64_t adesc = mn ? umma_desc_mnmajor_sw128_32b(sa, BK * 128) : umma_desc_kmajor_sw128(sa);
-          const uint64_t bdesc = mn ? umma_desc_mnmajor_sw128_32b(sa + S::A_BYTES, BK * 128) : umma_desc_kmajor_sw128(sa + S::A_BYTES);
+          const uint64_t adesc = a_mn ? umma_desc_mnmajor_sw128_32b(sa, BK * 128) : umma_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = b_mn ? umma_desc_mnmajor_sw128_32b(sa + S::A_BYTES, BK * 128) : umma_desc_kmajor_sw128(sa + S::A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
-            tc_mma_tf32(tmem_d, adesc + kstep * k, bdesc + kstep * k, idesc, ((kb - u.kb0) | k) != 0);
+            tc_mma_tf32(tmem_d, adesc + kstep_a * k, bdesc + kstep_b * k, idesc, ((kb - u.kb0) | k) != 0);
             if (SPLIT) {
               const uint64_t alo = adesc + (S::HI_BYTES >> 4), blo = bdesc + (S::HI_BYTES >> 4);
-              tc_mma_tf32(tmem_d, alo + kstep * k, bdesc + kstep * k, idesc, 1u);   // lo(A) * hi(B)
-              tc_mma_tf32(tmem_d, adesc + kstep * k, blo + kstep * k, idesc, 1u);   // hi(A) * lo(B)
+              tc_mma_tf32(tmem_d, alo + kstep_a * k, bdesc + kstep_b * k, idesc, 1u);   // lo(A) * hi(B)
+              tc_mma_tf32(tmem_d, adesc + kstep_a * k, blo + kstep_b * k, idesc, 1u);   // hi(A) * lo(B)
             }
           }
           tc_commit(empty_bar + stage);          // frees the smem slot when these MMAs retire
@@ -302,78 +388,12 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
     // ===== epilogue: TMEM -> registers -> smem transpose -> 128-bit coalesced global accesses =====
     const int ew = warp - 4, q = ew & 3, half = ew >> 2;   // TMEM lane quadrant = warp % 4
     float* tile_s = epi_tiles + ew * 32 * EPI_PITCH;
-    const bool vec = ((p.ldd & 3) == 0) && ((p.N & 3) == 0) && aligned16(p.D) && (!p.residual || aligned16(p.residual));
-    const int lr = lane >> 2, lc = (lane & 3) * 4;          // store phase: lane -> (row lr + 8 i, 4 columns from lc)
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const Unit u = decode_unit(p, tile, BN);
       const int m0 = u.m0, n0 = u.n0;
       float* const Dt = p.D + (int64_t)u.tap * p.tap_dstride;
-      // the four output rows this lane stores (fixed for the whole tile)
-      int64_t orow[4];
-      float rscale[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = m0 + q * 32 + lr + 8 * i;
-        orow[i] = -1; rscale[i] = 1.f;
-        if (row < p.M) {
-          orow[i] = row;
-          if (p.conv_Wp) {   // padded flattened pixel -> interior test and unpadded row
-            const int xp = row % p.conv_Wp, t2 = row / p.conv_Wp, yp = t2 % p.conv_Hp, n = t2 / p.conv_Hp;
-            orow[i] = (xp == 0 || xp == p.conv_Wp - 1 || yp == 0 || yp == p.conv_Hp - 1)
-                          ? -1 : ((int64_t)n * (p.conv_Hp - 2) + (yp - 1)) * (p.conv_Wp - 2) + (xp - 1);
-          }
-          if (p.row_scale && orow[i] >= 0) rscale[i] = __ldg(p.row_scale + orow[i] / p.rows_per_batch);
-        }
-      }
-      mbar_wait(tmem_full + acc, acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
-        uint32_t v[16];
-        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *(float4*)(tile_s + lane * EPI_PITCH + 4 * j) =
-              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-        __syncwarp();
-        const int col = n0 + c0 + lc;
-        if (col < p.N) {
-          float bias[4] = {0.f, 0.f, 0.f, 0.f};
-          if (p.bias) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) if (col + e < p.N) bias[e] = __ldg(p.bias + col + e);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (orow[i] < 0) continue;
-            const float4 t = *(const float4*)(tile_s + (lr + 8 * i) * EPI_PITCH + lc);
-            float x[4] = {t.x + bias[0], t.y + bias[1], t.z + bias[2], t.w + bias[3]};
-            if (p.D_pre) {
-              if (vec) *(float4*)(p.D_pre + orow[i] * p.ldd + col) = make_float4(x[0], x[1], x[2], x[3]);
-              else for (int e = 0; e < 4; ++e) if (col + e < p.N) p.D_pre[orow[i] * p.ldd + col + e] = x[e];
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] = apply_act(x[e], p.act, p.slope) * rscale[i];
-            float* dst = Dt + orow[i] * p.ldd + col;
-            if (p.mode != 0) {          // split-K partial: accumulate (D is zero-initialised / holds the running gradient)
-              if (vec && ((p.tap_dstride & 3) == 0)) atomicAdd((float4*)dst, make_float4(x[0], x[1], x[2], x[3]));
-              else for (int e = 0; e < 4; ++e) if (col + e < p.N) atomicAdd(dst + e, x[e]);
-            } else if (vec) {
-              if (p.residual) {
-                const float4 r = __ldg((const float4*)(p.residual + orow[i] * p.ldd + col));
-                x[0] += r.x; x[1] += r.y; x[2] += r.z; x[3] += r.w;
-              }
-              *(float4*)dst = make_float4(x[0], x[1], x[2], x[3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (col + e < p.N) dst[e] = x[e] + (p.residual ? __ldg(p.residual + orow[i] * p.ldd + col + e) : 0.f);
-            }
-          }
-        }
-        __syncwarp();
-      }
+      epilogue_tile<BN>(p, tile_s, tmem_base + (uint32_t)(acc * BN), tmem_full + acc, acc_phase, m0, n0, Dt, q, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);
@@ -411,6 +431,249 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// =================================================================================================
+// CTA-pair variant (cta_group::2): two CTAs of a cluster (the two SMs of a TPC) compute one 256 x BN tile.
+// CTA r stages its own 128 rows of A and HALF of the B tile (BN/2 rows); one tcgen05.mma.cta_group::2 issued by
+// the leader (rank 0) reads A from each CTA's shared memory and B from both, and writes 128 x BN accumulators
+// into each CTA's TMEM.  Per flop every SM stages and re-reads half the operand bytes of the single-CTA kernel:
+// the 3xTF32 path is shared-memory-bandwidth bound and the 1-pass path L2-bandwidth bound (profiles/), so this
+// is where the time goes.
+//
+// Signalling: TMA lands in the issuing CTA's shared memory and completes on that CTA's full barrier; the
+// splitter warps (3xTF32) or a relay thread (1 pass) of each CTA then arrive on the LEADER's ready barrier
+// (remote mbarrier arrive); the leader's MMA thread waits on it, issues, and multicasts tcgen05.commit to the
+// empty / tmem_full barriers of both CTAs; epilogue warps of both CTAs arrive on the leader's tmem_empty.
+// =================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `bar` (a shared::cta object of THIS CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_rank(const void* bar, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(bar)), "r"(rank));
+  return r;
+}
+// Default (.release.cta) semantics as in CUTLASS's ClusterBarrier::arrive: a cluster-scope release costs a
+// ~1300-cycle fence per arrive (measured: it capped the pair kernel at one k-block per 0.7 us).  What the leader's
+// tensor core reads was written by TMA (async proxy) or made visible to it by fence.proxy.async before this arrive.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAITC_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONEC_%=;\n\t"
+      "bra WAITC_%=;\n\t"
+      "DONEC_%=:\n\t}"
+      :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {      // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+constexpr int BM2 = 256;   // rows per CTA-pair tile
+
+template <int BN, int STAGES, bool SPLIT>
+struct Gemm2Smem {
+  static constexpr int A_BYTES = BM * BK * 4;              // this CTA's 128 rows
+  static constexpr int B_BYTES = (BN / 2) * BK * 4;        // this CTA's half of the B tile
+  static constexpr int HI_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = HI_BYTES * (SPLIT ? 2 : 1);
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
+  static constexpr int BAR_BYTES = (3 * STAGES + 4) * 8 + 16;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
+  static constexpr int THREADS = 128 + EPI_WARPS * 32 + (SPLIT ? SPLIT_WARPS * 32 : 0);
+};
+
+__device__ __forceinline__ Unit decode_unit2(const GemmParams& p, int u, int BN_) {
+  Unit t;
+  t.tap = 0;
+  t.m0 = (u / p.num_n_tiles) * BM2;
+  t.n0 = (u % p.num_n_tiles) * BN_;
+  t.kb0 = 0;
+  t.kb1 = p.total_kb;
+  return t;
+}
+
+template <int BN, int STAGES, bool SPLIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES, SPLIT>::THREADS, 1) gemm2_tf32_kernel(
+    const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
+  using S = Gemm2Smem<BN, STAGES, SPLIT>;
+  constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t READY_COUNT = 2 * (SPLIT ? SPLIT_WARPS : 1);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  float* epi_tiles = (float*)(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* full_bar = (uint64_t*)((uint8_t*)epi_tiles + S::EPI_BYTES);   // local: this CTA's TMA bytes
+  uint64_t* empty_bar = full_bar + STAGES;                                // local: MMAs that read this slot retired
+  uint64_t* ready_bar = empty_bar + STAGES;                               // leader's copy is the one that counts
+  uint64_t* tmem_full = ready_bar + STAGES;                               // [2] local
+  uint64_t* tmem_empty = tmem_full + 2;                                   // [2] leader's copy counts
+  uint32_t* tmem_ptr = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_units = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&map_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); mbar_init(ready_bar + i, READY_COUNT); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, 2 * EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer: this CTA's 128 rows of A and its half of B =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+        const Unit u = decode_unit2(p, unit, BN);
+        const int m0 = u.m0 + (int)rank * BM, n0 = u.n0 + (int)rank * (BN / 2);
+        for (int kb = u.kb0; kb < u.kb1; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* sa = stage_base + stage * S::STAGE_BYTES;
+          mbar_expect_tx(full_bar + stage, S::HI_BYTES);
+          const int t = kb / p.kblocks_per_tap, kc = kb - t * p.kblocks_per_tap;
+          tma_load_2d(sa, &map_a, full_bar + stage, kc * BK, m0 + p.tap_off[t]);
+          if (!p.b_mn) {
+            tma_load_2d(sa + S::A_BYTES, &map_b, full_bar + stage, t * p.Kt + kc * BK, n0);
+          } else {
+#pragma unroll
+            for (int pnl = 0; pnl < BN / 64; ++pnl)
+              tma_load_2d(sa + S::A_BYTES + pnl * (BK * 128), &map_b, full_bar + stage,
+                          t * p.b_tap_cols + n0 + 32 * pnl, kc * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA =====
+    if (lane == 0 && rank == 0) {
+      const bool b_mn = p.b_mn != 0;
+      const uint32_t idesc = umma_idesc_tf32(BM2, BN, false, b_mn);
+      const uint32_t kstep_b = b_mn ? 64u : 2u;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+        const Unit u = decode_unit2(p, unit, BN);
+        mbar_wait_cluster(tmem_empty + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = u.kb0; kb < u.kb1; ++kb) {
+          mbar_wait_cluster(ready_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = b_mn ? umma_desc_mnmajor_sw128_32b(sa + S::A_BYTES, BK * 128) : umma_desc_kmajor_sw128(sa + S::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            tc_mma_tf32_pair(tmem_d, adesc + 2 * k, bdesc + kstep_b * k, idesc, ((kb - u.kb0) | k) != 0);
+            if (SPLIT) {
+              const uint64_t alo = adesc + (S::HI_BYTES >> 4), blo = bdesc + (S::HI_BYTES >> 4);
+              tc_mma_tf32_pair(tmem_d, alo + 2 * k, bdesc + kstep_b * k, idesc, 1u);
+              tc_mma_tf32_pair(tmem_d, adesc + 2 * k, blo + kstep_b * k, idesc, 1u);
+            }
+          }
+          tc_commit_pair(empty_bar + stage);
+          if (kb == u.kb1 - 1) tc_commit_pair(tmem_full + acc);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // ===== relay (1-pass arithmetic): this CTA's operands have landed -> tell the leader =====
+    if (!SPLIT && lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+        for (int kb = 0; kb < p.total_kb; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          mbar_arrive_remote(mapa_rank(ready_bar + stage, 0));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + EPI_WARPS) {
+    // ===== epilogue: this CTA's 128 rows of the pair tile =====
+    const int ew = warp - 4, q = ew & 3, half = ew >> 2;
+    float* tile_s = epi_tiles + ew * 32 * EPI_PITCH;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+      const Unit u = decode_unit2(p, unit, BN);
+      epilogue_tile<BN>(p, tile_s, tmem_base + (uint32_t)(acc * BN), tmem_full + acc, acc_phase, u.m0 + (int)rank * BM, u.n0,
+                        p.D, q, half, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(mapa_rank(tmem_empty + acc, 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (SPLIT && warp >= 4 + EPI_WARPS) {
+    // ===== splitter: lo = x - tf32(x) for this CTA's operand tiles, then tell the leader =====
+    const int st = threadIdx.x - (4 + EPI_WARPS) * 32;
+    int stage = 0; uint32_t phase = 0;
+    for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+      for (int kb = 0; kb < p.total_kb; ++kb) {
+        mbar_wait(full_bar + stage, phase);
+        const float4* hi = (const float4*)(stage_base + stage * S::STAGE_BYTES);
+        float4* lo = (float4*)(stage_base + stage * S::STAGE_BYTES + S::HI_BYTES);
+#pragma unroll 4
+        for (int i = st; i < S::HI_BYTES / 16; i += SPLIT_WARPS * 32) {
+          const float4 x = hi[i];
+          float4 l;
+          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          lo[i] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(mapa_rank(ready_bar + stage, 0));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // the peer may still read this CTA's shared memory / signal its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -529,6 +792,65 @@ static int dispatch(int bn, const CUtensorMap& ma, const CUtensorMap& mb, GemmPa
   }
 }
 
+
+static int g_pair = 1;        // 1 = use the CTA-pair kernel for large problems, 0 = never
+
+template <int BN, int STAGES, bool SPLIT>
+static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
+  using S = Gemm2Smem<BN, STAGES, SPLIT>;
+  static_assert(S::TOTAL <= 232448, "shared memory budget (227 KB)");
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm2_tf32_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return GED_ERR_LAUNCH;
+    attr_set = true;
+  }
+  p.num_m_tiles = cdiv(p.M, BM2);
+  p.num_n_tiles = cdiv(p.N, BN);
+  p.out_taps = 1; p.tap_dstride = 0; p.splits = 1;
+  p.total_kb = p.ntaps * p.kblocks_per_tap; p.kb_per_split = p.total_kb;
+  const int units = p.num_m_tiles * p.num_n_tiles;
+  const int max_clusters = g_num_sms / 2;
+  const int clusters = units < max_clusters ? units : max_clusters;
+  gemm2_tf32_kernel<BN, STAGES, SPLIT><<<2 * clusters, S::THREADS, S::TOTAL, stream>>>(ma, mb, p);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+// Pair-tile width: the widest of 256 / 192 / 128 that wastes <= 15 % of the columns; 0 = do not use the pair kernel.
+// Measured (tools/ab_pair.py): 1.3-1.5x for the 3xTF32 arithmetic at N >= 128 (shared-memory bound: the pair halves
+// the operand bytes each SM stages and re-reads); no gain for single-pass TF32 (already ~600 TFLOP/s on the wide
+// single-CTA tiles), for 64-column outputs (the A operand dominates) or for problems with fewer tiles than SM pairs.
+static int pick_bn_pair(int M, int N) {
+  if (!g_pair || g_precision != 3 || N < 128) return 0;
+  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  const int cands[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    const int n_tiles = cdiv(N, bn);
+    if ((int64_t)n_tiles * bn * 100 > (int64_t)N * 115) continue;
+    if ((int64_t)cdiv(M, BM2) * n_tiles < sms / 2) return 0;
+    return bn;
+  }
+  return 0;
+}
+
+static int dispatch2(int bn, const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
+  if (g_precision == 3) {
+    switch (bn) {
+      case 64: return launch_gemm2<64, 4, true>(ma, mb, p, stream);
+      case 128: return launch_gemm2<128, 4, true>(ma, mb, p, stream);
+      case 192: return launch_gemm2<192, 3, true>(ma, mb, p, stream);
+      default: return launch_gemm2<256, 3, true>(ma, mb, p, stream);
+    }
+  }
+  switch (bn) {
+    case 64: return launch_gemm2<64, 8, false>(ma, mb, p, stream);
+    case 128: return launch_gemm2<128, 8, false>(ma, mb, p, stream);
+    case 192: return launch_gemm2<192, 7, false>(ma, mb, p, stream);
+    default: return launch_gemm2<256, 6, false>(ma, mb, p, stream);
+  }
+}
+
 static int run(const float* A, int64_t a_rows, int lda, const float* Bw, int ldb, GemmParams& p, cudaStream_t stream) {
   if (!aligned16(A) || !aligned16(Bw) || (lda % 4) || (ldb % 4)) return GED_ERR_ALIGN;
   if (!g_num_sms) {
@@ -536,13 +858,20 @@ static int run(const float* A, int64_t a_rows, int lda, const float* Bw, int ldb
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int bn = pick_bn(p.M, p.N, g_precision == 3);
+  const int bn2 = pick_bn_pair(p.M, p.N);
+  const int bn = bn2 ? bn2 : pick_bn(p.M, p.N, g_precision == 3);
   CUtensorMap ma, mb;
   const int Kt = p.K / p.ntaps;
   if (int e = make_map_2d(&ma, A, a_rows, Kt, lda, BM)) return e;
-  if (int e = make_map_2d(&mb, Bw, p.N, p.K, ldb, bn)) return e;
+  if (!p.b_mn) {
+    if (int e = make_map_2d(&mb, Bw, p.N, p.K, ldb, bn2 ? bn2 / 2 : bn)) return e;
+  } else {      // [Kt rows][ntaps * b_tap_cols cols] as stored, 32-column panels
+    const int64_t cols = p.ntaps > 1 ? (int64_t)p.ntaps * p.b_tap_cols : p.N;
+    if (int e = make_map_2d(&mb, Bw, Kt, cols, ldb, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
+  }
   p.kblocks_per_tap = cdiv(Kt, BK);
   p.Kt = Kt;
+  if (bn2) return dispatch2(bn2, ma, mb, p, stream);
   return dispatch(bn, ma, mb, p, stream);
 }
 
@@ -575,6 +904,13 @@ GED_API int ged_set_gemm_precision(int passes) {
   return prev;
 }
 
+// 1 = CTA-pair (cta_group::2) kernel for large forward / dX problems (default), 0 = single-CTA kernels only.
+GED_API int ged_set_gemm_pair(int on) {
+  const int prev = g_pair;
+  g_pair = on ? 1 : 0;
+  return prev;
+}
+
 // 1 = allow 192/256-wide output tiles (default), 0 = at most 128.  Returns the previous setting.
 GED_API int ged_set_gemm_wide_tiles(int on) {
   const int prev = g_wide_tiles;
@@ -600,6 +936,34 @@ GED_API int ged_gemm_dw_tf32(const float* G, int ldg, const float* X, int ldx, f
   p.bias = nullptr; p.residual = nullptr; p.row_scale = nullptr; p.rows_per_batch = 1;
   p.D = D; p.D_pre = nullptr; p.ldd = ldd; p.act = 0; p.slope = 0.f; p.conv_Hp = 0; p.conv_Wp = 0;
   return run_dw(G, ldg, X, ldx, P, Px, p, stream);
+}
+
+// D[M,N] = A[M,K] @ Wt[K,N]: the dX GEMM of a linear layer / 1x1 conv reading the forward weight matrix
+// ([N_out = K][K_in = N], row pitch ldw) in place as an MN-major B operand - no transposed copy.
+GED_API int ged_gemm_tf32_bt(const float* A, int lda, const float* Wt, int ldw, float* D, int ldd, int M, int N,
+                             int K, cudaStream_t stream) {
+  if (!A || !Wt || !D || M <= 0 || N <= 0 || K <= 0) return GED_ERR_ARG;
+  if ((K % 4) || (N % 4)) return GED_ERR_SHAPE;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.ntaps = 1; p.tap_off[0] = 0; p.b_mn = 1; p.b_tap_cols = 0;
+  p.rows_per_batch = 1; p.D = D; p.ldd = ldd;
+  return run(A, M, lda, Wt, ldw, p, stream);
+}
+
+// dX of the 3x3/s1/p1 conv: DX[B,H,W,Cin] = sum_t Gpad[p - off_t, :] @ Wk[:, t, :] with Gpad the zero-bordered dY
+// [B,H+2,W+2,Cout] and Wk the FORWARD weights [Cout][3][3][Cin] read in place (MN-major B operand, one 32-column
+// panel set per tap) - no flipped / transposed weight copy.
+GED_API int ged_conv3x3_dx_tf32(const float* Gpad, const float* Wk, float* DX, int ldx, int B, int H, int W, int Cin,
+                                int Cout, cudaStream_t stream) {
+  if (!Gpad || !Wk || !DX || B <= 0 || H <= 0 || W <= 0) return GED_ERR_ARG;
+  if ((Cin % 4) || (Cout % 4)) return GED_ERR_SHAPE;
+  const int Hp = H + 2, Wp = W + 2;
+  GemmParams p{};
+  p.M = B * Hp * Wp; p.N = Cin; p.K = 9 * Cout; p.ntaps = 9; p.b_mn = 1; p.b_tap_cols = Cin;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) p.tap_off[ky * 3 + kx] = -((ky - 1) * Wp + (kx - 1));
+  p.rows_per_batch = 1; p.D = DX; p.ldd = ldx; p.conv_Hp = Hp; p.conv_Wp = Wp;
+  return run(Gpad, (int64_t)p.M, Cout, Wk, 9 * Cin, p, stream);
 }
 
 // D[M,N] = epi(A[M,K] @ W[N,K]^T).  A row pitch lda, W row pitch ldw, D/residual row pitch ldd (floats).

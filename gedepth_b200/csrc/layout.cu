@@ -174,6 +174,30 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
   }
 }
 
+// General im2col for a strided / padded conv on NCHW planes: tok[(b,oy,ox)][k], k = (c*kh + ky)*kw + kx < Cin*kh*kw in
+// Conv2d weight order, zero for taps outside the image and for the padding columns k >= Cin*kh*kw (row pitch Kp, a
+// multiple of 4 so the rows are TMA-addressable).  Turns the 7x7/s2/p3 stem conv (depthformer_swin.py:1032-1039,
+// K = 147 -> Kp = 148) into a tcgen05 GEMM.
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ img, int64_t bstride,
+                                                      float* __restrict__ tok, int Cin, int H, int W, int kh, int kw,
+                                                      int stride, int pad, int Ho, int Wo, int Kp, int64_t total) {
+  const int K = Cin * kh * kw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kp);
+    int64_t t = i / Kp;
+    const int ox = (int)(t % Wo); t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float v = 0.f;
+    if (k < K) {
+      const int c = k / (kh * kw), r = k - c * kh * kw, ky = r / kw, kx = r - ky * kw;
+      const int y = oy * stride - pad + ky, x = ox * stride - pad + kx;
+      if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(img + b * bstride + ((int64_t)c * H + y) * W + x);
+    }
+    tok[i] = v;
+  }
+}
+
 // x (B, H, W, C) tokens -> (B, ceil(H/2)*ceil(W/2), 4C) in nn.Unfold(2,2) order: feature = c*4 + ky*2 + kx
 // (depthformer_swin.py:86,115; zero padding bottom/right for odd sizes :110-111).  dir=1: backward (scatter = gather).
 __global__ void __launch_bounds__(256) merge_patches_kernel(const float* __restrict__ src, float* __restrict__ dst,
@@ -274,6 +298,19 @@ GED_API int ged_patchify(const float* img, int64_t batch_stride, float* tok, int
   const int DH = cdiv(H, P), DW = cdiv(W, P);
   const int64_t total = (int64_t)B * DH * DW * Cin * P * P;
   patchify_kernel<<<grid_for(total), 256, 0, stream>>>(img, batch_stride, tok, Cin, H, W, P, DH, DW, total);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+// tok (B*Ho*Wo, Kp) from channels [0,Cin) of an NCHW batch (batch stride in floats); Ho = (H+2p-kh)/s+1.
+GED_API int ged_im2col(const float* img, int64_t batch_stride, float* tok, int B, int Cin, int H, int W, int kh, int kw,
+                       int stride, int pad, int Kp, cudaStream_t stream) {
+  if (!img || !tok || B <= 0 || Cin <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0) return GED_ERR_ARG;
+  if (Kp < Cin * kh * kw || (Kp & 3)) return GED_ERR_SHAPE;
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  if (Ho <= 0 || Wo <= 0) return GED_ERR_SHAPE;
+  const int64_t total = (int64_t)B * Ho * Wo * Kp;
+  im2col_kernel<<<grid_for(total), 256, 0, stream>>>(img, batch_stride, tok, Cin, H, W, kh, kw, stride, pad, Ho, Wo, Kp, total);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }

@@ -48,12 +48,16 @@ SIGNATURES = {
     "ged_bn_train_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
     "ged_patchify": [_P, _I64, _P, _I, _I, _I, _I, _I, _P],
     "ged_merge_patches": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "ged_im2col": [_P, _I64, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_clamp_resize": [_P, _P, _I, _I, _I, _I, _I, _F, _F, _P],
     "ged_conv3x3_tf32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _F, _P],
     "ged_msda_fwd": [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_msda_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ged_gemm_tf32_bt": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P],
+    "ged_conv3x3_dx_tf32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ged_set_gemm_precision": [_I],
     "ged_set_gemm_wide_tiles": [_I],
+    "ged_set_gemm_pair": [_I],
     "ged_set_msda_variant": [_I],
     "ged_gemm_dw_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I64, _I64, _I, _P, _I, _P],
     "ged_sumsq": [_P, _I64, _P, _P],
@@ -88,6 +92,8 @@ def load():
     _lib = lib
     if os.environ.get("GEDEPTH_GEMM_PASSES"):
         lib.ged_set_gemm_precision(int(os.environ["GEDEPTH_GEMM_PASSES"]))
+    if os.environ.get("GEDEPTH_GEMM_PAIR"):
+        lib.ged_set_gemm_pair(int(os.environ["GEDEPTH_GEMM_PAIR"]))
     if os.environ.get("GEDEPTH_MSDA_VARIANT"):
         lib.ged_set_msda_variant(int(os.environ["GEDEPTH_MSDA_VARIANT"]))
     return lib
@@ -127,6 +133,15 @@ def _call(name, *args):
     LAUNCHES += 1
     if rc != 0:
         raise RuntimeError(f"{name} failed: {_ERR.get(rc, rc)}")
+
+
+def _sink(p):
+    """The running-gradient buffer of a parameter that lives in train.FlatArena (marked ``_ged_sink``), or None.
+    Backward kernels that ACCUMULATE (weight-gradient GEMM, bias/LayerNorm/relative-position column sums) then add
+    straight into the arena and return no gradient to autograd: no per-parameter zero-fill, no `grad += dw` pass."""
+    if p is None or not getattr(p, "_ged_sink", False) or p.grad is None or not torch.is_grad_enabled():
+        return None
+    return p.grad
 
 
 def _stream():
@@ -361,7 +376,8 @@ def cross_entropy(logits, target, ignore_index=255):
 # =============================================================================================
 class _LayerNorm(Function):
     @staticmethod
-    def forward(ctx, x, w, b, eps):
+    def forward(ctx, x, w, b, eps, w_sink=None, b_sink=None):
+        ctx.sinks = (w_sink, b_sink) if (w_sink is not None and b_sink is not None) else None
         xc = _f32c(x)
         Cc = xc.shape[-1]
         rows = xc.numel() // Cc
@@ -380,21 +396,26 @@ class _LayerNorm(Function):
         g = _f32c(g)
         dx = torch.empty_like(xc)
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        if need_w and ctx.sinks is not None:
+            _call("ged_layernorm_bwd", _p(g), _p(xc), _p(w), _p(mean), _p(rstd), _p(dx), _p(ctx.sinks[0]), _p(ctx.sinks[1]),
+                  rows, Cc, _stream())
+            return dx, None, None, None, None, None
         dw = torch.zeros(Cc, dtype=torch.float32, device=xc.device) if need_w else None
         db = torch.zeros_like(dw) if need_w else None
         _call("ged_layernorm_bwd", _p(g), _p(xc), _p(w), _p(mean), _p(rstd), _p(dx), _p(dw), _p(db), rows, Cc, _stream())
-        return dx, dw, db, None
+        return dx, dw, db, None, None, None
 
 
 def layer_norm(x, w, b, eps):
     if x.shape[-1] % 4:
         return L.layer_norm(x, w, b, eps)
-    return _LayerNorm.apply(x, w, b, eps)
+    return _LayerNorm.apply(x, w, b, eps, _sink(w), _sink(b))
 
 
 class _WinAttn(Function):
     @staticmethod
-    def forward(ctx, qkv, qkv_bias, table, index, H, W, nH, ws, shift, scale):
+    def forward(ctx, qkv, qkv_bias, table, index, H, W, nH, ws, shift, scale, bias_sink=None, table_sink=None):
+        ctx.sinks = (bias_sink, table_sink)
         qkv = _f32c(qkv)
         B, Lt, C3 = qkv.shape
         Cc = C3 // 3
@@ -414,15 +435,21 @@ class _WinAttn(Function):
         B, H, W, Cc, nH, ws, shift, scale, has_bias = ctx.cfg
         g = _f32c(g)
         g_qkv = torch.empty_like(qkv)
-        g_table = torch.zeros_like(table)
-        g_bias = torch.zeros(3 * Cc, dtype=torch.float32, device=qkv.device) if has_bias else None
+        bias_sink, table_sink = ctx.sinks
+        g_table = table_sink if table_sink is not None else torch.zeros_like(table)
+        g_bias = None
+        if has_bias:
+            g_bias = bias_sink if bias_sink is not None else torch.zeros(3 * Cc, dtype=torch.float32, device=qkv.device)
         _call("ged_winattn_bwd", _p(qkv), _p(bias if has_bias else None), _p(table), _p(idx), _p(g), _p(g_qkv),
               _p(g_bias), _p(g_table), B, H, W, Cc, nH, ws, shift, scale, _stream())
-        return g_qkv, g_bias, g_table, None, None, None, None, None, None, None
+        return (g_qkv, None if bias_sink is not None else g_bias, None if table_sink is not None else g_table,
+                None, None, None, None, None, None, None, None, None)
 
 
 def window_attention(qkv, qkv_bias, table, index, hw, nH, ws, shift, scale):
-    return _WinAttn.apply(qkv, qkv_bias, table, index, int(hw[0]), int(hw[1]), nH, ws, shift, scale)
+    ts = _sink(table)
+    ts = ts if (ts is not None and ts.is_contiguous() and table.is_contiguous()) else None
+    return _WinAttn.apply(qkv, qkv_bias, table, index, int(hw[0]), int(hw[1]), nH, ws, shift, scale, _sink(qkv_bias), ts)
 
 
 # =============================================================================================
@@ -450,6 +477,11 @@ def gemm(a2d: torch.Tensor, w: torch.Tensor, bias=None, act=None, slope=0.01, re
 DW_MODE = int(os.environ.get("GEDEPTH_DW_MODE", "1"))
 
 
+def set_gemm_pair(on: bool) -> int:
+    """CTA-pair (cta_group::2) GEMM kernel for large problems on/off; returns the previous setting."""
+    return load().ged_set_gemm_pair(int(bool(on)))
+
+
 def set_gemm_wide_tiles(on: bool) -> int:
     return load().ged_set_gemm_wide_tiles(int(bool(on)))
 
@@ -469,13 +501,32 @@ def gemm_dw(g2d: torch.Tensor, x2d: torch.Tensor, out: Optional[torch.Tensor] = 
     return out
 
 
+def gemm_bt(a2d: torch.Tensor, wt: torch.Tensor) -> torch.Tensor:
+    """a2d[M,K] @ wt[K,N] with wt read in place (the dX GEMM: grad_output @ weight)."""
+    M, K = a2d.shape
+    N = wt.shape[1]
+    assert wt.shape[0] == K and a2d.stride(1) == 1 and wt.stride(1) == 1
+    out = torch.empty(M, N, dtype=torch.float32, device=a2d.device)
+    _call("ged_gemm_tf32_bt", _p(a2d), a2d.stride(0), _p(wt), wt.stride(0), _p(out), N, M, N, K, _stream())
+    return out
+
+
+def conv3x3_dx(gzp: torch.Tensor, wk: torch.Tensor) -> torch.Tensor:
+    """gzp (B,H+2,W+2,Cout) zero-bordered dY, wk [Cout,3,3,Cin] forward weights -> dX (B,H,W,Cin)."""
+    B, Hp, Wp, Cout = gzp.shape
+    Cin = wk.shape[3]
+    dx = torch.empty(B, Hp - 2, Wp - 2, Cin, dtype=torch.float32, device=gzp.device)
+    _call("ged_conv3x3_dx_tf32", _p(gzp), _p(wk), _p(dx), Cin, B, Hp - 2, Wp - 2, Cin, Cout, _stream())
+    return dx
+
+
 def _dw_ok(N, K, *tensors):
     return DW_MODE == 1 and N % 4 == 0 and K % 4 == 0 and N >= 16 and K >= 16 and all(
         t.dtype == torch.float32 and t.data_ptr() % 16 == 0 for t in tensors)
 
 
 def act_bwd(g2d: torch.Tensor, ref: Optional[torch.Tensor], act, slope=0.01, row_scale=None, rows_per_batch=1,
-            want_db=False):
+            want_db=False, db_sink: Optional[torch.Tensor] = None):
     """gz = g * act'(ref) * row_scale and (optionally) db = column sums of gz, in ONE pass.  With no
     activation and no scale gz is g itself and only the column sums are computed."""
     rows, N = g2d.shape
@@ -483,10 +534,12 @@ def act_bwd(g2d: torch.Tensor, ref: Optional[torch.Tensor], act, slope=0.01, row
     if ident and not want_db:
         return g2d, None
     gz = g2d if ident else torch.empty_like(g2d)
-    db = torch.zeros(N, dtype=torch.float32, device=g2d.device) if want_db else None
+    db = None
+    if want_db:
+        db = db_sink if db_sink is not None else torch.zeros(N, dtype=torch.float32, device=g2d.device)
     _call("ged_act_bwd", _p(g2d), _p(ref), _p(None if ident else gz), _p(db), _p(row_scale), int(rows_per_batch), rows,
           N, _ACT[act], float(slope), _stream())
-    return gz, db
+    return gz, (None if db_sink is not None else db)
 
 
 def _act_grad(gz, act, slope, pre, post):
@@ -519,7 +572,8 @@ class _Linear(Function):
     the bias gradient are one fused pass; dW = gz^T @ x is a cuBLAS TF32 GEMM for now."""
 
     @staticmethod
-    def forward(ctx, x, w, b, act, residual, row_scale):
+    def forward(ctx, x, w, b, act, residual, row_scale, w_sink=None, b_sink=None):
+        ctx.w_sink, ctx.b_sink = w_sink, b_sink
         K = x.shape[-1]
         x2 = _f32c(x).reshape(-1, K)
         M, N = x2.shape[0], w.shape[0]
@@ -548,27 +602,30 @@ class _Linear(Function):
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
         ref = pre if ctx.act == "gelu" else (post if ctx.act is not None else None)
         if N % 4 == 0:
-            gz, db = act_bwd(g2, ref, ctx.act, 0.01, row_scale if row_scale.numel() else None, ctx.rpb, want_db)
+            gz, db = act_bwd(g2, ref, ctx.act, 0.01, row_scale if row_scale.numel() else None, ctx.rpb, want_db,
+                             ctx.b_sink)
         else:
             gz = g2 if not row_scale.numel() else g2 * row_scale.repeat_interleave(ctx.rpb).unsqueeze(1)
             gz = _act_grad(gz, ctx.act, 0.01, pre, post).contiguous()
             db = gz.sum(0) if want_db else None
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            wt = w.t().contiguous()                      # [K, N]: the [N'][K'] operand of dX = gz @ w
-            if _gemm_ok(gz.shape[0], K, N, gz, wt):
+            if _gemm_ok(gz.shape[0], K, N, gz, w) and w.stride(1) == 1:
                 with _bwd_precision():
-                    dx = gemm(gz, wt).reshape(ctx.xshape)
+                    dx = gemm_bt(gz, w).reshape(ctx.xshape)      # w [N][K] read in place as the [K'][N'] operand
             else:
                 dx = (gz @ w).reshape(ctx.xshape)
         if ctx.needs_input_grad[1]:
             if _dw_ok(N, K, gz, x2):
                 with _bwd_precision():
-                    dw = gemm_dw(gz, x2)
+                    if ctx.w_sink is not None:
+                        gemm_dw(gz, x2, out=ctx.w_sink)
+                    else:
+                        dw = gemm_dw(gz, x2)
             else:
                 dw = gz.t() @ x2
         dres = g if ctx.has_res else None
-        return dx, dw, db, None, dres, None
+        return dx, dw, db, None, dres, None, None, None
 
 
 def linear(x, w, b=None, act=None, residual=None, row_scale=None):
@@ -576,7 +633,9 @@ def linear(x, w, b=None, act=None, residual=None, row_scale=None):
     M = x.numel() // K
     if not _gemm_ok(M, N, K, x, w, b, residual) or act not in _ACT:
         return L.linear(x, w, b, act, residual, row_scale)
-    return _Linear.apply(x, w, b, act, residual, row_scale)
+    ws = _sink(w)
+    ws = ws if (ws is not None and ws.is_contiguous()) else None
+    return _Linear.apply(x, w, b, act, residual, row_scale, ws, _sink(b))
 
 
 # =============================================================================================
@@ -626,7 +685,8 @@ class _Conv(Function):
     transposed kernel); activation derivative + bias gradient one fused pass; dW via cuDNN for now."""
 
     @staticmethod
-    def forward(ctx, x0, x1, w, b, act, slope):
+    def forward(ctx, x0, x1, w, b, act, slope, w_sink=None, b_sink=None):
+        ctx.w_sink, ctx.b_sink = w_sink, b_sink
         Cout, Cin, kh, kw = w.shape
         a0 = _nhwc(x0)
         a1 = None if x1 is None else _nhwc(x1)
@@ -656,7 +716,7 @@ class _Conv(Function):
         db = None
         if Cout % 4 == 0:
             gz2, db = act_bwd(gh.reshape(-1, Cout), y.reshape(-1, Cout) if act is not None else None, act, slope,
-                              None, 1, want_db)
+                              None, 1, want_db, ctx.b_sink)
             gz = gz2.reshape(B, H, W, Cout)
         else:
             gz = _act_grad(gh, act, slope, None, y)
@@ -671,24 +731,29 @@ class _Conv(Function):
             gzp = prep_conv_input(gz, None, H, W)                            # zero-bordered dY, shared by dX and dW
         if need_dx:
             if kh == 3 and Cout % 32 == 0:
-                wt = w.flip(2, 3).permute(1, 2, 3, 0).contiguous()          # [Cin,3,3,Cout]
+                wk = w.permute(0, 2, 3, 1)                                   # [Cout,3,3,Cin]: a view inside the arena
                 with _bwd_precision():
-                    dxc = conv3x3_padded(gzp, wt, None, None, 0.0)            # (B,H,W,Cin)
+                    dxc = conv3x3_dx(gzp, wk if wk.is_contiguous() else wk.contiguous())   # (B,H,W,Cin)
             elif kh == 1 and _gemm_ok(B * H * W, Cin, Cout, gz):
                 with _bwd_precision():
-                    dxc = gemm(gz.reshape(-1, Cout), w.reshape(Cout, Cin).t().contiguous()).reshape(B, H, W, Cin)
+                    dxc = gemm_bt(gz.reshape(-1, Cout), w.reshape(Cout, Cin)).reshape(B, H, W, Cin)
         if dw_native:
             with _bwd_precision():
+                # the arena keeps conv weights / gradients channels-last ([Cout][kh][kw][Cin]): accumulate in place
+                sink = None if ctx.w_sink is None else ctx.w_sink.permute(0, 2, 3, 1)
                 if kh == 3:
                     Wp = W + 2
                     taps = [(ky - 1) * Wp + (kx - 1) for ky in range(3) for kx in range(3)]
-                    dwk = gemm_dw(gzp.reshape(-1, Cout), xin.reshape(-1, Cin), None, taps)    # [Cout, 9, Cin]
-                    dw = dwk.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+                    dwk = gemm_dw(gzp.reshape(-1, Cout), xin.reshape(-1, Cin),
+                                  None if sink is None else sink.view(Cout, 9, Cin), taps)    # [Cout, 9, Cin]
+                    dw = None if sink is not None else dwk.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
                 else:
-                    dw = gemm_dw(gz.reshape(-1, Cout), xin.reshape(-1, Cin)).reshape(Cout, Cin, 1, 1)
+                    dwk = gemm_dw(gz.reshape(-1, Cout), xin.reshape(-1, Cin), None if sink is None else sink.view(Cout, Cin))
+                    dw = None if sink is not None else dwk.reshape(Cout, Cin, 1, 1)
+                need_dw = False
         pad = 0                                     # xin already carries the zero border for 3x3
         xin_nchw = xin.permute(0, 3, 1, 2)
-        mask = [need_dx and dxc is None, need_dw and dw is None, False]
+        mask = [need_dx and dxc is None, need_dw, False]
         if any(mask):
             r = torch.ops.aten.convolution_backward(gz.permute(0, 3, 1, 2), xin_nchw, w, None, [1, 1], [pad, pad],
                                                     [1, 1], False, [0, 0], 1, mask)
@@ -709,16 +774,23 @@ class _Conv(Function):
                     dx0 = d0.permute(0, 3, 1, 2)
                 else:
                     dx0 = (dxc[..., :C0] if C1 is not None else dxc).permute(0, 3, 1, 2)
-        return dx0, dx1, dw, db, None, None
+        return dx0, dx1, dw, db, None, None, None, None
+
+
+def _conv_apply(x0, x1, w, b, act, slope):
+    ws = _sink(w)
+    if ws is not None and not ws.permute(0, 2, 3, 1).is_contiguous():
+        ws = None
+    return _Conv.apply(x0, x1, w, b, act, slope, ws, _sink(b))
 
 
 def conv2d(x, w, b=None, stride=1, padding=0, act=None, slope=0.01):
-    return _Conv.apply(x, None, w, b, act, slope)
+    return _conv_apply(x, None, w, b, act, slope)
 
 
 def conv2d_cat(x0, x1, w, b=None, act=None, slope=0.01):
     """3x3 conv over cat([bilinear(x0 -> size of x1, align_corners=True), x1], channels)."""
-    return _Conv.apply(x0, x1, w, b, act, slope)
+    return _conv_apply(x0, x1, w, b, act, slope)
 
 
 def conv2d_cat_supported(x0, x1, w) -> bool:
@@ -736,13 +808,13 @@ def conv_bn_act(x, w, b, bn, stride=1, padding=0, act=None):
 
 def conv_bn_act_cat(x0, x1, w, b, bn, act=None):
     if bn is None:
-        return _Conv.apply(x0, x1, w, b, act, 0.01)
+        return _conv_apply(x0, x1, w, b, act, 0.01)
     if not bn.training:
         s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
         wf = w * s.view(-1, 1, 1, 1)
         bf = bn.bias - bn.running_mean * s + (b * s if b is not None else 0)
         return _Conv.apply(x0, x1, wf, bf, act, 0.01)
-    y = _Conv.apply(x0, x1, w, b, None, 0.0)
+    y = _conv_apply(x0, x1, w, b, None, 0.0)
     if act in (None, "relu") and y.shape[1] % 4 == 0 and bn.momentum is not None and bn.track_running_stats:
         return bn_act_train(y, bn, relu=act == "relu")
     return L._act(bn(y), act)
@@ -824,6 +896,30 @@ def patch_embed(x, w, b, patch):
     tok = torch.empty(B, DH * DW, K, dtype=torch.float32, device=x.device)
     _call("ged_patchify", _p(x), x.stride(0), _p(tok), B, Cin, H, W, patch, _stream())
     return linear(tok, w.reshape(w.shape[0], K), b), (DH, DW)
+
+
+def conv_im2col_supported(x, w, stride, padding) -> bool:
+    """Strided / large-kernel convs on an input that needs no gradient (the 7x7/s2 RGB stem)."""
+    Cout, Cin, kh, kw = w.shape
+    return (x.dtype == torch.float32 and not x.requires_grad and x.stride(3) == 1 and x.stride(2) == x.shape[3]
+            and x.stride(1) == x.shape[2] * x.shape[3] and Cout % 4 == 0 and Cout >= 16 and Cin * kh * kw >= 32)
+
+
+def conv_im2col(x, w, b, stride, padding, act=None, slope=0.01):
+    """conv2d as im2col (one gather pass) + tcgen05 GEMM; returns logical NCHW in channels-last memory.
+    The weight gradient comes back through the GEMM's dW kernel; x gets no gradient."""
+    B, Cin, H, W = x.shape
+    Cout, _, kh, kw = w.shape
+    K = Cin * kh * kw
+    Kp = (K + 3) // 4 * 4
+    Ho, Wo = (H + 2 * padding - kh) // stride + 1, (W + 2 * padding - kw) // stride + 1
+    tok = torch.empty(B * Ho * Wo, Kp, dtype=torch.float32, device=x.device)
+    _call("ged_im2col", _p(x), x.stride(0), _p(tok), B, Cin, H, W, kh, kw, stride, padding, Kp, _stream())
+    w2 = w.reshape(Cout, K)
+    if Kp != K:
+        w2 = torch.nn.functional.pad(w2, (0, Kp - K))
+    y = linear(tok, w2, b, act)
+    return y.view(B, Ho, Wo, Cout).permute(0, 3, 1, 2)
 
 
 class _MergePatches(Function):

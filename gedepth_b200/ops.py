@@ -66,9 +66,20 @@ def conv_bn_act(x, w, b, bn, stride=1, padding=0, act=None):
     require_cuda(x, w)
     if use_native("conv_bn_act") and _k().conv2d_supported(x, w, stride, padding):
         return _k().conv_bn_act(x, w, b, bn, stride, padding, act)
+    if use_native("conv_bn_act") and _k().conv_im2col_supported(x, w, stride, padding):
+        # stem 7x7/s2 conv on the RGB planes (K = 147): im2col gather + tcgen05 GEMM, then BN (+ReLU)
+        if bn is None:
+            return _k().conv_im2col(x, w, b, stride, padding, act)
+        if not bn.training:
+            s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+            bf = bn.bias - bn.running_mean * s + (b * s if b is not None else 0)
+            return _k().conv_im2col(x, w * s.view(-1, 1, 1, 1), bf, stride, padding, act)
+        y = _k().conv_im2col(x, w, b, stride, padding, None)
+        if act in (None, "relu") and bn.momentum is not None and bn.track_running_stats and use_native("batch_norm"):
+            return _k().bn_act_train(y, bn, relu=act == "relu")
+        return L._act(bn(y), act)
     if (bn is not None and bn.training and use_native("batch_norm") and w.shape[0] % 4 == 0 and act in (None, "relu")
             and bn.momentum is not None and bn.track_running_stats):
-        # stem 7x7/s2 conv (K = 147): library conv, native train-mode BN + ReLU
         return _k().bn_act_train(L.conv2d(x, w, b, stride, padding), bn, relu=act == "relu")
     return L.conv_bn_act(x, w, b, bn, stride, padding, act)
 

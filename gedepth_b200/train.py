@@ -35,13 +35,25 @@ class FlatArena:
         self.wd_mask = torch.ones(self.total, dtype=torch.uint8, device=dev)
         off = 0
         for (n, p), sz in zip(params, sizes):
-            view = self.flat_p[off:off + p.numel()].view_as(p)
+            view = self._segment(self.flat_p, off, p)
             view.copy_(p.data)
             p.data = view
-            p.grad = self.flat_g[off:off + p.numel()].view_as(p)
+            p.grad = self._segment(self.flat_g, off, p)
+            p._ged_sink = True            # backward kernels accumulate straight into p.grad (kernels._sink)
             if any(k in n for k in NO_DECAY_KEYS):
                 self.wd_mask[off:off + sz] = 0
             off += sz
+
+    @staticmethod
+    def _segment(flat, off, p):
+        """View of one parameter inside a flat buffer.  4-D conv weights are kept channels-last in memory
+        ([Cout][kh][kw][Cin] - the layout the implicit-GEMM conv and its weight-gradient kernel use), exposed with
+        the logical (Cout, Cin, kh, kw) shape, so state_dict() shapes are the reference's."""
+        seg = flat[off:off + p.numel()]
+        if p.dim() == 4:
+            co, ci, kh, kw = p.shape
+            return seg.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+        return seg.view_as(p)
 
     def zero_grad(self):
         self.flat_g.zero_()
@@ -92,6 +104,7 @@ class Trainer:
                 self.step(self._static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()      # the eager warm-up's activation blocks would otherwise sit beside the graph's pool
         self._graph = torch.cuda.CUDAGraph()
         n0 = kernels.LAUNCHES
         with torch.cuda.graph(self._graph):
@@ -100,6 +113,13 @@ class Trainer:
         self.launches_per_step = kernels.LAUNCHES - n0
         self.step_idx -= 1            # the capture pass itself does not execute
         return self
+
+    def release_graph(self):
+        """Drop the captured graph and its private memory pool (shapes may change afterwards)."""
+        self._graph = None
+        self._static_loss = None
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
 
     def step_graph(self, data_batch: Optional[Dict] = None):
         """Replay the captured step.  Tensors of ``data_batch`` are copied into the static inputs first

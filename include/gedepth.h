@@ -127,10 +127,21 @@ int ged_bn_train_bwd(const float* g, const float* x, const float* y, const float
 int ged_gemm_tf32(const float* A, int lda, const float* W, int ldw, float* D, int ldd, int M, int N,
                   int K, const float* bias, int act, float slope, const float* residual,
                   const float* row_scale, int rows_per_batch, float* D_pre, cudaStream_t stream);
+/* dX of a linear / 1x1 conv: D[M,N] = A[M,K] @ Wt[K,N], Wt = the forward weight [N_out=K][K_in=N] read in place
+ * as an MN-major UMMA operand (no transposed copy; torch.autograd's grad_output @ weight). */
+int ged_gemm_tf32_bt(const float* A, int lda, const float* Wt, int ldw, float* D, int ldd, int M, int N, int K,
+                     cudaStream_t stream);
+/* dX of the 3x3/s1/p1 conv from the zero-bordered dY [B,H+2,W+2,Cout] and the FORWARD weights [Cout][3][3][Cin]
+ * read in place (cuDNN dgrad in the reference); DX [B,H,W,*] with channel pitch ldx. */
+int ged_conv3x3_dx_tf32(const float* Gpad, const float* Wk, float* DX, int ldx, int B, int H, int W, int Cin,
+                        int Cout, cudaStream_t stream);
 /* Process-wide GEMM/conv arithmetic: 3 (default) = error-compensated 3xTF32 (each fp32 operand split into
  * tf32 hi + lo, three tcgen05 MMAs per k-step: fp32-accurate, the parity mode); 1 = single-pass TF32 (what
  * PyTorch 1.8 / cuDNN run by default on Ampere+ for the reference).  Returns the previous value. */
 int ged_set_gemm_precision(int passes);
+/* 1 (default) = large forward / dX problems run on CTA pairs (tcgen05 cta_group::2: a 256 x BN tile per two SMs,
+ * each staging half of the operands), 0 = single-CTA kernels only.  Returns the previous value. */
+int ged_set_gemm_pair(int on);
 /* 1 (default) = allow 192/256-column output tiles, 0 = at most 128.  Returns the previous value. */
 int ged_set_gemm_wide_tiles(int on);
 /* Weight gradients (autograd of every nn.Linear / Conv2d on the path; the reference gets them from cuBLAS /
@@ -167,6 +178,11 @@ int ged_act_bwd(const float* g, const float* ref, float* gz, float* db, const fl
  * padded bottom/right (embed.py:282-297): the patch-embedding conv becomes ged_gemm_tf32. */
 int ged_patchify(const float* img, int64_t batch_stride, float* tok, int B, int Cin, int H, int W, int P,
                  cudaStream_t stream);
+/* im2col of a strided/padded conv over channels [0,Cin) of an NCHW batch: tok (B*Ho*Wo, Kp), column
+ * k = (c*kh+ky)*kw+kx (Conv2d weight order), zeros outside the image and in columns >= Cin*kh*kw (Kp % 4 == 0).
+ * The 7x7/s2/p3 stem conv (depthformer_swin.py:1032-1039, 1152) becomes ged_gemm_tf32 with K = 148. */
+int ged_im2col(const float* img, int64_t batch_stride, float* tok, int B, int Cin, int H, int W, int kh, int kw,
+               int stride, int pad, int Kp, cudaStream_t stream);
 /* nn.Unfold(2,2) gather of PatchMerging (depthformer_swin.py:98-117): (B,H,W,C) -> (B,ceil(H/2)*ceil(W/2),4C),
  * feature = c*4 + ky*2 + kx; backward=1 applies the adjoint. */
 int ged_merge_patches(const float* src, float* dst, int B, int H, int W, int C, int backward, cudaStream_t stream);

@@ -145,6 +145,40 @@ def test_cuda_graph_step_equals_eager_steps():
     assert float((d > 5e-5).float().mean()) < 1e-3                # Adam sign flips on round-off gradients only
 
 
+@pytest.mark.parametrize("name", ["vanilla_train", "adaptive_train"])
+def test_arena_gradient_sinks_equal_autograd_accumulation(name):
+    """With train.FlatArena the backward kernels add weight / bias / LayerNorm / rel-pos-bias gradients straight
+    into the flat gradient buffer (conv weights channels-last) and hand autograd nothing; the result must be the
+    gradient plain autograd accumulation gives on the same model."""
+    from gedepth_b200.train import FlatArena
+    case, g, b = load_case(name)
+    data = dict(img=torch.from_numpy(b["img"]).to(DEV), img_metas=metas_for(case),
+                depth_gt=torch.from_numpy(b["depth_gt"]).to(DEV))
+    if "pe_k_gt" in b:
+        data["pe_k_gt"] = torch.from_numpy(b["pe_k_gt"]).to(DEV)
+    grads = {}
+    for mode in ("autograd", "arena"):
+        model, _ = build_host_model(case, DEV)
+        model.train()
+        arena = FlatArena(model) if mode == "arena" else None
+        if arena is not None:
+            arena.zero_grad()
+            w = dict(model.named_parameters())["decode_head.conv_list.1.convA.conv.weight"]
+            assert w.shape[2:] == (3, 3) and w.permute(0, 2, 3, 1).is_contiguous()      # channels-last inside the arena
+        model.train_step(data, None)["loss"].backward()
+        grads[mode] = {n: p.grad.detach().clone().contiguous() for n, p in model.named_parameters()}
+        if arena is not None:
+            assert float(arena.flat_g.abs().sum()) > 0
+    top = max(float(v.abs().max()) for v in grads["autograd"].values())
+    for n, ga in grads["autograd"].items():
+        if n in ZERO_GRAD_KEYS:
+            continue
+        gb = grads["arena"][n]
+        assert ga.shape == gb.shape, n
+        tol = 3e-3 * float(ga.abs().max()) + 1e-6 * top     # atomics-order round-off, amplified through 12 blocks of backward
+        assert float((ga - gb).abs().max()) <= tol, (n, float((ga - gb).abs().max()), float(ga.abs().max()))
+
+
 def test_product_fails_loudly_without_extension(monkeypatch):
     from gedepth_b200 import kernels
     monkeypatch.setattr(kernels, "_lib", None)

@@ -299,6 +299,59 @@ def test_conv3x3_dw_taps(B, H, W, Cin, Cout, passes):
     _close(dw, ref, 0, _gemm_tol(ref, passes, B * H * W) * (3.0 if passes == 1 else 1.0), "conv dW")
 
 
+@pytest.mark.parametrize("M,N,K", [(24640, 384, 96), (40000, 512, 512), (33000, 256, 96), (20000, 64, 64), (19000, 1536, 384),
+                                   (50001, 288, 100), (70000, 96, 384)])
+def test_gemm_pair_kernel(M, N, K, passes):
+    """CTA-pair (cta_group::2) kernel: large problems, all epilogue features, against fp64 and against the
+    single-CTA kernel."""
+    from gedepth_b200 import kernels as Kn, ops_lib as L
+    g = torch.Generator().manual_seed(41)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    rs = (torch.rand(4, generator=g) + 0.5).to(DEV)
+    rpb = -(-M // 4)
+    ref = L._act((a.double() @ w.double().t() + bias.double()).float(), "gelu")
+    ref = ref * rs.repeat_interleave(rpb)[:M].unsqueeze(1) + res
+    outs = {}
+    for pair in (1, 0):
+        prev = Kn.set_gemm_pair(pair)
+        try:
+            outs[pair] = Kn.gemm(a, w, bias, "gelu", 0.01, res, rs, rpb)
+        finally:
+            Kn.set_gemm_pair(prev)
+        _close(outs[pair], ref, 0, _gemm_tol(ref, passes, K), f"pair={pair} gemm {M}x{N}x{K}")
+    _close(outs[1], outs[0], 0, 2e-6 * float(ref.abs().max()) + 1e-6, "pair vs single-CTA")
+    # dX form: B operand [K][N] read in place (MN-major)
+    if N % 4 == 0 and K % 4 == 0:
+        wt = (torch.randn(K, N, generator=g) / K ** 0.5).to(DEV)
+        out = Kn.gemm_bt(a, wt)
+        ref2 = (a.double() @ wt.double()).float()
+        _close(out, ref2, 0, _gemm_tol(ref2, passes, K), f"gemm_bt {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(4, 64, 160, 64, 64), (2, 44, 140, 96, 192), (2, 88, 280, 128, 32)])
+def test_conv3x3_pair_kernel(B, H, W, Cin, Cout, passes):
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(B, H, W, Cin, generator=g).to(DEV)
+    wk = (torch.randn(Cout, 3, 3, Cin, generator=g) / (9 * Cin) ** 0.5).to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    xp = Kn.prep_conv_input(x, None, H, W)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), wk.permute(0, 3, 1, 2).double(), bias.double(), padding=1).permute(0, 2, 3, 1).float()
+    y = Kn.conv3x3_padded(xp, wk, bias, None, 0.0)
+    _close(y, ref, 0, _gemm_tol(ref, passes, 9 * Cin), "conv fwd (pair)")
+    # dX from the forward weights in place
+    gy = torch.randn(B, H, W, Cout, generator=g).to(DEV)
+    gp = Kn.prep_conv_input(gy, None, H, W)
+    dx = Kn.conv3x3_dx(gp, wk)
+    xd = x.permute(0, 3, 1, 2).double().requires_grad_(True)
+    (F.conv2d(xd, wk.permute(0, 3, 1, 2).double(), None, padding=1) * gy.permute(0, 3, 1, 2).double()).sum().backward()
+    ref_dx = xd.grad.permute(0, 2, 3, 1).float()
+    _close(dx, ref_dx, 0, _gemm_tol(ref_dx, passes, 9 * Cout), "conv dX (pair)")
+
+
 @pytest.mark.parametrize("act", [None, "relu", "gelu", "leaky_relu", "sigmoid"])
 def test_gemm_epilogue(act, passes):
     from gedepth_b200 import kernels as Kn, ops_lib as L
@@ -554,6 +607,29 @@ def test_patch_embed_as_gemm(H, W, passes):
     (t2 * go).sum().backward()
     _close(w.grad, w2.grad, 0, 2e-3 * float(w2.grad.abs().max()), "dw")     # dW: library GEMM in both
     _close(b.grad, b2.grad, 1e-4, 1e-3, "db")
+
+
+@pytest.mark.parametrize("H,W", [(64, 160), (35, 83)])
+def test_stem_conv_as_im2col_gemm(H, W, passes):
+    """7x7/s2/p3 stem conv on channels 0-2 of the 5-channel batch (depthformer_swin.py:1032-1039,1152) as
+    im2col + tcgen05 GEMM, forward and weight gradient, vs F.conv2d in fp64."""
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(31)
+    img = torch.randn(2, 5, H, W, generator=g).to(DEV)
+    w0 = (torch.randn(64, 3, 7, 7, generator=g) / 147 ** 0.5)
+    w1 = w0.to(DEV).requires_grad_(True)
+    w2 = w0.to(DEV).double().requires_grad_(True)
+    x = img[:, 0:3]
+    assert Kn.conv_im2col_supported(x, w1, 2, 3)
+    y1 = Kn.conv_im2col(x, w1, None, 2, 3, "relu")
+    pre2 = F.conv2d(x.double(), w2, None, stride=2, padding=3)
+    y2 = torch.where(y1.detach() > 0, pre2, torch.zeros_like(pre2))       # the branch the kernel took
+    assert y1.shape == y2.shape
+    _close(y1, F.relu(pre2), 0, _gemm_tol(pre2, passes, 147), "stem fwd")
+    go = torch.randn_like(y2).float()
+    (y1 * go).sum().backward()
+    (y2 * go.double()).sum().backward()
+    _close(w1.grad, w2.grad, 0, 2 * _gemm_tol(w2.grad, passes, 2 * (H // 2) * (W // 2)), "stem dW")
 
 
 @pytest.mark.parametrize("H,W,C", [(16, 40, 96), (9, 21, 192), (5, 11, 384)])
