@@ -86,6 +86,31 @@ __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Counter-based dropout mask shared by the GEMM epilogue (forward) and ged_dropout_bwd.  One 32-bit hash serves two
+// neighbouring elements (16 bits each): element idx is kept iff its 16 bits >= round(p * 65536); the survivors are
+// scaled by 1 / (1 - round(p*65536)/65536), so the estimator stays unbiased for the quantised p (0.1 -> 0.100006).
+// seed = host seed + step counter (device) * odd constant, so a captured CUDA graph draws a fresh mask at every
+// replay.  Replaces nn.Dropout(0.1) of mmcv's MultiScaleDeformableAttention (hahi.py:179-188 [external default]);
+// same distribution, not the same stream as torch.
+__host__ __device__ __forceinline__ uint32_t drop_mix(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {      // 16-bit threshold
+  const int t = (int)(p * 65536.f + 0.5f);
+  return (uint32_t)(t < 0 ? 0 : (t > 65535 ? 65535 : t));
+}
+__host__ __device__ __forceinline__ float drop_scale(uint32_t thresh16) { return 65536.f / (float)(65536u - thresh16); }
+// idx must be a multiple of 4: keep flags of elements idx .. idx+3 as bits 0..3
+__host__ __device__ __forceinline__ uint32_t drop_keep4(uint32_t seed, uint32_t idx, uint32_t thresh16) {
+  const uint32_t h0 = drop_mix((idx >> 1) * 0x9E3779B9u + seed), h1 = drop_mix(((idx >> 1) + 1u) * 0x9E3779B9u + seed);
+  return ((h0 & 0xFFFFu) >= thresh16 ? 1u : 0u) | ((h0 >> 16) >= thresh16 ? 2u : 0u) |
+         ((h1 & 0xFFFFu) >= thresh16 ? 4u : 0u) | ((h1 >> 16) >= thresh16 ? 8u : 0u);
+}
+__device__ __forceinline__ uint32_t drop_seed_eff(uint32_t seed, const int* step_dev) {
+  return seed + (step_dev ? (uint32_t)__ldg(step_dev) * 0x9E3779B1u : 0u);
+}
+
 __host__ __device__ __forceinline__ int cdiv(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ __forceinline__ bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 

@@ -43,6 +43,10 @@ struct GemmParams {
   int ldd;                  // row pitch of D / residual in floats
   int act;
   float slope;
+  // dropout on the activated output, before row scale / residual (0 = off)
+  float drop_p;
+  uint32_t drop_seed;
+  const int* drop_step;
   // conv epilogue: padded row -> (n, y, x); 0 disables
   int conv_Hp, conv_Wp;     // padded extents (H+2, W+2)
   int num_m_tiles, num_n_tiles;
@@ -209,6 +213,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* tile_s
       if (p.row_scale && orow[i] >= 0) rscale[i] = __ldg(p.row_scale + orow[i] / p.rows_per_batch);
     }
   }
+  const bool drop = p.drop_p > 0.f;
+  const uint32_t dseed = drop ? drop_seed_eff(p.drop_seed, p.drop_step) : 0u, dthresh = drop_threshold(p.drop_p);
+  const float dinv = drop ? drop_scale(dthresh) : 1.f;
   mbar_wait(full_bar, full_phase);
   tc_fence_after();
 #pragma unroll 1
@@ -238,6 +245,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* tile_s
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) x[e] = apply_act(x[e], p.act, p.slope) * rscale[i];
+        if (drop) {
+          const uint32_t keep = drop_keep4(dseed, (uint32_t)(orow[i] * p.N + col), dthresh);   // N % 4 == 0, col % 4 == 0
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = ((keep >> e) & 1u) ? x[e] * dinv : 0.f;
+        }
         float* dst = Dt + orow[i] * p.ldd + col;
         if (p.mode != 0) {          // split-K partial: accumulate (D is zero-initialised / holds the running gradient)
           if (vec && ((p.tap_dstride & 3) == 0)) atomicAdd((float4*)dst, make_float4(x[0], x[1], x[2], x[3]));
@@ -884,8 +896,9 @@ static int run_dw(const float* G, int ldg, const float* X, int ldx, int64_t P, i
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  // panels of 32 features: at most four boxes per operand and stage
-  const int bn = p.N <= 32 ? 32 : p.N <= 64 ? 64 : p.N <= 96 ? 96 : (p.N % 128 != 0 && p.N % 96 == 0) ? 96 : 128;
+  // B panels of 32 features; wide tiles (192 / 256 columns) halve the re-reads of the G operand through L2
+  int bn = p.N <= 32 ? 32 : p.N <= 64 ? 64 : p.N <= 96 ? 96 : (p.N % 128 != 0 && p.N % 96 == 0) ? 96 : 128;
+  if (g_wide_tiles && p.N >= 192) bn = (p.N % 256 == 0) ? 256 : (p.N % 192 == 0) ? 192 : bn;
   CUtensorMap ma, mb;
   if (int e = make_map_2d(&ma, G, P, p.M, ldg, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
   if (int e = make_map_2d(&mb, X, Px, p.N, ldx, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
@@ -972,14 +985,16 @@ GED_API int ged_conv3x3_dx_tf32(const float* Gpad, const float* Wk, float* DX, i
 // depthformer_swin.py:96,119,174-176,193,222 ; mmcv FFN ; hahi.py:122-165 (1x1) ; MSDA linears.
 GED_API int ged_gemm_tf32(const float* A, int lda, const float* W, int ldw, float* D, int ldd, int M,
                           int N, int K, const float* bias, int act, float slope, const float* residual,
-                          const float* row_scale, int rows_per_batch, float* D_pre, cudaStream_t stream) {
+                          const float* row_scale, int rows_per_batch, float* D_pre, float drop_p,
+                          unsigned drop_seed, const int* drop_step, cudaStream_t stream) {
   if (!A || !W || !D || M <= 0 || N <= 0 || K <= 0) return GED_ERR_ARG;
-  if (K % 4) return GED_ERR_SHAPE;
+  if (K % 4 || drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && ((int64_t)M * N > 0xFFFFFFFFll || (N % 4)))) return GED_ERR_SHAPE;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.ntaps = 1; p.tap_off[0] = 0;
   p.bias = bias; p.residual = residual; p.row_scale = row_scale;
   p.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
   p.D = D; p.D_pre = D_pre; p.ldd = ldd; p.act = act; p.slope = slope; p.conv_Hp = 0; p.conv_Wp = 0;
+  p.drop_p = drop_p; p.drop_seed = drop_seed; p.drop_step = drop_step;
   return run(A, M, lda, W, ldw, p, stream);
 }
 

@@ -165,13 +165,15 @@ __device__ __forceinline__ void slope_eval(const float* L, float pe, float h, fl
   for (int c = 1; c < NSLOPE; ++c) mx = fmaxf(mx, L[c]);
   float sum = 0.f;
 #pragma unroll
-  for (int c = 0; c < NSLOPE; ++c) { e.p[c] = expf(L[c] - mx); sum += e.p[c]; }
+  for (int c = 0; c < NSLOPE; ++c) { e.p[c] = __expf(L[c] - mx); sum += e.p[c]; }
   const float inv = 1.f / sum;
   float th = 0.f;
 #pragma unroll
   for (int c = 0; c < NSLOPE; ++c) { e.p[c] *= inv; th += e.p[c] * (float)(c - 5); }
   e.theta = th;
-  e.k = tanf(th * 0.017453292519943295f);
+  // |theta| <= 5 degrees (a convex combination of the bins): tan by its series, exact to fp32 for |x| <= 0.0873
+  const float xr = th * 0.017453292519943295f, x2 = xr * xr;
+  e.k = xr * (1.f + x2 * (0.33333333333f + x2 * (0.13333333333f + x2 * 0.05396825397f)));
   const float a = -h / (pe + 1e-8f);
   e.den = (a - e.k) + 1e-8f;
   e.off = -h / e.den;
@@ -184,6 +186,10 @@ __device__ __forceinline__ void slope_eval(const float* L, float pe, float h, fl
   e.m = mm;
 }
 
+// LOGITS: also write the 11 full-resolution logits (training: CE loss input).  A thread takes 4 pixels of one row
+// spaced TX apart, so a warp covers 32 CONSECUTIVE pixels: every global access is one coalesced 128-byte segment
+// and the half-resolution taps of neighbouring lanes coincide pairwise (bank-conflict-free shared-memory reads).
+template <bool LOGITS>
 __global__ void __launch_bounds__(TX * TILE_H) ge_adaptive_fwd_kernel(
     const float* __restrict__ pe_raw, int64_t pe_bstride, const float* __restrict__ y_half,
     const float* __restrict__ logits_half, const float* __restrict__ height, float height_scalar,
@@ -202,57 +208,36 @@ __global__ void __launch_bounds__(TX * TILE_H) ge_adaptive_fwd_kernel(
     for (int ch = 0; ch < NSLOPE; ++ch) s_l[ch][r][c] = __ldg(logits_half + ((int64_t)b * NSLOPE + ch) * hw2 + so);
   }
   __syncthreads();
-  const int oy = oy0 + threadIdx.y, ox = ox0 + threadIdx.x * 4;
-  if (oy >= H || ox >= W) return;
+  const int oy = oy0 + threadIdx.y;
+  if (oy >= H) return;
   const float h = height ? __ldg(height + b) : height_scalar;
   const Tap ty = tap(oy, sy, false, h2);
   const int r0 = ty.i0 - sw.y0, r1 = ty.i1 - sw.y0;
-  const int64_t o = ((int64_t)b * H + oy) * W + ox;
   const int64_t HW = (int64_t)H * W;
-  const int n = min(4, W - ox);
-  const bool vec = (n == 4) && ((W & 3) == 0);
-  float yo[4], mo[4], lo[NSLOPE][4], pev[4];
-  {
-    const float* pp = pe_raw + (int64_t)b * pe_bstride + (int64_t)oy * W + ox;
-    if (vec && aligned16(pp)) { float4 t = ldg_stream((const float4*)pp); pev[0] = t.x; pev[1] = t.y; pev[2] = t.z; pev[3] = t.w; }
-    else { for (int i = 0; i < n; ++i) pev[i] = __ldg(pp + i); }
-  }
-#pragma unroll
+  const int64_t row = ((int64_t)b * H + oy) * W;
+  const float* pp = pe_raw + (int64_t)b * pe_bstride + (int64_t)oy * W;
+#pragma unroll 2
   for (int i = 0; i < 4; ++i) {
-    if (i >= n) break;
-    const Tap tx = tap(ox + i, sx, false, w2);
+    const int ox = ox0 + i * TX + threadIdx.x;
+    if (ox >= W) break;
+    const Tap tx = tap(ox, sx, false, w2);
     const int c0 = tx.i0 - sw.x0, c1 = tx.i1 - sw.x0;
     float L[NSLOPE];
 #pragma unroll
-    for (int ch = 0; ch < NSLOPE; ++ch) {
+    for (int ch = 0; ch < NSLOPE; ++ch)
       L[ch] = ty.l0 * (tx.l0 * s_l[ch][r0][c0] + tx.l1 * s_l[ch][r0][c1]) +
               ty.l1 * (tx.l0 * s_l[ch][r1][c0] + tx.l1 * s_l[ch][r1][c1]);
-      lo[ch][i] = L[ch];
-    }
     const float yv = ty.l0 * (tx.l0 * s_y[r0][c0] + tx.l1 * s_y[r0][c1]) +
                      ty.l1 * (tx.l0 * s_y[r1][c0] + tx.l1 * s_y[r1][c1]);
-    SlopeEval e;
-    slope_eval(L, pev[i], h, depth_scale, e);
-    yo[i] = yv;
-    mo[i] = (e.off * e.m) * yv;
-  }
-  if (vec) {
-    stg_stream((float4*)(y + o), make_float4(yo[0], yo[1], yo[2], yo[3]));
-    stg_stream((float4*)(pe_mask + o), make_float4(mo[0], mo[1], mo[2], mo[3]));
-    if (logits_full) {
+    if (LOGITS) {
 #pragma unroll
       for (int ch = 0; ch < NSLOPE; ++ch)
-        stg_stream((float4*)(logits_full + ((int64_t)b * NSLOPE + ch) * HW + (int64_t)oy * W + ox),
-                   make_float4(lo[ch][0], lo[ch][1], lo[ch][2], lo[ch][3]));
+        __stcs(logits_full + ((int64_t)b * NSLOPE + ch) * HW + (int64_t)oy * W + ox, L[ch]);
     }
-  } else {
-    for (int i = 0; i < n; ++i) {
-      y[o + i] = yo[i];
-      pe_mask[o + i] = mo[i];
-      if (logits_full)
-        for (int ch = 0; ch < NSLOPE; ++ch)
-          logits_full[((int64_t)b * NSLOPE + ch) * HW + (int64_t)oy * W + ox + i] = lo[ch][i];
-    }
+    SlopeEval e;
+    slope_eval(L, __ldcs(pp + ox), h, depth_scale, e);
+    __stcs(y + row + ox, yv);
+    __stcs(pe_mask + row + ox, (e.off * e.m) * yv);
   }
 }
 
@@ -327,26 +312,37 @@ __global__ void __launch_bounds__(TX * TILE_H) ge_adaptive_bwd_kernel(
   for (int i = tid; i < sw.h * sw.w; i += TX * TILE_H) {
     const int r = i / sw.w, c = i - r * sw.w;
     const int j = sw.y0 + r, k = sw.x0 + c;
-    int ylo, yhi, xlo, xhi;
-    adjoint_range(j, sy, false, h2, H, ylo, yhi);
+    float wyv[TILE_H];
+    bool any_y = false;
+#pragma unroll
+    for (int yy = 0; yy < TILE_H; ++yy) {
+      wyv[yy] = 0.f;
+      if (yy < th) {
+        const Tap ty = tap(oy0 + yy, sy, false, h2);
+        wyv[yy] = (ty.i0 == j ? ty.l0 : 0.f) + (ty.i1 == j ? ty.l1 : 0.f);
+      }
+      any_y |= wyv[yy] != 0.f;
+    }
+    if (!any_y) continue;
+    int xlo, xhi;
     adjoint_range(k, sx, false, w2, W, xlo, xhi);
-    ylo = max(ylo, oy0) - oy0; yhi = min(yhi, oy0 + th - 1) - oy0;
     xlo = max(xlo, ox0) - ox0; xhi = min(xhi, ox0 + tw - 1) - ox0;
     float acc[NSLOPE + 1];
 #pragma unroll
     for (int ch = 0; ch <= NSLOPE; ++ch) acc[ch] = 0.f;
     bool any = false;
-    for (int yy = ylo; yy <= yhi; ++yy) {
-      const Tap ty = tap(oy0 + yy, sy, false, h2);
-      const float wy = (ty.i0 == j ? ty.l0 : 0.f) + (ty.i1 == j ? ty.l1 : 0.f);
-      if (wy == 0.f) continue;
-      for (int xx = xlo; xx <= xhi; ++xx) {
-        const Tap tx = tap(ox0 + xx, sx, false, w2);
-        const float wx = (tx.i0 == k ? tx.l0 : 0.f) + (tx.i1 == k ? tx.l1 : 0.f);
-        if (wx == 0.f) continue;
-        any = true;
+    for (int xx = xlo; xx <= xhi; ++xx) {
+      const Tap tx = tap(ox0 + xx, sx, false, w2);
+      const float wx = (tx.i0 == k ? tx.l0 : 0.f) + (tx.i1 == k ? tx.l1 : 0.f);
+      if (wx == 0.f) continue;
+      any = true;
 #pragma unroll
-        for (int ch = 0; ch <= NSLOPE; ++ch) acc[ch] += wy * wx * s_g[ch][yy][xx];
+      for (int yy = 0; yy < TILE_H; ++yy) {
+        const float w = wyv[yy] * wx;
+        if (w != 0.f) {
+#pragma unroll
+          for (int ch = 0; ch <= NSLOPE; ++ch) acc[ch] += w * s_g[ch][yy][xx];
+        }
       }
     }
     if (any) {
@@ -514,13 +510,11 @@ GED_API int ged_ge_adaptive_fwd(const float* pe_raw, int64_t pe_batch_stride, co
   if (!half_shape_ok(H, W, h2, w2)) return GED_ERR_SHAPE;
   if ((W % 4 == 0) && !(aligned16(y) && aligned16(pe_mask) && (!logits_full || aligned16(logits_full)))) return GED_ERR_ALIGN;
   const float sy = resize_scale(h2, H, false), sx = resize_scale(w2, W, false);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(ge_adaptive_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-    attr_set = true;
-  }
   dim3 block(TX, TILE_H), grid(cdiv(W, TILE_W), cdiv(H, TILE_H), B);
-  ge_adaptive_fwd_kernel<<<grid, block, 0, stream>>>(pe_raw, pe_batch_stride, y_half, logits_half, height, height_scalar, depth_scale, y, pe_mask, logits_full, H, W, h2, w2, sy, sx);
+  if (logits_full)
+    ge_adaptive_fwd_kernel<true><<<grid, block, 0, stream>>>(pe_raw, pe_batch_stride, y_half, logits_half, height, height_scalar, depth_scale, y, pe_mask, logits_full, H, W, h2, w2, sy, sx);
+  else
+    ge_adaptive_fwd_kernel<false><<<grid, block, 0, stream>>>(pe_raw, pe_batch_stride, y_half, logits_half, height, height_scalar, depth_scale, y, pe_mask, logits_full, H, W, h2, w2, sy, sx);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }

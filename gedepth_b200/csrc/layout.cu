@@ -81,9 +81,9 @@ __global__ void __launch_bounds__(256) upsample_nhwc_bwd_kernel(
   }
 }
 
-// acc (B,H,W,C) += bilinear(t (B,h0,w0,C) -> HxW, align_corners=True)
+// out (B,H,W,C) = base + bilinear(t (B,h0,w0,C) -> HxW, align_corners=True); out may alias base (in place)
 __global__ void __launch_bounds__(256) resize_add_nhwc_kernel(
-    const float* __restrict__ t, float* __restrict__ acc, int C, int B, int H, int W, int h0, int w0, float sy,
+    const float* __restrict__ t, const float* base_in, float* acc, int C, int B, int H, int W, int h0, int w0, float sy,
     float sx) {
   const int C4 = C >> 2;
   const int64_t total = (int64_t)B * H * W * C4;
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) resize_add_nhwc_kernel(
     const float4 v01 = __ldg((const float4*)(base + ((int64_t)ty.i0 * w0 + tx.i1) * C));
     const float4 v10 = __ldg((const float4*)(base + ((int64_t)ty.i1 * w0 + tx.i0) * C));
     const float4 v11 = __ldg((const float4*)(base + ((int64_t)ty.i1 * w0 + tx.i1) * C));
-    float4 a = *((float4*)acc + i);
+    float4 a = *((const float4*)base_in + i);
     a.x += ty.l0 * (tx.l0 * v00.x + tx.l1 * v01.x) + ty.l1 * (tx.l0 * v10.x + tx.l1 * v11.x);
     a.y += ty.l0 * (tx.l0 * v00.y + tx.l1 * v01.y) + ty.l1 * (tx.l0 * v10.y + tx.l1 * v11.y);
     a.z += ty.l0 * (tx.l0 * v00.z + tx.l1 * v01.z) + ty.l1 * (tx.l0 * v10.z + tx.l1 * v11.z);
@@ -111,18 +111,29 @@ __global__ void __launch_bounds__(256) resize_add_nhwc_kernel(
 // gz[r, c] = g[r, c] * act'(ref[r, c]) * row_scale[r / rows_per_batch];  db[c] += sum_r gz[r, c]
 // act: 1 relu, 2 leaky (ref = output), 3 gelu (ref = pre-activation), 4 sigmoid (ref = output), 0 none.
 // grid (ceil(N/128), row chunks), block (32, 8): a thread owns 4 consecutive columns.
-__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ ref,
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ ref,
                                                        float* __restrict__ gz, float* __restrict__ db,
                                                        const float* __restrict__ row_scale, int rows_per_batch,
                                                        int64_t rows, int N, int act, float slope,
-                                                       int rows_per_block) {
+                                                       int rows_per_block, float drop_p, uint32_t drop_seed,
+                                                       const int* drop_step) {
   __shared__ float4 s_red[8][32];
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool drop = drop_p > 0.f;
+  const uint32_t dseed = drop ? drop_seed_eff(drop_seed, drop_step) : 0u, dthresh = drop_threshold(drop_p);
+  const float dinv = drop ? drop_scale(dthresh) : 1.f;
   if (c < N) {
     for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
-      float4 v = __ldg((const float4*)(g + r * N + c));
+      float4 v = __ldg((const float4*)(g + r * ldg + c));
+      if (drop) {      // the mask the GEMM epilogue drew for this element
+        const uint32_t keep = drop_keep4(dseed, (uint32_t)(r * N + c), dthresh);
+        v.x = (keep & 1u) ? v.x * dinv : 0.f;
+        v.y = (keep & 2u) ? v.y * dinv : 0.f;
+        v.z = (keep & 4u) ? v.z * dinv : 0.f;
+        v.w = (keep & 8u) ? v.w * dinv : 0.f;
+      }
       if (act) {
         const float4 y = __ldg((const float4*)(ref + r * N + c));
         float d[4] = {y.x, y.y, y.z, y.w};
@@ -265,28 +276,42 @@ GED_API int ged_upsample_nhwc_bwd(const float* g, int ldg, float* out, int C0, i
   return GED_OK;
 }
 
-GED_API int ged_resize_add_nhwc(const float* t, float* acc, int C, int B, int H, int W, int h0, int w0,
-                                cudaStream_t stream) {
-  if (!t || !acc || B <= 0 || C <= 0) return GED_ERR_ARG;
+GED_API int ged_resize_add_nhwc(const float* t, const float* base, float* out, int C, int B, int H, int W, int h0,
+                                int w0, cudaStream_t stream) {
+  if (!t || !base || !out || B <= 0 || C <= 0) return GED_ERR_ARG;
   if (C % 4) return GED_ERR_SHAPE;
-  if (!aligned16(t) || !aligned16(acc)) return GED_ERR_ALIGN;
+  if (!aligned16(t) || !aligned16(base) || !aligned16(out)) return GED_ERR_ALIGN;
   const int64_t total = (int64_t)B * H * W * (C / 4);
-  resize_add_nhwc_kernel<<<grid_for(total), 256, 0, stream>>>(t, acc, C, B, H, W, h0, w0, resize_scale(h0, H, true),
+  resize_add_nhwc_kernel<<<grid_for(total), 256, 0, stream>>>(t, base, out, C, B, H, W, h0, w0, resize_scale(h0, H, true),
                                                              resize_scale(w0, W, true));
   GED_CHECK_LAUNCH();
   return GED_OK;
 }
 
 // db (N floats) is ACCUMULATED into when non-NULL.  ref: output (relu/leaky/sigmoid) or pre-activation (gelu).
-GED_API int ged_act_bwd(const float* g, const float* ref, float* gz, float* db, const float* row_scale,
+GED_API int ged_act_bwd(const float* g, int64_t ldg, const float* ref, float* gz, float* db, const float* row_scale,
                         int rows_per_batch, int64_t rows, int N, int act, float slope, cudaStream_t stream) {
-  if (!g || (!gz && !db) || rows <= 0 || N <= 0 || (act && !ref)) return GED_ERR_ARG;
-  if (N % 4) return GED_ERR_SHAPE;
+  if (!g || (!gz && !db) || rows <= 0 || N <= 0 || (act && !ref) || ldg < N) return GED_ERR_ARG;
+  if ((N % 4) || (ldg % 4)) return GED_ERR_SHAPE;
   if (!aligned16(g) || (gz && !aligned16(gz)) || (ref && !aligned16(ref))) return GED_ERR_ALIGN;
   const int rpb = 128;
   dim3 grid(cdiv(N, 128), (unsigned)((rows + rpb - 1) / rpb));
-  act_bwd_kernel<<<grid, dim3(32, 8), 0, stream>>>(g, ref, gz, db, row_scale, rows_per_batch > 0 ? rows_per_batch : 1,
-                                                  rows, N, act, slope, rpb);
+  act_bwd_kernel<<<grid, dim3(32, 8), 0, stream>>>(g, ldg, ref, gz, db, row_scale, rows_per_batch > 0 ? rows_per_batch : 1,
+                                                  rows, N, act, slope, rpb, 0.f, 0u, nullptr);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+// Backward of the dropout drawn in the GEMM epilogue (same p / seed / step counter): gz = g * keep / (1-p) and
+// db += column sums of gz (db may be NULL).  No activation on this path.
+GED_API int ged_dropout_bwd(const float* g, int64_t ldg, float* gz, float* db, int64_t rows, int N, float drop_p,
+                            unsigned drop_seed, const int* drop_step, cudaStream_t stream) {
+  if (!g || !gz || rows <= 0 || N <= 0 || ldg < N) return GED_ERR_ARG;
+  if ((N % 4) || (ldg % 4) || drop_p <= 0.f || drop_p >= 1.f || rows * N > 0xFFFFFFFFll) return GED_ERR_SHAPE;
+  if (!aligned16(g) || !aligned16(gz)) return GED_ERR_ALIGN;
+  const int rpb = 128;
+  dim3 grid(cdiv(N, 128), (unsigned)((rows + rpb - 1) / rpb));
+  act_bwd_kernel<<<grid, dim3(32, 8), 0, stream>>>(g, ldg, nullptr, gz, db, nullptr, 1, rows, N, 0, 0.f, rpb, drop_p, drop_seed, drop_step);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }

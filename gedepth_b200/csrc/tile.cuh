@@ -41,26 +41,38 @@ __device__ __forceinline__ void tile_adjoint_upsample(
   for (int i = tid; i < sw.h * sw.w; i += TX * TILE_H) {
     const int r = i / sw.w, c = i - r * sw.w;
     const int j = sw.y0 + r, k = sw.x0 + c;
-    int ylo, yhi, xlo, xhi;
-    adjoint_range(j, sy, align, h2, H, ylo, yhi);
+    // weights of source row j in each of the tile's (<= TILE_H) output rows: evaluated once, not per column
+    float wyv[TILE_H];
+    bool any_y = false;
+#pragma unroll
+    for (int yy = 0; yy < TILE_H; ++yy) {
+      wyv[yy] = 0.f;
+      if (yy < th) {
+        const Tap ty = tap(oy0 + yy, sy, align, h2);
+        wyv[yy] = (ty.i0 == j ? ty.l0 : 0.f) + (ty.i1 == j ? ty.l1 : 0.f);
+      }
+      any_y |= wyv[yy] != 0.f;
+    }
+    if (!any_y) continue;
+    int xlo, xhi;
     adjoint_range(k, sx, align, w2, W, xlo, xhi);
-    ylo = max(ylo, oy0) - oy0; yhi = min(yhi, oy0 + th - 1) - oy0;
     xlo = max(xlo, ox0) - ox0; xhi = min(xhi, ox0 + tw - 1) - ox0;
     float acc[C];
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) acc[ch] = 0.f;
     bool any = false;
-    for (int yy = ylo; yy <= yhi; ++yy) {
-      const Tap ty = tap(oy0 + yy, sy, align, h2);
-      const float wy = (ty.i0 == j ? ty.l0 : 0.f) + (ty.i1 == j ? ty.l1 : 0.f);
-      if (wy == 0.f) continue;
-      for (int xx = xlo; xx <= xhi; ++xx) {
-        const Tap tx = tap(ox0 + xx, sx, align, w2);
-        const float wx = (tx.i0 == k ? tx.l0 : 0.f) + (tx.i1 == k ? tx.l1 : 0.f);
-        if (wx == 0.f) continue;
-        any = true;
+    for (int xx = xlo; xx <= xhi; ++xx) {
+      const Tap tx = tap(ox0 + xx, sx, align, w2);
+      const float wx = (tx.i0 == k ? tx.l0 : 0.f) + (tx.i1 == k ? tx.l1 : 0.f);
+      if (wx == 0.f) continue;
+      any = true;
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) acc[ch] += wy * wx * s_g[ch][yy][xx];
+      for (int yy = 0; yy < TILE_H; ++yy) {
+        const float w = wyv[yy] * wx;
+        if (w != 0.f) {
+#pragma unroll
+          for (int ch = 0; ch < C; ++ch) acc[ch] += w * s_g[ch][yy][xx];
+        }
       }
     }
     if (any) {

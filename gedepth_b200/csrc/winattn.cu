@@ -13,7 +13,8 @@
 
 namespace ged {
 
-constexpr int WS = 7, WN = 49, HD = 32, KP = 33, SP = 50;   // KP/SP: padded smem pitches
+constexpr int WS = 7, WN = 49, HD = 32, KP = 36, SP = 49;   // KP: 16-byte aligned row pitch (float4 reads, conflict-free
+                                                            // for 8 consecutive rows); SP: odd pitch of the 49x49 tiles
 constexpr int WA_THREADS = 128;
 
 struct WinGeom {
@@ -45,6 +46,18 @@ __device__ __forceinline__ void load_qkv(const float* __restrict__ qkv, const fl
   }
 }
 
+__device__ __forceinline__ float dot32(const float* a, const float* b) {
+  const float4* a4 = (const float4*)a;
+  const float4* b4 = (const float4*)b;
+  float acc = 0.f;
+#pragma unroll
+  for (int d = 0; d < HD / 4; ++d) {
+    const float4 x = a4[d], y = b4[d];
+    acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+  }
+  return acc;
+}
+
 // S = q k^T + bias + mask, then row softmax, in place in s_s
 __device__ __forceinline__ void scores_softmax(const float (*s_q)[KP], const float (*s_k)[KP],
                                                float (*s_s)[SP], const float* __restrict__ table,
@@ -52,9 +65,7 @@ __device__ __forceinline__ void scores_softmax(const float (*s_q)[KP], const flo
                                                const int* s_lab, bool masked) {
   for (int e = threadIdx.x; e < WN * WN; e += WA_THREADS) {
     const int i = e / WN, j = e - i * WN;
-    float acc = 0.f;
-#pragma unroll
-    for (int d = 0; d < HD; ++d) acc += s_q[i][d] * s_k[j][d];
+    float acc = dot32(s_q[i], s_k[j]);
     acc += __ldg(table + (int64_t)__ldg(index + e) * nH + head);
     if (masked && s_lab[i] != s_lab[j]) acc += -100.0f;
     s_s[i][j] = acc;
@@ -75,7 +86,8 @@ __device__ __forceinline__ void scores_softmax(const float (*s_q)[KP], const flo
 __global__ void __launch_bounds__(WA_THREADS) winattn_fwd_kernel(
     const float* __restrict__ qkv, const float* __restrict__ bias, const float* __restrict__ table,
     const long long* __restrict__ index, float* __restrict__ ctx, WinGeom g, int C, int nH, float scale) {
-  __shared__ float s_q[WN][KP], s_k[WN][KP], s_v[WN][KP], s_s[WN][SP];
+  __shared__ __align__(16) float s_q[WN][KP], s_k[WN][KP], s_v[WN][KP];
+  __shared__ float s_s[WN][SP];
   __shared__ int s_tok[WN], s_lab[WN];
   const int win = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int wy = win / g.nWx, wx = win - wy * g.nWx;
@@ -85,14 +97,18 @@ __global__ void __launch_bounds__(WA_THREADS) winattn_fwd_kernel(
   load_qkv(qkv, bias, (int64_t)b * L * 3 * C, C, head, s_tok, s_q, s_k, s_v, scale);
   __syncthreads();
   scores_softmax(s_q, s_k, s_s, table, index, nH, head, s_lab, g.shift > 0);
-  for (int e = threadIdx.x; e < WN * HD; e += WA_THREADS) {
-    const int i = e >> 5, d = e & 31;
+  for (int e = threadIdx.x; e < WN * (HD / 4); e += WA_THREADS) {
+    const int i = e >> 3, d4 = e & 7;
     const int t = s_tok[i];
     if (t < 0) continue;                       // padded rows are cropped away (:354-355)
-    float acc = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 7
-    for (int j = 0; j < WN; ++j) acc += s_s[i][j] * s_v[j][d];
-    ctx[((int64_t)b * L + t) * C + head * HD + d] = acc;
+    for (int j = 0; j < WN; ++j) {
+      const float pij = s_s[i][j];
+      const float4 v = ((const float4*)s_v[j])[d4];
+      acc.x += pij * v.x; acc.y += pij * v.y; acc.z += pij * v.z; acc.w += pij * v.w;
+    }
+    *(float4*)(ctx + ((int64_t)b * L + t) * C + head * HD + d4 * 4) = acc;
   }
 }
 
@@ -103,7 +119,8 @@ __global__ void __launch_bounds__(WA_THREADS) winattn_bwd_kernel(
     const float* __restrict__ qkv, const float* __restrict__ bias, const float* __restrict__ table,
     const long long* __restrict__ index, const float* __restrict__ g_ctx, float* __restrict__ g_qkv,
     float* __restrict__ g_bias, float* __restrict__ g_table, WinGeom g, int C, int nH, float scale) {
-  __shared__ float s_q[WN][KP], s_k[WN][KP], s_v[WN][KP], s_o[WN][KP], s_s[WN][SP], s_d[WN][SP];
+  __shared__ __align__(16) float s_q[WN][KP], s_k[WN][KP], s_v[WN][KP], s_o[WN][KP];
+  __shared__ float s_s[WN][SP], s_d[WN][SP];
   __shared__ float s_tab[(2 * WS - 1) * (2 * WS - 1)];
   __shared__ int s_tok[WN], s_lab[WN];
   const int win = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
@@ -122,10 +139,7 @@ __global__ void __launch_bounds__(WA_THREADS) winattn_bwd_kernel(
   // dP -> s_d
   for (int e = threadIdx.x; e < WN * WN; e += WA_THREADS) {
     const int i = e / WN, j = e - i * WN;
-    float acc = 0.f;
-#pragma unroll
-    for (int d = 0; d < HD; ++d) acc += s_o[i][d] * s_v[j][d];
-    s_d[i][j] = acc;
+    s_d[i][j] = dot32(s_o[i], s_v[j]);
   }
   __syncthreads();
   // dS = P o (dP - sum_j dP P), in place in s_d; bias-table gradient
@@ -146,22 +160,28 @@ __global__ void __launch_bounds__(WA_THREADS) winattn_bwd_kernel(
     if (s_tab[i] != 0.f) atomicAdd(g_table + (int64_t)i * nH + head, s_tab[i]);
   // dQ, dK, dV
   const int64_t boff = (int64_t)b * L * 3 * C;
-  for (int e = threadIdx.x; e < WN * HD; e += WA_THREADS) {
-    const int n = e >> 5, d = e & 31, t = s_tok[n];
-    float dq = 0.f, dk = 0.f, dv = 0.f;
+  for (int e = threadIdx.x; e < WN * (HD / 4); e += WA_THREADS) {
+    const int n = e >> 3, d4 = e & 7, t = s_tok[n];
+    float4 dq = make_float4(0.f, 0.f, 0.f, 0.f), dk = dq, dv = dq;
 #pragma unroll 7
     for (int j = 0; j < WN; ++j) {
-      dq += s_d[n][j] * s_k[j][d];
-      dk += s_d[j][n] * s_q[j][d];
-      dv += s_s[j][n] * s_o[j][d];
+      const float a = s_d[n][j], bq = s_d[j][n], c = s_s[j][n];
+      const float4 k = ((const float4*)s_k[j])[d4], q = ((const float4*)s_q[j])[d4], o = ((const float4*)s_o[j])[d4];
+      dq.x += a * k.x; dq.y += a * k.y; dq.z += a * k.z; dq.w += a * k.w;
+      dk.x += bq * q.x; dk.y += bq * q.y; dk.z += bq * q.z; dk.w += bq * q.w;
+      dv.x += c * o.x; dv.y += c * o.y; dv.z += c * o.z; dv.w += c * o.w;
     }
-    const int col = head * HD + d;
+    const int col = head * HD + d4 * 4;
     if (t >= 0) {
       float* gp = g_qkv + boff + (int64_t)t * 3 * C;
-      gp[col] = dq * scale; gp[C + col] = dk; gp[2 * C + col] = dv;
+      *(float4*)(gp + col) = make_float4(dq.x * scale, dq.y * scale, dq.z * scale, dq.w * scale);
+      *(float4*)(gp + C + col) = dk;
+      *(float4*)(gp + 2 * C + col) = dv;
     } else if (g_bias) {
-      atomicAdd(g_bias + C + col, dk);
-      atomicAdd(g_bias + 2 * C + col, dv);
+      atomicAdd(g_bias + C + col, dk.x); atomicAdd(g_bias + C + col + 1, dk.y);
+      atomicAdd(g_bias + C + col + 2, dk.z); atomicAdd(g_bias + C + col + 3, dk.w);
+      atomicAdd(g_bias + 2 * C + col, dv.x); atomicAdd(g_bias + 2 * C + col + 1, dv.y);
+      atomicAdd(g_bias + 2 * C + col + 2, dv.z); atomicAdd(g_bias + 2 * C + col + 3, dv.w);
     }
   }
 }

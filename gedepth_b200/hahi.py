@@ -108,10 +108,9 @@ class MultiScaleDeformableAttention(BaseModule):
         logit = ops.linear(q, self.attention_weights.weight, self.attention_weights.bias)
         out = ops.msda_sample(v, spatial_shapes, reference_points, off, logit, self.num_heads,
                               self.num_points)
-        if self.training and self.dropout.p > 0:
-            out = self.dropout(ops.linear(out, self.output_proj.weight, self.output_proj.bias))
-            return out + identity
-        return ops.linear(out, self.output_proj.weight, self.output_proj.bias, residual=identity)
+        # dropout(output_proj(sampled)) + identity: mask and residual ride in the GEMM epilogue
+        p = self.dropout.p if self.training else 0.0
+        return ops.linear(out, self.output_proj.weight, self.output_proj.bias, residual=identity, dropout_p=p)
 
 
 @NECKS.register_module()

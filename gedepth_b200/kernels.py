@@ -39,11 +39,12 @@ SIGNATURES = {
     "ged_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P],
     "ged_winattn_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "ged_winattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
-    "ged_gemm_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _I, _P, _P],
+    "ged_gemm_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _I, _P, _F, C.c_uint, _P, _P],
+    "ged_dropout_bwd": [_P, _I64, _P, _P, _I64, _I, _F, C.c_uint, _P, _P],
     "ged_prep_conv_input": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P],
     "ged_upsample_nhwc_bwd": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
-    "ged_resize_add_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
-    "ged_act_bwd": [_P, _P, _P, _P, _P, _I, _I64, _I, _I, _F, _P],
+    "ged_resize_add_nhwc": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ged_act_bwd": [_P, _I64, _P, _P, _P, _P, _I, _I64, _I, _I, _F, _P],
     "ged_bn_train_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _F, _F, _I, _P],
     "ged_bn_train_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _P],
     "ged_patchify": [_P, _I64, _P, _I, _I, _I, _I, _I, _P],
@@ -150,6 +151,19 @@ def _stream():
 
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _rows(g: torch.Tensor, N: int) -> torch.Tensor:
+    """g (..., N) as a 2-D [rows, N] tensor with unit inner stride and a 16-byte aligned, uniform row pitch - a VIEW when
+    g is e.g. a channel slice of a wider NHWC gradient (the kernels take the pitch), a dense copy otherwise."""
+    if g.dtype == torch.float32 and g.dim() >= 2 and g.stride(-1) == 1:
+        try:
+            g2 = g.view(-1, N)
+            if g2.stride(0) % 4 == 0 and g2.data_ptr() % 16 == 0:
+                return g2
+        except RuntimeError:
+            pass
+    return _f32c(g).reshape(-1, N)
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -458,17 +472,32 @@ def window_attention(qkv, qkv_bias, table, index, hw, nH, ws, shift, scale):
 _ACT = {None: 0, "relu": 1, "leaky_relu": 2, "gelu": 3, "sigmoid": 4}
 
 
+# Dropout inside the GEMM epilogue: (p, seed, step) with `step` an optional int32 device tensor mixed into the seed
+# (train.Trainer registers its step counter here so a replayed CUDA graph draws a new mask every step).
+RNG_STEP: Optional[torch.Tensor] = None
+_DROP_CALLS = 0
+
+
+def next_dropout_seed() -> int:
+    global _DROP_CALLS
+    _DROP_CALLS += 1
+    return (0x2545F491 * _DROP_CALLS + 0x1234567) & 0xFFFFFFFF
+
+
 def gemm(a2d: torch.Tensor, w: torch.Tensor, bias=None, act=None, slope=0.01, residual=None,
          row_scale=None, rows_per_batch=1, out: Optional[torch.Tensor] = None,
-         pre_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[M,N] = epi(a2d[M,K] @ w[N,K]^T).  a2d / w: last dim contiguous, 16B-aligned pitches."""
+         pre_out: Optional[torch.Tensor] = None, dropout=None) -> torch.Tensor:
+    """out[M,N] = epi(a2d[M,K] @ w[N,K]^T).  a2d / w: last dim contiguous, 16B-aligned pitches.
+    dropout = (p, seed, step_tensor|None): applied after the activation, before row scale / residual."""
     M, K = a2d.shape
     N = w.shape[0]
     assert w.shape[1] == K and a2d.stride(1) == 1 and w.stride(1) == 1
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=a2d.device)
+    dp, dseed, dstep = dropout if dropout is not None else (0.0, 0, None)
     _call("ged_gemm_tf32", _p(a2d), a2d.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K,
-          _p(bias), _ACT[act], float(slope), _p(residual), _p(row_scale), int(rows_per_batch), _p(pre_out), _stream())
+          _p(bias), _ACT[act], float(slope), _p(residual), _p(row_scale), int(rows_per_batch), _p(pre_out),
+          float(dp), int(dseed), _p(dstep), _stream())
     return out
 
 
@@ -533,12 +562,12 @@ def act_bwd(g2d: torch.Tensor, ref: Optional[torch.Tensor], act, slope=0.01, row
     ident = act is None and row_scale is None
     if ident and not want_db:
         return g2d, None
-    gz = g2d if ident else torch.empty_like(g2d)
+    gz = g2d if ident else torch.empty(rows, N, dtype=torch.float32, device=g2d.device)
     db = None
     if want_db:
         db = db_sink if db_sink is not None else torch.zeros(N, dtype=torch.float32, device=g2d.device)
-    _call("ged_act_bwd", _p(g2d), _p(ref), _p(None if ident else gz), _p(db), _p(row_scale), int(rows_per_batch), rows,
-          N, _ACT[act], float(slope), _stream())
+    _call("ged_act_bwd", _p(g2d), g2d.stride(0), _p(ref), _p(None if ident else gz), _p(db), _p(row_scale),
+          int(rows_per_batch), rows, N, _ACT[act], float(slope), _stream())
     return gz, (None if db_sink is not None else db)
 
 
@@ -572,8 +601,8 @@ class _Linear(Function):
     the bias gradient are one fused pass; dW = gz^T @ x is a cuBLAS TF32 GEMM for now."""
 
     @staticmethod
-    def forward(ctx, x, w, b, act, residual, row_scale, w_sink=None, b_sink=None):
-        ctx.w_sink, ctx.b_sink = w_sink, b_sink
+    def forward(ctx, x, w, b, act, residual, row_scale, w_sink=None, b_sink=None, dropout=None):
+        ctx.w_sink, ctx.b_sink, ctx.dropout = w_sink, b_sink, dropout
         K = x.shape[-1]
         x2 = _f32c(x).reshape(-1, K)
         M, N = x2.shape[0], w.shape[0]
@@ -582,7 +611,7 @@ class _Linear(Function):
         rpb = M // x.shape[0] if row_scale is not None else 1
         need_pre = act == "gelu" and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         pre = torch.empty(M, N, dtype=torch.float32, device=x.device) if need_pre else None
-        out = gemm(x2, wc, b, act, 0.01, res2, row_scale, rpb, pre_out=pre)
+        out = gemm(x2, wc, b, act, 0.01, res2, row_scale, rpb, pre_out=pre, dropout=dropout)
         ctx.act, ctx.rpb, ctx.has_res, ctx.has_bias = act, rpb, residual is not None, b is not None
         empty = torch.empty(0, device=x.device)
         # relu/leaky/sigmoid derive from the output - only valid when nothing was added after the activation
@@ -598,13 +627,25 @@ class _Linear(Function):
     def backward(ctx, g):
         x2, w, pre, post, row_scale = ctx.saved_tensors
         N, K = w.shape
-        g2 = _f32c(g).reshape(-1, N)
+        g2 = _rows(g, N)
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
         ref = pre if ctx.act == "gelu" else (post if ctx.act is not None else None)
-        if N % 4 == 0:
+        if ctx.dropout is not None:
+            # y = drop(x w^T + b) + residual: re-draw the epilogue's mask (no activation / row scale on this path)
+            dp, dseed, dstep = ctx.dropout
+            gz = torch.empty(g2.shape[0], N, dtype=torch.float32, device=g2.device)
+            db = None
+            if want_db:
+                db = ctx.b_sink if ctx.b_sink is not None else torch.zeros(N, dtype=torch.float32, device=g2.device)
+            _call("ged_dropout_bwd", _p(g2), g2.stride(0), _p(gz), _p(db), g2.shape[0], N, float(dp), int(dseed), _p(dstep),
+                  _stream())
+            if ctx.b_sink is not None:
+                db = None
+        elif N % 4 == 0:
             gz, db = act_bwd(g2, ref, ctx.act, 0.01, row_scale if row_scale.numel() else None, ctx.rpb, want_db,
                              ctx.b_sink)
         else:
+            g2 = g2.contiguous()
             gz = g2 if not row_scale.numel() else g2 * row_scale.repeat_interleave(ctx.rpb).unsqueeze(1)
             gz = _act_grad(gz, ctx.act, 0.01, pre, post).contiguous()
             db = gz.sum(0) if want_db else None
@@ -625,17 +666,26 @@ class _Linear(Function):
             else:
                 dw = gz.t() @ x2
         dres = g if ctx.has_res else None
-        return dx, dw, db, None, dres, None, None, None
+        return dx, dw, db, None, dres, None, None, None, None
 
 
-def linear(x, w, b=None, act=None, residual=None, row_scale=None):
+def linear(x, w, b=None, act=None, residual=None, row_scale=None, dropout_p: float = 0.0):
+    """dropout_p > 0 (training): residual + dropout(x w^T + b) with the mask drawn in the GEMM epilogue."""
     K, N = x.shape[-1], w.shape[0]
     M = x.numel() // K
     if not _gemm_ok(M, N, K, x, w, b, residual) or act not in _ACT:
-        return L.linear(x, w, b, act, residual, row_scale)
+        y = L.linear(x, w, b, act, None if dropout_p > 0 else residual, row_scale)
+        if dropout_p > 0:
+            y = torch.nn.functional.dropout(y, dropout_p, True)
+            y = y if residual is None else y + residual
+        return y
     ws = _sink(w)
     ws = ws if (ws is not None and ws.is_contiguous()) else None
-    return _Linear.apply(x, w, b, act, residual, row_scale, ws, _sink(b))
+    dropout = None
+    if dropout_p > 0:
+        assert act is None and row_scale is None and N % 4 == 0 and M * N < 2 ** 32
+        dropout = (float(dropout_p), next_dropout_seed(), RNG_STEP)
+    return _Linear.apply(x, w, b, act, residual, row_scale, ws, _sink(b), dropout)
 
 
 # =============================================================================================
@@ -865,9 +915,9 @@ class _ResizeAdd(Function):
     @staticmethod
     def forward(ctx, t, acc):
         th, ah = _nhwc(t), _nhwc(acc)
-        out = ah.clone()
+        out = torch.empty_like(ah)
         B, H, W, Cc = out.shape
-        _call("ged_resize_add_nhwc", _p(th), _p(out), Cc, B, H, W, th.shape[1], th.shape[2], _stream())
+        _call("ged_resize_add_nhwc", _p(th), _p(ah), _p(out), Cc, B, H, W, th.shape[1], th.shape[2], _stream())
         ctx.shape = th.shape
         return out.permute(0, 3, 1, 2)
 

@@ -48,11 +48,16 @@ OPS = ["linear", "layer_norm", "patch_embed", "merge_patches", "window_attention
 
 
 # ---- GEMM-shaped ---------------------------------------------------------------------------
-def linear(x, w, b=None, act=None, residual=None, row_scale=None):
+def linear(x, w, b=None, act=None, residual=None, row_scale=None, dropout_p: float = 0.0):
+    """residual + dropout_p(act(x w^T + b) * row_scale); dropout only when dropout_p > 0 (training)."""
     require_cuda(x, w)
     if use_native("linear"):
-        return _k().linear(x, w, b, act, residual, row_scale)
-    return L.linear(x, w, b, act, residual, row_scale)
+        return _k().linear(x, w, b, act, residual, row_scale, dropout_p)
+    y = L.linear(x, w, b, act, None if dropout_p > 0 else residual, row_scale)
+    if dropout_p > 0:
+        y = torch.nn.functional.dropout(y, dropout_p, True)
+        y = y if residual is None else y + residual
+    return y
 
 
 def conv2d(x, w, b=None, stride=1, padding=0, act=None, slope=0.01):

@@ -70,6 +70,7 @@ class Trainer:
         self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_norm
         self.step_idx = 0
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.arena.flat_p.device)
+        kernels.RNG_STEP = self.step_dev     # epilogue dropout mixes the device step counter into its seed
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self._graph = None
         self._static = None

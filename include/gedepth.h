@@ -126,7 +126,13 @@ int ged_bn_train_bwd(const float* g, const float* x, const float* y, const float
  * D_pre (optional, pitch ldd): copy of the pre-activation x+bias, kept for the GELU derivative. */
 int ged_gemm_tf32(const float* A, int lda, const float* W, int ldw, float* D, int ldd, int M, int N,
                   int K, const float* bias, int act, float slope, const float* residual,
-                  const float* row_scale, int rows_per_batch, float* D_pre, cudaStream_t stream);
+                  const float* row_scale, int rows_per_batch, float* D_pre, float drop_p, unsigned drop_seed,
+                  const int* drop_step, cudaStream_t stream);
+/* drop_p > 0: dropout on the activated output before row scale / residual (nn.Dropout(0.1) after output_proj in
+ * mmcv's MultiScaleDeformableAttention [external]); counter-based mask from (drop_seed, *drop_step, element index).
+ * ged_dropout_bwd re-draws the same mask: gz = g * keep / (1-p), db += column sums (db may be NULL). */
+int ged_dropout_bwd(const float* g, int64_t ldg, float* gz, float* db, int64_t rows, int N, float drop_p,
+                    unsigned drop_seed, const int* drop_step, cudaStream_t stream);
 /* dX of a linear / 1x1 conv: D[M,N] = A[M,K] @ Wt[K,N], Wt = the forward weight [N_out=K][K_in=N] read in place
  * as an MN-major UMMA operand (no transposed copy; torch.autograd's grad_output @ weight). */
 int ged_gemm_tf32_bt(const float* A, int lda, const float* Wt, int ldw, float* D, int ldd, int M, int N, int K,
@@ -167,12 +173,14 @@ int ged_prep_conv_input(const float* src0, int C0, int h0, int w0, const float* 
 /* out (B,h0,w0,C0) = resize^T of channels [0,C0) of g (B,H,W,ldg). */
 int ged_upsample_nhwc_bwd(const float* g, int ldg, float* out, int C0, int B, int H, int W, int h0, int w0,
                           cudaStream_t stream);
-/* acc (B,H,W,C) += bilinear(t (B,h0,w0,C) -> HxW, align_corners=True): pemask_neck.py:52-63. */
-int ged_resize_add_nhwc(const float* t, float* acc, int C, int B, int H, int W, int h0, int w0, cudaStream_t stream);
-/* gz = g * act'(ref) * row_scale[row / rows_per_batch]; db[c] += column sums (db may be NULL).
+/* out (B,H,W,C) = base + bilinear(t (B,h0,w0,C) -> HxW, align_corners=True); out may alias base: pemask_neck.py:52-63. */
+int ged_resize_add_nhwc(const float* t, const float* base, float* out, int C, int B, int H, int W, int h0, int w0,
+                        cudaStream_t stream);
+/* gz = g * act'(ref) * row_scale[row / rows_per_batch]; db[c] += column sums (db may be NULL).  g has row pitch ldg
+ * (a channel slice of a wider gradient is read in place); gz / ref are dense [rows][N].
  * ref = layer output for relu(1)/leaky(2)/sigmoid(4), pre-activation for gelu(3); act 0: copy/scale only. */
-int ged_act_bwd(const float* g, const float* ref, float* gz, float* db, const float* row_scale, int rows_per_batch,
-                int64_t rows, int N, int act, float slope, cudaStream_t stream);
+int ged_act_bwd(const float* g, int64_t ldg, const float* ref, float* gz, float* db, const float* row_scale,
+                int rows_per_batch, int64_t rows, int N, int act, float slope, cudaStream_t stream);
 
 /* tokens (B, ceil(H/P)*ceil(W/P), Cin*P*P) in Conv2d weight order from channels [0,Cin) of an NCHW batch, zero
  * padded bottom/right (embed.py:282-297): the patch-embedding conv becomes ged_gemm_tf32. */

@@ -51,7 +51,7 @@ def test_no_torch_types_in_abi():
 def test_null_arguments_are_rejected_without_a_gpu(lib):
     # argument validation happens before any CUDA call
     assert lib.ged_ge_vanilla_fwd(None, 0, None, None, None, 1, 4, 4, 2, 2, None) == -1
-    assert lib.ged_gemm_tf32(None, 0, None, 0, None, 0, 1, 1, 4, None, 0, 0.0, None, None, 1, None, None) == -1
+    assert lib.ged_gemm_tf32(None, 0, None, 0, None, 0, 1, 1, 4, None, 0, 0.0, None, None, 1, None, 0.0, 0, None, None) == -1
 
 
 def test_sass_has_tcgen05_and_tma():

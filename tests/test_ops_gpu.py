@@ -352,6 +352,46 @@ def test_conv3x3_pair_kernel(B, H, W, Cin, Cout, passes):
     _close(dx, ref_dx, 0, _gemm_tol(ref_dx, passes, 9 * Cout), "conv dX (pair)")
 
 
+def test_linear_epilogue_dropout_fwd_bwd(passes):
+    """residual + dropout_0.1(x w^T + b) with the mask drawn in the GEMM epilogue (counter-based hash of seed, device
+    step counter and element index) and re-drawn by ged_dropout_bwd: keep rate, 1/(1-p) scaling, fwd/bwd mask
+    consistency, seed / step dependence."""
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(51)
+    M, K, N, p = 3000, 128, 256, 0.1
+    x0 = torch.randn(M, K, generator=g).to(DEV)
+    w0 = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b0 = torch.randn(N, generator=g).to(DEV)
+    r0 = torch.randn(M, N, generator=g).to(DEV)
+    y0 = (x0.double() @ w0.double().t() + b0.double()).float()
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out = Kn.gemm(x0, w0, b0, None, 0.01, r0, dropout=(p, 1234, step))
+    keep = (out - r0) != 0
+    assert abs(float(keep.float().mean()) - (1 - p)) < 4e-3
+    pq = round(p * 65536) / 65536            # the kernels quantise p to 16 bits and scale by 1/(1-pq)
+    _close(torch.where(keep, out - r0, torch.zeros_like(out)), torch.where(keep, y0 / (1 - pq), torch.zeros_like(y0)), 0,
+           _gemm_tol(y0, passes, K) * 1.2 + 2e-6 * float(r0.abs().max()), "kept entries")
+    assert torch.equal(out, Kn.gemm(x0, w0, b0, None, 0.01, r0, dropout=(p, 1234, step)))          # deterministic
+    assert not torch.equal(out, Kn.gemm(x0, w0, b0, None, 0.01, r0, dropout=(p, 1235, step)))      # seed
+    step.add_(1)
+    out2 = Kn.gemm(x0, w0, b0, None, 0.01, r0, dropout=(p, 1234, step))                            # step counter
+    keep2 = (out2 - r0) != 0
+    assert 0.75 < float((keep == keep2).float().mean()) < 0.9           # independent masks agree on ~0.82 of entries
+    # autograd through kernels.linear: the backward re-draws the forward's mask
+    Kn.RNG_STEP = step
+    xs, ws, bs, rs = (t.clone().requires_grad_(True) for t in (x0, w0, b0, r0))
+    y = Kn.linear(xs, ws, bs, None, rs, None, p)
+    m = ((y.detach() - r0) != 0).float() / (1 - pq)
+    go = torch.randn_like(y)
+    (y * go).sum().backward()
+    gz = (go * m).double()
+    _close(xs.grad, (gz @ w0.double()).float(), 0, 2 * _gemm_tol(xs.grad, passes, N), "dx")
+    _close(ws.grad, (gz.t() @ x0.double()).float(), 0, 2 * _gemm_tol(ws.grad, passes, M), "dw")
+    _close(bs.grad, gz.sum(0).float(), 1e-5, 1e-4 * float(bs.grad.abs().max()), "db")
+    assert torch.equal(rs.grad, go)
+    Kn.RNG_STEP = None
+
+
 @pytest.mark.parametrize("act", [None, "relu", "gelu", "leaky_relu", "sigmoid"])
 def test_gemm_epilogue(act, passes):
     from gedepth_b200 import kernels as Kn, ops_lib as L

@@ -15,6 +15,18 @@ if which in ('all', 'gemm'):
         r = rnd(M, N) if res else None
         K.gemm(a, w, bias, None, 0.01, r)
         torch.cuda.synchronize()
+if which in ('all', 'dw'):
+    K.set_gemm_precision(1)
+    for (P, N, Kd) in [(B * 98560, 512, 512), (T0, 384, 96)]:
+        g, x = rnd(P, N), rnd(P, Kd)
+        K.gemm_dw(g, x)
+        torch.cuda.synchronize()
+    x = rnd(B, 88, 280, 576); gy = rnd(B, 88, 280, 192)
+    xp, gp = K.prep_conv_input(x, None, 88, 280), K.prep_conv_input(gy, None, 88, 280)
+    taps = [(ky - 1) * 282 + (kx - 1) for ky in range(3) for kx in range(3)]
+    K.gemm_dw(gp.reshape(-1, 192), xp.reshape(-1, 576), None, taps)
+    torch.cuda.synchronize()
+    K.set_gemm_precision(3)
 if which in ('all', 'conv'):
     for (Bc, H, W, Ci, Co) in [(B, 176, 560, 256, 64), (B, 22, 70, 2304, 768), (B, 88, 280, 576, 192)]:
         x = rnd(Bc, H, W, Ci); wk = rnd(Co, 3, 3, Ci) / (9 * Ci) ** .5
