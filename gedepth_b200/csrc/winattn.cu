@@ -46,16 +46,39 @@ __device__ __forceinline__ void load_qkv(const float* __restrict__ qkv, const fl
   }
 }
 
-__device__ __forceinline__ float dot32(const float* a, const float* b) {
-  const float4* a4 = (const float4*)a;
-  const float4* b4 = (const float4*)b;
-  float acc = 0.f;
+// 49x49 product a b^T (rows of 32 floats, pitch KP) with a 2 x 4 register tile per thread: rows {ti, ti+25},
+// columns {tj, tj+13, tj+26, tj+39}.  Neighbouring lanes take neighbouring columns, so the float4 reads of b are
+// bank-conflict free and a is a 2-3 address broadcast; per 8 outputs a thread issues 6 LDS.128 per 4 k instead of 16.
+template <class Store>
+__device__ __forceinline__ void tile_abt(const float (*a)[KP], const float (*b)[KP], Store store) {
+  for (int t = threadIdx.x; t < 25 * 13; t += WA_THREADS) {
+    const int ti = t / 13, tj = t - ti * 13;
+    const int i1 = min(ti + 25, WN - 1);
+    int j[4];
 #pragma unroll
-  for (int d = 0; d < HD / 4; ++d) {
-    const float4 x = a4[d], y = b4[d];
-    acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+    for (int c = 0; c < 4; ++c) j[c] = min(tj + 13 * c, WN - 1);
+    float acc[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD / 4; ++d) {
+      const float4 a0 = ((const float4*)a[ti])[d], a1 = ((const float4*)a[i1])[d];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 y = ((const float4*)b[j[c]])[d];
+        acc[0][c] += a0.x * y.x + a0.y * y.y + a0.z * y.z + a0.w * y.w;
+        acc[1][c] += a1.x * y.x + a1.y * y.y + a1.z * y.z + a1.w * y.w;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (tj + 13 * c >= WN) break;
+      store(ti, tj + 13 * c, acc[0][c]);
+      if (ti + 25 < WN) store(ti + 25, tj + 13 * c, acc[1][c]);
+    }
   }
-  return acc;
 }
 
 // S = q k^T + bias + mask, then row softmax, in place in s_s
@@ -63,13 +86,11 @@ __device__ __forceinline__ void scores_softmax(const float (*s_q)[KP], const flo
                                                float (*s_s)[SP], const float* __restrict__ table,
                                                const long long* __restrict__ index, int nH, int head,
                                                const int* s_lab, bool masked) {
-  for (int e = threadIdx.x; e < WN * WN; e += WA_THREADS) {
-    const int i = e / WN, j = e - i * WN;
-    float acc = dot32(s_q[i], s_k[j]);
-    acc += __ldg(table + (int64_t)__ldg(index + e) * nH + head);
+  tile_abt(s_q, s_k, [&](int i, int j, float acc) {
+    acc += __ldg(table + (int64_t)__ldg(index + i * WN + j) * nH + head);
     if (masked && s_lab[i] != s_lab[j]) acc += -100.0f;
     s_s[i][j] = acc;
-  }
+  });
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = warp; i < WN; i += WA_THREADS / 32) {
@@ -137,10 +158,7 @@ __global__ void __launch_bounds__(WA_THREADS) winattn_bwd_kernel(
   __syncthreads();
   scores_softmax(s_q, s_k, s_s, table, index, nH, head, s_lab, g.shift > 0);
   // dP -> s_d
-  for (int e = threadIdx.x; e < WN * WN; e += WA_THREADS) {
-    const int i = e / WN, j = e - i * WN;
-    s_d[i][j] = dot32(s_o[i], s_v[j]);
-  }
+  tile_abt(s_o, s_v, [&](int i, int j, float acc) { s_d[i][j] = acc; });
   __syncthreads();
   // dS = P o (dP - sum_j dP P), in place in s_d; bias-table gradient
   {
