@@ -515,16 +515,31 @@ def set_gemm_wide_tiles(on: bool) -> int:
     return load().ged_set_gemm_wide_tiles(int(bool(on)))
 
 
+# Weight-gradient GEMMs have no consumer before the optimizer, so train.Trainer can move them off the backward's
+# critical path: DW_SIDE = {"stream": side stream, "keep": [operands kept alive until the join]} (GEDEPTH_DW_STREAM=1).
+DW_SIDE = None
+
+
 def gemm_dw(g2d: torch.Tensor, x2d: torch.Tensor, out: Optional[torch.Tensor] = None, tap_off=None) -> torch.Tensor:
     """out[n, t, k] += sum_p g2d[p, n] * x2d[p + tap_off[t], k]  (rows of x2d outside the tensor count as zero).
     g2d [P, N], x2d [Px, K] with unit inner stride.  out: [N, K] (no taps) or [N, T, K]; allocated zeroed if None."""
     P, N = g2d.shape
     Px, K = x2d.shape
     T = 1 if tap_off is None else len(tap_off)
+    sunk = out is not None
     if out is None:
         out = torch.zeros((N, K) if tap_off is None else (N, T, K), dtype=torch.float32, device=g2d.device)
     taps = None if tap_off is None else (C.c_int * T)(*[int(t) for t in tap_off])
     assert g2d.stride(1) == 1 and x2d.stride(1) == 1
+    side = DW_SIDE
+    if side is not None and sunk:
+        # accumulating into the arena: fork to the side stream (joined by Trainer.step before the all-reduce)
+        side["stream"].wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side["stream"]):
+            _call("ged_gemm_dw_tf32", _p(g2d), g2d.stride(0), _p(x2d), x2d.stride(0), _p(out), T * K, N, K, P, Px, T, taps,
+                  K, _stream())
+        side["keep"].append((g2d, x2d))
+        return out
     _call("ged_gemm_dw_tf32", _p(g2d), g2d.stride(0), _p(x2d), x2d.stride(0), _p(out), T * K, N, K, P, Px, T, taps, K,
           _stream())
     return out

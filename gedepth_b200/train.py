@@ -10,6 +10,7 @@ per-GPU exactly as in the reference).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -71,6 +72,10 @@ class Trainer:
         self.step_idx = 0
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.arena.flat_p.device)
         kernels.RNG_STEP = self.step_dev     # epilogue dropout mixes the device step counter into its seed
+        # optional: weight-gradient GEMMs on a side stream, overlapping the rest of the backward (A/B switch)
+        self._dw_side = None
+        if os.environ.get("GEDEPTH_DW_STREAM", "0") == "1" and self.arena.flat_p.is_cuda:
+            self._dw_side = dict(stream=torch.cuda.Stream(), keep=[])
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self._graph = None
         self._static = None
@@ -82,7 +87,14 @@ class Trainer:
         self.arena.zero_grad()
         losses = self.model(**data_batch)
         loss, log_vars = self.model._parse_losses(losses, sync=sync_logs)
-        loss.backward()
+        kernels.DW_SIDE = self._dw_side
+        try:
+            loss.backward()
+        finally:
+            kernels.DW_SIDE = None
+        if self._dw_side is not None:               # join: every dW has landed in the arena before it is reduced / read
+            torch.cuda.current_stream().wait_stream(self._dw_side["stream"])
+            self._dw_side["keep"].clear()
         if self.world > 1:
             dist.all_reduce(self.arena.flat_g)            # ONE collective per step, NCCL over NVLink
         self.step_idx += 1
