@@ -453,11 +453,16 @@ def test_conv3x3(B, H, W, Cin, Cout, act, passes):
         y2 = L._act(pre2, act, 0.01)
         _close(y1, y2, 0, _gemm_tol(pre2, passes, 9 * Cin), "conv fwd")
     assert y1.shape == y2.shape
-    go = torch.randn_like(y2).float()
+    go = torch.randn(y2.shape, generator=g).to(DEV)
     (y1 * go).sum().backward()
     (y2 * go.double()).sum().backward()
     for n, p, q in zip(("dx", "dw", "db"), a1, a2):
-        _close(p.grad, q.grad, 0, 2 * _gemm_tol(q.grad, passes, 9 * max(Cin, Cout)), n)
+        tol = 2 * _gemm_tol(q.grad, passes, 9 * max(Cin, Cout))
+        if n == "db" and act == "sigmoid":
+            # a column sum of B*H*W terms g * y(1-y) whose y carries the forward's GEMM round-off: the error scales with
+            # sqrt(#terms), not with the (cancelling) sum itself
+            tol += (1.5e-3 if passes == 1 else 1e-5) * 0.1 * (B * H * W) ** 0.5
+        _close(p.grad, q.grad, 0, tol, n)
 
 
 def test_conv1x1_and_folded_bn():
