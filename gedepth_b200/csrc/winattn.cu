@@ -15,7 +15,7 @@ namespace ged {
 
 constexpr int WS = 7, WN = 49, HD = 32, KP = 36, SP = 49;   // KP: 16-byte aligned row pitch (float4 reads, conflict-free
                                                             // for 8 consecutive rows); SP: odd pitch of the 49x49 tiles
-constexpr int WA_THREADS = 128;
+constexpr int WA_THREADS = 256;
 
 struct WinGeom {
   int H, W, Hp, Wp, nWx, shift;
@@ -104,7 +104,7 @@ __device__ __forceinline__ void scores_softmax(const float (*s_q)[KP], const flo
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(WA_THREADS) winattn_fwd_kernel(
+__global__ void __launch_bounds__(WA_THREADS, 4) winattn_fwd_kernel(
     const float* __restrict__ qkv, const float* __restrict__ bias, const float* __restrict__ table,
     const long long* __restrict__ index, float* __restrict__ ctx, WinGeom g, int C, int nH, float scale) {
   __shared__ __align__(16) float s_q[WN][KP], s_k[WN][KP], s_v[WN][KP];
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(WA_THREADS) winattn_fwd_kernel(
 // Backward: recompute P; dV = P^T dO; dP = dO V^T; dS = P o (dP - rowsum(dP o P));
 // dQ = dS K * scale; dK = dS^T (Q*scale); d table[index] += dS.  Padded tokens send their dK, dV
 // to the qkv-bias gradient (their k, v ARE the bias).
-__global__ void __launch_bounds__(WA_THREADS) winattn_bwd_kernel(
+__global__ void __launch_bounds__(WA_THREADS, 4) winattn_bwd_kernel(
     const float* __restrict__ qkv, const float* __restrict__ bias, const float* __restrict__ table,
     const long long* __restrict__ index, const float* __restrict__ g_ctx, float* __restrict__ g_qkv,
     float* __restrict__ g_bias, float* __restrict__ g_table, WinGeom g, int C, int nH, float scale) {
