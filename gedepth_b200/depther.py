@@ -213,6 +213,16 @@ class DepthEncoderDecoder(BaseDepther):
         kwargs["pe_ori_point_test"] = kwargs["pe_ori_point"][0]
         if "pe_k_gt" in kwargs:
             kwargs["pe_k_gt_test"] = kwargs["pe_k_gt"][0]
+        m0, m1 = img_metas[0][0], (img_metas[1][0] if len(imgs) == 2 else None)
+        if (m1 is not None and not m0.get("flip") and m1.get("flip") and m1.get("flip_direction") == "horizontal"
+                and self.test_cfg["mode"] == "whole" and ops.use_native("tta_merge")):
+            # the two-view flip TTA of every GE config: un-flip + average in one kernel (ops.tta_merge)
+            p0 = self.whole_inference(imgs[0], img_metas[0], rescale, **kwargs)
+            kwargs.update({"pe_ori_point_test": kwargs["pe_ori_point"][1]})
+            if "pe_k_gt" in kwargs:
+                kwargs.update({"pe_k_gt_test": kwargs["pe_k_gt"][1]})
+            p1 = self.whole_inference(imgs[1], img_metas[1], rescale, **kwargs)
+            return list(ops.tta_merge(p0, p1).cpu().numpy())
         depth_pred = self.inference(imgs[0], img_metas[0], rescale, **kwargs)
         for i in range(1, len(imgs)):
             kwargs.update({"pe_ori_point_test": kwargs["pe_ori_point"][i]})

@@ -61,6 +61,8 @@ SIGNATURES = {
     "ged_set_gemm_pair": [_I],
     "ged_set_msda_variant": [_I],
     "ged_gemm_dw_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I64, _I64, _I, _P, _I, _P],
+    "ged_depth_metrics": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P],
+    "ged_tta_merge": [_P, _P, _P, _I, _I, _I, _P],
     "ged_sumsq": [_P, _I64, _P, _P],
     "ged_adamw_step": [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _F, _I, _P, _P],
 }
@@ -71,7 +73,7 @@ _load_error: Optional[str] = None
 # ops whose sm_100a kernel is wired in (ops.py consults has()); everything else is a library call
 NATIVE_OPS = {"ground_plane", "ge_vanilla", "ge_adaptive", "fuse_head", "silog", "cross_entropy",
               "layer_norm", "window_attention", "msda_sample", "linear", "conv2d", "conv_bn_act",
-              "conv2d_cat", "resize_add", "batch_norm", "patch_embed", "merge_patches", "clamp_resize", "find_k", "adamw"}
+              "conv2d_cat", "resize_add", "batch_norm", "patch_embed", "merge_patches", "clamp_resize", "find_k", "depth_metrics", "tta_merge", "adamw"}
 
 
 def load():
@@ -1067,6 +1069,31 @@ def msda_sample(v, shapes, ref, off, logit, nH, P):
     if ref.shape[0] == 1 and ref.requires_grad and B > 1:
         ref = ref.expand(B, -1, -1)        # learnable reference points shared over the batch
     return _MSDA.apply(v, ref, off, logit, shapes, nH, P)
+
+
+# =============================================================================================
+# evaluation
+# =============================================================================================
+def depth_metric_sums(pred: torch.Tensor, gt: torch.Tensor, rect, min_depth: float, max_depth: float,
+                      sums: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B,10) fp64 per-image sums (see include/gedepth.h); pred / gt (B,H,W) or (B,1,H,W) fp32 on the device."""
+    pred, gt = _f32c(pred), _f32c(gt)
+    H, W = gt.shape[-2], gt.shape[-1]
+    B = gt.numel() // (H * W)
+    assert pred.numel() == gt.numel()
+    if sums is None:
+        sums = torch.zeros(B, 10, dtype=torch.float64, device=gt.device)
+    y0, y1, x0, x1 = (0, H, 0, W) if rect is None else [int(v) for v in rect]
+    _call("ged_depth_metrics", _p(pred), _p(gt), _p(sums), B, H, W, y0, y1, x0, x1, float(min_depth), float(max_depth), _stream())
+    return sums
+
+
+def tta_merge(a: torch.Tensor, b_flipped: torch.Tensor) -> torch.Tensor:
+    a, b_flipped = _f32c(a), _f32c(b_flipped)
+    H, W = a.shape[-2], a.shape[-1]
+    out = torch.empty_like(a)
+    _call("ged_tta_merge", _p(a), _p(b_flipped), _p(out), a.numel() // (H * W), H, W, _stream())
+    return out
 
 
 # =============================================================================================

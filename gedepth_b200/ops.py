@@ -44,7 +44,8 @@ def native_table():
 
 OPS = ["linear", "layer_norm", "patch_embed", "merge_patches", "window_attention", "conv2d",
        "conv_bn_act", "conv2d_cat", "batch_norm", "resize", "resize_add", "msda_sample", "ground_plane", "ge_vanilla",
-       "ge_adaptive", "fuse_head", "silog", "cross_entropy", "clamp_resize", "find_k", "adamw"]
+       "ge_adaptive", "fuse_head", "silog", "cross_entropy", "clamp_resize", "find_k", "depth_metrics", "tta_merge",
+       "adamw"]
 
 
 # ---- GEMM-shaped ---------------------------------------------------------------------------
@@ -237,6 +238,17 @@ def cross_entropy(logits, target, ignore_index=255):
     if use_native("cross_entropy"):
         return _k().cross_entropy(logits, target, ignore_index)
     return L.cross_entropy(logits, target, ignore_index)
+
+
+def depth_metric_sums(pred, gt, rect, min_depth, max_depth, sums=None):
+    """(B,10) fp64 sums of the nine-metric reduction (metrics.py:8-45) over the evaluation mask."""
+    require_cuda(pred, gt)
+    return _k().depth_metric_sums(pred, gt, rect, min_depth, max_depth, sums)
+
+
+def tta_merge(a, b_flipped):
+    require_cuda(a, b_flipped)
+    return _k().tta_merge(a, b_flipped)
 
 
 def find_k(gt, pe, h, truncate=False):

@@ -215,6 +215,15 @@ int ged_msda_bwd(const float* value, const float* ref, int ref_batch, const floa
  * (one query x 8 heads when Q >= 2 S).  Returns the previous value. */
 int ged_set_msda_variant(int v);
 
+/* ---- evaluation on the device (depth/core/evaluation/metrics.py:8-45, depth/datasets/kitti.py:355-385) ---- */
+/* Per-image sums over the mask {y0<=y<y1, x0<=x<x1, min_depth < gt < max_depth}; sums (B,10) fp64, ACCUMULATED:
+ * [count, #thresh<1.25, #<1.25^2, #<1.25^3, sum|g-p|/g, sum(g-p)^2/g, sum(g-p)^2, sum(ln g-ln p)^2, sum(ln p-ln g),
+ *  sum|log10 g-log10 p|] from which a1,a2,a3,abs_rel,rmse,log_10,rmse_log,silog,sq_rel follow. */
+int ged_depth_metrics(const float* pred, const float* gt, double* sums, int B, int H, int W, int y0, int y1, int x0,
+                      int x1, float min_depth, float max_depth, cudaStream_t stream);
+/* Flip test-time augmentation (encoder_decoder.py:226-233,262-270): out = (a + hflip(b_flipped)) / 2. */
+int ged_tta_merge(const float* a, const float* b_flipped, float* out, int B, int H, int W, cudaStream_t stream);
+
 /* ---- optimizer (configs/depthformer/depthformer_v.py:128-148) ---------------------------------- */
 int ged_sumsq(const float* g, int64_t n, double* out, cudaStream_t stream);
 int ged_adamw_step(float* p, const float* g, float* m, float* v, const uint8_t* wd_mask, int64_t n,

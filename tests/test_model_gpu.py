@@ -90,6 +90,25 @@ def test_inference_matches_reference(name):
     assert abs(a - r) < 1e-4, (a, r)
 
 
+def test_flip_tta_fused_average_equals_reference_sequence(monkeypatch):
+    """aug_test with the two views of every GE config (plain + horizontal flip, encoder_decoder.py:249-274): the fused
+    un-flip + average kernel gives what the reference's flip / add / divide sequence gives."""
+    from gedepth_b200 import ops
+    case, g, b = load_case("vanilla_eval_ragged")
+    model, _ = build_host_model(case, DEV)
+    model.eval()
+    img = torch.from_numpy(b["img"]).to(DEV)
+    metas0 = metas_for(case)
+    metas1 = [dict(m, flip=True, flip_direction="horizontal") for m in metas0]
+    kw = dict(pe_ori_point=[torch.zeros(1), torch.zeros(1)])
+    with torch.no_grad():
+        fast = model(img=[img, img.flip(3)], img_metas=[metas0, metas1], return_loss=False, **kw)
+        monkeypatch.setattr(ops, "_FORCE_LIB", {"tta_merge"})
+        slow = model(img=[img, img.flip(3)], img_metas=[metas0, metas1], return_loss=False, **kw)
+    np.testing.assert_allclose(fast[0], slow[0], rtol=1e-6, atol=1e-6)
+    assert np.abs(fast[0] - g["pred"][0]).max() > 1e-4          # it really is a two-view average, not view 0
+
+
 def test_library_statement_path_equals_reference_on_gpu(monkeypatch):
     """Same host mirror with every op forced to its library statement (fp32, no TF32): isolates
     wiring errors from kernel numerics."""

@@ -724,3 +724,45 @@ def test_batchnorm_train_fwd_bwd(B, C, H, W, relu):
     _close(a.grad, c.grad, 1e-3, 2e-5 * float(c.grad.abs().max()), "dx")
     _close(bn1.weight.grad, bn2.weight.grad, 1e-3, 1e-4 * float(bn2.weight.grad.abs().max()), "dw")
     _close(bn1.bias.grad, bn2.bias.grad, 1e-3, 1e-4 * float(bn2.bias.grad.abs().max()), "db")
+
+
+# ------------------------------------------------------------------------------------------------
+# evaluation on the device
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,garg", [(3, 352, 1216, True), (2, 70, 166, False), (2, 384, 640, True)])
+def test_depth_metrics_match_reference_numpy(B, H, W, garg):
+    """Nine metrics + Garg crop + min/max mask + nan-mean over images vs the numpy restatement of
+    depth/core/evaluation/metrics.py / kitti.py:366-385 (oracle.ground.depth_metrics)."""
+    from gedepth_b200 import metrics as Mx
+    from oracle import ground as og
+    g = torch.Generator().manual_seed(61)
+    gt = torch.rand(B, H, W, generator=g) * 90 + 0.5
+    gt[torch.rand(B, H, W, generator=g) < 0.8] = 0          # LiDAR-sparse
+    gt[B - 1] = 0                                           # an image without valid pixels -> NaN row, skipped by nanmean
+    pred = (gt * (1 + 0.1 * torch.randn(B, H, W, generator=g))).clamp(1e-3, 80) + (gt == 0) * 10.0
+    dm = Mx.DepthMetrics(1e-3, 80.0, garg_crop=garg)
+    per_image = dm.update(pred.to(DEV), gt.to(DEV)).cpu().numpy()
+    rect = Mx.crop_rect(H, W, garg)
+    rows = []
+    for b in range(B):
+        gtb, pb = gt[b].numpy(), pred[b].numpy()
+        mask = np.ones((H, W), bool)
+        if rect is not None:
+            mask[:] = False
+            mask[rect[0]:rect[1], rect[2]:rect[3]] = True
+        valid = mask & (gtb > 1e-3) & (gtb < 80.0)
+        rows.append(og.depth_metrics(gtb[valid], pb[valid], 1e-3, 80.0))
+    ref = np.array(rows, dtype=np.float64)
+    assert np.isnan(per_image[B - 1]).all() and np.isnan(ref[B - 1]).all()
+    np.testing.assert_allclose(per_image[:B - 1], ref[:B - 1], rtol=2e-5, atol=1e-6)
+    out = dm.compute()
+    assert list(out) == ["a1", "a2", "a3", "abs_rel", "rmse", "log_10", "rmse_log", "silog", "sq_rel"]
+    np.testing.assert_allclose(list(out.values()), np.nanmean(ref, 0), rtol=2e-5, atol=1e-6)
+    assert abs(out["abs_rel"] - np.nanmean(ref, 0)[3]) < 1e-4        # the north star's Abs-Rel bar
+
+
+def test_tta_merge_is_unflip_and_average():
+    from gedepth_b200 import kernels as Kn
+    a = torch.randn(2, 1, 37, 53, device=DEV)
+    b = torch.randn(2, 1, 37, 53, device=DEV)
+    _close(Kn.tta_merge(a, b), (a + b.flip(3)) / 2, 0, 1e-7, "tta")
