@@ -1,8 +1,9 @@
 // TF32 tensor-core GEMM / implicit-GEMM 3x3 convolution for sm_100a: tcgen05.mma (kind::tf32) with
 // the accumulator in TMEM, operands staged by TMA into 128B-swizzled shared memory through an
-// mbarrier ring, warp-specialised (TMA producer / single-thread MMA issuer / 4 epilogue warps),
-// persistent over output tiles with a double-buffered TMEM accumulator so the epilogue of tile i
-// overlaps the main loop of tile i+1.
+// mbarrier ring, warp-specialised (TMA producer / single-thread MMA issuer / 8 epilogue warps / 4 splitter warps
+// for 3xTF32), persistent over output tiles with a double-buffered TMEM accumulator so the epilogue of tile i
+// overlaps the main loop of tile i+1.  Two kernels share the epilogue: gemm_tf32_kernel (one CTA per 128 x BN tile)
+// and gemm2_tf32_kernel (a CTA pair, cta_group::2, per 256 x BN tile - used for the 3xTF32 arithmetic).
 //
 //   D[M,N] = epi( sum_t  A[m + tap_off[t], 0:Kt] . B[n, t*Kt : (t+1)*Kt]^T )
 //
@@ -15,7 +16,11 @@
 // fp32 in HBM, tf32 multiply, fp32 accumulate: the reference's cuDNN convs run TF32 by default
 // (torch.backends.cudnn.allow_tf32) and its fp32 linears are the precision bar.
 //
-// Epilogue (fused, in order): + bias[n] -> activation -> * row_scale[batch(m)] -> + residual[m,n].
+// The same kernel also runs the backward: dX with the forward weight read in place as an MN-major B operand
+// (ged_gemm_tf32_bt, ged_conv3x3_dx_tf32) and dW with BOTH operands MN-major, the contraction over pixels split across
+// SMs and accumulated with vector atomics (ged_gemm_dw_tf32).
+//
+// Epilogue (fused, in order): + bias[n] -> activation -> dropout -> * row_scale[batch(m)] -> + residual[m,n].
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include "common.cuh"

@@ -615,7 +615,8 @@ def _gemm_ok(M, N, K, *tensors):
 class _Linear(Function):
     """y = [residual +] [row_scale *] act(x @ w^T + b).  Forward and dX on tcgen05 (GELU keeps its
     pre-activation through the epilogue's second store); the activation derivative, DropPath scale and
-    the bias gradient are one fused pass; dW = gz^T @ x is a cuBLAS TF32 GEMM for now."""
+    the bias gradient are one fused pass; dX reads the weight in place (MN-major operand); dW = gz^T @ x runs on the
+    activations as stored and accumulates into the arena when the parameter lives there."""
 
     @staticmethod
     def forward(ctx, x, w, b, act, residual, row_scale, w_sink=None, b_sink=None, dropout=None):
@@ -749,7 +750,8 @@ def conv3x3_raw(x_nhwc: torch.Tensor, wk: torch.Tensor, bias, act, slope) -> tor
 class _Conv(Function):
     """3x3/s1/p1 or 1x1 conv + bias + activation over [resize(x0) | x1] (x1 optional, resize only when
     x0 is smaller).  Forward and dX on tcgen05 (dX of a 3x3 conv is the 3x3 conv of dY with the flipped,
-    transposed kernel); activation derivative + bias gradient one fused pass; dW via cuDNN for now."""
+    transposed kernel, read in place from the forward weights); activation derivative + bias gradient one fused pass;
+    dW = nine row-shifted contractions of bordered dY against bordered X on tcgen05.  Cout in {1, 11} go to cuDNN."""
 
     @staticmethod
     def forward(ctx, x0, x1, w, b, act, slope, w_sink=None, b_sink=None):
@@ -869,7 +871,7 @@ def conv2d_cat_supported(x0, x1, w) -> bool:
 def conv_bn_act(x, w, b, bn, stride=1, padding=0, act=None):
     """ConvModule(conv -> BN -> act).  Eval mode: BN folds into the conv's weight/bias and the
     activation into its epilogue.  Train mode needs batch statistics between conv and activation:
-    conv (tcgen05) -> BatchNorm (library, per-GPU statistics as in the reference) -> act."""
+    conv (tcgen05) -> ged_bn_train (per-GPU batch statistics as in the reference) (+ReLU)."""
     return conv_bn_act_cat(x, None, w, b, bn, act)
 
 
