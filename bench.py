@@ -417,6 +417,47 @@ def main():
               at_sweep_max=dict(shape=[32, 1024, 2048], achieved=bw_big, frac=bw_big / pk["hbm"], us=us_big),
               traffic=ncu_traffic.get("ge_vanilla_fwd_kernel"), l2_flushed_between_iterations=True)
 
+    # ---- Swin window attention (QKV GEMM -> 49x49 core -> proj GEMM), the north star's tensor-pipe target -----
+    def swin_attention(tokens_hw, Cc, nH, shift):
+        hh, ww = tokens_hw
+        T = Bn * hh * ww
+        x = torch.randn(Bn, hh * ww, Cc, device=dev)
+        wq, bq = torch.randn(3 * Cc, Cc, device=dev) / Cc ** 0.5, torch.randn(3 * Cc, device=dev) * 0.02
+        wp, bp = torch.randn(Cc, Cc, device=dev) / Cc ** 0.5, torch.randn(Cc, device=dev) * 0.02
+        table = torch.randn(169, nH, device=dev) * 0.2
+        from gedepth_b200.swin import WindowMSA
+        index = WindowMSA(Cc, nH, (7, 7)).relative_position_index.to(dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        with torch.no_grad():
+            def run(record):
+                if record: ev[0].record()
+                qkv = kernels.linear(x, wq, bq)
+                if record: ev[1].record()
+                ctx = kernels.window_attention(qkv, bq, table, index, (hh, ww), nH, 7, shift, 32 ** -0.5)
+                if record: ev[2].record()
+                out = kernels.linear(ctx, wp, bp, None, x)
+                if record: ev[3].record()
+                return out
+            for _ in range(3):
+                run(False)
+            run(True)
+            torch.cuda.synchronize()
+        t = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+        nW = (-(-hh // 7)) * (-(-ww // 7)) * Bn
+        f_gemm = 2.0 * T * Cc * 3 * Cc + 2.0 * T * Cc * Cc
+        f_core = 2.0 * nW * nH * 49 * 49 * 32 * 2
+        ms = sum(t)
+        return dict(shape=dict(tokens=[Bn, hh, ww], C=Cc, heads=nH, shift=shift), ms=dict(qkv=t[0], core=t[1], proj=t[2]),
+                    algorithmic_tflops=(f_gemm + f_core) / ms / 1e9,
+                    issued_mma_tflops=args.passes * f_gemm / ms / 1e9,
+                    tensor_pipe_frac=args.passes * f_gemm / ms / 1e9 / (pk["bf16_sustained"] / 2.0),
+                    note="QKV and proj run on tcgen05 (3xTF32 when passes=3); the 49x49 core is a SIMT fp32 kernel, so its "
+                         "flops do not count towards the tensor pipe")
+    e0 = 96 if args.backbone == "swin_t" else 192
+    h0 = 3 if args.backbone == "swin_t" else 6
+    swin_attn = [swin_attention((-(-H // 4), -(-W // 4)), e0, h0, 3),
+                 swin_attention((-(-H // 16), -(-W // 16)), 4 * e0, 4 * h0, 0)]
+
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
@@ -435,6 +476,7 @@ def main():
                             l2="inputs + activations per step (>2 GB) exceed the 126 MB L2"),
                 e2e=dict(value=e2e_val, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e),
                 gpu_launches=launches, clocks=clk, roofline=roof, roofline_tensor=roof_tensor, ground_embed=ge,
+                swin_window_attention=swin_attn,
                 cpu_baseline=cpu,
                 native_ops=ops.native_table(),
                 kernel_ms={k: round(v["ms"], 3) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])},
