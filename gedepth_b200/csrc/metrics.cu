@@ -62,8 +62,48 @@ __global__ void __launch_bounds__(256) tta_merge_kernel(const float* __restrict_
   }
 }
 
+// Test-time input (configs/depthformer/depthformer_v.py:33-53): KBCrop window (transforms.py:176-197) -> optional
+// horizontal flip (RandomFlip) -> Normalize = mmcv.imnormalize [external]: BGR->RGB, then cv2.subtract / cv2.multiply
+// on a float32 image with float64 scalars, i.e. each op in double, rounded to float32 (verified against cv2).
+// src: uint8 (H0, W0, 3) BGR as cv2 / mmcv.imfrombytes deliver it; dst: planes 0..2 of a (5, H, W) float32 image.
+__global__ void __launch_bounds__(256) rgb_crop_normalize_kernel(const uint8_t* __restrict__ src, int W0, int top, int left,
+                                                                  int flip, int to_rgb, double m0, double m1, double m2,
+                                                                  double i0, double i1, double i2, float* __restrict__ dst,
+                                                                  int H, int W) {
+  const int64_t total = (int64_t)H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+    const int sx = left + (flip ? W - 1 - x : x);
+    const uint8_t* px = src + ((int64_t)(top + y) * W0 + sx) * 3;
+    const double mean[3] = {m0, m1, m2}, inv[3] = {i0, i1, i2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = (float)px[to_rgb ? 2 - c : c];
+      const float r1 = (float)((double)v - mean[c]);
+      dst[(int64_t)c * total + i] = (float)((double)r1 * inv[c]);
+    }
+  }
+}
+
 }  // namespace ged
 using namespace ged;
+
+// dst (5,H,W): planes 0..2 <- normalised RGB of the crop window [top, top+H) x [left, left+W) of the uint8 BGR image
+// (H0, W0, 3); flip = horizontal mirror of the cropped image.  mean / std: 3 values each (as in img_norm_cfg).
+// Planes 3 / 4 (the ground-plane channels) come from ged_ground_plane with u0 = left (or left+W-1, su = -1 when flipped).
+GED_API int ged_rgb_crop_normalize(const unsigned char* bgr, int H0, int W0, int top, int left, int flip, int to_rgb,
+                                   const float* mean3, const float* std3, float* dst, int H, int W, cudaStream_t stream) {
+  if (!bgr || !mean3 || !std3 || !dst || H <= 0 || W <= 0) return GED_ERR_ARG;
+  if (top < 0 || left < 0 || top + H > H0 || left + W > W0) return GED_ERR_SHAPE;
+  const int64_t total = (int64_t)H * W;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  rgb_crop_normalize_kernel<<<blocks, 256, 0, stream>>>(bgr, W0, top, left, flip, to_rgb, (double)mean3[0], (double)mean3[1],
+                                                       (double)mean3[2], 1.0 / (double)std3[0], 1.0 / (double)std3[1],
+                                                       1.0 / (double)std3[2], dst, H, W);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
 
 // sums (B,10) fp64 must be zeroed by the caller (accumulated, so several crops / chunks can be added up).
 // Mask: y0 <= y < y1, x0 <= x < x1 and min_depth < gt < max_depth (kitti.py:366-385, metrics.py:35-41).

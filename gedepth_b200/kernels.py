@@ -63,6 +63,7 @@ SIGNATURES = {
     "ged_gemm_dw_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I64, _I64, _I, _P, _I, _P],
     "ged_depth_metrics": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P],
     "ged_tta_merge": [_P, _P, _P, _I, _I, _I, _P],
+    "ged_rgb_crop_normalize": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P],
     "ged_sumsq": [_P, _I64, _P, _P],
     "ged_adamw_step": [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _F, _I, _P, _P],
 }
@@ -1088,6 +1089,19 @@ def depth_metric_sums(pred: torch.Tensor, gt: torch.Tensor, rect, min_depth: flo
     y0, y1, x0, x1 = (0, H, 0, W) if rect is None else [int(v) for v in rect]
     _call("ged_depth_metrics", _p(pred), _p(gt), _p(sums), B, H, W, y0, y1, x0, x1, float(min_depth), float(max_depth), _stream())
     return sums
+
+
+def rgb_crop_normalize_into(img5: torch.Tensor, bgr_u8: torch.Tensor, top: int, left: int, flip: bool, mean, std,
+                            to_rgb: bool = True):
+    """Planes 0..2 of one (5,H,W) slice of the input batch from a uint8 (H0,W0,3) BGR image on the device."""
+    assert bgr_u8.dtype == torch.uint8 and bgr_u8.is_contiguous() and bgr_u8.dim() == 3 and bgr_u8.shape[2] == 3
+    assert img5.dtype == torch.float32 and img5.is_contiguous() and img5.shape[0] == 5
+    H, W = img5.shape[1], img5.shape[2]
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    sd = (C.c_float * 3)(*[float(v) for v in std])
+    _call("ged_rgb_crop_normalize", _p(bgr_u8), bgr_u8.shape[0], bgr_u8.shape[1], int(top), int(left), int(bool(flip)),
+          int(bool(to_rgb)), m, sd, _p(img5), H, W, _stream())
+    return img5
 
 
 def tta_merge(a: torch.Tensor, b_flipped: torch.Tensor) -> torch.Tensor:

@@ -224,6 +224,12 @@ int ged_depth_metrics(const float* pred, const float* gt, double* sums, int B, i
 /* Flip test-time augmentation (encoder_decoder.py:226-233,262-270): out = (a + hflip(b_flipped)) / 2. */
 int ged_tta_merge(const float* a, const float* b_flipped, float* out, int B, int H, int W, cudaStream_t stream);
 
+/* Test-time input on the device (configs/depthformer/depthformer_v.py:33-53: KBCrop -> flip -> Normalize): planes
+ * 0..2 of dst (5,H,W) <- mmcv.imnormalize of the [top,left] crop of a uint8 BGR image (H0,W0,3), optionally mirrored;
+ * bit-exact with cv2's float32 arithmetic.  mean3 / std3 are HOST pointers.  Planes 3/4: ged_ground_plane. */
+int ged_rgb_crop_normalize(const unsigned char* bgr, int H0, int W0, int top, int left, int flip, int to_rgb,
+                           const float* mean3, const float* std3, float* dst, int H, int W, cudaStream_t stream);
+
 /* ---- optimizer (configs/depthformer/depthformer_v.py:128-148) ---------------------------------- */
 int ged_sumsq(const float* g, int64_t n, double* out, cudaStream_t stream);
 int ged_adamw_step(float* p, const float* g, float* m, float* v, const uint8_t* wd_mask, int64_t n,

@@ -766,3 +766,35 @@ def test_tta_merge_is_unflip_and_average():
     a = torch.randn(2, 1, 37, 53, device=DEV)
     b = torch.randn(2, 1, 37, 53, device=DEV)
     _close(Kn.tta_merge(a, b), (a + b.flip(3)) / 2, 0, 1e-7, "tta")
+
+
+@pytest.mark.parametrize("H0,W0", [(375, 1242), (370, 1226)])
+def test_test_time_views_bit_exact_vs_reference_pipeline(H0, W0):
+    """KBCrop -> (flip) -> Normalize of the reference's test pipeline (transforms.py:40-48,176-197; mmcv.imnormalize via
+    cv2) on the 5-channel image of loading.py:490-527, restated with numpy / cv2, vs the device-side builder."""
+    import cv2
+    from gedepth_b200 import inputs as I
+    from oracle import ground as og
+    rng = np.random.default_rng(5)
+    bgr = rng.integers(0, 256, (H0, W0, 3), dtype=np.uint8)
+    coef = og.plane_coefficients(og.kitti_projection(), og.KITTI_CAM_HEIGHT)
+    imgs, metas, pts = I.build_test_views(torch.from_numpy(bgr).to(DEV), coef)
+    # reference restatement
+    pe = og.ground_plane(coef, H0, W0)
+    ch3, ch4 = og.load_channels(pe, 200.0)
+    img5 = np.concatenate([bgr.astype(np.float32), ch3[..., None], ch4[..., None]], -1)          # loading.py:524-527
+    top, left = int(H0 - 352), int((W0 - 1216) / 2)
+    img5 = img5[top:top + 352, left:left + 1216]
+    assert abs(float(pts[0]) - float(ch4[-1, -1])) <= 1e-6 * abs(float(ch4[-1, -1]))
+    for view, flip in zip(imgs, (False, True)):
+        x = img5[:, ::-1].copy() if flip else img5.copy()                                      # mmcv.imflip horizontal
+        rgb = x[:, :, 0:3].copy().astype(np.uint8).astype(np.float32)
+        mean = np.float64(np.array(I.KITTI_MEAN, np.float32).reshape(1, -1))
+        stdinv = 1 / np.float64(np.array(I.KITTI_STD, np.float32).reshape(1, -1))
+        cv2.cvtColor(rgb, cv2.COLOR_BGR2RGB, rgb); cv2.subtract(rgb, mean, rgb); cv2.multiply(rgb, stdinv, rgb)
+        want = np.concatenate([rgb, og.normalize_pe(x[:, :, 3], 200.0)[..., None], x[:, :, 4:5]], -1).transpose(2, 0, 1)
+        got = view[0].cpu().numpy()
+        assert got.shape == (5, 352, 1216)
+        assert np.array_equal(got[0:3], want[0:3]), "RGB planes must equal cv2's float32 result bit for bit"
+        assert np.array_equal(got[3], want[3]) and np.array_equal(got[4], want[4]), "ground-plane channels"
+    assert metas[1][0]["flip"] and metas[1][0]["flip_direction"] == "horizontal"
