@@ -198,6 +198,22 @@ def test_arena_gradient_sinks_equal_autograd_accumulation(name):
         assert float((ga - gb).abs().max()) <= tol, (n, float((ga - gb).abs().max()), float(ga.abs().max()))
 
 
+def test_training_reduces_the_loss_on_a_fixed_batch():
+    """Functional check of the whole optimisation loop (forward, SiLog, backward with gradient sinks, clip, AdamW on
+    the flat arena, CUDA-graph replay): 40 steps on one fixed batch must drive the loss down."""
+    from gedepth_b200.train import Trainer
+    case, g, b = load_case("vanilla_train")
+    data = dict(img=torch.from_numpy(b["img"]).to(DEV), img_metas=metas_for(case),
+                depth_gt=torch.from_numpy(b["depth_gt"]).to(DEV))
+    model, _ = build_host_model(case, DEV)
+    model.train()
+    tr = Trainer(model, lr=3e-4)
+    tr.capture(data, warmup=2)
+    losses = [float(tr.step_graph(data).detach()) for _ in range(40)]
+    assert all(np.isfinite(losses)), losses
+    assert np.mean(losses[-5:]) < 0.8 * losses[0], (losses[0], losses[-5:])       # measured: 0.689 -> 0.456
+
+
 def test_product_fails_loudly_without_extension(monkeypatch):
     from gedepth_b200 import kernels
     monkeypatch.setattr(kernels, "_lib", None)
