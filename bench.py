@@ -297,7 +297,10 @@ def main():
             elif name == "ged_msda_bwd":       # + g_out read, g_value read-modify-write, g_off / g_logit written
                 Bq, Sq, Qq, nHq = a[12], a[13], a[14], a[15]
                 flops = 4.0 * (3 * Bq * Sq * nHq * 64 + 2 * Bq * Qq * nHq * 96 + Bq * Qq * nHq * 64)
-            records.append((name, s, e, flops))
+            atom = 0.0
+            if name == "ged_msda_bwd":
+                atom = 32.0 * 4 * 256 * a[12] * a[14] * a[15]          # B * Q * nH rows of 128 corner segments
+            records.append((name, s, e, flops, atom))
 
         step_eager(1)                      # re-warm the eager path (allocator pools differ from the graph's)
         kernels._call = prof_call
@@ -309,7 +312,7 @@ def main():
         torch.cuda.synchronize()
         kernels._call = orig_call
         step_ms = e0.elapsed_time(e1)
-        for name, s, e, fl in records:
+        for name, s, e, fl, _atom in records:
             d = prof.setdefault(name, dict(ms=0.0, calls=0, flops=0.0))
             d["ms"] += s.elapsed_time(e)
             d["calls"] += 1
@@ -359,8 +362,18 @@ def main():
         # gather/atomics-bound kernel (MSDA): algorithmic bytes = 32 points x 4 corners x 256 B per (query, head),
         # served by L1/L2, not HBM - reported against the HBM peak for scale only
         gbs = kern[dom]["flops"] / (kern[dom]["ms"] / 1e3) / 1e9 if kern[dom]["flops"] else None
+        l2_atomic = None
+        if dom == "ged_msda_bwd":
+            # what actually bounds it: L2 atomic throughput.  Payload = 32 points x 4 corners x 256 B per (query, head)
+            # of every MSDA call of the step, against the measured rate of the bare scatter pattern.
+            peak_atom = kernels.msda_atomic_probe(device=dev)
+            payload = sum(r[4] for r in records if r[0] == "ged_msda_bwd")
+            ach = payload / (kern[dom]["ms"] / 1e3) / 1e9
+            l2_atomic = dict(achieved=ach, peak=peak_atom, unit="GB/s of red.global.add.v4.f32 payload", frac=ach / peak_atom,
+                             peak_src="ged_msda_atomic_probe (same 256-byte row scatter, no gathers), measured in this run",
+                             note="the fused kernel also gathers the same rows for the offset / weight gradients")
         roof = dict(kernel=dom, bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s",
-                    frac=(gbs / pk["hbm"]) if gbs else None, traffic=ncu_traffic.get(dom),
+                    frac=(gbs / pk["hbm"]) if gbs else None, traffic=ncu_traffic.get(dom), l2_atomic=l2_atomic,
                     calls_per_step=kern[dom]["calls"], share_of_step=kern[dom]["ms"] / ms_step,
                     note="achieved = COMPULSORY HBM bytes (each operand once) / time. The deformable-attention "
                          "kernels are bound by the L1 gather of 32x4 corner segments per (query, head) and by L2 "

@@ -220,8 +220,35 @@ __global__ void __launch_bounds__(MS_WARPS * 32) msda_bwd_kernel(
   }
 }
 
+// Roofline probe for the backward: nothing but the scatter pattern of msda_bwd - every half-warp adds one 256-byte
+// row (16 lanes x red.global.add.v4.f32) at a pseudo-random position of a value-map-sized buffer, full occupancy, no
+// gathers, no arithmetic.  Its payload rate is the L2 atomic throughput the backward can at best reach.
+__global__ void __launch_bounds__(256) atomic_probe_kernel(float* __restrict__ buf, int rows, int rowpitch, int heads,
+                                                            int iters) {
+  const int lane = threadIdx.x & 31, half = lane >> 4, cl = (lane & 15) * 4;
+  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int h = wid % heads;
+  uint32_t state = wid * 2654435761u + 12345u;
+  const float4 v = make_float4(1e-9f, 1e-9f, 1e-9f, 1e-9f);
+  for (int i = 0; i < iters; ++i) {
+    state = state * 1664525u + 1013904223u;
+    const uint32_t r = ((state >> 8) + (uint32_t)half * 7919u) % (uint32_t)rows;
+    atomicAdd((float4*)(buf + (int64_t)r * rowpitch + h * MS_HD + cl), v);
+  }
+}
+
 }  // namespace ged
 using namespace ged;
+
+// Measures nothing itself: enqueues `iters` row-atomics per half-warp (2 * 256 bytes per warp and iteration) on a
+// (rows, heads*64) buffer; bench.py times it with CUDA events.  Returns the number of warps launched.
+GED_API int ged_msda_atomic_probe(float* buf, int rows, int heads, int iters, cudaStream_t stream) {
+  if (!buf || rows <= 0 || heads <= 0 || iters <= 0) return GED_ERR_ARG;
+  const int blocks = 148 * 8;
+  atomic_probe_kernel<<<blocks, 256, 0, stream>>>(buf, rows, heads * MS_HD, heads, iters);
+  if (cudaGetLastError() != cudaSuccess) return GED_ERR_LAUNCH;
+  return blocks * 8;
+}
 
 // bit0: MAP (1 = one query x 8 heads per CTA), bit1: split backward (scatter + gather kernels), -1 = auto: MAP 1 for
 // cross-attention-sized query sets (Q >= 2 S; measured 4-5 % faster there, slightly slower for Q = S)

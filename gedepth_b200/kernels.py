@@ -1061,6 +1061,23 @@ class _MSDA(Function):
         return g_v, g_ref, g_off, g_logit, None, None, None
 
 
+def msda_atomic_probe(rows: int = 32725, heads: int = 8, iters: int = 2000, device="cuda") -> float:
+    """GB/s of atomic payload the L2 sustains for the MSDA backward's scatter pattern (roofline denominator)."""
+    lib = load()
+    lib.ged_msda_atomic_probe.argtypes = [_P, _I, _I, _I, _P]
+    lib.ged_msda_atomic_probe.restype = C.c_int
+    buf = torch.zeros(rows, heads * 64, dtype=torch.float32, device=device)
+    lib.ged_msda_atomic_probe(_p(buf), rows, heads, 50, _stream())
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    warps = lib.ged_msda_atomic_probe(_p(buf), rows, heads, iters, _stream())
+    e.record()
+    torch.cuda.synchronize()
+    if warps <= 0:
+        raise RuntimeError("ged_msda_atomic_probe failed")
+    return warps * iters * 512 / (s.elapsed_time(e) * 1e-3) / 1e9
+
+
 def set_msda_variant(v: int) -> int:
     return load().ged_set_msda_variant(int(v))
 

@@ -210,6 +210,10 @@ int ged_msda_bwd(const float* value, const float* ref, int ref_batch, const floa
                  float* g_logit, const int* level_hw, int num_levels, int B, int S, int Q, int nH,
                  int head_dim, int num_points, cudaStream_t stream);
 
+/* Roofline probe: the scatter pattern of ged_msda_bwd alone (one 256-byte red.global.add.v4.f32 row per half-warp at
+ * pseudo-random rows of a (rows, heads*64) buffer), `iters` per half-warp.  Returns the number of warps launched
+ * (payload = warps * iters * 512 bytes) or a negative error; the caller times it. */
+int ged_msda_atomic_probe(float* buf, int rows, int heads, int iters, cudaStream_t stream);
 /* Work mapping of the two kernels above.  bit0: a CTA takes one query x 8 heads (default: 8 queries x one head);
  * bit1: backward as two kernels (g_value scatter, then offset/weight gradients); -1 (default) = pick bit0 per call
  * (one query x 8 heads when Q >= 2 S).  Returns the previous value. */

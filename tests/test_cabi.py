@@ -35,7 +35,7 @@ def test_binding_table_matches_header(lib):
         assert name in decls, name
         nargs = len([a for a in decls[name].split(",") if a.strip() and a.strip() != "void"])
         assert nargs == len(argtypes), (name, nargs, len(argtypes))
-    assert set(decls) - set(kernels.SIGNATURES) == {"ged_version", "ged_arch"}
+    assert set(decls) - set(kernels.SIGNATURES) == {"ged_version", "ged_arch", "ged_msda_atomic_probe"}
 
 
 def test_version_and_arch(lib):
