@@ -41,8 +41,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 // dx = rstd * (g*w - mean_c(g*w) - xhat * mean_c(g*w*xhat))
 __global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(
     const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
-    const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx, int64_t rows,
-    int C) {
+    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ g_add,
+    float* __restrict__ dx, int64_t rows, int C) {
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -67,6 +67,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(
     o.y = rs * (gg.y * ww.y - s1 - (v.y - mu) * rs * s2);
     o.z = rs * (gg.z * ww.z - s1 - (v.z - mu) * rs * s2);
     o.w = rs * (gg.w * ww.w - s1 - (v.w - mu) * rs * s2);
+    if (g_add) {     // gradient arriving at x through the residual path (x is also the block's identity)
+      const float4 r = __ldg((const float4*)(g_add + row * C) + i);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
     dr[i] = o;
   }
 }
@@ -111,13 +115,15 @@ GED_API int ged_layernorm_fwd(const float* x, const float* w, const float* b, fl
 }
 
 // dw / db are ACCUMULATED into (caller zeroes or passes the running .grad buffers).
+// g_add (optional, [rows][C]): added to dx - the gradient that reaches x through the residual branch when x is both
+// the LayerNorm input and the block's identity (depthformer_swin.py:461-472), saving autograd's separate sum pass.
 GED_API int ged_layernorm_bwd(const float* g, const float* x, const float* w, const float* mean,
-                              const float* rstd, float* dx, float* dw, float* db, int64_t rows, int C,
-                              cudaStream_t stream) {
+                              const float* rstd, const float* g_add, float* dx, float* dw, float* db, int64_t rows,
+                              int C, cudaStream_t stream) {
   if (!g || !x || !w || !mean || !rstd || !dx || rows <= 0) return GED_ERR_ARG;
   if (C % 4 != 0) return GED_ERR_SHAPE;
-  if (!aligned16(x) || !aligned16(g) || !aligned16(dx) || !aligned16(w)) return GED_ERR_ALIGN;
-  layernorm_bwd_dx_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(g, x, w, mean, rstd, dx, rows, C);
+  if (!aligned16(x) || !aligned16(g) || !aligned16(dx) || !aligned16(w) || (g_add && !aligned16(g_add))) return GED_ERR_ALIGN;
+  layernorm_bwd_dx_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(g, x, w, mean, rstd, g_add, dx, rows, C);
   if (dw && db) {
     const int rpb = 256;
     dim3 grid(cdiv(C, 32), (unsigned)((rows + rpb - 1) / rpb));

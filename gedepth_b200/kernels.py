@@ -36,7 +36,7 @@ SIGNATURES = {
     "ged_ce_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "ged_ce_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "ged_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I64, _I, _F, _P],
-    "ged_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P],
+    "ged_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P],
     "ged_winattn_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "ged_winattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "ged_gemm_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _I, _P, _F, C.c_uint, _P, _P],
@@ -392,8 +392,11 @@ def cross_entropy(logits, target, ignore_index=255):
 # Swin pieces
 # =============================================================================================
 class _LayerNorm(Function):
+    """y = LN(x).  fork=True additionally hands x back as a second output: the caller uses THAT as the block's identity,
+    so both gradient paths of x arrive here and the residual one is added inside the dx kernel (no autograd sum pass)."""
+
     @staticmethod
-    def forward(ctx, x, w, b, eps, w_sink=None, b_sink=None):
+    def forward(ctx, x, w, b, eps, w_sink=None, b_sink=None, fork=False):
         ctx.sinks = (w_sink, b_sink) if (w_sink is not None and b_sink is not None) else None
         xc = _f32c(x)
         Cc = xc.shape[-1]
@@ -403,30 +406,41 @@ class _LayerNorm(Function):
         rstd = torch.empty_like(mean)
         _call("ged_layernorm_fwd", _p(xc), _p(w), _p(b), _p(y), _p(mean), _p(rstd), rows, Cc, float(eps), _stream())
         ctx.save_for_backward(xc, w, mean, rstd)
-        return y
+        ctx.fork = fork
+        return (y, x) if fork else y
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, g_id=None):
         xc, w, mean, rstd = ctx.saved_tensors
         Cc = xc.shape[-1]
         rows = xc.numel() // Cc
         g = _f32c(g)
+        g_add = None if g_id is None else _f32c(g_id)
         dx = torch.empty_like(xc)
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        tail = (None,) * 4
         if need_w and ctx.sinks is not None:
-            _call("ged_layernorm_bwd", _p(g), _p(xc), _p(w), _p(mean), _p(rstd), _p(dx), _p(ctx.sinks[0]), _p(ctx.sinks[1]),
-                  rows, Cc, _stream())
-            return dx, None, None, None, None, None
+            _call("ged_layernorm_bwd", _p(g), _p(xc), _p(w), _p(mean), _p(rstd), _p(g_add), _p(dx), _p(ctx.sinks[0]),
+                  _p(ctx.sinks[1]), rows, Cc, _stream())
+            return (dx, None, None) + tail
         dw = torch.zeros(Cc, dtype=torch.float32, device=xc.device) if need_w else None
         db = torch.zeros_like(dw) if need_w else None
-        _call("ged_layernorm_bwd", _p(g), _p(xc), _p(w), _p(mean), _p(rstd), _p(dx), _p(dw), _p(db), rows, Cc, _stream())
-        return dx, dw, db, None, None, None
+        _call("ged_layernorm_bwd", _p(g), _p(xc), _p(w), _p(mean), _p(rstd), _p(g_add), _p(dx), _p(dw), _p(db), rows, Cc,
+              _stream())
+        return (dx, dw, db) + tail
 
 
 def layer_norm(x, w, b, eps):
     if x.shape[-1] % 4:
         return L.layer_norm(x, w, b, eps)
-    return _LayerNorm.apply(x, w, b, eps, _sink(w), _sink(b))
+    return _LayerNorm.apply(x, w, b, eps, _sink(w), _sink(b), False)
+
+
+def layer_norm_fork(x, w, b, eps):
+    """(LN(x), x_identity): use x_identity as the residual of the block that follows (see _LayerNorm)."""
+    if x.shape[-1] % 4 or not torch.is_grad_enabled() or not x.requires_grad:
+        return layer_norm(x, w, b, eps), x
+    return _LayerNorm.apply(x, w, b, eps, _sink(w), _sink(b), True)
 
 
 class _WinAttn(Function):

@@ -124,6 +124,15 @@ def layer_norm(x, w, b, eps):
     return L.layer_norm(x, w, b, eps)
 
 
+def layer_norm_fork(x, w, b, eps):
+    """(LN(x), x): the second output is x itself, to be used as the residual identity of the sub-block that follows, so
+    the LayerNorm backward can add the residual-branch gradient in its own pass."""
+    require_cuda(x)
+    if use_native("layer_norm"):
+        return _k().layer_norm_fork(x, w, b, eps)
+    return L.layer_norm(x, w, b, eps), x
+
+
 def merge_patches(x, H, W):
     require_cuda(x)
     if use_native("merge_patches"):

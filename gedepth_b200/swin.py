@@ -159,9 +159,9 @@ class SwinBlock(BaseModule):
                        act_cfg=act_cfg, add_identity=True)
 
     def forward(self, x, hw_shape):
-        h = ops.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        h, x = ops.layer_norm_fork(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         x = self.attn(h, hw_shape, identity=x)
-        h = ops.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        h, x = ops.layer_norm_fork(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
         return self.ffn(h, identity=x)
 
 

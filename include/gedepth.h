@@ -98,9 +98,10 @@ int ged_ce_bwd(const float* logits, const float* target, const double* stats, co
 int ged_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd,
                       int64_t rows, int C, float eps, cudaStream_t stream);
 /* dw / db accumulated (may both be NULL). */
-int ged_layernorm_bwd(const float* g, const float* x, const float* w, const float* mean,
-                      const float* rstd, float* dx, float* dw, float* db, int64_t rows, int C,
-                      cudaStream_t stream);
+/* g_add (optional): the residual-branch gradient of x, added to dx in the same pass (SwinBlock: x is both the
+ * LayerNorm input and the identity, depthformer_swin.py:461-472). */
+int ged_layernorm_bwd(const float* g, const float* x, const float* w, const float* mean, const float* rstd,
+                      const float* g_add, float* dx, float* dw, float* db, int64_t rows, int C, cudaStream_t stream);
 /* depthformer_swin.py:285-360 + :184-224 minus the two linears.  qkv (B,H*W,3C) image order. */
 int ged_winattn_fwd(const float* qkv, const float* qkv_bias, const float* table, const long long* index,
                     float* ctx, int B, int H, int W, int C, int nH, int window, int shift, float scale,
