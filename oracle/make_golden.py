@@ -30,11 +30,14 @@ NECK_IN_T = [64, 96, 192, 384, 768]
 
 CASES = {
     # name: (config file, B, H, W, mode, extras)
-    "vanilla_train": dict(cfg="depthformer_v.py", B=2, H=64, W=160, train=True),
-    "adaptive_train": dict(cfg="depthformer_a.py", B=2, H=64, W=160, train=True),
-    "vanilla_eval_ragged": dict(cfg="depthformer_v.py", B=1, H=70, W=166, train=False),
-    "adaptive_eval": dict(cfg="depthformer_a.py", B=1, H=64, W=160, train=False),
-    "adaptive_ddad_train": dict(cfg="depthformer_a_ddad.py", B=2, H=96, W=160, train=True, ddad=True),
+    # seeds are explicit so that adding a case never changes the inputs of the others
+    "vanilla_train": dict(cfg="depthformer_v.py", B=2, H=64, W=160, train=True, seed=1238),
+    "adaptive_train": dict(cfg="depthformer_a.py", B=2, H=64, W=160, train=True, seed=1236),
+    "vanilla_eval_ragged": dict(cfg="depthformer_v.py", B=1, H=70, W=166, train=False, seed=1237),
+    "adaptive_eval": dict(cfg="depthformer_a.py", B=1, H=64, W=160, train=False, seed=1235),
+    "adaptive_ddad_train": dict(cfg="depthformer_a_ddad.py", B=2, H=96, W=160, train=True, ddad=True, seed=1234),
+    # the reference's own aug_test (encoder_decoder.py:249-274) on the two views of its test pipeline
+    "vanilla_eval_tta": dict(cfg="depthformer_v.py", B=1, H=64, W=160, train=False, tta=True, seed=1239),
 }
 FULL_GRADS = ["decode_head.conv_depth.weight", "pe_mask_neck.convfinal.weight",
               "backbone.patch_embed.projection.weight", "neck.level_embed",
@@ -61,7 +64,7 @@ def model_cfg_for(case: dict, config_dir: str = None) -> dict:
 def case_inputs(name: str) -> dict:
     c = CASES[name]
     ddad = c.get("ddad", False)
-    b = synth_batch(c["B"], c["H"], c["W"], seed=1234 + sorted(CASES).index(name),
+    b = synth_batch(c["B"], c["H"], c["W"], seed=c["seed"],
                     depth_scale=250.0 if ddad else 200.0, max_depth=200.0 if ddad else 80.0,
                     adaptive="adaptive" in name)
     if ddad:
@@ -120,6 +123,13 @@ def run_case(name: str) -> dict:
             out["grad." + n] = dict(model.named_parameters())[n].grad.float().numpy()
         for i, f in enumerate(x):
             out[f"neck{i}_stats"] = np.array([float(f.mean()), float(f.std())])
+    elif c.get("tta"):
+        model.eval()
+        metas_f = [dict(m, flip=True, flip_direction="horizontal") for m in metas]
+        with torch.no_grad():
+            res = model.aug_test([img, img.flip(3)], [metas, metas_f], rescale=True,
+                                 pe_ori_point=[torch.zeros(1), torch.zeros(1)])
+        out.update(pred=np.stack([np.asarray(r, dtype=np.float32) for r in res]))
     else:
         model.eval()
         with torch.no_grad():
@@ -137,7 +147,10 @@ def run_case(name: str) -> dict:
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(8)
+    only = sys.argv[1:]
     for name in CASES:
+        if only and name not in only:
+            continue
         out = run_case(name)
         path = os.path.join(GOLDEN_DIR, f"{name}.npz")
         np.savez_compressed(path, **out)

@@ -46,6 +46,21 @@ def test_host_inference_matches_reference(name, host_ops_on_cpu):
     np.testing.assert_allclose(res[0], g["pred"][0], rtol=3e-5, atol=3e-5)
 
 
+def test_host_flip_tta_matches_reference_aug_test(host_ops_on_cpu):
+    """The reference's own aug_test on (image, mirrored image) (encoder_decoder.py:249-274) vs the host mirror."""
+    case, g, b = load_case("vanilla_eval_tta")
+    model, _ = build_host_model(case)
+    model.eval()
+    img = torch.from_numpy(b["img"])
+    metas0 = metas_for(case)
+    metas1 = [dict(m, flip=True, flip_direction="horizontal") for m in metas0]
+    with torch.no_grad():
+        res = model(img=[img, img.flip(3)], img_metas=[metas0, metas1], return_loss=False,
+                    pe_ori_point=[torch.zeros(1), torch.zeros(1)])
+    assert isinstance(res, list) and res[0].shape == (1, case["H"], case["W"])
+    np.testing.assert_allclose(res[0], g["pred"][0], rtol=3e-5, atol=3e-5)
+
+
 def test_product_refuses_cpu_tensors():
     case, _, b = load_case("vanilla_eval_ragged")
     model, _ = build_host_model(case)

@@ -109,6 +109,22 @@ def test_flip_tta_fused_average_equals_reference_sequence(monkeypatch):
     assert np.abs(fast[0] - g["pred"][0]).max() > 1e-4          # it really is a two-view average, not view 0
 
 
+def test_flip_tta_matches_reference_aug_test():
+    """Fixture produced by the reference's own aug_test (oracle/make_golden.py, case vanilla_eval_tta)."""
+    case, g, b = load_case("vanilla_eval_tta")
+    model, _ = build_host_model(case, DEV)
+    model.eval()
+    img = torch.from_numpy(b["img"]).to(DEV)
+    metas0 = metas_for(case)
+    metas1 = [dict(m, flip=True, flip_direction="horizontal") for m in metas0]
+    with torch.no_grad():
+        res = model(img=[img, img.flip(3)], img_metas=[metas0, metas1], return_loss=False,
+                    pe_ori_point=[torch.zeros(1), torch.zeros(1)])
+    rel = _rel(res[0], g["pred"][0])
+    print(f"tta: pred rel err p50 {np.percentile(rel, 50):.2e} p99.9 {np.percentile(rel, 99.9):.2e} max {rel.max():.2e}")
+    assert np.percentile(rel, 99.9) < 1e-3 and rel.max() < 5e-3
+
+
 def test_library_statement_path_equals_reference_on_gpu(monkeypatch):
     """Same host mirror with every op forced to its library statement (fp32, no TF32): isolates
     wiring errors from kernel numerics."""
