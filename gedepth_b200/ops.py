@@ -42,8 +42,9 @@ def native_table():
     return {name: (k.has(name) and name not in _FORCE_LIB and "all" not in _FORCE_LIB) for name in OPS}
 
 
+# ops reached by the four GE configs (``resize`` alone is not: it only serves a non-SiLog loss, heads.py `_loss_depth`)
 OPS = ["linear", "layer_norm", "patch_embed", "merge_patches", "window_attention", "conv2d",
-       "conv_bn_act", "conv2d_cat", "batch_norm", "resize", "resize_add", "msda_sample", "ground_plane", "ge_vanilla",
+       "conv_bn_act", "conv2d_cat", "batch_norm", "resize_add", "msda_sample", "ground_plane", "ge_vanilla",
        "ge_adaptive", "fuse_head", "silog", "cross_entropy", "clamp_resize", "find_k", "depth_metrics", "tta_merge",
        "adamw"]
 
