@@ -508,7 +508,9 @@ def main():
 
     line = dict(metric="frames/sec (352x1120) fwd+bwd", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
                 warmup=max(3, args.warmup), ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32 (3xTF32 split on tcgen05, fp32 accumulate)" if args.passes == 3 else "tf32", data="synthetic",
+                dtype=("f32 (fp32 storage and accumulation; forward GEMMs/convs error-compensated 3xTF32 on tcgen05, backward GEMMs "
+                       "single-pass TF32 = what the reference's PyTorch 1.8 runs on Ampere+)") if args.passes == 3
+                else "tf32 (single-pass TF32 forward and backward, fp32 storage and accumulation)", data="synthetic",
                 config=dict(workload=workload, global_batch=frames, parallelism=f"dp{world}",
                             step="fwd + SiLog + bwd + allreduce(N>1) + clip + AdamW", drop_path_rate=0.3,
                             launch="one captured CUDA graph per step" if use_graph else "eager",
