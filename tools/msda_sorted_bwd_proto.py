@@ -78,3 +78,42 @@ print(f"T={T}: records/tile mean {n_rec.mean():.0f} max {n_rec.max()}, distinct 
 print(f"global adds: {n_rec.sum()} (scatter) -> {flushes} (sorted tiles): {n_rec.sum() / flushes:.1f}x fewer")
 print(f"shared memory per tile at 64 channels: rows {n_rows.max() * 256 / 1024:.0f} KB max, records {n_rec.max() * 12 / 1024:.0f} KB, g_out {T * 256 / 1024:.0f} KB")
 print("equal to the scatter-add result: OK")
+
+# (c) the exact logic of tools/experimental/msda_bwd_sorted.cu: T = 32, per-level 12 x 12 windows anchored at the mean
+# floor coordinate of the tile's points, window cells reduced and flushed once, everything else added directly
+WIN, TT = 12, 32
+g_k = np.zeros((S, HD))
+n_in = n_out = n_flush = 0
+for t0 in range(0, Q, TT):
+    idx = order[t0:t0 + TT]
+    for l, (H, W) in enumerate(shapes):
+        x = (ref[idx, None, 0] + off[idx, l, :, 0] / W) * W - 0.5            # (T, 8)
+        y = (ref[idx, None, 1] + off[idx, l, :, 1] / H) * H - 0.5
+        x0, y0 = np.floor(x).astype(int), np.floor(y).astype(int)
+        lx, ly = x - x0, y - y0
+        near = (x0 >= -1) & (x0 < W) & (y0 >= -1) & (y0 < H)
+        n = max(int(near.sum()), 1)
+        wx0 = int(np.floor(x0[near].sum() / n + 0.5)) - WIN // 2 + 1
+        wy0 = int(np.floor(y0[near].sum() / n + 0.5)) - WIN // 2 + 1
+        cells = np.zeros((WIN, WIN, HD))
+        touched = np.zeros((WIN, WIN), bool)
+        a = aw[idx, l * 8:(l + 1) * 8]
+        for dy in (0, 1):
+            for dx in (0, 1):
+                xx, yy = x0 + dx, y0 + dy
+                wgt = a * (lx if dx else 1 - lx) * (ly if dy else 1 - ly)
+                valid = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+                cx, cy = xx - wx0, yy - wy0
+                inside = valid & (cx >= 0) & (cx < WIN) & (cy >= 0) & (cy < WIN)
+                qq = np.broadcast_to(idx[:, None], xx.shape)
+                np.add.at(cells, (cy[inside], cx[inside]), wgt[inside][:, None] * go[qq[inside]])
+                touched[cy[inside], cx[inside]] = True
+                outside = valid & ~inside
+                np.add.at(g_k, starts[l] + yy[outside] * W + xx[outside], wgt[outside][:, None] * go[qq[outside]])
+                n_in += int(inside.sum()); n_out += int(outside.sum())
+        cy, cx = np.nonzero(touched)
+        g_k[starts[l] + (wy0 + cy) * W + (wx0 + cx)] += cells[cy, cx]
+        n_flush += len(cy)
+assert np.allclose(g_k, g_ref, rtol=1e-12, atol=1e-12)
+print(f"draft-kernel logic (T=32, 12x12 windows, mean anchor): equal; {100 * n_out / (n_in + n_out):.2f} % of the records "
+      f"outside their window, global adds {n_in + n_out} -> {n_flush + n_out} ({(n_in + n_out) / (n_flush + n_out):.1f}x fewer)")
