@@ -2,7 +2,7 @@
 import sys, torch
 sys.path.insert(0, '.')
 from gedepth_b200 import kernels as K
-from oracle import model as om
+from gedepth_b200.swin import WindowMSA
 DEV = 'cuda:0'
 torch.manual_seed(0)
 B = 8
@@ -56,7 +56,7 @@ if which in ('all', 'msda'):
         torch.cuda.synchronize()
 if which in ('all', 'attn'):
     qkv = rnd(B, 88 * 280, 288).requires_grad_(True)
-    idx = om.relative_position_index(7).to(DEV)
+    idx = WindowMSA(96, 3, (7, 7)).relative_position_index.to(DEV)
     o = K.window_attention(qkv, rnd(288), rnd(169, 3), idx, (88, 280), 3, 7, 3, 32 ** -.5)
     o.backward(rnd(*o.shape))
     torch.cuda.synchronize()
