@@ -54,6 +54,10 @@ SIGNATURES = {
     "ged_conv3x3_tf32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _F, _P],
     "ged_msda_fwd": [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_msda_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ged_msda_sort_queries": [_P, _I, _I, _I, _P, _P, _I64, _P],
+    "ged_msda_tile_fwd": [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ged_msda_tile_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ged_msda_tc_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_gemm_tf32_bt": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P],
     "ged_conv3x3_dx_tf32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ged_set_gemm_precision": [_I],
@@ -1044,6 +1048,35 @@ def clamp_resize(x, lo, hi, size):
 # =============================================================================================
 # deformable attention sampling
 # =============================================================================================
+# Tile kernels (csrc/msda_tile.cu: queries sorted by reference point, shared-memory windows) unless GEDEPTH_MSDA_TILE=0,
+# which keeps the round-1 one-warp-per-(query, head) kernels of csrc/msda.cu as the A/B partner.
+MSDA_TILE = os.environ.get("GEDEPTH_MSDA_TILE", "1") != "0"
+MSDA_TILE_Q = 32
+# Backward of the sampling on tcgen05 (csrc/msda_tc.cu, one-pass TF32 like the other backward GEMMs) unless
+# GEDEPTH_MSDA_TC=0 or GEDEPTH_BWD_GEMM_PASSES=3 ask for the fp32 SIMT tile kernels.
+MSDA_TC = os.environ.get("GEDEPTH_MSDA_TC", "1") != "0"
+
+
+def msda_query_order(ref: torch.Tensor, shapes) -> torch.Tensor:
+    """int32 (Q,) permutation of the queries grouped by reference point (band of y, bucket of x) so that a tile of
+    32 consecutive entries samples a compact patch of every level.  Only locality depends on it, never the result.
+    Constant reference points (no grad) keep their order cached on the tensor."""
+    cached = getattr(ref, "_ged_order", None)
+    if cached is not None and not ref.requires_grad and cached[0] == ref._version:
+        return cached[1]
+    Q = ref.shape[1]
+    H0, W0 = int(shapes[0][0]), int(shapes[0][1])
+    side = max(1.0, (MSDA_TILE_Q * H0 * W0 / max(Q, 1)) ** 0.5)       # tile side in level-0 pixels
+    bands = max(1, min(H0, int(round(H0 / side))))
+    xb = max(1, min(8 * W0, 65536 // bands))
+    order = torch.empty(Q, dtype=torch.int32, device=ref.device)
+    work = torch.empty(bands * xb, dtype=torch.int32, device=ref.device)
+    _call("ged_msda_sort_queries", _p(ref), Q, bands, xb, _p(order), _p(work), work.numel(), _stream())
+    if not ref.requires_grad:
+        ref._ged_order = (ref._version, order)
+    return order
+
+
 class _MSDA(Function):
     @staticmethod
     def forward(ctx, v, ref, off, logit, shapes, nH, P):
@@ -1052,24 +1085,37 @@ class _MSDA(Function):
         Q = off.shape[1]
         hw = (C.c_int * (2 * len(shapes)))(*[int(a) for s in shapes for a in s])
         out = torch.empty(B, Q, E, dtype=torch.float32, device=v.device)
-        _call("ged_msda_fwd", _p(v), _p(ref), ref.shape[0], _p(off), _p(logit), _p(out), hw, len(shapes), B, S, Q,
-              nH, E // nH, P, _stream())
-        ctx.save_for_backward(v, ref, off, logit)
+        order = None
+        if MSDA_TILE:
+            order = msda_query_order(ref, shapes)
+            _call("ged_msda_tile_fwd", _p(v), _p(ref), ref.shape[0], _p(off), _p(logit), _p(order), _p(out), hw,
+                  len(shapes), B, S, Q, nH, E // nH, P, _stream())
+        else:
+            _call("ged_msda_fwd", _p(v), _p(ref), ref.shape[0], _p(off), _p(logit), _p(out), hw, len(shapes), B, S, Q,
+                  nH, E // nH, P, _stream())
+        ctx.save_for_backward(v, ref, off, logit, order if order is not None else torch.empty(0, device=v.device))
         ctx.cfg = (tuple(tuple(s) for s in shapes), nH, P)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        v, ref, off, logit = ctx.saved_tensors
+        v, ref, off, logit, order = ctx.saved_tensors
         shapes, nH, P = ctx.cfg
         B, S, E = v.shape
         Q = off.shape[1]
         hw = (C.c_int * (2 * len(shapes)))(*[int(a) for s in shapes for a in s])
         g = _f32c(g)
         g_v = torch.zeros_like(v)
+        g_off, g_logit = torch.empty_like(off), torch.empty_like(logit)
+        if order.numel():
+            # reference points shared by the batch (ref_batch == 1): their gradient is summed over the batch in place
+            g_ref = torch.zeros_like(ref) if ctx.needs_input_grad[1] else None
+            name = "ged_msda_tc_bwd" if (MSDA_TC and BACKWARD_PASSES == 1) else "ged_msda_tile_bwd"
+            _call(name, _p(v), _p(ref), ref.shape[0], _p(off), _p(logit), _p(order), _p(g), _p(g_v),
+                  _p(g_ref), _p(g_off), _p(g_logit), hw, len(shapes), B, S, Q, nH, E // nH, P, _stream())
+            return g_v, g_ref, g_off, g_logit, None, None, None
         need_ref = ctx.needs_input_grad[1] and ref.shape[0] == B
         g_ref = torch.zeros_like(ref) if need_ref else None
-        g_off, g_logit = torch.empty_like(off), torch.empty_like(logit)
         _call("ged_msda_bwd", _p(v), _p(ref), ref.shape[0], _p(off), _p(logit), _p(g), _p(g_v), _p(g_ref),
               _p(g_off), _p(g_logit), hw, len(shapes), B, S, Q, nH, E // nH, P, _stream())
         return g_v, g_ref, g_off, g_logit, None, None, None
@@ -1100,8 +1146,8 @@ def msda_sample(v, shapes, ref, off, logit, nH, P):
     B = v.shape[0]
     if ref.shape[0] not in (1, B):
         raise ValueError("reference_points batch must be 1 or B")
-    if ref.shape[0] == 1 and ref.requires_grad and B > 1:
-        ref = ref.expand(B, -1, -1)        # learnable reference points shared over the batch
+    if ref.shape[0] == 1 and ref.requires_grad and B > 1 and not MSDA_TILE:
+        ref = ref.expand(B, -1, -1)        # round-1 kernels: learnable reference points need one copy per sample
     return _MSDA.apply(v, ref, off, logit, shapes, nH, P)
 
 

@@ -211,6 +211,28 @@ int ged_msda_bwd(const float* value, const float* ref, int ref_batch, const floa
                  float* g_logit, const int* level_hw, int num_levels, int B, int S, int Q, int nH,
                  int head_dim, int num_points, cudaStream_t stream);
 
+/* Locality-aware versions (csrc/msda_tile.cu): `order` (Q) int32 is any permutation of the queries; a CTA takes 32
+ * consecutive entries of one (batch, head), stages a 12 x 12 window of value rows per level in shared memory and
+ * reduces the value gradient per window cell before it leaves the SM.  ged_msda_sort_queries groups the queries by
+ * reference point (band of y, bucket of x; ref (Q,2), work: bands * xbuckets ints) - only locality depends on the
+ * order.  g_ref is (ref_batch,Q,2): with ref_batch == 1 the gradient is summed over the batch. */
+int ged_msda_sort_queries(const float* ref, int Q, int bands, int xbuckets, int* order, int* work, int64_t work_ints,
+                          cudaStream_t stream);
+int ged_msda_tile_fwd(const float* value, const float* ref, int ref_batch, const float* off, const float* logit,
+                      const int* order, float* out, const int* level_hw, int num_levels, int B, int S, int Q, int nH,
+                      int head_dim, int num_points, cudaStream_t stream);
+int ged_msda_tile_bwd(const float* value, const float* ref, int ref_batch, const float* off, const float* logit,
+                      const int* order, const float* g_out, float* g_value, float* g_ref, float* g_off, float* g_logit,
+                      const int* level_hw, int num_levels, int B, int S, int Q, int nH, int head_dim, int num_points,
+                      cudaStream_t stream);
+
+/* ged_msda_tile_bwd on the tensor cores (csrc/msda_tc.cu): per tile and level the value gradient and the corner dot
+ * products are two tcgen05.mma GEMMs over an 11 x 11 window (one-pass TF32, fp32 accumulate in TMEM). */
+int ged_msda_tc_bwd(const float* value, const float* ref, int ref_batch, const float* off, const float* logit,
+                    const int* order, const float* g_out, float* g_value, float* g_ref, float* g_off, float* g_logit,
+                    const int* level_hw, int num_levels, int B, int S, int Q, int nH, int head_dim, int num_points,
+                    cudaStream_t stream);
+
 /* Roofline probe: the scatter pattern of ged_msda_bwd alone (one 256-byte red.global.add.v4.f32 row per half-warp at
  * pseudo-random rows of a (rows, heads*64) buffer), `iters` per half-warp.  Returns the number of warps launched
  * (payload = warps * iters * 512 bytes) or a negative error; the caller times it. */
