@@ -13,6 +13,8 @@
 // Operands are written straight into 128B-swizzled K-major (and, for V_l^T, MN-major) UMMA tiles by the staging code;
 // accumulators live in TMEM and are read back with tcgen05.ld.  Corners outside their window (~1-3 %) take a direct
 // warp-cooperative path in fp32.
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include "common.cuh"
 
 namespace ged {
@@ -21,11 +23,14 @@ constexpr int CL = 4, CP = 8, CHD = 64;
 constexpr int CQ = 32;                       // queries per tile
 constexpr int CWARPS = 8, CTHREADS = CWARPS * 32;
 constexpr int CWX = 11, CWY = 11, CCELLS = CWX * CWY;   // 121 cells, padded to the 128 TMEM lanes
-constexpr int DPITCH = 36;                   // floats per cell row of the corner-dot table (conflict-free float4 stores)
 
 struct TcShapes {
   int h[CL], w[CL], start[CL];
 };
+struct TcMaps {          // one 4-D tensor map (channel, x, y, batch) per level of the value tensor
+  CUtensorMap m[CL];
+};
+constexpr uint32_t WIN_BYTES = CCELLS * 128;      // one TMA box: 121 cells x 32 channels
 
 // ---- PTX wrappers (same forms as gemm_tcgen05.cu) ----------------------------------------------------------------
 __device__ __forceinline__ uint32_t c_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -41,6 +46,15 @@ __device__ __forceinline__ void c_mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra CWAIT_%=;\n\t"
       "CDONE_%=:\n\t}"
       :: "r"(c_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void c_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(c_smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA: one {32 channels, CWX, CWY, 1} box of a level map -> [121 rows][128 B] in the swizzle mode of the tensor map
+__device__ __forceinline__ void c_tma_window(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int ch, int x, int y, int b) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :: "r"(c_smem_u32(smem_dst)), "l"((uint64_t)map), "r"(c_smem_u32(bar)), "r"(ch), "r"(x), "r"(y), "r"(b) : "memory");
 }
 __device__ __forceinline__ void c_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void c_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -152,40 +166,85 @@ __device__ __forceinline__ void tc_origin(const int* s_sum, int* s_org, const Tc
   s_org[l * 2 + 1] = max(0, min(my - (CWY / 2 - 1), cpick(sh.h, l) - CWY));
 }
 
+// Valid corners outside the window of one level, fp32, warp-cooperative (2 channels per lane): the event is handled per
+// POINT (the corners of a stray point usually leave the window together).  FWD: extra[slot] += w * V[pos];
+// BWD: g_value[pos] += w * g_out[q] and the corner's dot product <g_out[q], V[pos]> back to the owner lane.
+template <bool FWD>
+__device__ __forceinline__ void stray_corners(unsigned omask, const int (&pos)[4], const float (&wgt)[4], float (&dk)[4], int q,
+                                              int slot, const float* __restrict__ vb, float* __restrict__ gvb,
+                                              const float* __restrict__ gob, float* s_extra, int rowpitch, int lane) {
+  unsigned m = __ballot_sync(0xffffffffu, omask != 0u);
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const unsigned sm = __shfl_sync(0xffffffffu, omask, src);
+    const int sq = __shfl_sync(0xffffffffu, q, src), sslot = __shfl_sync(0xffffffffu, slot, src);
+    float2 g2 = make_float2(0.f, 0.f);
+    if (!FWD) g2 = __ldg((const float2*)(gob + (int64_t)sq * rowpitch) + lane);
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int spos = __shfl_sync(0xffffffffu, pos[k], src);
+      const float sw = __shfl_sync(0xffffffffu, wgt[k], src);
+      if (!((sm >> k) & 1u)) continue;                       // warp-uniform
+      const float2 v2 = __ldg((const float2*)(vb + (int64_t)spos * rowpitch) + lane);
+      if (FWD) { acc.x += sw * v2.x; acc.y += sw * v2.y; }
+      else {
+        atomicAdd((float2*)(gvb + (int64_t)spos * rowpitch) + lane, make_float2(sw * g2.x, sw * g2.y));
+        const float d = warp_sum(g2.x * v2.x + g2.y * v2.y);
+        if (lane == src) dk[k] = d;
+      }
+    }
+    if (FWD) {      // rows of s_extra belong to the warp that owns the slot: plain read-modify-write
+      float2* e = (float2*)(s_extra + sslot * CHD) + lane;
+      float2 t = *e;
+      t.x += acc.x; t.y += acc.y;
+      *e = t;
+    }
+  }
+}
+
 // =================================================================================================================
 // backward
 // =================================================================================================================
 // shared memory (bytes from the 1024-aligned base)
-constexpr int B_V = 0;                 // V_l: 2 K-blocks [128 cells][32 ch] swizzled (A of D^T)      32 KB; reused as the
-                                       //      corner-dot table [128][DPITCH] once the MMAs have retired
+constexpr int B_V = 0;                 // V_l: 2 K-blocks [128 cells][32 ch], written by TMA (A of D^T)  32 KB; block 0 is
+                                       //      reused as the corner-dot table once the MMAs have retired
 constexpr int B_AT = 32768;            // A_l^T [128 cells][32 queries] swizzled (A of dV)             16 KB
 constexpr int B_GT = 49152;            // G^T [64 ch][32 queries] swizzled (B of dV)                    8 KB
 constexpr int B_GQ = 57344;            // G: 2 K-blocks [32 queries][32 ch] swizzled (B of D^T)         8 KB
-constexpr int B_MISC = 65536;          // mbarrier, TMEM base, window sums / origins
+constexpr int B_MISC = 65536;          // mbarriers, TMEM base, window sums / origins
 constexpr int B_TOTAL = B_MISC + 128 + 1024;
 
 __global__ void __launch_bounds__(CTHREADS, 3) msda_tc_bwd_kernel(
-    const float* __restrict__ value, const float* __restrict__ ref, const float* __restrict__ off,
-    const float* __restrict__ logit, const int* __restrict__ order, const float* __restrict__ g_out,
-    float* __restrict__ g_value, float* __restrict__ g_ref, float* __restrict__ g_off, float* __restrict__ g_logit,
-    TcShapes sh, int B, int S, int Q, int nH, int ref_bstride) {
+    const __grid_constant__ TcMaps maps, const float* __restrict__ value, const float* __restrict__ ref,
+    const float* __restrict__ off, const float* __restrict__ logit, const int* __restrict__ order,
+    const float* __restrict__ g_out, float* __restrict__ g_value, float* __restrict__ g_ref, float* __restrict__ g_off,
+    float* __restrict__ g_logit, TcShapes sh, int B, int S, int Q, int nH, int ref_bstride) {
   extern __shared__ uint8_t c_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)c_smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bar = (uint64_t*)(smem + B_MISC);
-  uint32_t* tmem_ptr = (uint32_t*)(smem + B_MISC + 8);
-  int* s_sum = (int*)(smem + B_MISC + 16);      // [12]
+  uint64_t* mma_bar = (uint64_t*)(smem + B_MISC);
+  uint64_t* tma_bar = mma_bar + 1;
+  uint32_t* tmem_ptr = (uint32_t*)(smem + B_MISC + 16);
+  int* s_sum = (int*)(smem + B_MISC + 32);      // [12]
   int* s_org = s_sum + 12;                      // [8]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int t0 = blockIdx.x * CQ, h = blockIdx.y, b = blockIdx.z;
   const int slot = warp * 4 + (lane >> 3), p = lane & 7;
   const int rowpitch = nH * CHD;
 
-  if (tid == 0) { c_mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (tid == 0) {
+    c_mbar_init(mma_bar, 1); c_mbar_init(tma_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int l = 0; l < CL; ++l) asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&maps.m[l]) : "memory");
+  }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(c_smem_u32(tmem_ptr)), "r"(128) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid < 12) s_sum[tid] = 0;
+  for (int idx = tid; idx < 16384 / 16; idx += CTHREADS) *(float4*)(smem + B_AT + idx * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   TcGeom g;
   tc_geometry(g, order, ref, off, logit, sh, b, h, Q, nH, ref_bstride, t0, warp, lane, s_sum);
@@ -210,6 +269,7 @@ __global__ void __launch_bounds__(CTHREADS, 3) msda_tc_bwd_kernel(
 
   const float* vb = value + (int64_t)b * S * rowpitch + h * CHD;
   float* gvb = g_value + (int64_t)b * S * rowpitch + h * CHD;
+  const float* gob = g_out + (int64_t)b * Q * rowpitch + h * CHD;
   float rgw[CL], rgx[CL], rgy[CL];
   const int qd = warp & 3, hf = warp >> 2;       // TMEM lane quadrant of this warp, column half it reads
   const int ecell = qd * 32 + lane;              // the window cell (TMEM lane) this thread reads back
@@ -218,70 +278,72 @@ __global__ void __launch_bounds__(CTHREADS, 3) msda_tc_bwd_kernel(
 #pragma unroll
   for (int l = 0; l < CL; ++l) {
     const int W = sh.w[l], H = sh.h[l], start = sh.start[l], wx0 = s_org[l * 2], wy0 = s_org[l * 2 + 1];
-    // ---- stage V_l (zero outside the map / beyond the 121 cells) and clear A_l^T --------------------------------
-    for (int idx = tid; idx < 128 * 16; idx += CTHREADS) {
-      const int cell = idx >> 4, part = idx & 15;
-      const int cy = cell / CWX, cx = cell - cy * CWX;
-      const int x = wx0 + cx, y = wy0 + cy;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (cell < CCELLS && x < W && y < H) v = __ldg((const float4*)(vb + (int64_t)(start + y * W + x) * rowpitch + part * 4));
-      *(float4*)(smem + B_V + (part >> 3) * 16384 + cell * 128 + (((part & 7) ^ (cell & 7)) << 4)) = v;
-    }
-    for (int idx = tid; idx < 16384 / 16; idx += CTHREADS) *(float4*)(smem + B_AT + idx * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    // ---- build A_l^T: every lane adds the four corner weights of its point --------------------------------------
+    // ---- build A_l^T.  A warp owns the columns of its four slots (cleared by its own epilogue); two points of one
+    //      query may share a cell, so the eight points of a slot take turns: plain read-modify-write, no atomics ------
     const float xf = floorf(g.px[l]), yf = floorf(g.py[l]);
     const int x0 = (int)xf, y0 = (int)yf;
     const float lx = g.px[l] - xf, ly = g.py[l] - yf, a = g.aw[l];
-    int cellk[4];
-    float dk[4];
+    int cellk[4], posk[4];
+    float dk[4], wk[4];
+    unsigned omask = 0u;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int x = x0 + (k & 1), y = y0 + (k >> 1);
       const bool valid = g.q >= 0 && x >= 0 && x < W && y >= 0 && y < H;
       const int cx = x - wx0, cy = y - wy0;
       const bool inwin = valid && (unsigned)cx < (unsigned)CWX && (unsigned)cy < (unsigned)CWY;
-      const float wgt = a * ((k & 1) ? lx : 1.f - lx) * ((k >> 1) ? ly : 1.f - ly);
+      wk[k] = a * ((k & 1) ? lx : 1.f - lx) * ((k >> 1) ? ly : 1.f - ly);
       cellk[k] = inwin ? cy * CWX + cx : -1;
+      posk[k] = start + y * W + x;
       dk[k] = 0.f;
-      if (inwin) atomicAdd((float*)(smem + B_AT + kmaj_off(cellk[k], slot)), wgt);
-      // valid corners outside the window: fp32, warp-cooperative (2 channels per lane), straight to / from L2
-      unsigned m = __ballot_sync(0xffffffffu, valid && !inwin);
-      while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const int spos = __shfl_sync(0xffffffffu, start + y * W + x, src);
-        const float sw = __shfl_sync(0xffffffffu, wgt, src);
-        const int sq = __shfl_sync(0xffffffffu, g.q, src);
-        const float2 g2 = __ldg((const float2*)(g_out + ((int64_t)b * Q + sq) * rowpitch + h * CHD) + lane);
-        const float2 v2 = __ldg((const float2*)(vb + (int64_t)spos * rowpitch) + lane);
-        atomicAdd((float2*)(gvb + (int64_t)spos * rowpitch) + lane, make_float2(sw * g2.x, sw * g2.y));
-        const float d = warp_sum(g2.x * v2.x + g2.y * v2.y);
-        if (lane == src) dk[k] = d;
+      if (valid && !inwin) omask |= 1u << k;
+    }
+    {
+      float* ap[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ap[k] = (float*)(smem + B_AT + kmaj_off(max(cellk[k], 0), slot));
+#pragma unroll
+      for (int r = 0; r < CP; ++r) {
+        if (p == r) {
+          float t[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) t[k] = cellk[k] >= 0 ? *ap[k] : 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) if (cellk[k] >= 0) *ap[k] = t[k] + wk[k];
+        }
+        __syncwarp();
       }
     }
     c_fence_async();
     __syncthreads();
-    // ---- tensor cores: dV_l = A_l^T . G (cols 0..63), D_l^T = V_l . G^T (cols 64..95) ------------------------------
+    // ---- TMA: V_l window; tensor cores: dV_l = A_l^T . G (cols 0..63), D_l^T = V_l . G^T (cols 64..95) -----------
     if (tid == 0) {
+      c_mbar_expect_tx(tma_bar, 2 * WIN_BYTES);
+      c_tma_window(smem + B_V, &maps.m[l], tma_bar, h * CHD, wx0, wy0, b);
+      c_tma_window(smem + B_V + 16384, &maps.m[l], tma_bar, h * CHD + 32, wx0, wy0, b);
       c_fence_after();
       const uint32_t base = c_smem_u32(smem);
       const uint64_t a_at = c_desc_kmajor(base + B_AT), b_gt = c_desc_kmajor(base + B_GT);
       constexpr uint32_t idv = c_idesc_tf32(128, 64, false, false), idd = c_idesc_tf32(128, 32, false, false);
 #pragma unroll
       for (int k = 0; k < 4; ++k) c_mma_tf32(tmem_base, a_at + 2 * k, b_gt + 2 * k, idv, k != 0);
+      c_mbar_wait(tma_bar, l & 1);
+      c_fence_after();
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
         const uint64_t a_v = c_desc_kmajor(base + B_V + kb * 16384), b_gq = c_desc_kmajor(base + B_GQ + kb * 4096);
 #pragma unroll
         for (int k = 0; k < 4; ++k) c_mma_tf32(tmem_base + 64, a_v + 2 * k, b_gq + 2 * k, idd, (kb | k) != 0);
       }
-      c_commit(bar);
+      c_commit(mma_bar);
     }
-    c_mbar_wait(bar, l & 1);
+    __syncwarp();
+    // corners outside the window: direct path, overlapped with the TMA / MMA latency
+    stray_corners<false>(omask, posk, wk, dk, g.q, slot, vb, gvb, gob, nullptr, rowpitch, lane);
+    c_mbar_wait(mma_bar, l & 1);
     c_fence_after();
-    // ---- epilogue: this thread's cell row.  dV half -> red.global (skipped when the cell was not touched), corner
-    //      dots -> shared-memory table over the (now dead) V tiles ------------------------------------------------------
+    // ---- epilogue: this thread's cell row.  dV half -> red.global (skipped when the cell was not touched); corner
+    //      dots -> swizzled table over V block 0 (dead now); clear the warp's own columns of A^T for the next level ---
     {
       uint32_t v[32];
       c_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(hf * 32), v);
@@ -297,24 +359,27 @@ __global__ void __launch_bounds__(CTHREADS, 3) msda_tc_bwd_kernel(
       }
       uint32_t d[16];
       c_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(64 + hf * 16), d);
-      float* drow = (float*)(smem + B_V) + ecell * DPITCH + hf * 16;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        *(float4*)(drow + 4 * j) = make_float4(__uint_as_float(d[4 * j]), __uint_as_float(d[4 * j + 1]),
-                                               __uint_as_float(d[4 * j + 2]), __uint_as_float(d[4 * j + 3]));
+        *(float4*)(smem + B_V + ecell * 128 + (((hf * 4 + j) ^ (ecell & 7)) << 4)) =
+            make_float4(__uint_as_float(d[4 * j]), __uint_as_float(d[4 * j + 1]), __uint_as_float(d[4 * j + 2]), __uint_as_float(d[4 * j + 3]));
+      if (l + 1 < CL) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {      // slots 4 warp .. 4 warp + 3 of cell row c are one 16-byte chunk
+          const int c = lane + 32 * j;
+          *(float4*)(smem + B_AT + c * 128 + ((warp ^ (c & 7)) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
     }
     c_fence_before();
     __syncthreads();
     // ---- per point: d/d weight, d/d x_pix, d/d y_pix from the four corner dots -------------------------------------
-    {
-      const float* dtab = (const float*)(smem + B_V);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) if (cellk[k] >= 0) dk[k] = dtab[cellk[k] * DPITCH + slot];
-      rgw[l] = (1.f - ly) * ((1.f - lx) * dk[0] + lx * dk[1]) + ly * ((1.f - lx) * dk[2] + lx * dk[3]);
-      rgx[l] = a * ((1.f - ly) * (dk[1] - dk[0]) + ly * (dk[3] - dk[2]));
-      rgy[l] = a * ((1.f - lx) * (dk[2] - dk[0]) + lx * (dk[3] - dk[1]));
-    }
-    __syncthreads();        // the table is overwritten by the next level's V tiles
+    for (int k = 0; k < 4; ++k) if (cellk[k] >= 0) dk[k] = *(const float*)(smem + B_V + kmaj_off(cellk[k], slot));
+    rgw[l] = (1.f - ly) * ((1.f - lx) * dk[0] + lx * dk[1]) + ly * ((1.f - lx) * dk[2] + lx * dk[3]);
+    rgx[l] = a * ((1.f - ly) * (dk[1] - dk[0]) + ly * (dk[3] - dk[2]));
+    rgy[l] = a * ((1.f - lx) * (dk[2] - dk[0]) + lx * (dk[3] - dk[1]));
+    // no barrier here: the next level's TMA (which overwrites the table) is issued after the next __syncthreads
   }
   // ---- softmax backward, stores ------------------------------------------------------------------------------------
   float dot = 0.f, grx = 0.f, gry = 0.f;
@@ -343,6 +408,197 @@ __global__ void __launch_bounds__(CTHREADS, 3) msda_tc_bwd_kernel(
   }
 }
 
+// =================================================================================================================
+// forward: out^T [64 ch x 32 queries] += V_l^T . A_l^T, 3xTF32 (hi*hi + lo*hi + hi*lo), accumulated over the four
+// levels in one TMEM tile.  V_l arrives by TMA as an MN-major operand (channels contiguous), A_l is K-major.
+// =================================================================================================================
+constexpr int F_VHI = 0;               // V_l: 2 panels [128 cells][32 ch] (SWIZZLE_128B_ATOM_32B), raw fp32 = hi   32 KB
+constexpr int F_VLO = 32768;           // x - tf32(x), pre-computed once per value tensor and fetched by TMA too     32 KB
+constexpr int F_AHI = 65536;           // A_l [32 queries][128 cells]: 4 K-blocks of [32][32] swizzled, fp32 = hi  16 KB
+constexpr int F_ALO = 81920;           //                                                                       16 KB
+constexpr int F_EXTRA = 98304;         // [32 slots][64 ch] fp32: corners outside the windows                    8 KB
+constexpr int F_MISC = 106496;
+constexpr int F_TOTAL = F_MISC + 256 + 1024;
+
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// lo = x - tf32(x) of a whole tensor (the tensor core truncates the fp32 operand to its top 19 bits, so hi is x itself)
+__global__ void __launch_bounds__(256) split_lo_kernel(const float4* __restrict__ x, float4* __restrict__ lo, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = ldg_stream(x + i);
+    lo[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+  }
+}
+
+__global__ void __launch_bounds__(CTHREADS, 2) msda_tc_fwd_kernel(
+    const __grid_constant__ TcMaps maps, const __grid_constant__ TcMaps maps_lo, const float* __restrict__ value,
+    const float* __restrict__ ref, const float* __restrict__ off, const float* __restrict__ logit,
+    const int* __restrict__ order, float* __restrict__ out, TcShapes sh, int B, int S, int Q, int nH, int ref_bstride) {
+  extern __shared__ uint8_t c_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)c_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* mma_bar = (uint64_t*)(smem + F_MISC);
+  uint64_t* tma_bar = mma_bar + 1;
+  uint32_t* tmem_ptr = (uint32_t*)(smem + F_MISC + 16);
+  int* s_sum = (int*)(smem + F_MISC + 32);      // [12]
+  int* s_org = s_sum + 12;                      // [8]
+  int* s_q = s_org + 8;                         // [32] original query index of every slot
+  float* s_extra = (float*)(smem + F_EXTRA);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t0 = blockIdx.x * CQ, h = blockIdx.y, b = blockIdx.z;
+  const int slot = warp * 4 + (lane >> 3), p = lane & 7;
+  const int rowpitch = nH * CHD;
+
+  if (tid == 0) {
+    c_mbar_init(mma_bar, 1); c_mbar_init(tma_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int l = 0; l < CL; ++l) {
+      asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&maps.m[l]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&maps_lo.m[l]) : "memory");
+    }
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(c_smem_u32(tmem_ptr)), "r"(32) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid < 12) s_sum[tid] = 0;
+  // A (hi) and the stray-corner rows start at zero; so do rows 121..127 of the V tiles, which TMA never writes but the
+  // contraction over 128 cells reads
+  for (int idx = tid; idx < (16384 + 8192) / 16; idx += CTHREADS) {
+    const int o = idx * 16;
+    *(float4*)(smem + (o < 16384 ? F_AHI + o : F_EXTRA + o - 16384)) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int idx = tid; idx < 4 * 7 * 8; idx += CTHREADS) {        // 4 tiles (hi/lo x 2 panels) x 7 rows x 8 chunks
+    const int t = idx / 56, r = idx - t * 56;
+    *(float4*)(smem + (t >> 1) * 32768 + (t & 1) * 16384 + CCELLS * 128 + r * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  c_fence_async();
+  __syncthreads();
+  TcGeom g;
+  tc_geometry(g, order, ref, off, logit, sh, b, h, Q, nH, ref_bstride, t0, warp, lane, s_sum);
+  if (p == 0) s_q[slot] = g.q;
+  c_fence_before();
+  __syncthreads();
+  c_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (tid < CL) tc_origin(s_sum, s_org, sh, tid);
+  __syncthreads();
+  const float* vb = value + (int64_t)b * S * rowpitch + h * CHD;
+
+#pragma unroll
+  for (int l = 0; l < CL; ++l) {
+    const int W = sh.w[l], H = sh.h[l], start = sh.start[l], wx0 = s_org[l * 2], wy0 = s_org[l * 2 + 1];
+    // ---- TMA for V_l hi / lo (the previous level's MMAs have retired), then build A_l while it is in flight -------
+    if (tid == 0) {
+      c_mbar_expect_tx(tma_bar, 4 * WIN_BYTES);
+      c_tma_window(smem + F_VHI, &maps.m[l], tma_bar, h * CHD, wx0, wy0, b);
+      c_tma_window(smem + F_VHI + 16384, &maps.m[l], tma_bar, h * CHD + 32, wx0, wy0, b);
+      c_tma_window(smem + F_VLO, &maps_lo.m[l], tma_bar, h * CHD, wx0, wy0, b);
+      c_tma_window(smem + F_VLO + 16384, &maps_lo.m[l], tma_bar, h * CHD + 32, wx0, wy0, b);
+    }
+    const float xf = floorf(g.px[l]), yf = floorf(g.py[l]);
+    const int x0 = (int)xf, y0 = (int)yf;
+    const float lx = g.px[l] - xf, ly = g.py[l] - yf, a = g.aw[l];
+    int cellk[4], posk[4];
+    float dk[4], wk[4];
+    unsigned omask = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = x0 + (k & 1), y = y0 + (k >> 1);
+      const bool valid = g.q >= 0 && x >= 0 && x < W && y >= 0 && y < H;
+      const int cx = x - wx0, cy = y - wy0;
+      const bool inwin = valid && (unsigned)cx < (unsigned)CWX && (unsigned)cy < (unsigned)CWY;
+      wk[k] = a * ((k & 1) ? lx : 1.f - lx) * ((k >> 1) ? ly : 1.f - ly);
+      cellk[k] = inwin ? cy * CWX + cx : -1;
+      posk[k] = start + y * W + x;
+      dk[k] = 0.f;
+      if (valid && !inwin) omask |= 1u << k;
+    }
+    // A warp owns the rows of its four slots: the eight points of a slot take turns (two of them may share a cell),
+    // plain read-modify-write; then the warp splits its own rows (lo = x - tf32(x)).  No CTA barrier until the MMA.
+    {
+      float* ap[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = max(cellk[k], 0);
+        ap[k] = (float*)(smem + F_AHI + (c >> 5) * 4096 + kmaj_off(slot, c & 31));
+      }
+#pragma unroll
+      for (int r = 0; r < CP; ++r) {
+        if (p == r) {
+          float t[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) t[k] = cellk[k] >= 0 ? *ap[k] : 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) if (cellk[k] >= 0) *ap[k] = t[k] + wk[k];
+        }
+        __syncwarp();
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {          // rows 4 warp .. 4 warp + 3: 4 K-blocks x 4 rows x 8 chunks = 128 float4
+        const int i = lane + 32 * j, kb = i >> 5, rr = (i >> 3) & 3, ck = i & 7;
+        const int o = kb * 4096 + (warp * 4 + rr) * 128 + ck * 16;
+        const float4 x = *(const float4*)(smem + F_AHI + o);
+        *(float4*)(smem + F_ALO + o) = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+      }
+    }
+    c_fence_async();
+    __syncthreads();
+    if (tid == 0) {
+      c_mbar_wait(tma_bar, l & 1);
+      c_fence_after();
+      const uint32_t base = c_smem_u32(smem);
+      const uint64_t vhi = c_desc_mnmajor(base + F_VHI, 16384), vlo = c_desc_mnmajor(base + F_VLO, 16384);
+      constexpr uint32_t idf = c_idesc_tf32(128, 32, true, false);
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        const uint64_t ahi = c_desc_kmajor(base + F_AHI + kb * 4096), alo = c_desc_kmajor(base + F_ALO + kb * 4096);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t ks = 64u * (uint32_t)(kb * 4 + k);       // 8 cells = two 512-byte atoms per k-step
+          c_mma_tf32(tmem_base, vhi + ks, ahi + 2 * k, idf, (l | kb | k) != 0);
+          c_mma_tf32(tmem_base, vlo + ks, ahi + 2 * k, idf, 1u);
+          c_mma_tf32(tmem_base, vhi + ks, alo + 2 * k, idf, 1u);
+        }
+      }
+      c_commit(mma_bar);
+    }
+    __syncwarp();
+    // corners outside the window: fp32 into the warp's own rows of s_extra, overlapped with the MMAs
+    stray_corners<true>(omask, posk, wk, dk, g.q, slot, vb, nullptr, nullptr, s_extra, rowpitch, lane);
+    c_mbar_wait(mma_bar, l & 1);
+    c_fence_after();
+    if (l + 1 < CL) {      // operands are dead: the warp clears its own rows of A for the next level
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = lane + 32 * j, kb = i >> 5, rr = (i >> 3) & 3, ck = i & 7;
+        *(float4*)(smem + F_AHI + kb * 4096 + (warp * 4 + rr) * 128 + ck * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();         // every warp's stray rows are final
+  // ---- epilogue: lanes 0..63 of the accumulator are the channels; warps (qd, hf) read 16 query columns each --------
+  const int qd = warp & 3, hf = warp >> 2;
+  if (qd < 2) {
+    uint32_t v[16];
+    c_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(hf * 16), v);
+    const int ch = qd * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int sl = hf * 16 + j, q = s_q[sl];
+      if (q >= 0) out[((int64_t)b * Q + q) * rowpitch + h * CHD + ch] = __uint_as_float(v[j]) + s_extra[sl * CHD + ch];
+    }
+  }
+  c_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    c_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(32) : "memory");
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------
 static int fill_tc_shapes(const int* hw, int L, int S, TcShapes& sh) {
   if (L != CL) return GED_ERR_SHAPE;
   int start = 0;
@@ -354,8 +610,54 @@ static int fill_tc_shapes(const int* hw, int L, int S, TcShapes& sh) {
   return start == S ? GED_OK : GED_ERR_SHAPE;
 }
 
+// 4-D map {channel, x, y, batch} of one level of value (B, S, nH*64); box {32, CWX, CWY, 1}; out-of-range cells read 0
+static int make_level_maps(TcMaps& maps, const float* value, const TcShapes& sh, int B, int S, int nH, CUtensorMapSwizzle swz) {
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+  if (!enc) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+      return GED_ERR_LAUNCH;
+    enc = (PFN_cuTensorMapEncodeTiled_v12000)ptr;
+  }
+  const cuuint64_t pitch = (cuuint64_t)nH * CHD * 4;
+  for (int l = 0; l < CL; ++l) {
+    cuuint64_t dims[4] = {(cuuint64_t)nH * CHD, (cuuint64_t)sh.w[l], (cuuint64_t)sh.h[l], (cuuint64_t)B};
+    cuuint64_t strides[3] = {pitch, pitch * (cuuint64_t)sh.w[l], pitch * (cuuint64_t)S};
+    cuuint32_t box[4] = {32, CWX, CWY, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(value + (int64_t)sh.start[l] * nH * CHD), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return GED_ERR_ARG;
+  }
+  return GED_OK;
+}
+
 }  // namespace ged
 using namespace ged;
+
+// Tensor-core forward: same contract as ged_msda_tile_fwd; 3xTF32 products with fp32 accumulation (fp32-accurate).
+// value_lo: workspace of the size of value (B*S*nH*64 floats); it receives value - tf32(value).
+GED_API int ged_msda_tc_fwd(const float* value, float* value_lo, const float* ref, int ref_batch, const float* off,
+                            const float* logit, const int* order, float* out, const int* level_hw, int num_levels, int B,
+                            int S, int Q, int nH, int head_dim, int num_points, cudaStream_t stream) {
+  if (!value || !value_lo || !ref || !off || !logit || !order || !out || !level_hw) return GED_ERR_ARG;
+  if (head_dim != CHD || num_points != CP || (ref_batch != 1 && ref_batch != B)) return GED_ERR_SHAPE;
+  if (!aligned16(value) || !aligned16(value_lo)) return GED_ERR_ALIGN;
+  TcShapes sh;
+  if (int e = fill_tc_shapes(level_hw, num_levels, S, sh)) return e;
+  TcMaps maps, maps_lo;
+  if (int e = make_level_maps(maps, value, sh, B, S, nH, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
+  if (int e = make_level_maps(maps_lo, value_lo, sh, B, S, nH, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
+  const int64_t n4 = (int64_t)B * S * nH * CHD / 4;
+  const int64_t split_blocks = (n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16;
+  split_lo_kernel<<<(int)split_blocks, 256, 0, stream>>>((const float4*)value, (float4*)value_lo, n4);
+  if (cudaFuncSetAttribute(msda_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_TOTAL) != cudaSuccess) return GED_ERR_LAUNCH;
+  msda_tc_fwd_kernel<<<dim3(cdiv(Q, CQ), nH, B), CTHREADS, F_TOTAL, stream>>>(maps, maps_lo, value, ref, off, logit, order, out, sh, B, S,
+                                                                           Q, nH, ref_batch == 1 ? 0 : Q * 2);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
 
 // Tensor-core backward: same contract as ged_msda_tile_bwd.  The products feeding g_value / g_off / g_logit / g_ref run
 // in one-pass TF32 (tcgen05.mma kind::tf32, fp32 accumulate) like the other backward GEMMs of the path;
@@ -369,9 +671,11 @@ GED_API int ged_msda_tc_bwd(const float* value, const float* ref, int ref_batch,
   if (!aligned16(value) || !aligned16(g_value) || !aligned16(g_out)) return GED_ERR_ALIGN;
   TcShapes sh;
   if (int e = fill_tc_shapes(level_hw, num_levels, S, sh)) return e;
+  TcMaps maps;
+  if (int e = make_level_maps(maps, value, sh, B, S, nH, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   if (cudaFuncSetAttribute(msda_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_TOTAL) != cudaSuccess) return GED_ERR_LAUNCH;
-  msda_tc_bwd_kernel<<<dim3(cdiv(Q, CQ), nH, B), CTHREADS, B_TOTAL, stream>>>(value, ref, off, logit, order, g_out, g_value, g_ref,
-                                                                           g_off, g_logit, sh, B, S, Q, nH,
+  msda_tc_bwd_kernel<<<dim3(cdiv(Q, CQ), nH, B), CTHREADS, B_TOTAL, stream>>>(maps, value, ref, off, logit, order, g_out, g_value,
+                                                                           g_ref, g_off, g_logit, sh, B, S, Q, nH,
                                                                            ref_batch == 1 ? 0 : Q * 2);
   GED_CHECK_LAUNCH();
   return GED_OK;

@@ -57,6 +57,7 @@ SIGNATURES = {
     "ged_msda_sort_queries": [_P, _I, _I, _I, _P, _P, _I64, _P],
     "ged_msda_tile_fwd": [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_msda_tile_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ged_msda_tc_fwd": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_msda_tc_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_gemm_tf32_bt": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P],
     "ged_conv3x3_dx_tf32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
@@ -1048,13 +1049,20 @@ def clamp_resize(x, lo, hi, size):
 # =============================================================================================
 # deformable attention sampling
 # =============================================================================================
-# Tile kernels (csrc/msda_tile.cu: queries sorted by reference point, shared-memory windows) unless GEDEPTH_MSDA_TILE=0,
-# which keeps the round-1 one-warp-per-(query, head) kernels of csrc/msda.cu as the A/B partner.
-MSDA_TILE = os.environ.get("GEDEPTH_MSDA_TILE", "1") != "0"
+# Three implementations of the sampling, selectable per direction (A/B partners of each other in the tests):
+#   "round1": one warp per (query, head) straight from / to L2 (csrc/msda.cu)
+#   "tile"  : queries sorted by reference point, 32-query tiles, shared-memory windows, fp32 SIMT (csrc/msda_tile.cu)
+#   "tc"    : the same tiles on tcgen05 - forward 3xTF32 (fp32-accurate), backward one-pass TF32 (csrc/msda_tc.cu)
+# Measured at B = 8, 352 x 1120 (tools/ab_msda_tile.py): forward round1 13.2 / tile 15.8 / tc 19.7 ms, backward
+# round1 48.1 / tile 48.5 / tc 17.3 ms -> forward stays on round1, the backward runs on the tensor cores (the fp32 tile
+# kernels when GEDEPTH_BWD_GEMM_PASSES=3 asks for fp32-accurate gradients).
+MSDA_FWD = os.environ.get("GEDEPTH_MSDA_FWD", "round1")
+MSDA_BWD = os.environ.get("GEDEPTH_MSDA_BWD", "tc")
 MSDA_TILE_Q = 32
-# Backward of the sampling on tcgen05 (csrc/msda_tc.cu, one-pass TF32 like the other backward GEMMs) unless
-# GEDEPTH_MSDA_TC=0 or GEDEPTH_BWD_GEMM_PASSES=3 ask for the fp32 SIMT tile kernels.
-MSDA_TC = os.environ.get("GEDEPTH_MSDA_TC", "1") != "0"
+
+
+def _msda_bwd_impl() -> str:
+    return "tile" if (MSDA_BWD == "tc" and BACKWARD_PASSES != 1) else MSDA_BWD
 
 
 def msda_query_order(ref: torch.Tensor, shapes) -> torch.Tensor:
@@ -1079,46 +1087,53 @@ def msda_query_order(ref: torch.Tensor, shapes) -> torch.Tensor:
 
 class _MSDA(Function):
     @staticmethod
-    def forward(ctx, v, ref, off, logit, shapes, nH, P):
+    def forward(ctx, v, ref, off, logit, shapes, nH, P, fwd_impl, bwd_impl):
         v, ref, off, logit = _f32c(v), _f32c(ref), _f32c(off), _f32c(logit)
         B, S, E = v.shape
         Q = off.shape[1]
         hw = (C.c_int * (2 * len(shapes)))(*[int(a) for s in shapes for a in s])
         out = torch.empty(B, Q, E, dtype=torch.float32, device=v.device)
+        need_bwd = any(ctx.needs_input_grad[:4])
         order = None
-        if MSDA_TILE:
+        if fwd_impl != "round1" or (need_bwd and bwd_impl != "round1"):
             order = msda_query_order(ref, shapes)
+        if fwd_impl == "tc":
+            v_lo = torch.empty_like(v)          # value - tf32(value), the lo operand of the 3xTF32 forward
+            _call("ged_msda_tc_fwd", _p(v), _p(v_lo), _p(ref), ref.shape[0], _p(off), _p(logit), _p(order), _p(out),
+                  hw, len(shapes), B, S, Q, nH, E // nH, P, _stream())
+        elif fwd_impl == "tile":
             _call("ged_msda_tile_fwd", _p(v), _p(ref), ref.shape[0], _p(off), _p(logit), _p(order), _p(out), hw,
                   len(shapes), B, S, Q, nH, E // nH, P, _stream())
         else:
             _call("ged_msda_fwd", _p(v), _p(ref), ref.shape[0], _p(off), _p(logit), _p(out), hw, len(shapes), B, S, Q,
                   nH, E // nH, P, _stream())
         ctx.save_for_backward(v, ref, off, logit, order if order is not None else torch.empty(0, device=v.device))
-        ctx.cfg = (tuple(tuple(s) for s in shapes), nH, P)
+        ctx.cfg = (tuple(tuple(s) for s in shapes), nH, P, bwd_impl)
         return out
 
     @staticmethod
     def backward(ctx, g):
         v, ref, off, logit, order = ctx.saved_tensors
-        shapes, nH, P = ctx.cfg
+        shapes, nH, P, bwd_impl = ctx.cfg
         B, S, E = v.shape
         Q = off.shape[1]
         hw = (C.c_int * (2 * len(shapes)))(*[int(a) for s in shapes for a in s])
         g = _f32c(g)
         g_v = torch.zeros_like(v)
         g_off, g_logit = torch.empty_like(off), torch.empty_like(logit)
-        if order.numel():
+        tail = (None,) * 5
+        if bwd_impl != "round1":
             # reference points shared by the batch (ref_batch == 1): their gradient is summed over the batch in place
             g_ref = torch.zeros_like(ref) if ctx.needs_input_grad[1] else None
-            name = "ged_msda_tc_bwd" if (MSDA_TC and BACKWARD_PASSES == 1) else "ged_msda_tile_bwd"
-            _call(name, _p(v), _p(ref), ref.shape[0], _p(off), _p(logit), _p(order), _p(g), _p(g_v),
-                  _p(g_ref), _p(g_off), _p(g_logit), hw, len(shapes), B, S, Q, nH, E // nH, P, _stream())
-            return g_v, g_ref, g_off, g_logit, None, None, None
+            _call("ged_msda_tc_bwd" if bwd_impl == "tc" else "ged_msda_tile_bwd", _p(v), _p(ref), ref.shape[0], _p(off),
+                  _p(logit), _p(order), _p(g), _p(g_v), _p(g_ref), _p(g_off), _p(g_logit), hw, len(shapes), B, S, Q, nH,
+                  E // nH, P, _stream())
+            return (g_v, g_ref, g_off, g_logit) + tail
         need_ref = ctx.needs_input_grad[1] and ref.shape[0] == B
         g_ref = torch.zeros_like(ref) if need_ref else None
         _call("ged_msda_bwd", _p(v), _p(ref), ref.shape[0], _p(off), _p(logit), _p(g), _p(g_v), _p(g_ref),
               _p(g_off), _p(g_logit), hw, len(shapes), B, S, Q, nH, E // nH, P, _stream())
-        return g_v, g_ref, g_off, g_logit, None, None, None
+        return (g_v, g_ref, g_off, g_logit) + tail
 
 
 def msda_atomic_probe(rows: int = 32725, heads: int = 8, iters: int = 2000, device="cuda") -> float:
@@ -1146,9 +1161,10 @@ def msda_sample(v, shapes, ref, off, logit, nH, P):
     B = v.shape[0]
     if ref.shape[0] not in (1, B):
         raise ValueError("reference_points batch must be 1 or B")
-    if ref.shape[0] == 1 and ref.requires_grad and B > 1 and not MSDA_TILE:
-        ref = ref.expand(B, -1, -1)        # round-1 kernels: learnable reference points need one copy per sample
-    return _MSDA.apply(v, ref, off, logit, shapes, nH, P)
+    bwd = _msda_bwd_impl()
+    if ref.shape[0] == 1 and ref.requires_grad and B > 1 and bwd == "round1":
+        ref = ref.expand(B, -1, -1)        # round-1 backward: learnable reference points need one copy per sample
+    return _MSDA.apply(v, ref, off, logit, shapes, nH, P, MSDA_FWD, bwd)
 
 
 # =============================================================================================

@@ -226,8 +226,13 @@ int ged_msda_tile_bwd(const float* value, const float* ref, int ref_batch, const
                       const int* level_hw, int num_levels, int B, int S, int Q, int nH, int head_dim, int num_points,
                       cudaStream_t stream);
 
-/* ged_msda_tile_bwd on the tensor cores (csrc/msda_tc.cu): per tile and level the value gradient and the corner dot
- * products are two tcgen05.mma GEMMs over an 11 x 11 window (one-pass TF32, fp32 accumulate in TMEM). */
+/* The same on the tensor cores (csrc/msda_tc.cu): per tile and level the sampling is a tcgen05.mma GEMM of a sparse
+ * (query x window cell) weight matrix against the 11 x 11 window of value rows (TMA-staged); forward in 3xTF32
+ * (fp32-accurate), backward (value gradient and corner dot products) in one-pass TF32, fp32 accumulate in TMEM. */
+int ged_msda_tc_fwd(const float* value, float* value_lo /* workspace, same size as value */, const float* ref,
+                    int ref_batch, const float* off, const float* logit, const int* order, float* out,
+                    const int* level_hw, int num_levels, int B, int S, int Q, int nH, int head_dim, int num_points,
+                    cudaStream_t stream);
 int ged_msda_tc_bwd(const float* value, const float* ref, int ref_batch, const float* off, const float* logit,
                     const int* order, const float* g_out, float* g_value, float* g_ref, float* g_off, float* g_logit,
                     const int* level_hw, int num_levels, int B, int S, int Q, int nH, int head_dim, int num_points,

@@ -496,22 +496,26 @@ def test_conv1x1_and_folded_bn():
                                                (1, [(18, 42), (9, 21), (5, 11), (3, 6)], 333, 1),
                                                (2, [(16, 40), (8, 20), (4, 10), (2, 5)], 1280, 2),
                                                (3, [(44, 140), (22, 70), (11, 35), (6, 18)], 6160, 1)])
-@pytest.mark.parametrize("variant", ["tc", "tile", 0, 1, 2, 3], ids=["tc", "tile", "q8xh1", "q1xh8", "q8xh1-split", "q1xh8-split"])
-def test_msda_fwd_bwd(B, shapes, Q, ref_b, variant):
+@pytest.mark.parametrize("impl", ["path", "tc", "tile", "round1-q8xh1", "round1-q1xh8", "round1-q8xh1-split", "round1-q1xh8-split"])
+def test_msda_fwd_bwd(B, shapes, Q, ref_b, impl):
     """Sampling + all four gradients against the grid_sample statement (ops_lib, which equals the oracle's msda_core).
-    `tc` = the path: sorted-tile forward + tcgen05 backward (csrc/msda_tc.cu, one-pass TF32 like the other backward
-    GEMMs, hence the 4e-3 gradient tolerance); `tile` = the fp32 sorted-tile kernels (csrc/msda_tile.cu, what
-    GEDEPTH_BWD_GEMM_PASSES=3 selects); 0..3 = the round-1 kernels kept as A/B partner.
-    ref_b == 1 with B > 1 is the cross-attention case: learnable reference points shared by the batch, so g_ref is
-    the sum over the batch."""
+    `path` = the defaults of kernels.py (round-1 forward + tcgen05 backward); `tc` = tcgen05 both ways (csrc/msda_tc.cu:
+    forward 3xTF32, backward one-pass TF32 like the other backward GEMMs, hence the 4e-3 gradient tolerance); `tile` =
+    the fp32 sorted-tile kernels (csrc/msda_tile.cu, what GEDEPTH_BWD_GEMM_PASSES=3 selects for the backward);
+    round1-* = the four work mappings of the round-1 kernels.  ref_b == 1 with B > 1 is the cross-attention case:
+    learnable reference points shared by the batch, so g_ref is the sum over the batch."""
     from gedepth_b200 import kernels as Kn
-    prev_tile, prev_tc, prev = Kn.MSDA_TILE, Kn.MSDA_TC, Kn.set_msda_variant(variant if isinstance(variant, int) else -1)
-    Kn.MSDA_TILE, Kn.MSDA_TC = variant in ("tile", "tc"), variant == "tc"
+    saved = (Kn.MSDA_FWD, Kn.MSDA_BWD, Kn.set_msda_variant(-1))
     try:
-        _msda_case(B, shapes, Q, ref_b, tf32=variant == "tc")
+        if impl.startswith("round1"):
+            Kn.MSDA_FWD = Kn.MSDA_BWD = "round1"
+            Kn.set_msda_variant(["round1-q8xh1", "round1-q1xh8", "round1-q8xh1-split", "round1-q1xh8-split"].index(impl))
+        elif impl != "path":
+            Kn.MSDA_FWD = Kn.MSDA_BWD = impl
+        _msda_case(B, shapes, Q, ref_b, tf32=Kn._msda_bwd_impl() == "tc")
     finally:
-        Kn.MSDA_TILE, Kn.MSDA_TC = prev_tile, prev_tc
-        Kn.set_msda_variant(prev)
+        Kn.MSDA_FWD, Kn.MSDA_BWD = saved[0], saved[1]
+        Kn.set_msda_variant(saved[2])
 
 
 def _msda_inputs(B, shapes, Q, ref_b, clustered):
@@ -549,22 +553,31 @@ def _msda_case(B, shapes, Q, ref_b, clustered=False, tf32=False):
 
 def test_msda_tile_outliers_and_order_invariance():
     """Corners far outside their window (and outside the map) take the direct path; the result does not depend on the
-    query order (identity, reversed and the sorted order agree to fp32 round-off of the atomics)."""
+    query order (identity, reversed and the sorted order agree: bit-identical for the fp32 tile forward, to 1e-5 for the
+    3xTF32 tensor-core forward whose rounding depends on the window)."""
     from gedepth_b200 import kernels as Kn
     shapes = [(44, 140), (22, 70), (11, 35), (6, 18)]
-    Kn.MSDA_TILE = True
-    for tc in (False, True):
-        Kn.MSDA_TC = tc
-        _msda_case(2, shapes, 3000, 1, clustered=True, tf32=tc)
-    v0, ref0, off0, lg0 = _msda_inputs(2, shapes, 3000, 1, True)
-    v, ref, off, lg = [t.to(DEV) for t in (v0, ref0, off0, lg0)]
-    order = Kn.msda_query_order(ref, shapes)
-    assert sorted(order.cpu().tolist()) == list(range(3000)), "the sort must return a permutation"
-    outs = []
-    for o in (order, torch.arange(3000, dtype=torch.int32, device=DEV), torch.arange(2999, -1, -1, dtype=torch.int32, device=DEV)):
-        ref._ged_order = (ref._version, o.contiguous())
-        outs.append(Kn.msda_sample(v, shapes, ref, off, lg, 8, 8))
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "forward must not depend on the query order"
+    saved = (Kn.MSDA_FWD, Kn.MSDA_BWD)
+    try:
+        for impl in ("tile", "tc"):
+            Kn.MSDA_FWD = Kn.MSDA_BWD = impl
+            _msda_case(2, shapes, 3000, 1, clustered=True, tf32=impl == "tc")
+        v0, ref0, off0, lg0 = _msda_inputs(2, shapes, 3000, 1, True)
+        v, ref, off, lg = [t.to(DEV) for t in (v0, ref0, off0, lg0)]
+        order = Kn.msda_query_order(ref, shapes)
+        assert sorted(order.cpu().tolist()) == list(range(3000)), "the sort must return a permutation"
+        Kn.MSDA_FWD = "tile"
+        outs = []
+        for o in (order, torch.arange(3000, dtype=torch.int32, device=DEV), torch.arange(2999, -1, -1, dtype=torch.int32, device=DEV)):
+            ref._ged_order = (ref._version, o.contiguous())
+            outs.append(Kn.msda_sample(v, shapes, ref, off, lg, 8, 8))
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "forward must not depend on the query order"
+        Kn.MSDA_FWD = "tc"
+        for o in (order, torch.arange(2999, -1, -1, dtype=torch.int32, device=DEV)):
+            ref._ged_order = (ref._version, o.contiguous())
+            _close(Kn.msda_sample(v, shapes, ref, off, lg, 8, 8), outs[0], 1e-5, 1e-5 * float(outs[0].abs().max()), "tc forward vs fp32 tile forward")
+    finally:
+        Kn.MSDA_FWD, Kn.MSDA_BWD = saved
 
 
 # ------------------------------------------------------------------------------------------------

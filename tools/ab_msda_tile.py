@@ -12,6 +12,7 @@ from gedepth_b200.synth import synth_batch, synth_state_dict
 DEV = 'cuda:0'
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 ONLY_TILE = len(sys.argv) > 2 and sys.argv[2] == "tile"      # for ncu: tile kernels only
+ONLY = sys.argv[3] if len(sys.argv) > 3 else ""               # "self" / "cross"
 cfg = model_cfg('v', 'kitti', 'swin_t', pretrained=None)
 model = M.build_depther(cfg)
 model.load_state_dict(synth_state_dict(model.state_dict(), 0))
@@ -48,16 +49,15 @@ def t_ms(fn, reps=5):
 
 
 for name, (v, shapes, ref, off, lg) in zip(("self", "cross"), taps):
+    if ONLY and name != ONLY:
+        continue
     Q = off.shape[1]
     go = torch.randn(B, Q, 512, device=DEV)
     res = {}
-    for label, tile, variant in (("round-1 auto", False, -1), ("tile fp32", True, -1), ("tile+tc", True, -2)):
-        if ONLY_TILE and not tile:
+    for label, fwd_impl, bwd_impl in (("round1", "round1", "round1"), ("tile fp32", "tile", "tile"), ("tc", "tc", "tc")):
+        if ONLY_TILE and label != "tc":
             continue
-        K.MSDA_TILE = tile
-        K.MSDA_TC = variant == -2
-        variant = max(variant, -1)
-        K.set_msda_variant(variant)
+        K.MSDA_FWD, K.MSDA_BWD = fwd_impl, bwd_impl
         vv, oo, ll = v.clone().requires_grad_(True), off.clone().requires_grad_(True), lg.clone().requires_grad_(True)
         rr = ref.clone().requires_grad_(ref.shape[0] == 1 and name == "cross")
         with torch.no_grad():
@@ -70,10 +70,8 @@ for name, (v, shapes, ref, off, lg) in zip(("self", "cross"), taps):
         print(f"{name} B={B} Q={Q} {label:14s}: fwd {f:7.3f} ms   bwd {bw:7.3f} ms (incl. zero-fill of g_value)", flush=True)
     if ONLY_TILE:
         continue
-    for other in ("tile fp32", "tile+tc"):
-      a, t = res["round-1 auto"], res[other]
+    for other in ("tile fp32", "tc"):
+      a, t = res["round1"], res[other]
       print(f"   {other} vs round-1: out max|d| {float((a[0] - t[0]).abs().max()):.3e} (max {float(a[0].abs().max()):.3e}); " +
             "; ".join(f"g{i} {float((x - y).abs().max()):.3e}/{float(x.abs().max()):.3e}" for i, (x, y) in enumerate(zip(a[1], t[1]))))
-K.MSDA_TILE = True
-K.set_msda_variant(-1)
 print("done")
