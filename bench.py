@@ -363,8 +363,8 @@ def library_baseline(c: Ctx, spec: dict, batch: int, steps: int):
     from gedepth_b200.synth import synth_batch, synth_state_dict
     H, W = spec["H"], spec["W"]
     adaptive, ddad = spec["variant"] == "a", spec["dataset"] == "ddad"
-    prev = set(ops._FORCE_LIB)
-    ops._FORCE_LIB.add("all")
+    from tests import ops_lib          # the library statement of every op: comparator only, never the product path
+    restore = ops_lib.install(ops)
     try:
         model = M.build_depther(model_cfg(spec["variant"], spec["dataset"], spec["backbone"], pretrained=None))
         model.load_state_dict(synth_state_dict(model.state_dict(), 0))
@@ -394,12 +394,11 @@ def library_baseline(c: Ctx, spec: dict, batch: int, steps: int):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         out = dict(frames_s=batch / (ms / 1e3), ms_per_step=ms, batch=batch, steps=steps, launch="eager",
-                   note="same model / step through ops_lib: cuDNN convs and cuBLAS linears with allow_tf32=True, ATen "
+                   note="same model / step through tests/ops_lib.py: cuDNN convs and cuBLAS linears with allow_tf32=True, ATen "
                         "elementwise + LayerNorm + BatchNorm, grid_sample deformable attention, torch AdamW + clip_grad_norm_")
         del model, opt, d
     finally:
-        ops._FORCE_LIB.clear()
-        ops._FORCE_LIB.update(prev)
+        restore()
         gc.collect()
         torch.cuda.synchronize()
         torch.cuda.empty_cache()

@@ -968,6 +968,18 @@ GED_API int ged_gemm_tf32_bt(const float* A, int lda, const float* Wt, int ldw, 
   return run(A, M, lda, Wt, ldw, p, stream);
 }
 
+// The same plus a residual: D = A @ Wt + R (R with D's row pitch; R == D accumulates in place).  Lets a gradient that
+// fans in from several consumers be summed inside the GEMM epilogues instead of by separate elementwise passes.
+GED_API int ged_gemm_tf32_bt_acc(const float* A, int lda, const float* Wt, int ldw, float* D, int ldd, int M, int N,
+                                 int K, const float* residual, cudaStream_t stream) {
+  if (!A || !Wt || !D || M <= 0 || N <= 0 || K <= 0) return GED_ERR_ARG;
+  if ((K % 4) || (N % 4)) return GED_ERR_SHAPE;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.ntaps = 1; p.tap_off[0] = 0; p.b_mn = 1; p.b_tap_cols = 0;
+  p.rows_per_batch = 1; p.D = D; p.ldd = ldd; p.residual = residual;
+  return run(A, M, lda, Wt, ldw, p, stream);
+}
+
 // dX of the 3x3/s1/p1 conv: DX[B,H,W,Cin] = sum_t Gpad[p - off_t, :] @ Wk[:, t, :] with Gpad the zero-bordered dY
 // [B,H+2,W+2,Cout] and Wk the FORWARD weights [Cout][3][3][Cin] read in place (MN-major B operand, one 32-column
 // panel set per tap) - no flipped / transposed weight copy.

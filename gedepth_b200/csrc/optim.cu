@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
                                                      const double* __restrict__ sumsq, float max_norm,
                                                      float grad_scale, float lr, float beta1, float beta2,
                                                      float eps, float wd, float bc1, float bc2,
-                                                     const int* __restrict__ step_dev) {
+                                                     const int* __restrict__ step_dev, const float* __restrict__ lr_dev) {
+  if (lr_dev) lr = *lr_dev;   // learning rate of this step lives on the device (schedules under CUDA-graph replay)
   if (step_dev) {   // step count lives on the device (CUDA-graph replays must not bake it in)
     const float t = (float)(*step_dev);
     bc1 = 1.f - powf(beta1, t);
@@ -76,15 +77,16 @@ GED_API int ged_sumsq(const float* g, int64_t n, double* out, cudaStream_t strea
 }
 
 // step >= 1, or step_dev != NULL: the 1-based step count is read from device memory at run time (for
-// CUDA-graph replay).  sumsq may be NULL (no clipping).  grad_scale folds the 1/world_size average.
+// CUDA-graph replay); likewise lr_dev != NULL overrides lr with a device scalar (warm-up / cosine schedules keep
+// working when the step is a replayed graph).  sumsq may be NULL (no clipping).  grad_scale folds the 1/world_size average.
 GED_API int ged_adamw_step(float* p, const float* g, float* m, float* v, const uint8_t* wd_mask, int64_t n,
                            const double* sumsq, float max_norm, float grad_scale, float lr, float beta1,
                            float beta2, float eps, float weight_decay, int step, const int* step_dev,
-                           cudaStream_t stream) {
+                           const float* lr_dev, cudaStream_t stream) {
   if (!p || !g || !m || !v || n <= 0 || (step < 1 && !step_dev)) return GED_ERR_ARG;
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   const unsigned grid = (unsigned)(n / 256 + 1 < 2368 ? n / 256 + 1 : 2368);
-  adamw_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, wd_mask, n, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, weight_decay, bc1, bc2, step_dev);
+  adamw_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, wd_mask, n, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, weight_decay, bc1, bc2, step_dev, lr_dev);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }

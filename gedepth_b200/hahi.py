@@ -4,9 +4,11 @@ depth/models/necks/hahi.py:84-356, depth/utils/position_encoding.py:10-99 and mm
 SURVEY.md §8(c)].  Same registry names, constructor keywords and state_dict keys.
 
 B200-first differences: feature maps are channels-last, so ``flatten(2).transpose(1, 2)`` is a
-view; the sine encodings and self-attention reference points are constants cached per shape; the
-softmax over the 32 (level, point) weights, the ``ref + offset / (W_l, H_l)`` location arithmetic
-and the bilinear gather run in ONE sampling kernel (ops.msda_sample).
+view; the sine encodings and self-attention reference points are constants cached per shape; a
+deformable-attention module is ONE autograd node (ops.msda_module): ``query + pos`` (+ the level
+embedding), the three input GEMMs, the sampling (softmax over the 32 (level, point) weights,
+``ref + offset / (W_l, H_l)``, bilinear gather) and ``output_proj`` + dropout + identity, with the
+query gradient's fan-in summed inside the backward GEMMs' epilogues.
 """
 from __future__ import annotations
 
@@ -94,23 +96,19 @@ class MultiScaleDeformableAttention(BaseModule):
 
     def forward(self, query, key=None, value=None, identity=None, query_pos=None,
                 key_padding_mask=None, reference_points=None, spatial_shapes=None,
-                level_start_index=None, **kwargs):
+                level_start_index=None, level_embed=None, **kwargs):
         """query (B, Q, E); value (B, S, E) or None (= query before pos); reference_points
         (B|1, Q, 2) shared by all levels (valid_ratios == 1 on this path); spatial_shapes: list of
-        (h, w).  Returns dropout(output_proj(sampled)) + identity."""
-        assert key_padding_mask is None
-        value = query if value is None else value
-        identity = query if identity is None else identity
-        q = query if query_pos is None else ops.add_bcast(query, query_pos)
-        B, Q, E = q.shape
-        v = ops.linear(value, self.value_proj.weight, self.value_proj.bias)
-        off = ops.linear(q, self.sampling_offsets.weight, self.sampling_offsets.bias)
-        logit = ops.linear(q, self.attention_weights.weight, self.attention_weights.bias)
-        out = ops.msda_sample(v, spatial_shapes, reference_points, off, logit, self.num_heads,
-                              self.num_points)
-        # dropout(output_proj(sampled)) + identity: mask and residual ride in the GEMM epilogue
+        (h, w).  query_pos: the CONSTANT part of the positional encoding, (1, Q, E); a learnable
+        per-level embedding (hahi.py:252-270 adds ``level_embed[i]`` to the sine encoding) is passed
+        as level_embed (4, E) + level_start_index (5 token offsets) so its gradient comes out of the
+        same node.  Returns dropout(output_proj(sampled)) + identity (identity = query)."""
+        assert key_padding_mask is None and identity is None
+        if query_pos is None:
+            query_pos = torch.zeros(1, query.shape[1], query.shape[2], dtype=query.dtype, device=query.device)
         p = self.dropout.p if self.training else 0.0
-        return ops.linear(out, self.output_proj.weight, self.output_proj.bias, residual=identity, dropout_p=p)
+        return ops.msda_module(query, value, query_pos, level_embed, level_start_index, reference_points,
+                               spatial_shapes, self, p)
 
 
 @NECKS.register_module()
@@ -174,6 +172,13 @@ class HAHIHeteroNeck(BaseModule):
             self._ref_cache[key] = torch.cat(refs, 0)[None].contiguous()
         return self._ref_cache[key]
 
+    def _self_pos(self, shapes, device):
+        """Sine encodings of the four levels, concatenated: the constant part of the self-attention query_pos."""
+        key = ("pos", tuple(shapes), str(device))
+        if key not in self._ref_cache:
+            self._ref_cache[key] = torch.cat([self.trans_positional_encoding.tokens(h, w, device) for h, w in shapes], 1).contiguous()
+        return self._ref_cache[key]
+
     @staticmethod
     def _cm(m: ConvModule, x, padding=0):
         return ops.conv_bn_act(x, m.conv.weight, m.conv.bias, m.norm, stride=1, padding=padding,
@@ -187,22 +192,21 @@ class HAHIHeteroNeck(BaseModule):
         shapes = [(int(t.shape[2]), int(t.shape[3])) for t in feats_trans]
 
         # HI: deformable self-attention over the four Swin levels
-        src, pos = [], []
-        for i, t in enumerate(feats_trans):
-            h, w = shapes[i]
-            pos.append(self.trans_positional_encoding.tokens(h, w, dev) + self.level_embed[i].view(1, 1, -1))
-            src.append(ops.map_to_tokens(self._cm(self.trans_proj[i], t)))
-        src, pos = torch.cat(src, 1), torch.cat(pos, 1)
+        src = ops.cat_tokens([ops.map_to_tokens(self._cm(self.trans_proj[i], t)) for i, t in enumerate(feats_trans)])
         if self.self_att:
-            src = self.self_attn(src, value=None, identity=None, query_pos=pos,
-                                 reference_points=self._self_ref(shapes, dev), spatial_shapes=shapes)
+            starts = [0]
+            for hh, ww in shapes:
+                starts.append(starts[-1] + hh * ww)
+            src = self.self_attn(src, value=None, identity=None, query_pos=self._self_pos(shapes, dev),
+                                 reference_points=self._self_ref(shapes, dev), spatial_shapes=shapes,
+                                 level_start_index=starts, level_embed=self.level_embed)
 
         # HA: deformable cross-attention from the stem grid into the Swin levels
         skip = self._cm(self.conv_proj[0], feat_conv)
         bs, c, h, w = skip.shape
         query = ops.map_to_tokens(skip)
         qpe = self.conv_positional_encoding.tokens(h, w, dev)
-        ref = torch.sigmoid(ops.linear(qpe, self.reference_points.weight, self.reference_points.bias))
+        ref = ops.linear_small(qpe, self.reference_points.weight, self.reference_points.bias, act="sigmoid")
         if self.cross_att:
             fused = self.multi_att(query, value=src, identity=None, query_pos=qpe,
                                    reference_points=ref, spatial_shapes=shapes)
@@ -211,11 +215,9 @@ class HAHIHeteroNeck(BaseModule):
         fused = ops.tokens_to_map(fused, (h, w))
         cf = self.conv_fusion[0]
         outs = [ops.conv_bn_act_cat(fused, feat_conv, cf.conv.weight, cf.conv.bias, cf.norm, act="relu")]
-        start = 0
+        levels = ops.split_levels(src, [hh * ww for hh, ww in shapes])
         for i, t in enumerate(feats_trans):
-            hh, ww = shapes[i]
-            f = ops.tokens_to_map(src[:, start:start + hh * ww], (hh, ww))
-            start += hh * ww
+            f = ops.tokens_to_map(levels[i], shapes[i])
             tf = self.trans_fusion[i]
             outs.append(ops.conv_bn_act_cat(t, f, tf.conv.weight, tf.conv.bias, tf.norm, act="relu"))
         return tuple(outs)

@@ -2,7 +2,8 @@
 that own tensors around it.  PyTorch is plumbing here: it allocates device memory and provides the
 current stream; every number is produced by the sm_100a kernels behind the C ABI.
 
-Fails loudly: a missing / unloadable library or a non-zero status raises RuntimeError.
+Fails loudly: a missing / unloadable library or a non-zero status raises RuntimeError; a shape the kernels do not
+cover raises NotImplementedError (there is no cuDNN / cuBLAS / ATen fallback in the product).
 """
 from __future__ import annotations
 
@@ -13,7 +14,6 @@ from typing import Optional, Sequence
 import torch
 from torch.autograd import Function
 
-from . import ops_lib as L
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgedepth_sm100.so")
@@ -60,6 +60,12 @@ SIGNATURES = {
     "ged_msda_tc_fwd": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_msda_tc_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_gemm_tf32_bt": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P],
+    "ged_gemm_tf32_bt_acc": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P],
+    "ged_conv3x3_small_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+    "ged_linear_small_fwd": [_P, _P, _P, _P, _I64, _I, _I, _I, _P],
+    "ged_linear_small_bwd": [_P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _P],
+    "ged_add_pos_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "ged_add_pos_bwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "ged_conv3x3_dx_tf32": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ged_set_gemm_precision": [_I],
     "ged_set_gemm_wide_tiles": [_I],
@@ -70,7 +76,7 @@ SIGNATURES = {
     "ged_tta_merge": [_P, _P, _P, _I, _I, _I, _P],
     "ged_rgb_crop_normalize": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P],
     "ged_sumsq": [_P, _I64, _P, _P],
-    "ged_adamw_step": [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _F, _I, _P, _P],
+    "ged_adamw_step": [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _F, _I, _P, _P, _P],
 }
 
 _lib = None
@@ -283,12 +289,13 @@ class _GEAdaptive(Function):
         return None, g_yh, g_lh, None, None, None, None
 
 
-def ge_adaptive(img, y_half, logits_half, height, depth_scale):
+def ge_adaptive(img, y_half, logits_half, height, depth_scale, want_logits=None):
+    """want_logits: also return the full-resolution logits (the CE loss input); default: whenever autograd records."""
     if torch.is_tensor(height):
         ht, hs = height.reshape(-1), 0.0
     else:
         ht, hs = None, float(height)
-    want_logits = torch.is_grad_enabled()
+    want_logits = torch.is_grad_enabled() if want_logits is None else bool(want_logits)
     y, pm, lf = _GEAdaptive.apply(img, y_half, logits_half, ht, hs, depth_scale, want_logits)
     return y, pm, (lf if want_logits else None)
 
@@ -389,7 +396,7 @@ class _CE(Function):
 
 def cross_entropy(logits, target, ignore_index=255):
     if logits.shape[1] != 11:
-        return L.cross_entropy(logits, target, ignore_index)
+        raise NotImplementedError("cross_entropy: the kernel covers the 11 slope classes of the GE path (encoder_decoder.py:68)")
     return _CE.apply(logits, target, ignore_index)
 
 
@@ -437,7 +444,7 @@ class _LayerNorm(Function):
 
 def layer_norm(x, w, b, eps):
     if x.shape[-1] % 4:
-        return L.layer_norm(x, w, b, eps)
+        raise NotImplementedError("layer_norm: channel count must be a multiple of 4")
     return _LayerNorm.apply(x, w, b, eps, _sink(w), _sink(b), False)
 
 
@@ -501,9 +508,15 @@ _DROP_CALLS = 0
 
 
 def next_dropout_seed() -> int:
+    """Per call site, mixed with torch's seed and the data-parallel rank: ranks draw different masks, torch.manual_seed
+    changes the stream (the reference's nn.Dropout uses the per-rank torch generator)."""
     global _DROP_CALLS
     _DROP_CALLS += 1
-    return (0x2545F491 * _DROP_CALLS + 0x1234567) & 0xFFFFFFFF
+    rank = 0
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank = torch.distributed.get_rank()
+    base = (torch.initial_seed() * 0x9E3779B1 + rank * 0x85EBCA77) & 0xFFFFFFFF
+    return (0x2545F491 * _DROP_CALLS + 0x1234567 + base) & 0xFFFFFFFF
 
 
 def gemm(a2d: torch.Tensor, w: torch.Tensor, bias=None, act=None, slope=0.01, residual=None,
@@ -567,13 +580,20 @@ def gemm_dw(g2d: torch.Tensor, x2d: torch.Tensor, out: Optional[torch.Tensor] = 
     return out
 
 
-def gemm_bt(a2d: torch.Tensor, wt: torch.Tensor) -> torch.Tensor:
-    """a2d[M,K] @ wt[K,N] with wt read in place (the dX GEMM: grad_output @ weight)."""
+def gemm_bt(a2d: torch.Tensor, wt: torch.Tensor, residual: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a2d[M,K] @ wt[K,N] (+ residual[M,N]) with wt read in place (the dX GEMM: grad_output @ weight).  `out` may be
+    the residual itself: the product is then accumulated in place (gradient fan-in summed in the epilogue)."""
     M, K = a2d.shape
     N = wt.shape[1]
     assert wt.shape[0] == K and a2d.stride(1) == 1 and wt.stride(1) == 1
-    out = torch.empty(M, N, dtype=torch.float32, device=a2d.device)
-    _call("ged_gemm_tf32_bt", _p(a2d), a2d.stride(0), _p(wt), wt.stride(0), _p(out), N, M, N, K, _stream())
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a2d.device)
+    if residual is None:
+        _call("ged_gemm_tf32_bt", _p(a2d), a2d.stride(0), _p(wt), wt.stride(0), _p(out), N, M, N, K, _stream())
+    else:
+        assert residual.shape == (M, N) and residual.is_contiguous() and out.is_contiguous()
+        _call("ged_gemm_tf32_bt_acc", _p(a2d), a2d.stride(0), _p(wt), wt.stride(0), _p(out), N, M, N, K, _p(residual), _stream())
     return out
 
 
@@ -608,26 +628,8 @@ def act_bwd(g2d: torch.Tensor, ref: Optional[torch.Tensor], act, slope=0.01, row
     return gz, (None if db_sink is not None else db)
 
 
-def _act_grad(gz, act, slope, pre, post):
-    """d act(z)/dz applied to gz; elementwise library ops (not on the GEMM critical path)."""
-    if act is None:
-        return gz
-    if act == "relu":
-        return gz * (post > 0)
-    if act == "leaky_relu":
-        return torch.where(post > 0, gz, gz * slope)
-    if act == "sigmoid":
-        return gz * post * (1 - post)
-    if act == "gelu":
-        z = pre
-        cdf = 0.5 * (1 + torch.erf(z * 0.7071067811865476))
-        pdf = torch.exp(-0.5 * z * z) * 0.3989422804014327
-        return gz * (cdf + z * pdf)
-    raise KeyError(act)
-
-
 def _gemm_ok(M, N, K, *tensors):
-    if K % 4 or N < 16 or K < 32:
+    if K % 4 or N % 4 or N < 16 or K < 32:
         return False
     return all(t is None or (t.dtype == torch.float32 and t.data_ptr() % 16 == 0) for t in tensors)
 
@@ -679,30 +681,23 @@ class _Linear(Function):
                   _stream())
             if ctx.b_sink is not None:
                 db = None
-        elif N % 4 == 0:
+        else:
             gz, db = act_bwd(g2, ref, ctx.act, 0.01, row_scale if row_scale.numel() else None, ctx.rpb, want_db,
                              ctx.b_sink)
-        else:
-            g2 = g2.contiguous()
-            gz = g2 if not row_scale.numel() else g2 * row_scale.repeat_interleave(ctx.rpb).unsqueeze(1)
-            gz = _act_grad(gz, ctx.act, 0.01, pre, post).contiguous()
-            db = gz.sum(0) if want_db else None
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            if _gemm_ok(gz.shape[0], K, N, gz, w) and w.stride(1) == 1:
-                with _bwd_precision():
-                    dx = gemm_bt(gz, w).reshape(ctx.xshape)      # w [N][K] read in place as the [K'][N'] operand
-            else:
-                dx = (gz @ w).reshape(ctx.xshape)
+            if not (_gemm_ok(gz.shape[0], K, N, gz, w) and w.stride(1) == 1):
+                raise NotImplementedError(f"linear backward: dX GEMM for weight {tuple(w.shape)} is not covered")
+            with _bwd_precision():
+                dx = gemm_bt(gz, w).reshape(ctx.xshape)      # w [N][K] read in place as the [K'][N'] operand
         if ctx.needs_input_grad[1]:
-            if _dw_ok(N, K, gz, x2):
-                with _bwd_precision():
-                    if ctx.w_sink is not None:
-                        gemm_dw(gz, x2, out=ctx.w_sink)
-                    else:
-                        dw = gemm_dw(gz, x2)
-            else:
-                dw = gz.t() @ x2
+            if not _dw_ok(N, K, gz, x2):
+                raise NotImplementedError(f"linear backward: dW GEMM for weight {tuple(w.shape)} is not covered")
+            with _bwd_precision():
+                if ctx.w_sink is not None:
+                    gemm_dw(gz, x2, out=ctx.w_sink)
+                else:
+                    dw = gemm_dw(gz, x2)
         dres = g if ctx.has_res else None
         return dx, dw, db, None, dres, None, None, None, None
 
@@ -711,12 +706,11 @@ def linear(x, w, b=None, act=None, residual=None, row_scale=None, dropout_p: flo
     """dropout_p > 0 (training): residual + dropout(x w^T + b) with the mask drawn in the GEMM epilogue."""
     K, N = x.shape[-1], w.shape[0]
     M = x.numel() // K
-    if not _gemm_ok(M, N, K, x, w, b, residual) or act not in _ACT:
-        y = L.linear(x, w, b, act, None if dropout_p > 0 else residual, row_scale)
-        if dropout_p > 0:
-            y = torch.nn.functional.dropout(y, dropout_p, True)
-            y = y if residual is None else y + residual
-        return y
+    if not _gemm_ok(M, N, K, x, w, b, residual) or act not in _ACT or K < 16:
+        if N <= 4 and K % 4 == 0 and residual is None and row_scale is None and dropout_p == 0 and act in (None, "sigmoid"):
+            return linear_small(x, w, b, act)
+        raise NotImplementedError(f"linear: x {tuple(x.shape)} w {tuple(w.shape)} act {act} is outside the tcgen05 GEMM's "
+                                  "(N % 4 == 0, N >= 16, K % 4 == 0, K >= 32, 16-byte aligned) and the small-N kernel's range")
     ws = _sink(w)
     ws = ws if (ws is not None and ws.is_contiguous()) else None
     dropout = None
@@ -771,7 +765,8 @@ class _Conv(Function):
     """3x3/s1/p1 or 1x1 conv + bias + activation over [resize(x0) | x1] (x1 optional, resize only when
     x0 is smaller).  Forward and dX on tcgen05 (dX of a 3x3 conv is the 3x3 conv of dY with the flipped,
     transposed kernel, read in place from the forward weights); activation derivative + bias gradient one fused pass;
-    dW = nine row-shifted contractions of bordered dY against bordered X on tcgen05.  Cout in {1, 11} go to cuDNN."""
+    dW = nine row-shifted contractions of bordered dY against bordered X on tcgen05.  The narrow heads (Cout in
+    {1, 2, 11}) take the SIMT kernels of csrc/small.cu."""
 
     @staticmethod
     def forward(ctx, x0, x1, w, b, act, slope, w_sink=None, b_sink=None):
@@ -802,68 +797,70 @@ class _Conv(Function):
         H, W = gh.shape[1], gh.shape[2]
         want_db = has_bias and ctx.needs_input_grad[3]
         need_dx = ctx.needs_input_grad[0] or (C1 is not None and ctx.needs_input_grad[1])
-        db = None
-        if Cout % 4 == 0:
+        need_dw = ctx.needs_input_grad[2]
+        db = dxc = dw = None
+        if Cout in SMALL_COUT and kh == 3:
+            # narrow heads (conv_depth 64->1, convfinal 64->1 / 64->11): SIMT kernels, activation derivative inside
+            wk = w.permute(0, 2, 3, 1)
+            wk = wk if wk.is_contiguous() else wk.contiguous()
+            gz = torch.empty_like(gh)
+            dxc = torch.empty(B, H, W, Cin, dtype=torch.float32, device=gh.device) if need_dx else None
+            sink = None if ctx.w_sink is None else ctx.w_sink.permute(0, 2, 3, 1)
+            dwk = None
+            if need_dw:
+                dwk = sink if sink is not None else torch.zeros(Cout, 3, 3, Cin, dtype=torch.float32, device=gh.device)
+            dbb = None
+            if want_db:
+                dbb = ctx.b_sink if ctx.b_sink is not None else torch.zeros(Cout, dtype=torch.float32, device=gh.device)
+            _call("ged_conv3x3_small_bwd", _p(gh), _p(y if act is not None else None), _p(gz), _p(xin), _p(wk), _p(dxc),
+                  _p(dwk), _p(dbb), B, H, W, Cin, Cout, _ACT[act], float(slope), _stream())
+            dw = None if (sink is not None or dwk is None) else dwk.permute(0, 3, 1, 2)
+            db = None if ctx.b_sink is not None else dbb
+        else:
+            if Cout % 4 or (kh == 3 and need_dx and Cout % 32) or (need_dw and not _dw_ok(Cout, Cin, gh, xin)):
+                raise NotImplementedError(f"conv backward: weight {tuple(w.shape)} is outside the tcgen05 dX / dW kernels' range")
             gz2, db = act_bwd(gh.reshape(-1, Cout), y.reshape(-1, Cout) if act is not None else None, act, slope,
                               None, 1, want_db, ctx.b_sink)
             gz = gz2.reshape(B, H, W, Cout)
-        else:
-            gz = _act_grad(gh, act, slope, None, y)
-            gz = gz if gz.is_contiguous() else gz.contiguous()
-            if want_db:
-                db = gz.sum((0, 1, 2))
-        dxc = dw = None
-        need_dw = ctx.needs_input_grad[2]
-        dw_native = need_dw and _dw_ok(Cout, Cin, gz, xin)
-        gzp = None
-        if kh == 3 and Cout % 4 == 0 and ((need_dx and Cout % 32 == 0) or dw_native):
-            gzp = prep_conv_input(gz, None, H, W)                            # zero-bordered dY, shared by dX and dW
-        if need_dx:
-            if kh == 3 and Cout % 32 == 0:
-                wk = w.permute(0, 2, 3, 1)                                   # [Cout,3,3,Cin]: a view inside the arena
+            gzp = prep_conv_input(gz, None, H, W) if kh == 3 else None      # zero-bordered dY, shared by dX and dW
+            if need_dx:
                 with _bwd_precision():
-                    dxc = conv3x3_dx(gzp, wk if wk.is_contiguous() else wk.contiguous())   # (B,H,W,Cin)
-            elif kh == 1 and _gemm_ok(B * H * W, Cin, Cout, gz):
+                    if kh == 3:
+                        wk = w.permute(0, 2, 3, 1)                           # [Cout,3,3,Cin]: a view inside the arena
+                        dxc = conv3x3_dx(gzp, wk if wk.is_contiguous() else wk.contiguous())   # (B,H,W,Cin)
+                    else:
+                        if not _gemm_ok(B * H * W, Cin, Cout, gz):
+                            raise NotImplementedError(f"1x1 conv backward: weight {tuple(w.shape)} not covered")
+                        dxc = gemm_bt(gz.reshape(-1, Cout), w.reshape(Cout, Cin)).reshape(B, H, W, Cin)
+            if need_dw:
                 with _bwd_precision():
-                    dxc = gemm_bt(gz.reshape(-1, Cout), w.reshape(Cout, Cin)).reshape(B, H, W, Cin)
-        if dw_native:
-            with _bwd_precision():
-                # the arena keeps conv weights / gradients channels-last ([Cout][kh][kw][Cin]): accumulate in place
-                sink = None if ctx.w_sink is None else ctx.w_sink.permute(0, 2, 3, 1)
-                if kh == 3:
-                    Wp = W + 2
-                    taps = [(ky - 1) * Wp + (kx - 1) for ky in range(3) for kx in range(3)]
-                    dwk = gemm_dw(gzp.reshape(-1, Cout), xin.reshape(-1, Cin),
-                                  None if sink is None else sink.view(Cout, 9, Cin), taps)    # [Cout, 9, Cin]
-                    dw = None if sink is not None else dwk.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
-                else:
-                    dwk = gemm_dw(gz.reshape(-1, Cout), xin.reshape(-1, Cin), None if sink is None else sink.view(Cout, Cin))
-                    dw = None if sink is not None else dwk.reshape(Cout, Cin, 1, 1)
-                need_dw = False
-        pad = 0                                     # xin already carries the zero border for 3x3
-        xin_nchw = xin.permute(0, 3, 1, 2)
-        mask = [need_dx and dxc is None, need_dw, False]
-        if any(mask):
-            r = torch.ops.aten.convolution_backward(gz.permute(0, 3, 1, 2), xin_nchw, w, None, [1, 1], [pad, pad],
-                                                    [1, 1], False, [0, 0], 1, mask)
-            if mask[0]:
-                dxc = r[0].permute(0, 2, 3, 1)
-                if kh == 3:
-                    dxc = dxc[:, 1:-1, 1:-1, :]
-            dw = r[1] if mask[1] else dw
+                    # the arena keeps conv weights / gradients channels-last ([Cout][kh][kw][Cin]): accumulate in place
+                    sink = None if ctx.w_sink is None else ctx.w_sink.permute(0, 2, 3, 1)
+                    if kh == 3:
+                        Wp = W + 2
+                        taps = [(ky - 1) * Wp + (kx - 1) for ky in range(3) for kx in range(3)]
+                        dwk = gemm_dw(gzp.reshape(-1, Cout), xin.reshape(-1, Cin),
+                                      None if sink is None else sink.view(Cout, 9, Cin), taps)    # [Cout, 9, Cin]
+                        dw = None if sink is not None else dwk.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+                    else:
+                        dwk = gemm_dw(gz.reshape(-1, Cout), xin.reshape(-1, Cin), None if sink is None else sink.view(Cout, Cin))
+                        dw = None if sink is not None else dwk.reshape(Cout, Cin, 1, 1)
         dx0 = dx1 = None
         if need_dx:
             if C1 is not None and ctx.needs_input_grad[1]:
                 dx1 = dxc[..., C0:].permute(0, 3, 1, 2)
             if ctx.needs_input_grad[0]:
                 if (h0, w0) != (H, W):
-                    d0 = torch.empty(B, h0, w0, C0, dtype=torch.float32, device=gz.device)
+                    d0 = torch.empty(B, h0, w0, C0, dtype=torch.float32, device=gh.device)
                     dcc = dxc if dxc.is_contiguous() else dxc.contiguous()
                     _call("ged_upsample_nhwc_bwd", _p(dcc), dcc.shape[3], _p(d0), C0, B, H, W, h0, w0, _stream())
                     dx0 = d0.permute(0, 3, 1, 2)
                 else:
                     dx0 = (dxc[..., :C0] if C1 is not None else dxc).permute(0, 3, 1, 2)
         return dx0, dx1, dw, db, None, None, None, None
+
+
+SMALL_COUT = (1, 2, 11)
 
 
 def _conv_apply(x0, x1, w, b, act, slope):
@@ -906,7 +903,7 @@ def conv_bn_act_cat(x0, x1, w, b, bn, act=None):
     y = _conv_apply(x0, x1, w, b, None, 0.0)
     if act in (None, "relu") and y.shape[1] % 4 == 0 and bn.momentum is not None and bn.track_running_stats:
         return bn_act_train(y, bn, relu=act == "relu")
-    return L._act(bn(y), act)
+    raise NotImplementedError("conv + train-mode BatchNorm: only (none | relu) activations with tracked running statistics")
 
 
 class _BNTrain(Function):
@@ -1167,6 +1164,240 @@ def msda_sample(v, shapes, ref, off, logit, nH, P):
     return _MSDA.apply(v, ref, off, logit, shapes, nH, P, MSDA_FWD, bwd)
 
 
+class _SplitLevels(Function):
+    """(B, S, C) token tensor -> one (B, n_l, C) view per level; the backward writes the four gradients into ONE buffer
+    instead of autograd's four zero-filled full-size tensors and three additions."""
+
+    @staticmethod
+    def forward(ctx, src, *sizes):
+        ctx.sizes = sizes
+        ctx.shape = src.shape
+        outs, start = [], 0
+        for n in sizes:
+            outs.append(src[:, start:start + n])
+            start += n
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        out = torch.empty(ctx.shape, dtype=torch.float32, device=gs[0].device)
+        start = 0
+        for g, n in zip(gs, ctx.sizes):
+            out[:, start:start + n].copy_(g.reshape(ctx.shape[0], n, ctx.shape[2]))
+            start += n
+        return (out,) + (None,) * len(ctx.sizes)
+
+
+def split_levels(src, sizes):
+    if not (torch.is_grad_enabled() and src.requires_grad):
+        outs, start = [], 0
+        for n in sizes:
+            outs.append(src[:, start:start + n])
+            start += n
+        return outs
+    return list(_SplitLevels.apply(src, *[int(n) for n in sizes]))
+
+
+class _LinearSmall(Function):
+    """y = act(x w^T + b) with N <= 4 outputs (csrc/small.cu): HAHIHeteroNeck.reference_points, 512 -> 2 + sigmoid."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, w_sink=None, b_sink=None):
+        K, N = x.shape[-1], w.shape[0]
+        x2 = _f32c(x).reshape(-1, K)
+        wc = _f32c(w)
+        y = torch.empty(x2.shape[0], N, dtype=torch.float32, device=x.device)
+        _call("ged_linear_small_fwd", _p(x2), _p(wc), _p(b), _p(y), x2.shape[0], N, K, _ACT[act], _stream())
+        ctx.save_for_backward(x2, wc, y)
+        ctx.cfg = (act, b is not None, x.shape, w_sink, b_sink)
+        return y.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, w, y = ctx.saved_tensors
+        act, has_bias, xshape, w_sink, b_sink = ctx.cfg
+        N, K = w.shape
+        g2 = _f32c(g).reshape(-1, N)
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw = w_sink if w_sink is not None else torch.zeros_like(w)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = b_sink if b_sink is not None else torch.zeros(N, dtype=torch.float32, device=w.device)
+        _call("ged_linear_small_bwd", _p(g2), _p(y), _p(x2), _p(w), _p(dx), _p(dw), _p(db), x2.shape[0], N, K, _ACT[act],
+              _stream())
+        return (None if dx is None else dx.reshape(xshape), None if w_sink is not None else dw,
+                None if b_sink is not None else db, None, None, None)
+
+
+def linear_small(x, w, b, act=None):
+    if w.shape[0] > 4 or x.shape[-1] % 4 or act not in (None, "sigmoid"):
+        raise NotImplementedError(f"linear_small: weight {tuple(w.shape)} act {act}")
+    ws = _sink(w)
+    ws = ws if (ws is not None and ws.is_contiguous() and w.is_contiguous()) else None
+    return _LinearSmall.apply(x, w, b, act, ws, _sink(b))
+
+
+def _level_starts(level_start):
+    return None if level_start is None else (C.c_int * 5)(*[int(v) for v in level_start])
+
+
+class _MSDAModule(Function):
+    """mmcv MultiScaleDeformableAttention.forward(batch_first=True) [external; hahi.py:179-188,280-289,316-325] as one
+    autograd node:  q = query + pos (+ level embedding);  v = value_proj(value);  off / logit = Linear(q);  sampling;
+    out = dropout(output_proj(sampled)) + query.
+    The backward keeps every sum inside a kernel: the query gradient's fan-in (identity + the two Linear(q) + - when
+    value is the query - value_proj) is accumulated through the residual input of the dX GEMMs, the level-embedding
+    gradient is the per-level column sum of dq, and parameter gradients go straight to the arena when there is one."""
+
+    @staticmethod
+    def forward(ctx, query, value, pos, level_embed, ref, w_v, b_v, w_so, b_so, w_aw, b_aw, w_o, b_o, cfg):
+        qc = _f32c(query)
+        B, Q, E = qc.shape
+        shapes, nH, P = cfg["shapes"], cfg["nH"], cfg["P"]
+        ls = _level_starts(cfg["level_start"]) if level_embed is not None else None
+        posc = _f32c(pos).reshape(-1, E)
+        assert posc.shape[0] == Q, "query_pos must be (1, Q, E)"
+        q = torch.empty_like(qc)
+        _call("ged_add_pos_fwd", _p(qc), _p(posc), _p(None if level_embed is None else _f32c(level_embed)), ls, _p(q),
+              B, Q, E, _stream())
+        vin = qc if value is None else _f32c(value)
+        S = vin.shape[1]
+        v = gemm(vin.reshape(-1, E), _f32c(w_v), b_v).reshape(B, S, E)
+        q2 = q.reshape(-1, E)
+        off = gemm(q2, _f32c(w_so), b_so).reshape(B, Q, -1)
+        logit = gemm(q2, _f32c(w_aw), b_aw).reshape(B, Q, -1)
+        refc = _f32c(ref)
+        hw = (C.c_int * (2 * len(shapes)))(*[int(a) for s in shapes for a in s])
+        fwd_impl, bwd_impl = MSDA_FWD, _msda_bwd_impl()
+        samp = torch.empty(B, Q, E, dtype=torch.float32, device=qc.device)
+        order = None
+        if fwd_impl != "round1" or bwd_impl != "round1":
+            order = msda_query_order(refc, shapes)
+        if fwd_impl == "tc":
+            v_lo = torch.empty_like(v)
+            _call("ged_msda_tc_fwd", _p(v), _p(v_lo), _p(refc), refc.shape[0], _p(off), _p(logit), _p(order), _p(samp),
+                  hw, len(shapes), B, S, Q, nH, E // nH, P, _stream())
+        elif fwd_impl == "tile":
+            _call("ged_msda_tile_fwd", _p(v), _p(refc), refc.shape[0], _p(off), _p(logit), _p(order), _p(samp), hw,
+                  len(shapes), B, S, Q, nH, E // nH, P, _stream())
+        else:
+            _call("ged_msda_fwd", _p(v), _p(refc), refc.shape[0], _p(off), _p(logit), _p(samp), hw, len(shapes), B, S, Q,
+                  nH, E // nH, P, _stream())
+        dropout = None
+        if cfg["dropout_p"] > 0:
+            assert B * Q * E < 2 ** 32
+            dropout = (float(cfg["dropout_p"]), next_dropout_seed(), RNG_STEP)
+        out = gemm(samp.reshape(-1, E), _f32c(w_o), b_o, None, 0.01, qc.reshape(-1, E), dropout=dropout).reshape(B, Q, E)
+        empty = torch.empty(0, device=qc.device)
+        ctx.save_for_backward(q, vin, v, refc, off, logit, samp,
+                              order if order is not None else empty, w_v, w_so, w_aw, w_o,
+                              level_embed if level_embed is not None else empty)
+        ctx.cfg = dict(cfg, dropout=dropout, bwd_impl=bwd_impl, shared_value=value is None, has_le=level_embed is not None,
+                       hw=hw, dims=(B, S, Q, E))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, vin, v, ref, off, logit, samp, order, w_v, w_so, w_aw, w_o, level_embed = ctx.saved_tensors
+        cfg = ctx.cfg
+        B, S, Q, E = cfg["dims"]
+        shapes, nH, P, sinks = cfg["shapes"], cfg["nH"], cfg["P"], cfg["sinks"]
+        dev = q.device
+        g2 = _f32c(g).reshape(-1, E)
+
+        def acc_or_new(name, shape):
+            return sinks[name] if sinks.get(name) is not None else torch.zeros(shape, dtype=torch.float32, device=dev)
+
+        def ret(name, t):
+            return None if sinks.get(name) is not None else t
+
+        # ---- output_proj: out = dropout(samp w_o^T + b_o) + query ----------------------------------------------------
+        db_o = acc_or_new("b_o", (E,))
+        if cfg["dropout"] is not None:
+            dp, dseed, dstep = cfg["dropout"]
+            gz = torch.empty_like(g2)
+            _call("ged_dropout_bwd", _p(g2), g2.stride(0), _p(gz), _p(db_o), g2.shape[0], E, float(dp), int(dseed), _p(dstep),
+                  _stream())
+        else:
+            gz = g2
+            act_bwd(g2, None, None, want_db=True, db_sink=db_o)
+        with _bwd_precision():
+            d_samp = gemm_bt(gz, w_o)
+            dw_o = gemm_dw(gz, samp.reshape(-1, E), out=sinks.get("w_o"))
+        del gz
+        # ---- sampling ------------------------------------------------------------------------------------------------
+        g_v = torch.zeros_like(v)
+        g_off, g_logit = torch.empty_like(off), torch.empty_like(logit)
+        need_ref = ctx.needs_input_grad[4]
+        bwd_impl = cfg["bwd_impl"]
+        if bwd_impl != "round1":
+            g_ref = torch.zeros_like(ref) if need_ref else None
+            _call("ged_msda_tc_bwd" if bwd_impl == "tc" else "ged_msda_tile_bwd", _p(v), _p(ref), ref.shape[0], _p(off),
+                  _p(logit), _p(order), _p(d_samp), _p(g_v), _p(g_ref), _p(g_off), _p(g_logit), cfg["hw"], len(shapes), B, S,
+                  Q, nH, E // nH, P, _stream())
+        else:
+            refb = ref if (ref.shape[0] == B or not need_ref) else ref.expand(B, -1, -1).contiguous()
+            g_refb = torch.zeros_like(refb) if need_ref else None
+            _call("ged_msda_bwd", _p(v), _p(refb), refb.shape[0], _p(off), _p(logit), _p(d_samp), _p(g_v), _p(g_refb),
+                  _p(g_off), _p(g_logit), cfg["hw"], len(shapes), B, S, Q, nH, E // nH, P, _stream())
+            g_ref = None if g_refb is None else (g_refb if ref.shape[0] == B else g_refb.sum(0, keepdim=True))
+        del d_samp
+        # ---- sampling_offsets / attention_weights: Linear(q) ------------------------------------------------------------
+        q2, go2, gl2 = q.reshape(-1, E), g_off.reshape(B * Q, -1), g_logit.reshape(B * Q, -1)
+        db_so, db_aw = acc_or_new("b_so", (go2.shape[1],)), acc_or_new("b_aw", (gl2.shape[1],))
+        act_bwd(go2, None, None, want_db=True, db_sink=db_so)
+        act_bwd(gl2, None, None, want_db=True, db_sink=db_aw)
+        with _bwd_precision():
+            dw_so = gemm_dw(go2, q2, out=sinks.get("w_so"))
+            dw_aw = gemm_dw(gl2, q2, out=sinks.get("w_aw"))
+            # g_query = g (identity) + g_off W_so + g_logit W_aw (+ g_v W_v when the value is the query itself)
+            g_le = None
+            if cfg["has_le"]:
+                dq = gemm_bt(go2, w_so)
+                gemm_bt(gl2, w_aw, residual=dq, out=dq)
+                g_le = acc_or_new("level_embed", tuple(level_embed.shape))
+                _call("ged_add_pos_bwd", _p(dq), _p(g2), _p(g_le), _level_starts(cfg["level_start"]), B, Q, E, _stream())
+            else:
+                dq = gemm_bt(go2, w_so, residual=g2)
+                gemm_bt(gl2, w_aw, residual=dq, out=dq)
+            # ---- value_proj ------------------------------------------------------------------------------------------
+            gv2 = g_v.reshape(-1, E)
+            db_v = acc_or_new("b_v", (E,))
+            act_bwd(gv2, None, None, want_db=True, db_sink=db_v)
+            dw_v = gemm_dw(gv2, vin.reshape(-1, E), out=sinks.get("w_v"))
+            g_value = None
+            if cfg["shared_value"]:          # value is the query itself (self-attention): one more term of its fan-in
+                gemm_bt(gv2, w_v, residual=dq, out=dq)
+            else:
+                g_value = gemm_bt(gv2, w_v).reshape(B, S, E)
+        g_query = dq.reshape(B, Q, E)
+        return (g_query, g_value, None, ret("level_embed", g_le), g_ref, ret("w_v", dw_v), ret("b_v", db_v),
+                ret("w_so", dw_so), ret("b_so", db_so), ret("w_aw", dw_aw), ret("b_aw", db_aw), ret("w_o", dw_o),
+                ret("b_o", db_o), None)
+
+
+def msda_module(query, value, pos, level_embed, level_start, ref, shapes, mod, dropout_p):
+    B = query.shape[0]
+    if ref.shape[0] not in (1, B):
+        raise ValueError("reference_points batch must be 1 or B")
+    if torch.is_tensor(pos) and pos.requires_grad:
+        raise NotImplementedError("msda_module: query_pos must be constant (a learnable level embedding goes in level_embed)")
+    named = dict(w_v=mod.value_proj.weight, b_v=mod.value_proj.bias, w_so=mod.sampling_offsets.weight,
+                 b_so=mod.sampling_offsets.bias, w_aw=mod.attention_weights.weight, b_aw=mod.attention_weights.bias,
+                 w_o=mod.output_proj.weight, b_o=mod.output_proj.bias, level_embed=level_embed)
+    sinks = {}
+    for k, p in named.items():
+        sk = _sink(p)
+        sinks[k] = sk if (sk is not None and sk.is_contiguous() and p.is_contiguous()) else None
+    qc = _f32c(query)
+    cfg = dict(shapes=tuple(tuple(int(a) for a in s) for s in shapes), nH=mod.num_heads, P=mod.num_points,
+               level_start=None if level_start is None else tuple(int(v) for v in level_start), dropout_p=float(dropout_p),
+               sinks=sinks)
+    return _MSDAModule.apply(qc, value, pos, level_embed, ref, named["w_v"], named["b_v"], named["w_so"], named["b_so"],
+                             named["w_aw"], named["b_aw"], named["w_o"], named["b_o"], cfg)
+
+
 # =============================================================================================
 # evaluation
 # =============================================================================================
@@ -1213,8 +1444,10 @@ def sumsq(flat_grad: torch.Tensor, out: torch.Tensor):
     return out
 
 
-def adamw_step(p, g, m, v, wd_mask, sumsq_buf, max_norm, grad_scale, lr, beta1, beta2, eps, wd, step, step_dev=None):
-    """step: host-side 1-based count, or step_dev: int32 device tensor holding it (CUDA-graph replay)."""
+def adamw_step(p, g, m, v, wd_mask, sumsq_buf, max_norm, grad_scale, lr, beta1, beta2, eps, wd, step, step_dev=None,
+               lr_dev=None):
+    """step: host-side 1-based count, or step_dev: int32 device tensor holding it (CUDA-graph replay); lr_dev: fp32
+    device scalar overriding lr (so that a schedule keeps working when the step is a replayed graph)."""
     _call("ged_adamw_step", _p(p), _p(g), _p(m), _p(v), _p(wd_mask), p.numel(), _p(sumsq_buf), float(max_norm),
           float(grad_scale), float(lr), float(beta1), float(beta2), float(eps), float(wd), int(step), _p(step_dev),
-          _stream())
+          _p(lr_dev), _stream())

@@ -1,21 +1,15 @@
 """Operator layer of the GEDepth path: every function takes CUDA tensors and launches hand-written
 sm_100a kernels through the C-ABI in ``libgedepth_sm100.so`` (include/gedepth.h) on the current
-stream.  There is no CPU path: CPU tensors raise, a missing extension raises.
-
-``native_table()`` lists, op by op, whether the sm_100a kernel is in place or the op still goes to
-the library statement in ops_lib.py (cuDNN/cuBLAS/ATen on the same CUDA tensors).
+stream.  There is ONE implementation per op: no CPU path, no library (cuDNN / cuBLAS / ATen) dispatch - CPU
+tensors raise, a missing extension raises, a shape the kernels do not cover raises ``NotImplementedError``.
+The library statement of every op lives in tests/ops_lib.py: the checker of the per-op tests and the
+``gpu_library_baseline`` of bench.py, never part of the product.
 """
 from __future__ import annotations
 
-import os
-from typing import Optional, Sequence
+from typing import Optional
 
 import torch
-
-from . import ops_lib as L
-
-_NATIVE = {}          # op name -> bool, filled by kernels.py when the extension is loaded
-_FORCE_LIB = set(filter(None, os.environ.get("GEDEPTH_FORCE_LIB", "").split(",")))
 
 
 def require_cuda(*tensors):
@@ -28,124 +22,117 @@ def require_cuda(*tensors):
 
 def _k():
     from . import kernels
+    kernels.load()
     return kernels
 
 
+def _unsupported(op: str, why: str):
+    raise NotImplementedError(f"gedepth_b200.ops.{op}: {why} - outside what the four GE configs use; there is no "
+                              f"library fallback in the product (tests/ops_lib.py holds the reference statement)")
+
+
+# ops reached by the four GE configs
+OPS = ["linear", "layer_norm", "patch_embed", "merge_patches", "window_attention", "conv2d",
+       "conv_bn_act", "conv2d_cat", "batch_norm", "resize_add", "msda_module", "ground_plane", "ge_vanilla",
+       "ge_adaptive", "fuse_head", "silog", "cross_entropy", "clamp_resize", "find_k", "depth_metrics", "tta_merge",
+       "adamw"]
+
+
 def use_native(name: str) -> bool:
-    if name in _FORCE_LIB or "all" in _FORCE_LIB:
-        return False
-    return _k().has(name)
+    """Kept for callers that used to ask; every op is native (or raises)."""
+    _k()
+    return True
 
 
 def native_table():
-    k = _k()
-    return {name: (k.has(name) and name not in _FORCE_LIB and "all" not in _FORCE_LIB) for name in OPS}
-
-
-# ops reached by the four GE configs (``resize`` alone is not: it only serves a non-SiLog loss, heads.py `_loss_depth`)
-OPS = ["linear", "layer_norm", "patch_embed", "merge_patches", "window_attention", "conv2d",
-       "conv_bn_act", "conv2d_cat", "batch_norm", "resize_add", "msda_sample", "ground_plane", "ge_vanilla",
-       "ge_adaptive", "fuse_head", "silog", "cross_entropy", "clamp_resize", "find_k", "depth_metrics", "tta_merge",
-       "adamw"]
+    _k()
+    return {name: True for name in OPS}
 
 
 # ---- GEMM-shaped ---------------------------------------------------------------------------
 def linear(x, w, b=None, act=None, residual=None, row_scale=None, dropout_p: float = 0.0):
     """residual + dropout_p(act(x w^T + b) * row_scale); dropout only when dropout_p > 0 (training)."""
     require_cuda(x, w)
-    if use_native("linear"):
-        return _k().linear(x, w, b, act, residual, row_scale, dropout_p)
-    y = L.linear(x, w, b, act, None if dropout_p > 0 else residual, row_scale)
-    if dropout_p > 0:
-        y = torch.nn.functional.dropout(y, dropout_p, True)
-        y = y if residual is None else y + residual
-    return y
+    return _k().linear(x, w, b, act, residual, row_scale, dropout_p)
 
 
 def conv2d(x, w, b=None, stride=1, padding=0, act=None, slope=0.01):
     require_cuda(x, w)
-    if use_native("conv2d") and _k().conv2d_supported(x, w, stride, padding):
-        return _k().conv2d(x, w, b, stride, padding, act, slope)
-    return L.conv2d(x, w, b, stride, padding, act, slope)
+    k = _k()
+    if not k.conv2d_supported(x, w, stride, padding):
+        _unsupported("conv2d", f"weight {tuple(w.shape)}, stride {stride}, padding {padding}")
+    return k.conv2d(x, w, b, stride, padding, act, slope)
 
 
 def conv_bn_act(x, w, b, bn, stride=1, padding=0, act=None):
     require_cuda(x, w)
-    if use_native("conv_bn_act") and _k().conv2d_supported(x, w, stride, padding):
-        return _k().conv_bn_act(x, w, b, bn, stride, padding, act)
-    if use_native("conv_bn_act") and _k().conv_im2col_supported(x, w, stride, padding):
+    k = _k()
+    if k.conv2d_supported(x, w, stride, padding):
+        return k.conv_bn_act(x, w, b, bn, stride, padding, act)
+    if k.conv_im2col_supported(x, w, stride, padding):
         # stem 7x7/s2 conv on the RGB planes (K = 147): im2col gather + tcgen05 GEMM, then BN (+ReLU)
         if bn is None:
-            return _k().conv_im2col(x, w, b, stride, padding, act)
+            return k.conv_im2col(x, w, b, stride, padding, act)
         if not bn.training:
             s = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
             bf = bn.bias - bn.running_mean * s + (b * s if b is not None else 0)
-            return _k().conv_im2col(x, w * s.view(-1, 1, 1, 1), bf, stride, padding, act)
-        y = _k().conv_im2col(x, w, b, stride, padding, None)
-        if act in (None, "relu") and bn.momentum is not None and bn.track_running_stats and use_native("batch_norm"):
-            return _k().bn_act_train(y, bn, relu=act == "relu")
-        return L._act(bn(y), act)
-    if (bn is not None and bn.training and use_native("batch_norm") and w.shape[0] % 4 == 0 and act in (None, "relu")
-            and bn.momentum is not None and bn.track_running_stats):
-        return _k().bn_act_train(L.conv2d(x, w, b, stride, padding), bn, relu=act == "relu")
-    return L.conv_bn_act(x, w, b, bn, stride, padding, act)
+            return k.conv_im2col(x, w * s.view(-1, 1, 1, 1), bf, stride, padding, act)
+        if act not in (None, "relu") or bn.momentum is None or not bn.track_running_stats:
+            _unsupported("conv_bn_act", "train-mode BatchNorm with this activation / momentum setting")
+        return k.bn_act_train(k.conv_im2col(x, w, b, stride, padding, None), bn, relu=act == "relu")
+    _unsupported("conv_bn_act", f"weight {tuple(w.shape)}, stride {stride}, padding {padding}")
 
 
 def conv2d_cat(x_low, x_skip, w, b=None, act=None, slope=0.01):
     """3x3 conv (+bias, +act) over cat([bilinear(x_low -> skip size, align_corners=True), x_skip], 1):
     the UpSample block of densedepth_head.py:24-27 without materialising the resize or the concat."""
     require_cuda(x_low, x_skip, w)
-    if use_native("conv2d_cat") and _k().conv2d_cat_supported(x_low, x_skip, w):
-        return _k().conv2d_cat(x_low, x_skip, w, b, act, slope)
-    up = L.resize(x_low, (x_skip.shape[2], x_skip.shape[3]), True) if x_low.shape[2:] != x_skip.shape[2:] else x_low
-    return L.conv2d(L.cat_channels([up, x_skip]), w, b, 1, 1, act, slope)
+    k = _k()
+    if not k.conv2d_cat_supported(x_low, x_skip, w):
+        _unsupported("conv2d_cat", f"weight {tuple(w.shape)} over {tuple(x_low.shape)} | {tuple(x_skip.shape)}")
+    return k.conv2d_cat(x_low, x_skip, w, b, act, slope)
 
 
 def conv_bn_act_cat(x0, x1, w, b, bn, act=None):
     """ConvModule(3x3, BN, act) over cat([x0, x1], 1) (hahi.py:329-353) without the concat copy."""
     require_cuda(x0, x1, w)
-    if use_native("conv2d_cat") and _k().conv2d_cat_supported(x0, x1, w) and x0.shape[2:] == x1.shape[2:]:
-        return _k().conv_bn_act_cat(x0, x1, w, b, bn, act)
-    return L.conv_bn_act(L.cat_channels([x0, x1]), w, b, bn, 1, 1, act)
+    k = _k()
+    if not (k.conv2d_cat_supported(x0, x1, w) and x0.shape[2:] == x1.shape[2:]):
+        _unsupported("conv_bn_act_cat", f"weight {tuple(w.shape)} over {tuple(x0.shape)} | {tuple(x1.shape)}")
+    return k.conv_bn_act_cat(x0, x1, w, b, bn, act)
 
 
 def patch_embed(x, w, b, patch):
     require_cuda(x, w)
-    if use_native("patch_embed") and x.dtype == torch.float32 and x.stride(3) == 1 and x.stride(2) == x.shape[3] \
-            and x.stride(1) == x.shape[2] * x.shape[3] and (x.shape[1] * patch * patch) % 32 == 0:
-        return _k().patch_embed(x, w, b, patch)
-    return L.patch_embed(x, w, b, patch)
+    if not (x.dtype == torch.float32 and x.stride(3) == 1 and x.stride(2) == x.shape[3]
+            and x.stride(1) == x.shape[2] * x.shape[3] and (x.shape[1] * patch * patch) % 32 == 0):
+        _unsupported("patch_embed", f"input {tuple(x.shape)} strides {x.stride()} patch {patch}")
+    return _k().patch_embed(x, w, b, patch)
 
 
 # ---- token-shaped --------------------------------------------------------------------------
 def layer_norm(x, w, b, eps):
     require_cuda(x)
-    if use_native("layer_norm"):
-        return _k().layer_norm(x, w, b, eps)
-    return L.layer_norm(x, w, b, eps)
+    return _k().layer_norm(x, w, b, eps)
 
 
 def layer_norm_fork(x, w, b, eps):
     """(LN(x), x): the second output is x itself, to be used as the residual identity of the sub-block that follows, so
     the LayerNorm backward can add the residual-branch gradient in its own pass."""
     require_cuda(x)
-    if use_native("layer_norm"):
-        return _k().layer_norm_fork(x, w, b, eps)
-    return L.layer_norm(x, w, b, eps), x
+    return _k().layer_norm_fork(x, w, b, eps)
 
 
 def merge_patches(x, H, W):
     require_cuda(x)
-    if use_native("merge_patches"):
-        return _k().merge_patches(x, H, W)
-    return L.merge_patches(x, H, W)
+    return _k().merge_patches(x, H, W)
 
 
 def window_attention(qkv, qkv_bias, table, index, hw, nH, ws, shift, scale):
     require_cuda(qkv)
-    if use_native("window_attention") and ws == 7 and qkv.shape[-1] // 3 // nH == 32:
-        return _k().window_attention(qkv, qkv_bias, table, index, hw, nH, ws, shift, scale)
-    return L.window_attention(qkv, qkv_bias, table, index, hw, nH, ws, shift, scale)
+    if ws != 7 or qkv.shape[-1] // 3 // nH != 32:
+        _unsupported("window_attention", f"window {ws}, head dim {qkv.shape[-1] // 3 // nH} (kernels: 7, 32)")
+    return _k().window_attention(qkv, qkv_bias, table, index, hw, nH, ws, shift, scale)
 
 
 def drop_path_scale(drop, x) -> Optional[torch.Tensor]:
@@ -160,49 +147,62 @@ def drop_path_scale(drop, x) -> Optional[torch.Tensor]:
 
 def tokens_to_map(x, hw):
     """(B, L, C) -> logical (B, C, h, w) in channels-last memory: a view, no copy."""
-    return L.tokens_to_map(x, hw)
+    B, L, C = x.shape
+    return x.reshape(B, hw[0], hw[1], C).permute(0, 3, 1, 2)
 
 
 def map_to_tokens(x):
     """logical (B, C, h, w) -> (B, h*w, C); a view when x is channels-last."""
-    return L.map_to_tokens(x)
+    B, C, H, W = x.shape
+    return x.permute(0, 2, 3, 1).reshape(B, H * W, C)
 
 
-def cat_channels(xs):
-    return L.cat_channels(xs)
+def cat_tokens(xs):
+    """Concatenate token sequences (B, L_i, C) along L (one copy; not arithmetic)."""
+    return torch.cat(xs, dim=1)
 
 
-def add_bcast(a, b):
-    return L.add_bcast(a, b)
+def split_levels(src, sizes):
+    """(B, S, C) -> list of (B, n_l, C) views; their gradients land in one buffer (kernels._SplitLevels)."""
+    require_cuda(src)
+    return _k().split_levels(src, sizes)
 
 
 # ---- resampling ----------------------------------------------------------------------------
 def resize(x, size, align_corners=True):
-    require_cuda(x)
-    if use_native("resize") and align_corners:
-        return _k().resize(x, size)
-    return L.resize(x, size, align_corners)
+    _unsupported("resize", "a materialised bilinear resize is not on the GE path (SiLog / conv inputs / fuse_head resize "
+                           "inside their own kernels)")
 
 
 def resize_add(t, size, acc):
     require_cuda(t)
-    if use_native("resize_add") and t.shape[1] % 4 == 0:
-        return _k().resize_add(t, size, acc)
-    return L.resize_add(t, size, acc)
+    if t.shape[1] % 4:
+        _unsupported("resize_add", f"{t.shape[1]} channels (multiple of 4 needed)")
+    return _k().resize_add(t, size, acc)
 
 
 def clamp_resize(x, lo, hi, size, align_corners=True):
     require_cuda(x)
-    if use_native("clamp_resize") and align_corners and x.shape[1] == 1 and not torch.is_grad_enabled():
-        return _k().clamp_resize(x, lo, hi, size)
-    return L.clamp_resize(x, lo, hi, size, align_corners)
+    if not (align_corners and x.shape[1] == 1) or torch.is_grad_enabled() and x.requires_grad:
+        _unsupported("clamp_resize", "inference-only, single channel, align_corners=True (encoder_decoder.py:132-138)")
+    return _k().clamp_resize(x, lo, hi, size)
 
 
-def msda_sample(v, shapes, ref, off, logit, nH, P):
-    require_cuda(v)
-    if use_native("msda_sample") and v.shape[-1] // nH == 64 and len(shapes) * P == 32:
-        return _k().msda_sample(v, shapes, ref, off, logit, nH, P)
-    return L.msda_sample(v, shapes, ref, off, logit, nH, P)
+# ---- deformable attention -------------------------------------------------------------------
+def msda_module(query, value, pos, level_embed, level_start, ref, shapes, mod, dropout_p):
+    """mmcv MultiScaleDeformableAttention.forward(batch_first=True) as ONE autograd node (kernels._MSDAModule):
+    q = query + pos (+ level embedding); value_proj / sampling_offsets / attention_weights GEMMs; sampling;
+    output_proj + dropout + identity.  The backward sums the query gradient's fan-in inside GEMM epilogues."""
+    require_cuda(query)
+    if mod.embed_dims // mod.num_heads != 64 or mod.num_levels * mod.num_points != 32 or len(shapes) != 4:
+        _unsupported("msda_module", "kernels cover 4 levels x 8 points, head dim 64 (hahi.py:179-188)")
+    return _k().msda_module(query, value, pos, level_embed, level_start, ref, shapes, mod, dropout_p)
+
+
+def linear_small(x, w, b, act=None):
+    """Linear with <= 4 outputs (+sigmoid): HAHIHeteroNeck.reference_points (hahi.py:299-300)."""
+    require_cuda(x, w)
+    return _k().linear_small(x, w, b, act)
 
 
 # ---- ground embedding ----------------------------------------------------------------------
@@ -210,44 +210,32 @@ def ground_plane(coef, H, W, device, batch=1, u0=0, v0=0, depth_scale=200.0, cla
                  su=1.0, sv=1.0):
     if torch.device(device).type != "cuda":
         raise RuntimeError("gedepth_b200 runs on sm_100a only (ground_plane on a non-CUDA device)")
-    if use_native("ground_plane"):
-        return _k().ground_plane(coef, H, W, device, batch, u0, v0, depth_scale, clamp_max, su, sv)
-    return L.ground_plane(coef, H, W, device, batch, u0, v0, depth_scale, clamp_max, su, sv)
+    return _k().ground_plane(coef, H, W, device, batch, u0, v0, depth_scale, clamp_max, su, sv)
 
 
 def ge_vanilla(img, y_half):
     require_cuda(img, y_half)
-    if use_native("ge_vanilla"):
-        return _k().ge_vanilla(img, y_half)
-    return L.ge_vanilla(img, y_half)
+    return _k().ge_vanilla(img, y_half)
 
 
-def ge_adaptive(img, y_half, logits_half, height, depth_scale):
+def ge_adaptive(img, y_half, logits_half, height, depth_scale, want_logits=None):
     require_cuda(img, y_half, logits_half)
-    if use_native("ge_adaptive"):
-        return _k().ge_adaptive(img, y_half, logits_half, height, depth_scale)
-    return L.ge_adaptive(img, y_half, logits_half, height, depth_scale)
+    return _k().ge_adaptive(img, y_half, logits_half, height, depth_scale, want_logits)
 
 
 def fuse_head(d, pe_mask, y, min_depth):
     require_cuda(d, pe_mask, y)
-    if use_native("fuse_head"):
-        return _k().fuse_head(d, pe_mask, y, min_depth)
-    return L.fuse_head(d, pe_mask, y, min_depth)
+    return _k().fuse_head(d, pe_mask, y, min_depth)
 
 
 def silog(pred, gt, eps=1e-3, lam=0.15, max_depth=None, upsample=False):
     require_cuda(pred, gt)
-    if use_native("silog"):
-        return _k().silog(pred, gt, eps, lam, max_depth, upsample)
-    return L.silog(pred, gt, eps, lam, max_depth, upsample)
+    return _k().silog(pred, gt, eps, lam, max_depth, upsample)
 
 
 def cross_entropy(logits, target, ignore_index=255):
     require_cuda(logits, target)
-    if use_native("cross_entropy"):
-        return _k().cross_entropy(logits, target, ignore_index)
-    return L.cross_entropy(logits, target, ignore_index)
+    return _k().cross_entropy(logits, target, ignore_index)
 
 
 def depth_metric_sums(pred, gt, rect, min_depth, max_depth, sums=None):

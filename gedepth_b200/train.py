@@ -21,6 +21,20 @@ from . import kernels
 NO_DECAY_KEYS = ("absolute_pos_embed", "relative_position_bias_table", "norm")
 
 
+def cosine_warmup_lr(step: int, base_lr: float = 1e-4, max_iters: int = 1600 * 48, warmup_iters: int = 16 * 1600,
+                     warmup_ratio: float = 1e-3, min_lr_ratio: float = 1e-8) -> float:
+    """Learning rate of 0-based iteration `step` under the GE configs' lr_config (depthformer_v.py:141-147):
+    mmcv CosineAnnealingLrUpdaterHook(by_epoch=False) with linear warm-up [external, mmcv 1.3.x]:
+    regular = target + (base - target) (1 + cos(pi t / T)) / 2, target = base * min_lr_ratio; during warm-up
+    lr = regular * (1 - (1 - t / warmup_iters) (1 - warmup_ratio))."""
+    import math
+    target = base_lr * min_lr_ratio
+    lr = target + 0.5 * (base_lr - target) * (1.0 + math.cos(math.pi * min(step, max_iters) / max_iters))
+    if step < warmup_iters:
+        lr *= 1.0 - (1.0 - step / warmup_iters) * (1.0 - warmup_ratio)
+    return lr
+
+
 class FlatArena:
     """All parameters (and their gradients) of a model as views into two contiguous fp32 buffers."""
 
@@ -62,8 +76,12 @@ class FlatArena:
 
 class Trainer:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_norm=35.0,
-                 native_optimizer: bool = True):
+                 native_optimizer: bool = True, lr_schedule=None):
+        """lr_schedule: None (constant lr) or a callable step -> lr (e.g. ``cosine_warmup_lr``).  The step's learning
+        rate lives in a device scalar that is refreshed before every step, eager or replayed, so a captured CUDA graph
+        follows the schedule (and ``trainer.lr = x`` takes effect on the next step)."""
         self.model = model
+        self.lr_schedule = lr_schedule
         self.arena = FlatArena(model)
         self.m = torch.zeros_like(self.arena.flat_p)
         self.v = torch.zeros_like(self.arena.flat_p)
@@ -71,6 +89,10 @@ class Trainer:
         self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_norm
         self.step_idx = 0
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.arena.flat_p.device)
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.arena.flat_p.device)
+        self._lr_host = torch.full((1,), float(lr), dtype=torch.float32)
+        if self.arena.flat_p.is_cuda:
+            self._lr_host = self._lr_host.pin_memory()
         kernels.RNG_STEP = self.step_dev     # epilogue dropout mixes the device step counter into its seed
         # optional: weight-gradient GEMMs on a side stream, overlapping the rest of the backward (A/B switch)
         self._dw_side = None
@@ -81,9 +103,19 @@ class Trainer:
         self._static = None
         self._static_loss = None
 
+    def _refresh_lr(self):
+        """Host -> device copy of this step's learning rate (a memcpy on the current stream, never captured)."""
+        if self.lr_schedule is not None:
+            self.lr = float(self.lr_schedule(self.step_idx))
+        if float(self._lr_host[0]) != float(self.lr):
+            self._lr_host[0] = float(self.lr)
+            self.lr_dev.copy_(self._lr_host, non_blocking=True)
+
     def step(self, data_batch: Dict, sync_logs: bool = False):
         """One optimisation step.  Returns the loss tensor (device) and, if ``sync_logs``, the
         rank-averaged log_vars of the reference's ``_parse_losses`` (one device->host copy)."""
+        if not torch.cuda.is_current_stream_capturing() if self.arena.flat_p.is_cuda else True:
+            self._refresh_lr()
         self.arena.zero_grad()
         losses = self.model(**data_batch)
         loss, log_vars = self.model._parse_losses(losses, sync=sync_logs)
@@ -102,7 +134,7 @@ class Trainer:
         kernels.sumsq(self.arena.flat_g, self.sumsq)
         kernels.adamw_step(self.arena.flat_p, self.arena.flat_g, self.m, self.v, self.arena.wd_mask, self.sumsq,
                            self.max_norm, 1.0 / self.world, self.lr, self.betas[0], self.betas[1], self.eps,
-                           self.wd, self.step_idx, self.step_dev)
+                           self.wd, self.step_idx, self.step_dev, self.lr_dev)
         return loss, log_vars
 
     # ---- CUDA-graph path: the whole step (forward, loss, backward, all-reduce, clip, AdamW) is captured
@@ -110,6 +142,12 @@ class Trainer:
     def capture(self, example_batch: Dict, warmup: int = 3):
         """Capture ``step`` on static copies of ``example_batch``'s tensors.  Shapes are then fixed."""
         self._static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_batch.items()}
+        # the warm-up below runs REAL optimisation steps: snapshot everything they mutate and put it back afterwards, so
+        # that capture() leaves parameters, Adam moments, BatchNorm statistics and the step counter untouched
+        snap = [t.clone() for t in (self.arena.flat_p, self.m, self.v, self.step_dev)]
+        bufs = [b for b in self.model.buffers()]
+        snap_bufs = [b.clone() for b in bufs]
+        step0 = self.step_idx
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -117,6 +155,12 @@ class Trainer:
                 self.step(self._static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        for t, s_ in zip((self.arena.flat_p, self.m, self.v, self.step_dev), snap):
+            t.copy_(s_)
+        for b, s_ in zip(bufs, snap_bufs):
+            b.copy_(s_)
+        self.step_idx = step0
+        del snap, snap_bufs
         torch.cuda.empty_cache()      # the eager warm-up's activation blocks would otherwise sit beside the graph's pool
         self._graph = torch.cuda.CUDAGraph()
         n0 = kernels.LAUNCHES
@@ -124,7 +168,7 @@ class Trainer:
             loss, _ = self.step(self._static)
             self._static_loss = loss.detach()
         self.launches_per_step = kernels.LAUNCHES - n0
-        self.step_idx -= 1            # the capture pass itself does not execute
+        self.step_idx -= 1            # the capture pass itself does not execute (neither step_dev.add_ nor BN updates ran)
         return self
 
     def release_graph(self):
@@ -141,6 +185,7 @@ class Trainer:
             for k, v in data_batch.items():
                 if torch.is_tensor(v):
                     self._static[k].copy_(v, non_blocking=True)
+        self._refresh_lr()
         self._graph.replay()
         self.step_idx += 1
         kernels.LAUNCHES += self.launches_per_step

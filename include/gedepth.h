@@ -138,6 +138,10 @@ int ged_dropout_bwd(const float* g, int64_t ldg, float* gz, float* db, int64_t r
  * as an MN-major UMMA operand (no transposed copy; torch.autograd's grad_output @ weight). */
 int ged_gemm_tf32_bt(const float* A, int lda, const float* Wt, int ldw, float* D, int ldd, int M, int N, int K,
                      cudaStream_t stream);
+/* D = A @ Wt + R: the same GEMM with a residual of D's row pitch (R may be D itself: accumulate in place), so that a
+ * gradient fanning in from several consumers is summed in the GEMM epilogues. */
+int ged_gemm_tf32_bt_acc(const float* A, int lda, const float* Wt, int ldw, float* D, int ldd, int M, int N, int K,
+                         const float* residual, cudaStream_t stream);
 /* dX of the 3x3/s1/p1 conv from the zero-bordered dY [B,H+2,W+2,Cout] and the FORWARD weights [Cout][3][3][Cin]
  * read in place (cuDNN dgrad in the reference); DX [B,H,W,*] with channel pitch ldx. */
 int ged_conv3x3_dx_tf32(const float* Gpad, const float* Wk, float* DX, int ldx, int B, int H, int W, int Cin,
@@ -238,6 +242,26 @@ int ged_msda_tc_bwd(const float* value, const float* ref, int ref_batch, const f
                     const int* level_hw, int num_levels, int B, int S, int Q, int nH, int head_dim, int num_points,
                     cudaStream_t stream);
 
+/* ---- the narrow ends of the path (csrc/small.cu, SIMT) ---- */
+/* Backward of a 3x3/s1/p1 conv with Cout in {1, 2, 11} (conv_depth decode_head.py:391, convfinal pemask_neck.py:36 /
+ * dynamicpe_neck.py:497).  g, y (output after act; NULL when act == 0), gz (workspace of g's size): (B,H,W,Cout);
+ * xp (B,H+2,W+2,Cin) zero-bordered input; w [Cout][3][3][Cin].  dx overwritten or NULL; dw, db ACCUMULATED or NULL. */
+int ged_conv3x3_small_bwd(const float* g, const float* y, float* gz, const float* xp, const float* w, float* dx,
+                          float* dw, float* db, int B, int H, int W, int Cin, int Cout, int act, float slope,
+                          cudaStream_t stream);
+/* Linear with N <= 4 outputs (HAHIHeteroNeck.reference_points 512 -> 2, hahi.py:176,299-300); act 0 none | 4 sigmoid. */
+int ged_linear_small_fwd(const float* x, const float* w, const float* b, float* y, int64_t M, int N, int K, int act,
+                         cudaStream_t stream);
+int ged_linear_small_bwd(const float* g, const float* y, const float* x, const float* w, float* dx, float* dw, float* db,
+                         int64_t M, int N, int K, int act, cudaStream_t stream);
+/* q (B,S,C) = query + pos (S,C) [+ level_embed (4,C) of the level each token belongs to; level_start[5]] - the
+ * `query + query_pos` of mmcv MultiScaleDeformableAttention with hahi.py:252-270's level embedding folded in. */
+int ged_add_pos_fwd(const float* query, const float* pos, const float* level_embed, const int* level_start, float* q,
+                    int B, int S, int C, cudaStream_t stream);
+/* adjoint: g_level_embed (4,C) += per-level column sums of dq (or NULL); dq += extra in place (or NULL). */
+int ged_add_pos_bwd(float* dq, const float* extra, float* g_level_embed, const int* level_start, int B, int S, int C,
+                    cudaStream_t stream);
+
 /* Roofline probe: the scatter pattern of ged_msda_bwd alone (one 256-byte red.global.add.v4.f32 row per half-warp at
  * pseudo-random rows of a (rows, heads*64) buffer), `iters` per half-warp.  Returns the number of warps launched
  * (payload = warps * iters * 512 bytes) or a negative error; the caller times it. */
@@ -267,7 +291,7 @@ int ged_sumsq(const float* g, int64_t n, double* out, cudaStream_t stream);
 int ged_adamw_step(float* p, const float* g, float* m, float* v, const uint8_t* wd_mask, int64_t n,
                    const double* sumsq, float max_norm, float grad_scale, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, const int* step_dev,
-                   cudaStream_t stream);
+                   const float* lr_dev /* NULL, or the step's learning rate in device memory */, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

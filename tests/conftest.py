@@ -13,14 +13,15 @@ def pytest_configure(config):
 
 
 @pytest.fixture
-def host_ops_on_cpu(monkeypatch):
+def host_ops_on_cpu():
     """TEST-ONLY: let the host-side mirror run on CPU tensors through the library statements
-    (ops_lib) so its wiring can be checked against the reference goldens without a GPU.  The product
-    has no such switch: ops.require_cuda raises on CPU tensors."""
+    (tests/ops_lib.py) so its wiring can be checked against the reference goldens without a GPU.  The product
+    has no such switch: ops.py has one (sm_100a) implementation per op and require_cuda raises on CPU tensors."""
     from gedepth_b200 import ops
-    monkeypatch.setattr(ops, "require_cuda", lambda *a, **k: None)
-    monkeypatch.setattr(ops, "use_native", lambda name: False)
+    from tests import ops_lib
+    restore = ops_lib.install(ops)
     yield
+    restore()
 
 
 @pytest.fixture(autouse=True)

@@ -1,12 +1,13 @@
-"""Library (cuDNN / cuBLAS / ATen) statements of every op in gedepth_b200.ops.
+"""Library (cuDNN / cuBLAS / ATen) statements of every op in gedepth_b200.ops - TEST INFRASTRUCTURE, not product.
 
-Two uses, both explicit:
+Three uses, all explicit:
   1. tests: the "plain PyTorch fp32 reference of the same op" each hand-written kernel is compared
      with, op by op, on the GPU box;
-  2. ops.py dispatches here - on CUDA tensors only - for the ops whose sm_100a kernel is not
-     written yet (``ops.native_table()`` reports which, bench.py prints it).  These are library
-     calls, i.e. the baseline this repo exists to replace, never a CPU fallback: ops.py refuses
-     CPU tensors before it gets here.
+  2. tests/conftest.py ``host_ops_on_cpu``: ``install(ops)`` swaps these in so the host-side mirror's wiring can be
+     checked against the reference goldens on CPU;
+  3. bench.py ``gpu_library_baseline``: the same step through cuDNN / cuBLAS-TF32 / grid_sample - the reference's own
+     design on the same B200 - as the comparator of the hand-written path.
+gedepth_b200 itself never imports this module: ops.py has one implementation per op and raises otherwise.
 Signatures match ops.py one for one.
 """
 from __future__ import annotations
@@ -232,3 +233,81 @@ def clamp_resize(x, lo, hi, size, align_corners):
     x = torch.clamp(x, min=lo, max=hi)
     return x if size is None else F.interpolate(x, size=tuple(size), mode="bilinear",
                                                 align_corners=align_corners)
+
+
+# ---- ops added with the fused / narrow kernels ---------------------------------------------------------------
+def linear_full(x, w, b=None, act=None, residual=None, row_scale=None, dropout_p: float = 0.0):
+    y = linear(x, w, b, act, None if dropout_p > 0 else residual, row_scale)
+    if dropout_p > 0:
+        y = F.dropout(y, dropout_p, True)
+        y = y if residual is None else y + residual
+    return y
+
+
+def linear_small(x, w, b, act=None):
+    return _act(F.linear(x, w, b), act)
+
+
+def layer_norm_fork(x, w, b, eps):
+    return layer_norm(x, w, b, eps), x
+
+
+def conv2d_cat(x_low, x_skip, w, b=None, act=None, slope=0.01):
+    up = resize(x_low, (x_skip.shape[2], x_skip.shape[3]), True) if x_low.shape[2:] != x_skip.shape[2:] else x_low
+    return conv2d(cat_channels([up, x_skip]), w, b, 1, 1, act, slope)
+
+
+def conv_bn_act_cat(x0, x1, w, b, bn, act=None):
+    return conv_bn_act(cat_channels([x0, x1]), w, b, bn, 1, 1, act)
+
+
+def cat_tokens(xs):
+    return torch.cat(xs, dim=1)
+
+
+def split_levels(src, sizes):
+    return list(src.split([int(n) for n in sizes], dim=1))
+
+
+def ge_adaptive_full(img, y_half, logits_half, height, depth_scale, want_logits=None):
+    y, pm, lf = ge_adaptive(img, y_half, logits_half, height, depth_scale)
+    want = torch.is_grad_enabled() if want_logits is None else want_logits
+    return y, pm, (lf if want else None)
+
+
+def msda_module(query, value, pos, level_embed, level_start, ref, shapes, mod, dropout_p):
+    """mmcv MultiScaleDeformableAttention.forward(batch_first=True) [external, mmcv-full 1.3.13] with the level embedding
+    of hahi.py:252-270 added to the constant part of query_pos."""
+    q = query + pos
+    if level_embed is not None:
+        q = q + torch.cat([level_embed[i].view(1, 1, -1).expand(1, level_start[i + 1] - level_start[i], -1)
+                           for i in range(len(level_start) - 1)], 1)
+    value = query if value is None else value
+    v = F.linear(value, mod.value_proj.weight, mod.value_proj.bias)
+    off = F.linear(q, mod.sampling_offsets.weight, mod.sampling_offsets.bias)
+    logit = F.linear(q, mod.attention_weights.weight, mod.attention_weights.bias)
+    out = msda_sample(v, shapes, ref, off, logit, mod.num_heads, mod.num_points)
+    y = F.linear(out, mod.output_proj.weight, mod.output_proj.bias)
+    if dropout_p > 0:
+        y = F.dropout(y, dropout_p, True)
+    return y + query
+
+
+def install(ops):
+    """Route every op of ``gedepth_b200.ops`` to its library statement (tests and bench's comparator only).  Returns a
+    callable that restores the product's functions."""
+    table = dict(linear=linear_full, conv2d=conv2d, conv_bn_act=conv_bn_act, conv2d_cat=conv2d_cat,
+                 conv_bn_act_cat=conv_bn_act_cat, patch_embed=patch_embed, layer_norm=layer_norm,
+                 layer_norm_fork=layer_norm_fork, merge_patches=merge_patches, window_attention=window_attention,
+                 cat_tokens=cat_tokens, split_levels=split_levels, resize=resize, resize_add=resize_add, clamp_resize=clamp_resize,
+                 msda_module=msda_module, linear_small=linear_small, ground_plane=ground_plane, ge_vanilla=ge_vanilla,
+                 ge_adaptive=ge_adaptive_full, fuse_head=fuse_head, silog=silog, cross_entropy=cross_entropy,
+                 require_cuda=lambda *a, **k: None, use_native=lambda name: False)
+    saved = {k: getattr(ops, k) for k in table}
+    for k, v in table.items():
+        setattr(ops, k, v)
+
+    def restore():
+        for k, v in saved.items():
+            setattr(ops, k, v)
+    return restore

@@ -21,13 +21,13 @@ def _free_port():
 def _inject_cpu_ops():
     """Returns an undo callable (the pytest process must not leak the injection into other tests)."""
     from gedepth_b200 import kernels, ops
-    saved = (ops.require_cuda, ops.use_native, kernels.sumsq, kernels.adamw_step)
+    from tests import ops_lib
+    saved = (kernels.sumsq, kernels.adamw_step)
+    restore = ops_lib.install(ops)          # library statements of every op (CPU tensors allowed)
 
     def undo():
-        ops.require_cuda, ops.use_native, kernels.sumsq, kernels.adamw_step = saved
-
-    ops.require_cuda = lambda *a, **k: None
-    ops.use_native = lambda name: False
+        restore()
+        kernels.sumsq, kernels.adamw_step = saved
 
     def sumsq(flat_g, out):
         out.copy_(flat_g.double().pow(2).sum().reshape(1))

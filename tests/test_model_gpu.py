@@ -103,7 +103,7 @@ def test_flip_tta_fused_average_equals_reference_sequence(monkeypatch):
     kw = dict(pe_ori_point=[torch.zeros(1), torch.zeros(1)])
     with torch.no_grad():
         fast = model(img=[img, img.flip(3)], img_metas=[metas0, metas1], return_loss=False, **kw)
-        monkeypatch.setattr(ops, "_FORCE_LIB", {"tta_merge"})
+        monkeypatch.setattr(ops, "use_native", lambda name: False)      # generic flip / add / divide path of aug_test
         slow = model(img=[img, img.flip(3)], img_metas=[metas0, metas1], return_loss=False, **kw)
     np.testing.assert_allclose(fast[0], slow[0], rtol=1e-6, atol=1e-6)
     assert np.abs(fast[0] - g["pred"][0]).max() > 1e-4          # it really is a two-view average, not view 0
@@ -129,7 +129,8 @@ def test_library_statement_path_equals_reference_on_gpu(monkeypatch):
     """Same host mirror with every op forced to its library statement (fp32, no TF32): isolates
     wiring errors from kernel numerics."""
     from gedepth_b200 import ops
-    monkeypatch.setattr(ops, "_FORCE_LIB", {"all"})
+    from tests import ops_lib
+    restore = ops_lib.install(ops)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     try:
@@ -140,6 +141,7 @@ def test_library_statement_path_equals_reference_on_gpu(monkeypatch):
             res = model(img=[torch.from_numpy(b["img"]).to(DEV)], img_metas=[metas_for(case)], return_loss=False)
         np.testing.assert_allclose(res[0], g["pred"][0], rtol=2e-4, atol=2e-4)
     finally:
+        restore()
         torch.backends.cuda.matmul.allow_tf32 = True
         torch.backends.cudnn.allow_tf32 = True
 
@@ -158,14 +160,14 @@ def test_cuda_graph_step_equals_eager_steps():
         model.train()
         tr = Trainer(model)
         if mode == "graph":
-            snapshot = (tr.arena.flat_p.clone(), tr.m.clone(), tr.v.clone())
+            snapshot = (tr.arena.flat_p.clone(), [b_.clone() for b_ in model.buffers()])
             tr.capture(data, warmup=2)
-            # warm-up steps inside capture() advanced the optimizer: rewind to the common start
-            tr.arena.flat_p.copy_(snapshot[0]); tr.m.copy_(snapshot[1]); tr.v.copy_(snapshot[2])
-            tr.step_dev.zero_(); tr.step_idx = 0
-            for mod in model.modules():
-                if isinstance(mod, torch.nn.BatchNorm2d):
-                    mod.reset_running_stats()
+            # capture() runs real warm-up steps but must hand back the state it found (parameters, Adam moments,
+            # BatchNorm statistics, step counters)
+            assert torch.equal(tr.arena.flat_p, snapshot[0]) and float(tr.m.abs().max()) == 0.0 and tr.step_idx == 0
+            assert int(tr.step_dev) == 0
+            for b_, s_ in zip(model.buffers(), snapshot[1]):
+                assert torch.equal(b_, s_)
         out = []
         for i in range(3):
             loss = tr.step_graph(data) if mode == "graph" else tr.step(data)[0]
@@ -178,6 +180,33 @@ def test_cuda_graph_step_equals_eager_steps():
     assert losses["eager"][2] != losses["eager"][0]              # the optimizer really stepped
     d = (params["eager"] - params["graph"]).abs()
     assert float((d > 5e-5).float().mean()) < 1e-3                # Adam sign flips on round-off gradients only
+
+
+def test_graph_replay_follows_the_lr_schedule():
+    """The learning rate is a device scalar refreshed before every replay: changing it between replays changes the
+    parameter update accordingly (lr = 0 freezes the parameters), and a schedule callable is honoured."""
+    from gedepth_b200.train import Trainer, cosine_warmup_lr
+    case, g, b = load_case("vanilla_train")
+    data = dict(img=torch.from_numpy(b["img"]).to(DEV), img_metas=metas_for(case),
+                depth_gt=torch.from_numpy(b["depth_gt"]).to(DEV))
+    model, _ = build_host_model(case, DEV)
+    model.train()
+    tr = Trainer(model, lr=1e-4, weight_decay=0.0)
+    tr.capture(data, warmup=1)
+    p0 = tr.arena.flat_p.clone()
+    tr.step_graph(data)
+    d1 = float((tr.arena.flat_p - p0).abs().max())
+    assert 0.5e-4 < d1 < 2e-4                         # first Adam step moves every touched parameter by ~lr
+    p1 = tr.arena.flat_p.clone()
+    tr.lr = 0.0
+    tr.step_graph(data)
+    assert torch.equal(tr.arena.flat_p, p1), "lr = 0 must freeze the parameters of a replayed step"
+    tr.lr_schedule = lambda step: 1e-6 * (step + 1)
+    tr.step_graph(data)
+    d3 = float((tr.arena.flat_p - p1).abs().max())
+    assert 1e-6 < d3 < 1e-5, d3                       # step_idx == 2 -> lr = 3e-6
+    assert cosine_warmup_lr(0) == pytest.approx(1e-4 * 1e-3, rel=1e-6)
+    assert cosine_warmup_lr(16 * 1600) == pytest.approx(1e-8 * 1e-4 + 0.5 * (1e-4 - 1e-12) * (1 + np.cos(np.pi / 3)), rel=1e-6)
 
 
 @pytest.mark.parametrize("name", ["vanilla_train", "adaptive_train"])

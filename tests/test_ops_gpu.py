@@ -84,7 +84,8 @@ def _ge_inputs(B, H, W, adaptive, seed=0):
 
 @pytest.mark.parametrize("B,H,W", [(2, 64, 160), (1, 70, 166), (3, 35, 83), (2, 352, 1120)])
 def test_ge_vanilla_fwd_bwd(B, H, W):
-    from gedepth_b200 import kernels as K, ops_lib as L
+    from gedepth_b200 import kernels as K
+    from tests import ops_lib as L
     from oracle import model as om
     img, y_half, _ = _ge_inputs(B, H, W, False)
     y_o, pm_o = om.ground_embed_vanilla(img, y_half)                       # oracle (CPU)
@@ -104,7 +105,8 @@ def test_ge_vanilla_fwd_bwd(B, H, W):
 
 @pytest.mark.parametrize("B,H,W,per_sample_h", [(2, 64, 160, False), (1, 70, 166, True), (2, 352, 1120, False)])
 def test_ge_adaptive_fwd_bwd(B, H, W, per_sample_h):
-    from gedepth_b200 import kernels as K, ops_lib as L
+    from gedepth_b200 import kernels as K
+    from tests import ops_lib as L
     from oracle import model as om
     img, y_half, logits_half = _ge_inputs(B, H, W, True)
     height = torch.tensor([1.56, 1.57, 1.53][:B]) if per_sample_h else 1.65
@@ -133,7 +135,8 @@ def test_ge_adaptive_fwd_bwd(B, H, W, per_sample_h):
 
 @pytest.mark.parametrize("B,H,W", [(2, 64, 160), (1, 70, 166), (2, 352, 1120)])
 def test_fuse_head_fwd_bwd(B, H, W):
-    from gedepth_b200 import kernels as K, ops_lib as L
+    from gedepth_b200 import kernels as K
+    from tests import ops_lib as L
     g = torch.Generator().manual_seed(3)
     h2, w2 = (H + 1) // 2, (W + 1) // 2
     d0, pm0, y0 = torch.rand(B, 1, h2, w2, generator=g) * 20, torch.rand(B, 1, H, W, generator=g) * 80, torch.rand(B, 1, H, W, generator=g)
@@ -155,7 +158,8 @@ def test_fuse_head_fwd_bwd(B, H, W):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,H,W,up", [(2, 64, 160, True), (1, 70, 166, True), (2, 352, 1120, True), (2, 64, 160, False)])
 def test_silog_fwd_bwd(B, H, W, up):
-    from gedepth_b200 import kernels as K, ops_lib as L
+    from gedepth_b200 import kernels as K
+    from tests import ops_lib as L
     from gedepth_b200.synth import synth_batch
     gt = torch.from_numpy(synth_batch(B, H, W, seed=5)["depth_gt"]).to(DEV)
     g = torch.Generator().manual_seed(4)
@@ -171,7 +175,8 @@ def test_silog_fwd_bwd(B, H, W, up):
 
 
 def test_cross_entropy_fwd_bwd():
-    from gedepth_b200 import kernels as K, ops_lib as L
+    from gedepth_b200 import kernels as K
+    from tests import ops_lib as L
     g = torch.Generator().manual_seed(6)
     l0 = torch.randn(2, 11, 64, 160, generator=g) * 2
     t = torch.randint(0, 11, (2, 64, 160), generator=g).float()
@@ -208,7 +213,8 @@ def test_layernorm_fwd_bwd(rows, C):
 
 @pytest.mark.parametrize("B,H,W,nH,shift", [(2, 16, 40, 3, 0), (2, 16, 40, 3, 3), (1, 9, 21, 6, 3), (2, 7, 7, 12, 0), (1, 18, 42, 3, 3)])
 def test_window_attention_fwd_bwd(B, H, W, nH, shift):
-    from gedepth_b200 import kernels as K, ops_lib as L
+    from gedepth_b200 import kernels as K
+    from tests import ops_lib as L
     from oracle import model as om
     C = nH * 32
     g = torch.Generator().manual_seed(8)
@@ -304,7 +310,8 @@ def test_conv3x3_dw_taps(B, H, W, Cin, Cout, passes):
 def test_gemm_pair_kernel(M, N, K, passes):
     """CTA-pair (cta_group::2) kernel: large problems, all epilogue features, against fp64 and against the
     single-CTA kernel."""
-    from gedepth_b200 import kernels as Kn, ops_lib as L
+    from gedepth_b200 import kernels as Kn
+    from tests import ops_lib as L
     g = torch.Generator().manual_seed(41)
     a = torch.randn(M, K, generator=g).to(DEV)
     w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
@@ -394,7 +401,8 @@ def test_linear_epilogue_dropout_fwd_bwd(passes):
 
 @pytest.mark.parametrize("act", [None, "relu", "gelu", "leaky_relu", "sigmoid"])
 def test_gemm_epilogue(act, passes):
-    from gedepth_b200 import kernels as Kn, ops_lib as L
+    from gedepth_b200 import kernels as Kn
+    from tests import ops_lib as L
     g = torch.Generator().manual_seed(10)
     B, T, K, N = 3, 215, 192, 160
     a = torch.randn(B * T, K, generator=g).to(DEV)
@@ -411,7 +419,8 @@ def test_gemm_epilogue(act, passes):
 
 @pytest.mark.parametrize("act", [None, "gelu"])
 def test_linear_autograd(act, passes):
-    from gedepth_b200 import kernels as Kn, ops_lib as L
+    from gedepth_b200 import kernels as Kn
+    from tests import ops_lib as L
     g = torch.Generator().manual_seed(11)
     x0, w0, b0 = torch.randn(2, 300, 96, generator=g), torch.randn(384, 96, generator=g) / 10, torch.randn(384, generator=g)
     r0 = torch.randn(2, 300, 384, generator=g)
@@ -430,7 +439,8 @@ def test_linear_autograd(act, passes):
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,act", [(2, 11, 35, 64, 64, "leaky_relu"), (1, 22, 70, 576, 192, "relu"),
                                                 (2, 16, 40, 96, 11, None), (1, 9, 12, 2304, 768, "leaky_relu"),
-                                                (2, 32, 80, 64, 1, "sigmoid")])
+                                                (2, 32, 80, 64, 1, "sigmoid"), (2, 20, 48, 64, 1, "relu"),
+                                                (1, 17, 33, 64, 11, None)])
 def test_conv3x3(B, H, W, Cin, Cout, act, passes):
     from gedepth_b200 import kernels as Kn
     g = torch.Generator().manual_seed(12)
@@ -441,7 +451,7 @@ def test_conv3x3(B, H, W, Cin, Cout, act, passes):
     a1[0] = x0.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
     a2 = [t.to(DEV).double().requires_grad_(True) for t in (x0, w0, b0)]
     y1 = Kn.conv2d(a1[0], a1[1], a1[2], 1, 1, act, 0.01)
-    from gedepth_b200 import ops_lib as L
+    from tests import ops_lib as L
     pre2 = F.conv2d(a2[0], a2[1], a2[2], padding=1)
     if act in ("relu", "leaky_relu"):
         # piecewise-linear activations: take the branch the kernel took (pre-activations within TF32
@@ -531,7 +541,8 @@ def _msda_inputs(B, shapes, Q, ref_b, clustered):
 
 
 def _msda_case(B, shapes, Q, ref_b, clustered=False, tf32=False):
-    from gedepth_b200 import kernels as Kn, ops_lib as L
+    from gedepth_b200 import kernels as Kn
+    from tests import ops_lib as L
     v0, ref0, off0, lg0 = _msda_inputs(B, shapes, Q, ref_b, clustered)
     a1 = [t.to(DEV).requires_grad_(True) for t in (v0, ref0, off0, lg0)]
     a2 = [t.to(DEV).requires_grad_(True) for t in (v0, ref0, off0, lg0)]
@@ -549,6 +560,78 @@ def _msda_case(B, shapes, Q, ref_b, clustered=False, tf32=False):
         tol = rel * q.grad.abs() + ab * float(q.grad.abs().max())
         # bilinear kinks: a sample landing within fp32 round-off of a pixel boundary may pick the other cell
         assert float((d > tol).float().mean()) < 2e-4, (n, float(d.max()), float(q.grad.abs().max()), float((d > tol).float().mean()))
+
+
+def test_linear_small_fwd_bwd():
+    """HAHIHeteroNeck.reference_points: Linear 512 -> 2 + sigmoid (csrc/small.cu) against torch fp64."""
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(21)
+    x0, w0, b0 = torch.randn(1, 3001, 512, generator=g), torch.randn(2, 512, generator=g) / 20, torch.randn(2, generator=g)
+    for act in ("sigmoid", None):
+        a1 = [t.to(DEV).requires_grad_(True) for t in (x0, w0, b0)]
+        a2 = [t.to(DEV).double().requires_grad_(True) for t in (x0, w0, b0)]
+        y1 = Kn.linear_small(a1[0], a1[1], a1[2], act)
+        y2 = F.linear(a2[0], a2[1], a2[2])
+        y2 = torch.sigmoid(y2) if act else y2
+        _close(y1, y2, 1e-5, 1e-5, "linear_small fwd")
+        go = torch.randn(y2.shape, generator=g).to(DEV)
+        (y1 * go).sum().backward()
+        (y2 * go.double()).sum().backward()
+        for n, p, q in zip(("dx", "dw", "db"), a1, a2):
+            _close(p.grad, q.grad, 1e-4, 1e-5 * float(q.grad.abs().max()) + 1e-6, "linear_small " + n)
+
+
+@pytest.mark.parametrize("shared_value", [True, False], ids=["self", "cross"])
+def test_msda_module_fwd_bwd(shared_value):
+    """The fused deformable-attention node (query + pos + level embedding, three input GEMMs, sampling, output_proj +
+    identity; gradient fan-in summed in GEMM epilogues) against the library statement built from the same module."""
+    from gedepth_b200 import hahi, ops
+    from tests import ops_lib as L
+    torch.manual_seed(3)
+    shapes = [(16, 40), (8, 20), (4, 10), (2, 5)]
+    S = sum(h * w for h, w in shapes)
+    B, Q = 2, (S if shared_value else 1280)
+    starts = [0]
+    for h, w in shapes:
+        starts.append(starts[-1] + h * w)
+    mods = []
+    for _ in range(2):
+        torch.manual_seed(5)
+        m = hahi.MultiScaleDeformableAttention(512, num_levels=4, num_heads=8, num_points=8, batch_first=True).to(DEV)
+        with torch.no_grad():
+            for p_ in m.parameters():
+                p_.add_(torch.randn_like(p_) * 0.05)
+        mods.append(m)
+    g = torch.Generator().manual_seed(4)
+    q0 = torch.randn(B, Q, 512, generator=g)
+    v0 = torch.randn(B, S, 512, generator=g)
+    pos0 = torch.randn(1, Q, 512, generator=g)
+    le0 = torch.randn(4, 512, generator=g)
+    ref0 = torch.rand(1, Q, 2, generator=g)
+    outs, grads = [], []
+    for m, fn in zip(mods, (ops.msda_module, L.msda_module)):
+        q, v, le, ref = [t.to(DEV).requires_grad_(True) for t in (q0, v0, le0, ref0)]
+        use_le = shared_value
+        out = fn(q, None if shared_value else v, pos0.to(DEV), le if use_le else None, starts if use_le else None, ref,
+                 shapes, m, 0.0)
+        go = torch.randn(out.shape, generator=torch.Generator().manual_seed(6)).to(DEV)
+        (out * go).sum().backward()
+        outs.append(out.detach())
+        gr = dict(query=q.grad, ref=ref.grad)
+        if not shared_value:
+            gr["value"] = v.grad
+        if use_le:
+            gr["level_embed"] = le.grad
+        for n, p_ in m.named_parameters():
+            gr[n] = p_.grad
+        grads.append(gr)
+    _close(outs[0], outs[1], 0, 2e-4 * float(outs[1].abs().max()), "msda_module out")
+    for n in grads[1]:
+        a, b = grads[0][n], grads[1][n]
+        assert a is not None, n
+        d = (a - b).abs()
+        tol = 1e-2 * b.abs() + 4e-3 * float(b.abs().max())        # one-pass TF32 backward GEMMs
+        assert float((d > tol).float().mean()) < 1e-3, (n, float(d.max()), float(b.abs().max()))
 
 
 def test_msda_tile_outliers_and_order_invariance():
@@ -631,7 +714,8 @@ def test_prep_conv_input_and_adjoint(B, h0, w0, H, W, C0, C1):
 
 @pytest.mark.parametrize("act", [None, "relu", "leaky_relu", "gelu", "sigmoid"])
 def test_act_bwd(act):
-    from gedepth_b200 import kernels as Kn, ops_lib as L
+    from gedepth_b200 import kernels as Kn
+    from tests import ops_lib as L
     g = torch.Generator().manual_seed(21)
     rows, N, T = 3 * 217, 96, 217
     pre = torch.randn(rows, N, generator=g).to(DEV).requires_grad_(True)
@@ -686,7 +770,8 @@ def test_conv2d_cat_upsample_fwd_bwd(passes):
 
 @pytest.mark.parametrize("H,W", [(64, 160), (70, 166)])
 def test_patch_embed_as_gemm(H, W, passes):
-    from gedepth_b200 import kernels as Kn, ops_lib as L
+    from gedepth_b200 import kernels as Kn
+    from tests import ops_lib as L
     g = torch.Generator().manual_seed(24)
     img = torch.randn(2, 5, H, W, generator=g).to(DEV)
     w = (torch.randn(96, 4, 4, 4, generator=g) / 8).to(DEV).requires_grad_(True)
@@ -728,7 +813,8 @@ def test_stem_conv_as_im2col_gemm(H, W, passes):
 
 @pytest.mark.parametrize("H,W,C", [(16, 40, 96), (9, 21, 192), (5, 11, 384)])
 def test_merge_patches_fwd_bwd(H, W, C):
-    from gedepth_b200 import kernels as Kn, ops_lib as L
+    from gedepth_b200 import kernels as Kn
+    from tests import ops_lib as L
     g = torch.Generator().manual_seed(25)
     x0 = torch.randn(2, H * W, C, generator=g)
     a, c = x0.to(DEV).requires_grad_(True), x0.to(DEV).requires_grad_(True)
@@ -741,7 +827,8 @@ def test_merge_patches_fwd_bwd(H, W, C):
 
 
 def test_clamp_resize():
-    from gedepth_b200 import kernels as Kn, ops_lib as L
+    from gedepth_b200 import kernels as Kn
+    from tests import ops_lib as L
     g = torch.Generator().manual_seed(26)
     x = (torch.rand(2, 1, 35, 83, generator=g) * 120 - 10).to(DEV)
     with torch.no_grad():

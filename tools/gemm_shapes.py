@@ -12,15 +12,13 @@ import torch
 sys.path.insert(0, ".")
 import gedepth_b200.models as M                      # noqa: E402
 from gedepth_b200 import ops                         # noqa: E402
-from gedepth_b200 import ops_lib as L                # noqa: E402
+from tests import ops_lib as L                       # noqa: E402  (library statements: test infrastructure)
 from gedepth_b200.presets import model_cfg           # noqa: E402
 from gedepth_b200.synth import synth_batch, synth_state_dict   # noqa: E402
 
 variant = sys.argv[1] if len(sys.argv) > 1 else "v"
 backbone = sys.argv[2] if len(sys.argv) > 2 else "swin_t"
 H, W = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (352, 1120)
-ops.require_cuda = lambda *a, **k: None
-ops.use_native = lambda name: False
 rec = defaultdict(lambda: [0, 0.0])
 
 
@@ -51,6 +49,7 @@ def conv_bn_act(x, w, b, bn, stride=1, padding=0, act=None):
 
 
 L.linear, L.conv2d, L.conv_bn_act = linear, conv2d, conv_bn_act
+L.install(ops)
 model = M.build_depther(model_cfg(variant, "kitti", backbone, pretrained=None))
 model.load_state_dict(synth_state_dict(model.state_dict(), 0))
 model.eval()

@@ -8,13 +8,14 @@ from gedepth_b200.train import Trainer
 from torch.profiler import profile, ProfilerActivity
 dev = 'cuda:0'
 torch.backends.cuda.matmul.allow_tf32 = True; torch.backends.cudnn.allow_tf32 = True
-B, H, W = 8, 352, 1120
-model = M.build_depther(model_cfg('v', 'kitti', 'swin_t', pretrained=None))
+VAR, BB, B = (sys.argv[1], sys.argv[2], int(sys.argv[3])) if len(sys.argv) > 3 else ('v', 'swin_t', 8)
+H, W = 352, 1120
+model = M.build_depther(model_cfg(VAR, 'kitti', BB, pretrained=None))
 model.load_state_dict(synth_state_dict(model.state_dict(), 0)); model.to(dev).train()
 tr = Trainer(model)
-b = synth_batch(B, H, W, seed=1)
+b = synth_batch(B, H, W, seed=1, adaptive=VAR == 'a')
 d = {k: torch.from_numpy(v).to(dev) for k, v in b.items()}
-def step(): tr.step(dict(img=d['img'], img_metas=[{}] * B, depth_gt=d['depth_gt']))
+def step(): tr.step(dict(img=d['img'], img_metas=[{}] * B, depth_gt=d['depth_gt'], **({'pe_k_gt': d['pe_k_gt']} if VAR == 'a' else {})))
 for _ in range(3): step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True, with_stack=True) as prof:
