@@ -35,25 +35,9 @@ def _install_stubs():
     from gedepth_b200 import compat
     from oracle import model as om
 
-    class FFN(compat.BaseModule):
-        """mmcv FFN(num_fcs=2, add_identity=True): identity + DropPath(Linear(act(Linear(x))))."""
-
-        def __init__(self, embed_dims=256, feedforward_channels=1024, num_fcs=2,
-                     act_cfg=dict(type="ReLU", inplace=True), ffn_drop=0.0, dropout_layer=None,
-                     add_identity=True, init_cfg=None, **kw):
-            super().__init__(init_cfg)
-            act = compat.build_activation_layer(act_cfg)
-            self.layers = compat.Sequential(
-                compat.Sequential(nn.Linear(embed_dims, feedforward_channels), act, nn.Dropout(ffn_drop)),
-                nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop))
-            self.dropout_layer = compat.build_dropout(dropout_layer) if dropout_layer else nn.Identity()
-            self.add_identity = add_identity
-
-        def forward(self, x, identity=None):
-            out = self.layers(x)
-            if not self.add_identity:
-                return self.dropout_layer(out)
-            return (x if identity is None else identity) + self.dropout_layer(out)
+    # arithmetic-bearing mmcv leaves: independent restatements (oracle/mmcv_stubs.py), NOT the product's compat.py
+    from oracle import mmcv_stubs as ms
+    FFN = ms.make_ffn(compat.BaseModule, compat.Sequential)
 
     class MultiScaleDeformableAttention(compat.BaseModule):
         """Pure-PyTorch (grid_sample) stand-in for mmcv.ops.MultiScaleDeformableAttention."""
@@ -99,14 +83,14 @@ def _install_stubs():
 
     mmcv = _mod("mmcv", __version__="1.3.13",
                 imdenormalize=lambda img, mean, std, to_bgr=True: img)
-    cnn = _mod("mmcv.cnn", MODELS=compat.MMCV_MODELS, ConvModule=compat.ConvModule,
-               build_norm_layer=compat.build_norm_layer, build_conv_layer=compat.build_conv_layer,
-               build_activation_layer=compat.build_activation_layer,
+    cnn = _mod("mmcv.cnn", MODELS=compat.MMCV_MODELS, ConvModule=ms.ConvModule,
+               build_norm_layer=ms.build_norm_layer, build_conv_layer=ms.build_conv_layer,
+               build_activation_layer=ms.build_activation_layer,
                trunc_normal_init=compat.trunc_normal_init, xavier_init=compat.xavier_init,
                constant_init=compat.constant_init, kaiming_init=compat.kaiming_init)
     bricks = _mod("mmcv.cnn.bricks")
     registry = _mod("mmcv.cnn.bricks.registry", ATTENTION=compat.Registry("attention"))
-    transformer = _mod("mmcv.cnn.bricks.transformer", FFN=FFN, build_dropout=compat.build_dropout,
+    transformer = _mod("mmcv.cnn.bricks.transformer", FFN=FFN, build_dropout=ms.build_dropout,
                        POSITIONAL_ENCODING=compat.POSITIONAL_ENCODING,
                        build_positional_encoding=compat.build_positional_encoding)
     utils_ = _mod("mmcv.cnn.utils")

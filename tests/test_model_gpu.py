@@ -1,8 +1,8 @@
 """Whole-path parity on the B200 against the fixtures produced by the REFERENCE's own modules
 (tests/golden/*.npz, see oracle/make_golden.py): forward depth map, losses, gradients, inference,
 Abs-Rel.  The CUDA path runs TF32 tensor-core GEMMs/convs (fp32 storage and accumulation); the
-tolerances below are the north star's: depth within 1e-3 relative (checked as a 99.9th percentile
-with a 5e-3 hard cap per pixel), Abs-Rel within 1e-4."""
+tolerances below are the north star's: depth within 1e-3 relative at EVERY pixel, Abs-Rel within 1e-4.  The *_k8
+cases run at the BASELINE shape 352 x 1120."""
 import numpy as np
 import pytest
 import torch
@@ -27,7 +27,7 @@ def _rel(a, b):
     return (np.abs(a - b) / np.maximum(np.abs(b), 1e-3))
 
 
-@pytest.mark.parametrize("name", ["vanilla_train", "adaptive_train", "adaptive_ddad_train"])
+@pytest.mark.parametrize("name", ["vanilla_train", "adaptive_train", "adaptive_ddad_train", "adaptive_train_k8"])
 def test_train_step_matches_reference(name):
     from gedepth_b200 import kernels, ops
     case, g, b = load_case(name)
@@ -44,8 +44,9 @@ def test_train_step_matches_reference(name):
     depth, _ = model.decode_head.forward(x, data["img_metas"], pe_mask, y)
     rel = _rel(depth.detach().cpu().numpy(), g["depth"])
     print(f"{name}: depth rel err p50 {np.percentile(rel, 50):.2e} p99.9 {np.percentile(rel, 99.9):.2e} max {rel.max():.2e}")
-    assert np.percentile(rel, 99.9) < 1e-3 and rel.max() < 5e-3
-    np.testing.assert_allclose(y.detach().cpu().numpy(), g["y"], rtol=2e-3, atol=2e-4)
+    assert rel.max() < 1e-3
+    sub = case.get("sub", 1)
+    np.testing.assert_allclose(y.detach().cpu().numpy()[..., ::sub, ::sub], g["y"], rtol=2e-3, atol=2e-4)
     out = model.train_step(data, None)
     assert kernels.LAUNCHES - n0 > 100, "the sm_100a kernels did not run"
     assert abs(out["log_vars"]["loss"] - float(g["loss"])) < 2e-3 * float(g["loss"])
@@ -71,7 +72,7 @@ def test_train_step_matches_reference(name):
     assert all(ops.native_table()[k] for k in ("ge_vanilla", "ge_adaptive", "fuse_head", "silog", "linear", "conv2d"))
 
 
-@pytest.mark.parametrize("name", ["vanilla_eval_ragged", "adaptive_eval"])
+@pytest.mark.parametrize("name", ["vanilla_eval_ragged", "adaptive_eval", "vanilla_eval_k8"])
 def test_inference_matches_reference(name):
     from oracle import ground as og
     case, g, b = load_case(name)
@@ -82,7 +83,7 @@ def test_inference_matches_reference(name):
     pred, ref = res[0], g["pred"][0]
     rel = _rel(pred, ref)
     print(f"{name}: pred rel err p50 {np.percentile(rel, 50):.2e} p99.9 {np.percentile(rel, 99.9):.2e} max {rel.max():.2e}")
-    assert np.percentile(rel, 99.9) < 1e-3 and rel.max() < 5e-3
+    assert rel.max() < 1e-3
     # Abs-Rel (metrics.py:17) of both predictions against the same synthetic ground truth
     from gedepth_b200.synth import synth_batch
     gt = synth_batch(case["B"], case["H"], case["W"], seed=99, sparsity=0.2)["depth_gt"][0]
@@ -122,7 +123,7 @@ def test_flip_tta_matches_reference_aug_test():
                     pe_ori_point=[torch.zeros(1), torch.zeros(1)])
     rel = _rel(res[0], g["pred"][0])
     print(f"tta: pred rel err p50 {np.percentile(rel, 50):.2e} p99.9 {np.percentile(rel, 99.9):.2e} max {rel.max():.2e}")
-    assert np.percentile(rel, 99.9) < 1e-3 and rel.max() < 5e-3
+    assert rel.max() < 1e-3
 
 
 def test_library_statement_path_equals_reference_on_gpu(monkeypatch):
