@@ -420,14 +420,17 @@ __global__ void __launch_bounds__(256) fuse_head_bwd_full_kernel(
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) find_k_kernel(const float* __restrict__ gt,
                                                       const float* __restrict__ pe, int64_t pe_bstride,
-                                                      float* __restrict__ k_out, int64_t HW, float h,
+                                                      float* __restrict__ k_out, int64_t HW, double h,
                                                       int truncate) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (i >= HW) return;
   const double g = (double)__ldg(gt + b * HW + i);
-  const double p = (double)__ldg(pe + b * pe_bstride + i);
-  double k = (double)h / g + (-(double)h) / p;
+  const float pf = __ldg(pe + b * pe_bstride + i);
+  // the arithmetic types of the reference scripts: KITTI divides -1.65 by the float32 plane IN float32 and adds it to
+  // the float64 1.65 / gt (preprocess_data_kitti.py:59-63,81); DDAD keeps everything in float64 (preprocess_data_ddad.py:47-51)
+  const double a = truncate ? (-h) / (double)pf : (double)__fdiv_rn(-(float)h, pf);
+  double k = h / g + a;
   k = atan(k) * 57.29577951308232;
   double r;
   if (truncate) r = isfinite(k) ? trunc(k) : 0.0; else r = rint(k);
@@ -564,7 +567,7 @@ GED_API int ged_fuse_head_bwd(const float* g_out, const float* g_yh_extra, const
 }
 
 GED_API int ged_find_k(const float* gt, const float* pe, int64_t pe_batch_stride, float* k_out, int B,
-                       int H, int W, float cam_height, int truncate, cudaStream_t stream) {
+                       int H, int W, double cam_height, int truncate, cudaStream_t stream) {
   if (!gt || !pe || !k_out || B <= 0) return GED_ERR_ARG;
   const int64_t HW = (int64_t)H * W;
   find_k_kernel<<<dim3((unsigned)((HW + 255) / 256), B), 256, 0, stream>>>(gt, pe, pe_batch_stride, k_out, HW, cam_height, truncate);

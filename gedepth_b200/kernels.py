@@ -30,7 +30,7 @@ SIGNATURES = {
     "ged_ge_adaptive_bwd": [_P, _I64, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ged_fuse_head_fwd": [_P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P],
     "ged_fuse_head_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "ged_find_k": [_P, _P, _I64, _P, _I, _I, _I, _F, _I, _P],
+    "ged_find_k": [_P, _P, _I64, _P, _I, _I, _I, _D, _I, _P],
     "ged_silog_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _I, _P],
     "ged_silog_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _I, _P],
     "ged_ce_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P],

@@ -76,7 +76,7 @@ int ged_fuse_head_bwd(const float* g_out, const float* g_yh_extra, const float* 
 /* tools/preprocess_data_kitti.py:59-63,86-89 (truncate=0: round half even) and
  * tools/preprocess_data_ddad.py:47-51,77-82 (truncate=1).  k_out in {-5..5} or 255 where gt==0. */
 int ged_find_k(const float* gt, const float* pe, int64_t pe_batch_stride, float* k_out, int B, int H,
-               int W, float cam_height, int truncate, cudaStream_t stream);
+               int W, double cam_height, int truncate, cudaStream_t stream);
 
 /* ---- losses ---------------------------------------------------------------------------------- */
 /* decode_head.py:586-599 + losses/sigloss.py:36-53.  upsample=1: pred is (B,1,hp,wp) and is

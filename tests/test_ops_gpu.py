@@ -3,6 +3,8 @@ ctypes -> libgedepth_sm100.so), against (i) the oracle's numpy/torch-CPU restate
 plain PyTorch fp32 statement of the same op (ops_lib) on the GPU.  Tolerances are stated per test:
 bit-exact for integer work, ~1e-5 for fp32 SIMT kernels, 2e-3 relative for TF32 tensor-core GEMMs.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -62,11 +64,30 @@ def test_find_k_matches_numpy():
     gt = np.where(rng.random((2, 96, 320)) < 0.3, np.abs(pe) * (1 + 0.2 * rng.standard_normal((2, 96, 320))), 0).astype(np.float32)
     got = K.find_k(torch.from_numpy(gt).to(DEV), torch.from_numpy(pe).to(DEV), 1.65, False).cpu().numpy()
     ref = np.stack([og.find_k_kitti(gt[b].astype(np.float64), pe) for b in range(2)])
-    assert (got != ref).mean() < 1e-4          # rounding ties of atan in fp64 vs numpy's libm
+    assert np.array_equal(got, ref)             # integer labels: bit-exact (same arithmetic types as the script)
     assert np.all(got[gt == 0] == 255)
     got_t = K.find_k(torch.from_numpy(gt).to(DEV), torch.from_numpy(pe).to(DEV), 1.56, True).cpu().numpy()
     ref_t = np.stack([og.find_k_ddad(gt[b].astype(np.float64), pe.astype(np.float64), 1.56) for b in range(2)])
-    assert (got_t != ref_t).mean() < 1e-4
+    assert np.array_equal(got_t, ref_t)
+
+
+def test_ground_plane_and_find_k_equal_the_reference_script():
+    """tests/golden/ref_preprocess_kitti.npz holds what the reference's own tools/preprocess_data_kitti.py wrote when it was
+    executed verbatim on a synthetic data/kitti tree (oracle/run_ref_preprocess.py): pe_165.npy (a1) and one slope-label
+    file (f1).  The generator kernel reproduces float32(pe) and ged_find_k reproduces every label, bit for bit."""
+    import hashlib
+    from gedepth_b200 import kernels as K
+    from oracle import ground as og
+    from oracle.run_ref_preprocess import H, W, synth_gt
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_preprocess_kitti.npz"))
+    coef = og.plane_coefficients(og.kitti_projection(), og.KITTI_CAM_HEIGHT)
+    pe = K.ground_plane(coef, H, W, DEV, 1, 0, 0, 200.0, 200.0, 1.0, 1.0)[0, 1].contiguous()
+    assert hashlib.sha256(pe.cpu().numpy().tobytes()).hexdigest() == str(g["pe_f32_sha256"])
+    gt16 = synth_gt()
+    assert hashlib.sha256(gt16.tobytes()).hexdigest() == str(g["gt_sha256"])
+    gt = torch.from_numpy((gt16.astype(np.float64) / 256).astype(np.float32)).to(DEV)       # k/256, k < 2^16: exact in fp32
+    k = K.find_k(gt[None], pe, 1.65, False)[0].cpu().numpy()
+    assert np.array_equal(k, g["k_img"].astype(np.float32)), int((k != g["k_img"]).sum())
 
 
 # ------------------------------------------------------------------------------------------------

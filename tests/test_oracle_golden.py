@@ -97,6 +97,22 @@ def test_ground_plane_known_answers():
     assert np.array_equal(sub, pe[23:375, 61:61 + 1120])
 
 
+def test_oracle_equals_the_reference_preprocessing_script():
+    """oracle/ground.py against what tools/preprocess_data_kitti.py itself wrote (executed verbatim by
+    oracle/run_ref_preprocess.py on a synthetic tree): pe_165.npy in float64 and the slope labels, bit for bit."""
+    import hashlib
+    import os
+    from oracle.run_ref_preprocess import H, W, synth_gt
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_preprocess_kitti.npz"))
+    pe = og.ground_plane(og.plane_coefficients(og.kitti_projection(), og.KITTI_CAM_HEIGHT), H, W)
+    assert hashlib.sha256(np.ascontiguousarray(pe).tobytes()).hexdigest() == str(g["pe_sha256"])
+    assert np.array_equal(pe[::25], g["pe_rows"])
+    gt16 = synth_gt()
+    assert hashlib.sha256(gt16.tobytes()).hexdigest() == str(g["gt_sha256"])
+    k = og.find_k_kitti(gt16.astype(np.float64) / 256, pe.astype(np.float32))
+    assert np.array_equal(k, g["k_img"]) and str(g["k_dtype"]) == str(k.dtype)
+
+
 def test_loader_channels_and_find_k():
     coef = og.plane_coefficients(og.kitti_projection(), og.KITTI_CAM_HEIGHT)
     pe = og.ground_plane(coef, 375, 1242)
