@@ -1,0 +1,328 @@
+// Swin (shifted-)window attention core on the 5th-generation tensor cores, sm_100a - forward.
+// a7 + a8: depthformer_swin.py:285-360 (pad to x7, roll(-3,-3), 9-region mask of -100, partition, reverse, un-roll,
+// crop) and :184-224 (q*scale @ k^T + rel-pos-bias (+mask), softmax, @ v); same contract as ged_winattn_fwd.
+//
+// A work item is a DUO: two consecutive (window, head) pairs.  Their 49-token Q / K / V tiles (head dim 32 = one
+// 128-byte swizzle row) are gathered by coordinate from the image-ordered qkv matrix straight into UMMA operand tiles
+// (padding, cyclic shift, partition are index arithmetic), split into hi + lo (3xTF32: fp32-accurate) while staging:
+//     S_p [128 x 64] = [Q_A ; Q_B] . K_p^T        p = A, B   (rows of the other pair are don't-care)    tcgen05.mma, TMEM
+//     P    = softmax(S + rel-pos bias + shift mask)            one accumulator row per thread, tcgen05.ld -> registers
+//     O_p [128 x 32] = [P_A ; P_B] . V_p                      P written back as a K-major operand, V MN-major
+// and the context rows leave from TMEM by tcgen05.ld as 128-byte stores.  Rows / keys 49..63 are padding: zero
+// probabilities, never stored.
+#include "common.cuh"
+
+namespace ged {
+
+constexpr int TW_WS = 7, TW_N = 49, TW_HD = 32;
+constexpr int TW_THREADS = 256;
+
+struct TwGeom {
+  int H, W, Hp, Wp, nWx, nWin, shift;
+};
+
+// ---- PTX wrappers (forms of gemm_tcgen05.cu) ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t w_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void w_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(w_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void w_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WDONE_%=;\n\t"
+      "bra WWAIT_%=;\n\t"
+      "WDONE_%=:\n\t}"
+      :: "r"(w_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void w_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void w_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void w_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void w_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(w_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void w_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void w_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint64_t w_desc_kmajor(uint32_t smem_addr) {      // rows of 32 floats, 128B swizzle, 8-row atoms
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t w_desc_mnmajor(uint32_t smem_addr, uint32_t panel_bytes) {   // Layout_MN_SW128_32B_Atom
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((panel_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+__host__ __device__ constexpr uint32_t w_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// element (row r, float c < 32) of a K-major 128B-swizzled tile; 16-byte chunk (r, ck) of an MN-major tile whose rows are
+// the contraction index (Swizzle<2,5,2>: 32-byte chunks XOR (row & 3))
+__device__ __forceinline__ uint32_t w_kmaj_chunk(int r, int ck) { return (uint32_t)(r * 128 + ((ck ^ (r & 7)) << 4)); }
+__device__ __forceinline__ uint32_t w_mnmaj_chunk(int r, int ck) { return (uint32_t)(r * 128 + ((((ck >> 1) ^ (r & 3)) << 5) | ((ck & 1) << 4))); }
+__device__ __forceinline__ float w_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float4 w_lo4(const float4& x) { return make_float4(w_lo(x.x), w_lo(x.y), w_lo(x.z), w_lo(x.w)); }
+
+// token n of window (wy,wx) -> image token index, or -1 for a padding token; also its shift-mask label
+__device__ __forceinline__ int tw_token(const TwGeom& g, int wy, int wx, int n, int& label) {
+  const int ty = n / TW_WS, tx = n - ty * TW_WS;
+  const int hs = wy * TW_WS + ty, ws = wx * TW_WS + tx;
+  label = (hs < g.Hp - TW_WS ? 0 : (hs < g.Hp - g.shift ? 1 : 2)) * 3 + (ws < g.Wp - TW_WS ? 0 : (ws < g.Wp - g.shift ? 1 : 2));
+  int h = hs + g.shift, w = ws + g.shift;
+  if (h >= g.Hp) h -= g.Hp;
+  if (w >= g.Wp) w -= g.Wp;
+  return (h < g.H && w < g.W) ? h * g.W + w : -1;
+}
+
+// shared memory (bytes from the 1024-aligned base)
+constexpr int W_QHI = 0;            // [128 rows: pair A 0..63, pair B 64..127][32]  K-major            16 KB
+constexpr int W_QLO = 16384;
+constexpr int W_KHI = 32768;        // 2 x [64 keys][32] K-major                                       16 KB
+constexpr int W_KLO = 49152;
+constexpr int W_PHI = 0;            // P [128 rows][64 keys] = 2 K-blocks x 16 KB, over Q / K once S has been read   32 KB
+constexpr int W_PLO = 32768;
+constexpr int W_VHI = 65536;        // 2 x [64 keys][32 d] MN-major                                     16 KB
+constexpr int W_VLO = 81920;
+constexpr int W_MISC = 98304;       // barriers, TMEM base, token / label tables, bias tables
+constexpr int W_TOTAL = W_MISC + 4096 + 1024;
+
+struct TwMisc {
+  uint64_t bar_s, bar_o;
+  uint32_t tmem;
+  int tok[2][64];                   // image token of each row, -1 = padding row
+  int lab[2][64];
+  float tab[2][176];                // relative-position bias of the pair's head, by (dy + 6) * 13 + (dx + 6)
+  int pair_b[2], pair_head[2], pair_valid[2];
+};
+
+__global__ void __launch_bounds__(TW_THREADS, 2) winattn_tc_fwd_kernel(
+    const float* __restrict__ qkv, const float* __restrict__ bias, const float* __restrict__ table, float* __restrict__ ctx,
+    TwGeom g, int B, int C, int nH, float scale, int num_pairs) {
+  extern __shared__ uint8_t w_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)w_smem_raw + 1023) & ~(uintptr_t)1023);
+  TwMisc& ms = *reinterpret_cast<TwMisc*>(smem + W_MISC);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int64_t L = (int64_t)g.H * g.W;
+
+  if (tid == 0) {
+    w_mbar_init(&ms.bar_s, 1); w_mbar_init(&ms.bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(w_smem_u32(&ms.tmem)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // every operand byte starts finite: padding rows / keys are never written again and only multiply zero probabilities
+  for (int i = tid; i < W_MISC / 16; i += TW_THREADS) *(float4*)(smem + i * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+  w_fence_before();
+  __syncthreads();
+  w_fence_after();
+  const uint32_t tmem = ms.tmem;
+  const uint32_t sbase = w_smem_u32(smem);
+  uint32_t phase = 0;
+
+  for (int duo = blockIdx.x; duo * 2 < num_pairs; duo += gridDim.x) {
+    // ---- which pairs; token / label / bias tables ---------------------------------------------------------------
+    if (tid < 128) {
+      const int p = tid >> 6, n = tid & 63;
+      const int pair = duo * 2 + p;
+      const bool valid = pair < num_pairs;
+      const int head = valid ? pair % nH : 0, wlin = valid ? pair / nH : 0;
+      const int win = wlin % g.nWin, b = wlin / g.nWin;
+      int lab = 0, tok = -1;
+      if (valid && n < TW_N) tok = tw_token(g, win / g.nWx, win % g.nWx, n, lab);
+      ms.tok[p][n] = (valid && n < TW_N) ? tok : -2;         // -2: not a token at all (row / key 49..63 or no pair)
+      ms.lab[p][n] = lab;
+      if (n == 0) { ms.pair_b[p] = b; ms.pair_head[p] = head; ms.pair_valid[p] = valid; }
+    }
+    for (int i = tid; i < 2 * 169; i += TW_THREADS) {
+      const int p = i / 169, e = i - p * 169, pair = duo * 2 + p;
+      ms.tab[p][e] = pair < num_pairs ? __ldg(table + (int64_t)e * nH + pair % nH) : 0.f;
+    }
+    __syncthreads();
+    // ---- stage Q (scaled), K, V of both pairs: hi + lo, swizzled operand tiles --------------------------------------
+    {
+      // all global loads of the thread are issued before the first one is consumed (10 x 16 bytes in flight per thread)
+      constexpr int ITEMS = 2 * TW_N * 3 * 8, ITERS = (ITEMS + TW_THREADS - 1) / TW_THREADS;
+      float4 v[ITERS];
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int i = tid + it * TW_THREADS;
+        v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < ITEMS) {
+          const int ck = i & 7, which = (i >> 3) % 3, r = (i >> 3) / 3;
+          const int p = r / TW_N, n = r - p * TW_N;
+          if (ms.pair_valid[p]) {
+            const int tok = ms.tok[p][n], col = which * C + ms.pair_head[p] * TW_HD + ck * 4;
+            if (tok >= 0) v[it] = __ldg((const float4*)(qkv + ((int64_t)ms.pair_b[p] * L + tok) * 3 * C + col));
+            else if (bias) v[it] = __ldg((const float4*)(bias + col));       // zero-padded token: q = k = v = bias
+          }
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int i = tid + it * TW_THREADS;
+        if (i >= ITEMS) continue;
+        const int ck = i & 7, which = (i >> 3) % 3, r = (i >> 3) / 3;
+        const int p = r / TW_N, n = r - p * TW_N;
+        if (!ms.pair_valid[p]) continue;
+        float4 x = v[it];
+        if (which == 0) {
+          x.x *= scale; x.y *= scale; x.z *= scale; x.w *= scale;
+          const uint32_t o = w_kmaj_chunk(p * 64 + n, ck);
+          *(float4*)(smem + W_QHI + o) = x; *(float4*)(smem + W_QLO + o) = w_lo4(x);
+        } else if (which == 1) {
+          const uint32_t o = p * 8192 + w_kmaj_chunk(n, ck);
+          *(float4*)(smem + W_KHI + o) = x; *(float4*)(smem + W_KLO + o) = w_lo4(x);
+        } else {
+          const uint32_t o = p * 8192 + w_mnmaj_chunk(n, ck);
+          *(float4*)(smem + W_VHI + o) = x; *(float4*)(smem + W_VLO + o) = w_lo4(x);
+        }
+      }
+    }
+    w_fence_async();
+    __syncthreads();
+    // ---- S_p = [Q_A ; Q_B] . K_p^T  (3xTF32) ------------------------------------------------------------------------
+    if (tid == 0) {
+      w_fence_after();
+      constexpr uint32_t ids = w_idesc_tf32(128, 64, false, false);
+      const uint64_t qhi = w_desc_kmajor(sbase + W_QHI), qlo = w_desc_kmajor(sbase + W_QLO);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const uint64_t khi = w_desc_kmajor(sbase + W_KHI + p * 8192), klo = w_desc_kmajor(sbase + W_KLO + p * 8192);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          w_mma_tf32(tmem + p * 64, qhi + 2 * k, khi + 2 * k, ids, k != 0);
+          w_mma_tf32(tmem + p * 64, qlo + 2 * k, khi + 2 * k, ids, 1u);
+          w_mma_tf32(tmem + p * 64, qhi + 2 * k, klo + 2 * k, ids, 1u);
+        }
+      }
+      w_commit(&ms.bar_s);
+    }
+    // ---- softmax: thread = accumulator row (warps 0..3 own TMEM lane quadrants 0..3) --------------------------------
+    const int row = tid & 127, rp = row >> 6, ri = row & 63;
+    if (warp < 4) {
+      w_mbar_wait(&ms.bar_s, phase);
+      w_fence_after();
+      float s[64];
+      w_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(rp * 64), (uint32_t*)s);
+      w_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(rp * 64 + 32), (uint32_t*)(s + 32));
+      const bool live = ri < TW_N && ms.pair_valid[rp];
+      float inv = 0.f;
+      if (live) {
+        const int yi = ri / TW_WS, xi = ri - yi * TW_WS, li = ms.lab[rp][ri];
+        const float* tb = ms.tab[rp];
+        const bool masked = g.shift > 0;
+        float mx = -3.0e38f;
+#pragma unroll
+        for (int j = 0; j < TW_N; ++j) {
+          const int yj = j / TW_WS, xj = j - yj * TW_WS;
+          float v = s[j] + tb[(yi - yj + 6) * 13 + (xi - xj + 6)];
+          if (masked && ms.lab[rp][j] != li) v += -100.0f;
+          s[j] = v;
+          mx = fmaxf(mx, v);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < TW_N; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
+        inv = 1.f / sum;
+      }
+      // P row -> K-major operand tiles (2 K-blocks of 32 keys), hi + lo; padding rows / keys are zero
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float4 v;
+        v.x = (live && 4 * c + 0 < TW_N) ? s[4 * c + 0] * inv : 0.f;
+        v.y = (live && 4 * c + 1 < TW_N) ? s[4 * c + 1] * inv : 0.f;
+        v.z = (live && 4 * c + 2 < TW_N) ? s[4 * c + 2] * inv : 0.f;
+        v.w = (live && 4 * c + 3 < TW_N) ? s[4 * c + 3] * inv : 0.f;
+        const uint32_t o = (c >> 3) * 16384 + w_kmaj_chunk(row, c & 7);
+        *(float4*)(smem + W_PHI + o) = v; *(float4*)(smem + W_PLO + o) = w_lo4(v);
+      }
+      w_fence_async();
+    }
+    w_fence_before();
+    __syncthreads();
+    // ---- O_p = [P_A ; P_B] . V_p  (3xTF32) --------------------------------------------------------------------------
+    if (tid == 0) {
+      w_fence_after();
+      constexpr uint32_t ido = w_idesc_tf32(128, 32, false, true);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const uint64_t vhi = w_desc_mnmajor(sbase + W_VHI + p * 8192, 8192), vlo = w_desc_mnmajor(sbase + W_VLO + p * 8192, 8192);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t phi = w_desc_kmajor(sbase + W_PHI + kb * 16384), plo = w_desc_kmajor(sbase + W_PLO + kb * 16384);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t ks = 64u * (uint32_t)(kb * 4 + k);       // 8 keys = two 512-byte atoms of the MN-major V tile
+            w_mma_tf32(tmem + 128 + p * 32, phi + 2 * k, vhi + ks, ido, (kb | k) != 0);
+            w_mma_tf32(tmem + 128 + p * 32, plo + 2 * k, vhi + ks, ido, 1u);
+            w_mma_tf32(tmem + 128 + p * 32, phi + 2 * k, vlo + ks, ido, 1u);
+          }
+        }
+      }
+      w_commit(&ms.bar_o);
+    }
+    if (warp < 4) {
+      w_mbar_wait(&ms.bar_o, phase);
+      w_fence_after();
+      float o[32];
+      w_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(128 + rp * 32), (uint32_t*)o);
+      const int tok = ms.tok[rp][ri];
+      if (tok >= 0) {                                            // padded rows are cropped away (:354-355)
+        float4* dst = (float4*)(ctx + ((int64_t)ms.pair_b[rp] * L + tok) * C + ms.pair_head[rp] * TW_HD);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+      }
+    }
+    phase ^= 1;
+    w_fence_before();
+    __syncthreads();          // TMEM and the operand tiles are free for the next duo
+    w_fence_after();
+  }
+  w_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    w_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256) : "memory");
+  }
+}
+
+}  // namespace ged
+using namespace ged;
+
+// Same contract as ged_winattn_fwd.  `index` must be the standard Swin relative-position index (depthformer_swin.py:
+// 168-172: (dy + 6) * 13 + (dx + 6)); the host wrapper checks that once per buffer.
+GED_API int ged_winattn_tc_fwd(const float* qkv, const float* qkv_bias, const float* table, float* ctx, int B, int H, int W,
+                               int C, int nH, int window, int shift, float scale, cudaStream_t stream) {
+  if (!qkv || !table || !ctx || B <= 0) return GED_ERR_ARG;
+  if (window != TW_WS || C != nH * TW_HD || H <= 0 || W <= 0 || shift < 0 || shift >= TW_WS) return GED_ERR_SHAPE;
+  if (!aligned16(qkv) || !aligned16(ctx) || (qkv_bias && !aligned16(qkv_bias))) return GED_ERR_ALIGN;
+  TwGeom g;
+  g.H = H; g.W = W; g.shift = shift;
+  g.Hp = cdiv(H, TW_WS) * TW_WS; g.Wp = cdiv(W, TW_WS) * TW_WS; g.nWx = g.Wp / TW_WS; g.nWin = (g.Hp / TW_WS) * g.nWx;
+  const int64_t pairs = (int64_t)B * g.nWin * nH;
+  if (pairs > 0x7fffffff) return GED_ERR_SHAPE;
+  if (cudaFuncSetAttribute(winattn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_TOTAL) != cudaSuccess) return GED_ERR_LAUNCH;
+  const int duos = (int)((pairs + 1) / 2);
+  const int grid = duos < 148 * 2 * 4 ? duos : 148 * 2 * 4;       // 2 CTAs per SM, a few duos each
+  winattn_tc_fwd_kernel<<<grid, TW_THREADS, W_TOTAL, stream>>>(qkv, qkv_bias, table, ctx, g, B, C, nH, scale, (int)pairs);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}

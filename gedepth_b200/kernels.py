@@ -38,6 +38,7 @@ SIGNATURES = {
     "ged_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I64, _I, _F, _P],
     "ged_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P],
     "ged_winattn_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    "ged_winattn_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "ged_winattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "ged_gemm_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _I, _P, _F, C.c_uint, _P, _P],
     "ged_dropout_bwd": [_P, _I64, _P, _P, _I64, _I, _F, C.c_uint, _P, _P],
@@ -455,6 +456,25 @@ def layer_norm_fork(x, w, b, eps):
     return _LayerNorm.apply(x, w, b, eps, _sink(w), _sink(b), True)
 
 
+# Forward of the 49 x 49 core on tcgen05 (csrc/winattn_tc.cu, 3xTF32) unless GEDEPTH_WINATTN_TC=0; the backward is the
+# SIMT kernel of csrc/winattn.cu (it recomputes P in fp32).
+WINATTN_TC = os.environ.get("GEDEPTH_WINATTN_TC", "1") != "0"
+_STD_INDEX = {}
+
+
+def _standard_rel_index(index: torch.Tensor) -> bool:
+    """True when `index` is Swin's relative-position index (dy + 6) * 13 + (dx + 6) (depthformer_swin.py:168-172), which the
+    tensor-core kernel evaluates in closed form.  Checked once per buffer (device -> host copy on first use)."""
+    key = (index.data_ptr(), index._version)
+    if key not in _STD_INDEX:
+        c = torch.arange(7)
+        yy, xx = torch.meshgrid(c, c, indexing="ij")
+        y, x = yy.reshape(-1), xx.reshape(-1)
+        want = (y[:, None] - y[None, :] + 6) * 13 + (x[:, None] - x[None, :] + 6)
+        _STD_INDEX[key] = tuple(index.shape) == (49, 49) and bool(torch.equal(index.detach().cpu().long(), want))
+    return _STD_INDEX[key]
+
+
 class _WinAttn(Function):
     @staticmethod
     def forward(ctx, qkv, qkv_bias, table, index, H, W, nH, ws, shift, scale, bias_sink=None, table_sink=None):
@@ -465,8 +485,12 @@ class _WinAttn(Function):
         ctx_out = torch.empty(B, Lt, Cc, dtype=torch.float32, device=qkv.device)
         idx = index if index.dtype == torch.int64 and index.is_contiguous() else index.long().contiguous()
         table_c = _f32c(table)
-        _call("ged_winattn_fwd", _p(qkv), _p(qkv_bias), _p(table_c), _p(idx), _p(ctx_out), B, H, W, Cc, nH, ws,
-              shift, float(scale), _stream())
+        if WINATTN_TC and _standard_rel_index(index):
+            _call("ged_winattn_tc_fwd", _p(qkv), _p(qkv_bias), _p(table_c), _p(ctx_out), B, H, W, Cc, nH, ws, shift,
+                  float(scale), _stream())
+        else:
+            _call("ged_winattn_fwd", _p(qkv), _p(qkv_bias), _p(table_c), _p(idx), _p(ctx_out), B, H, W, Cc, nH, ws,
+                  shift, float(scale), _stream())
         ctx.save_for_backward(qkv, qkv_bias if qkv_bias is not None else torch.empty(0, device=qkv.device),
                               table_c, idx)
         ctx.cfg = (B, H, W, Cc, nH, ws, shift, float(scale), qkv_bias is not None)

@@ -107,6 +107,11 @@ int ged_winattn_fwd(const float* qkv, const float* qkv_bias, const float* table,
                     float* ctx, int B, int H, int W, int C, int nH, int window, int shift, float scale,
                     cudaStream_t stream);
 /* g_qkv overwritten; g_bias (3C, may be NULL) and g_table (169,nH) accumulated. */
+/* ged_winattn_fwd on the tensor cores (csrc/winattn_tc.cu): two (window, head) pairs per work item, S = Q K^T and O = P V
+ * as tcgen05.mma (3xTF32, accumulators in TMEM), softmax one accumulator row per thread.  The relative-position index is
+ * Swin's closed form (dy + 6) * 13 + (dx + 6) (depthformer_swin.py:168-172). */
+int ged_winattn_tc_fwd(const float* qkv, const float* qkv_bias, const float* table, float* ctx, int B, int H, int W, int C,
+                       int nH, int window, int shift, float scale, cudaStream_t stream);
 int ged_winattn_bwd(const float* qkv, const float* qkv_bias, const float* table, const long long* index,
                     const float* g_ctx, float* g_qkv, float* g_bias, float* g_table, int B, int H, int W,
                     int C, int nH, int window, int shift, float scale, cudaStream_t stream);

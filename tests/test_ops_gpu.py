@@ -232,11 +232,18 @@ def test_layernorm_fwd_bwd(rows, C):
         _close(p.grad, q.grad, 1e-4, 2e-5 * float(q.grad.abs().max()), n)
 
 
-@pytest.mark.parametrize("B,H,W,nH,shift", [(2, 16, 40, 3, 0), (2, 16, 40, 3, 3), (1, 9, 21, 6, 3), (2, 7, 7, 12, 0), (1, 18, 42, 3, 3)])
-def test_window_attention_fwd_bwd(B, H, W, nH, shift):
+@pytest.mark.parametrize("core", ["tcgen05", "simt"])
+@pytest.mark.parametrize("B,H,W,nH,shift", [(2, 16, 40, 3, 0), (2, 16, 40, 3, 3), (1, 9, 21, 6, 3), (2, 7, 7, 12, 0), (1, 18, 42, 3, 3),
+                                            (2, 11, 35, 24, 3), (1, 11, 35, 48, 0), (3, 12, 20, 3, 3), (1, 88, 280, 3, 3)])
+def test_window_attention_fwd_bwd(B, H, W, nH, shift, core, monkeypatch):
+    """`tcgen05`: the forward of the 49 x 49 core on the tensor cores (csrc/winattn_tc.cu, 3xTF32 - what the path runs);
+    `simt`: the fp32 SIMT forward (csrc/winattn.cu).  The backward is the SIMT kernel either way.  11 x 35 (stage 3 at
+    352 x 1120, padded to 14 x 35) and 12 x 20 maps exercise padding tokens whose q = k = v = the qkv bias; odd pair
+    counts exercise the half-empty last work item."""
     from gedepth_b200 import kernels as K
     from tests import ops_lib as L
     from oracle import model as om
+    monkeypatch.setattr(K, "WINATTN_TC", core == "tcgen05")
     C = nH * 32
     g = torch.Generator().manual_seed(8)
     qkv0 = torch.randn(B, H * W, 3 * C, generator=g)
