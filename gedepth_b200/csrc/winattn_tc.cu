@@ -100,17 +100,91 @@ constexpr int W_PLO = 32768;
 constexpr int W_VHI = 65536;        // 2 x [64 keys][32 d] MN-major                                     16 KB
 constexpr int W_VLO = 81920;
 constexpr int W_MISC = 98304;       // barriers, TMEM base, token / label tables, bias tables
-constexpr int W_TOTAL = W_MISC + 4096 + 1024;
+constexpr int W_TOTAL = W_MISC + 6144 + 1024;
 
-struct TwMisc {
-  uint64_t bar_s, bar_o;
-  uint32_t tmem;
-  int tok[2][64];                   // image token of each row, -1 = padding row
+struct TwMeta {                     // per work item (double-buffered: producers fill the next one while consumers read this)
+  int tok[2][64];                   // image token of each row, -1 = zero-padded token, -2 = not a token (rows 49..63 / no pair)
   int lab[2][64];
   float tab[2][176];                // relative-position bias of the pair's head, by (dy + 6) * 13 + (dx + 6)
   int pair_b[2], pair_head[2], pair_valid[2];
 };
+struct TwMisc {
+  uint64_t bar_s, bar_o;
+  uint32_t tmem;
+  TwMeta meta[2];
+};
+constexpr int TW_ITEMS = 2 * TW_N * 3 * 8;                    // 16-byte chunks of Q, K, V of both pairs
+constexpr int TW_PROD = 128;                                  // producer threads (warps 4..7)
+constexpr int TW_ITERS = (TW_ITEMS + TW_PROD - 1) / TW_PROD;  // 19 chunks per producer thread
 
+// producers: tables of work item `duo`
+__device__ __forceinline__ void tw_prepare(TwMeta& m, const TwGeom& g, const float* __restrict__ table, int duo, int num_pairs,
+                                           int nH, int ptid) {
+  {
+    const int p = ptid >> 6, n = ptid & 63;
+    const int pair = duo * 2 + p;
+    const bool valid = pair < num_pairs;
+    const int head = valid ? pair % nH : 0, wlin = valid ? pair / nH : 0;
+    const int win = wlin % g.nWin, b = wlin / g.nWin;
+    int lab = 0, tok = -1;
+    if (valid && n < TW_N) tok = tw_token(g, win / g.nWx, win % g.nWx, n, lab);
+    m.tok[p][n] = (valid && n < TW_N) ? tok : -2;
+    m.lab[p][n] = lab;
+    if (n == 0) { m.pair_b[p] = b; m.pair_head[p] = head; m.pair_valid[p] = valid; }
+  }
+  for (int i = ptid; i < 2 * 169; i += TW_PROD) {
+    const int p = i / 169, e = i - p * 169, pair = duo * 2 + p;
+    m.tab[p][e] = pair < num_pairs ? __ldg(table + (int64_t)e * nH + pair % nH) : 0.f;
+  }
+}
+
+// producers: issue every global load of the work item (Q, K, V rows of both pairs) into registers
+__device__ __forceinline__ void tw_load(float4 (&v)[TW_ITERS], const TwMeta& m, const float* __restrict__ qkv,
+                                        const float* __restrict__ bias, int64_t L, int C, int ptid) {
+#pragma unroll
+  for (int it = 0; it < TW_ITERS; ++it) {
+    const int i = ptid + it * TW_PROD;
+    v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < TW_ITEMS) {
+      const int ck = i & 7, which = (i >> 3) % 3, r = (i >> 3) / 3;
+      const int p = r / TW_N, n = r - p * TW_N;
+      if (m.pair_valid[p]) {
+        const int tok = m.tok[p][n], col = which * C + m.pair_head[p] * TW_HD + ck * 4;
+        if (tok >= 0) v[it] = __ldg((const float4*)(qkv + ((int64_t)m.pair_b[p] * L + tok) * 3 * C + col));
+        else if (bias) v[it] = __ldg((const float4*)(bias + col));       // zero-padded token: q = k = v = bias
+      }
+    }
+  }
+}
+
+// producers: registers -> swizzled operand tiles, hi + lo
+__device__ __forceinline__ void tw_store(const float4 (&v)[TW_ITERS], uint8_t* smem, float scale, int ptid) {
+#pragma unroll
+  for (int it = 0; it < TW_ITERS; ++it) {
+    const int i = ptid + it * TW_PROD;
+    if (i >= TW_ITEMS) continue;
+    const int ck = i & 7, which = (i >> 3) % 3, r = (i >> 3) / 3;
+    const int p = r / TW_N, n = r - p * TW_N;
+    float4 x = v[it];
+    if (which == 0) {
+      x.x *= scale; x.y *= scale; x.z *= scale; x.w *= scale;
+      const uint32_t o = w_kmaj_chunk(p * 64 + n, ck);
+      *(float4*)(smem + W_QHI + o) = x; *(float4*)(smem + W_QLO + o) = w_lo4(x);
+    } else if (which == 1) {
+      const uint32_t o = p * 8192 + w_kmaj_chunk(n, ck);
+      *(float4*)(smem + W_KHI + o) = x; *(float4*)(smem + W_KLO + o) = w_lo4(x);
+    } else {
+      const uint32_t o = p * 8192 + w_mnmaj_chunk(n, ck);
+      *(float4*)(smem + W_VHI + o) = x; *(float4*)(smem + W_VLO + o) = w_lo4(x);
+    }
+  }
+}
+__device__ __forceinline__ void tw_producer_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void tw_cta_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+
+// Warp-specialised: warps 4..7 are PRODUCERS (tables, global loads of the NEXT work item into registers while the current
+// one is in the softmax, then registers -> operand tiles), warps 0..3 CONSUMERS (one accumulator row per thread: softmax
+// from TMEM, P back to shared memory, context rows out of TMEM); thread 0 issues the MMAs.
 __global__ void __launch_bounds__(TW_THREADS, 2) winattn_tc_fwd_kernel(
     const float* __restrict__ qkv, const float* __restrict__ bias, const float* __restrict__ table, float* __restrict__ ctx,
     TwGeom g, int B, int C, int nH, float scale, int num_pairs) {
@@ -118,6 +192,8 @@ __global__ void __launch_bounds__(TW_THREADS, 2) winattn_tc_fwd_kernel(
   uint8_t* smem = (uint8_t*)(((uintptr_t)w_smem_raw + 1023) & ~(uintptr_t)1023);
   TwMisc& ms = *reinterpret_cast<TwMisc*>(smem + W_MISC);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const bool producer = warp >= 4;
+  const int ptid = tid - 128;
   const int64_t L = (int64_t)g.H * g.W;
 
   if (tid == 0) {
@@ -135,166 +211,135 @@ __global__ void __launch_bounds__(TW_THREADS, 2) winattn_tc_fwd_kernel(
   w_fence_after();
   const uint32_t tmem = ms.tmem;
   const uint32_t sbase = w_smem_u32(smem);
-  uint32_t phase = 0;
 
-  for (int duo = blockIdx.x; duo * 2 < num_pairs; duo += gridDim.x) {
-    // ---- which pairs; token / label / bias tables ---------------------------------------------------------------
-    if (tid < 128) {
-      const int p = tid >> 6, n = tid & 63;
-      const int pair = duo * 2 + p;
-      const bool valid = pair < num_pairs;
-      const int head = valid ? pair % nH : 0, wlin = valid ? pair / nH : 0;
-      const int win = wlin % g.nWin, b = wlin / g.nWin;
-      int lab = 0, tok = -1;
-      if (valid && n < TW_N) tok = tw_token(g, win / g.nWx, win % g.nWx, n, lab);
-      ms.tok[p][n] = (valid && n < TW_N) ? tok : -2;         // -2: not a token at all (row / key 49..63 or no pair)
-      ms.lab[p][n] = lab;
-      if (n == 0) { ms.pair_b[p] = b; ms.pair_head[p] = head; ms.pair_valid[p] = valid; }
-    }
-    for (int i = tid; i < 2 * 169; i += TW_THREADS) {
-      const int p = i / 169, e = i - p * 169, pair = duo * 2 + p;
-      ms.tab[p][e] = pair < num_pairs ? __ldg(table + (int64_t)e * nH + pair % nH) : 0.f;
-    }
-    __syncthreads();
-    // ---- stage Q (scaled), K, V of both pairs: hi + lo, swizzled operand tiles --------------------------------------
-    {
-      // all global loads of the thread are issued before the first one is consumed (10 x 16 bytes in flight per thread)
-      constexpr int ITEMS = 2 * TW_N * 3 * 8, ITERS = (ITEMS + TW_THREADS - 1) / TW_THREADS;
-      float4 v[ITERS];
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int i = tid + it * TW_THREADS;
-        v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < ITEMS) {
-          const int ck = i & 7, which = (i >> 3) % 3, r = (i >> 3) / 3;
-          const int p = r / TW_N, n = r - p * TW_N;
-          if (ms.pair_valid[p]) {
-            const int tok = ms.tok[p][n], col = which * C + ms.pair_head[p] * TW_HD + ck * 4;
-            if (tok >= 0) v[it] = __ldg((const float4*)(qkv + ((int64_t)ms.pair_b[p] * L + tok) * 3 * C + col));
-            else if (bias) v[it] = __ldg((const float4*)(bias + col));       // zero-padded token: q = k = v = bias
-          }
-        }
-      }
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int i = tid + it * TW_THREADS;
-        if (i >= ITEMS) continue;
-        const int ck = i & 7, which = (i >> 3) % 3, r = (i >> 3) / 3;
-        const int p = r / TW_N, n = r - p * TW_N;
-        if (!ms.pair_valid[p]) continue;
-        float4 x = v[it];
-        if (which == 0) {
-          x.x *= scale; x.y *= scale; x.z *= scale; x.w *= scale;
-          const uint32_t o = w_kmaj_chunk(p * 64 + n, ck);
-          *(float4*)(smem + W_QHI + o) = x; *(float4*)(smem + W_QLO + o) = w_lo4(x);
-        } else if (which == 1) {
-          const uint32_t o = p * 8192 + w_kmaj_chunk(n, ck);
-          *(float4*)(smem + W_KHI + o) = x; *(float4*)(smem + W_KLO + o) = w_lo4(x);
-        } else {
-          const uint32_t o = p * 8192 + w_mnmaj_chunk(n, ck);
-          *(float4*)(smem + W_VHI + o) = x; *(float4*)(smem + W_VLO + o) = w_lo4(x);
-        }
-      }
-    }
-    w_fence_async();
-    __syncthreads();
-    // ---- S_p = [Q_A ; Q_B] . K_p^T  (3xTF32) ------------------------------------------------------------------------
-    if (tid == 0) {
-      w_fence_after();
-      constexpr uint32_t ids = w_idesc_tf32(128, 64, false, false);
-      const uint64_t qhi = w_desc_kmajor(sbase + W_QHI), qlo = w_desc_kmajor(sbase + W_QLO);
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const uint64_t khi = w_desc_kmajor(sbase + W_KHI + p * 8192), klo = w_desc_kmajor(sbase + W_KLO + p * 8192);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          w_mma_tf32(tmem + p * 64, qhi + 2 * k, khi + 2 * k, ids, k != 0);
-          w_mma_tf32(tmem + p * 64, qlo + 2 * k, khi + 2 * k, ids, 1u);
-          w_mma_tf32(tmem + p * 64, qhi + 2 * k, klo + 2 * k, ids, 1u);
-        }
-      }
-      w_commit(&ms.bar_s);
-    }
-    // ---- softmax: thread = accumulator row (warps 0..3 own TMEM lane quadrants 0..3) --------------------------------
-    const int row = tid & 127, rp = row >> 6, ri = row & 63;
-    if (warp < 4) {
-      w_mbar_wait(&ms.bar_s, phase);
-      w_fence_after();
-      float s[64];
-      w_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(rp * 64), (uint32_t*)s);
-      w_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(rp * 64 + 32), (uint32_t*)(s + 32));
-      const bool live = ri < TW_N && ms.pair_valid[rp];
-      float inv = 0.f;
-      if (live) {
-        const int yi = ri / TW_WS, xi = ri - yi * TW_WS, li = ms.lab[rp][ri];
-        const float* tb = ms.tab[rp];
-        const bool masked = g.shift > 0;
-        float mx = -3.0e38f;
-#pragma unroll
-        for (int j = 0; j < TW_N; ++j) {
-          const int yj = j / TW_WS, xj = j - yj * TW_WS;
-          float v = s[j] + tb[(yi - yj + 6) * 13 + (xi - xj + 6)];
-          if (masked && ms.lab[rp][j] != li) v += -100.0f;
-          s[j] = v;
-          mx = fmaxf(mx, v);
-        }
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < TW_N; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
-        inv = 1.f / sum;
-      }
-      // P row -> K-major operand tiles (2 K-blocks of 32 keys), hi + lo; padding rows / keys are zero
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        float4 v;
-        v.x = (live && 4 * c + 0 < TW_N) ? s[4 * c + 0] * inv : 0.f;
-        v.y = (live && 4 * c + 1 < TW_N) ? s[4 * c + 1] * inv : 0.f;
-        v.z = (live && 4 * c + 2 < TW_N) ? s[4 * c + 2] * inv : 0.f;
-        v.w = (live && 4 * c + 3 < TW_N) ? s[4 * c + 3] * inv : 0.f;
-        const uint32_t o = (c >> 3) * 16384 + w_kmaj_chunk(row, c & 7);
-        *(float4*)(smem + W_PHI + o) = v; *(float4*)(smem + W_PLO + o) = w_lo4(v);
-      }
+  if (producer) {
+    // ================= producers: separate loop so that their 19 x float4 of in-flight loads and the consumers' 64-float
+    // accumulator rows never share a register allocation; the three CTA barriers per work item pair up with the
+    // consumers' ones (bar.sync 2) =====================================================================================
+    float4 v[TW_ITERS];
+    tw_prepare(ms.meta[0], g, table, blockIdx.x, num_pairs, nH, ptid);
+    tw_producer_sync();
+    tw_load(v, ms.meta[0], qkv, bias, L, C, ptid);
+    int buf = 0;
+    for (int duo = blockIdx.x; duo * 2 < num_pairs; duo += gridDim.x, buf ^= 1) {
+      tw_store(v, smem, scale, ptid);
       w_fence_async();
+      tw_cta_sync();                                   // (A) operand tiles complete
+      const int nxt = duo + gridDim.x;
+      if (nxt * 2 < num_pairs) {                        // next work item: tables, then every global load in flight
+        tw_prepare(ms.meta[buf ^ 1], g, table, nxt, num_pairs, nH, ptid);
+        tw_producer_sync();
+        tw_load(v, ms.meta[buf ^ 1], qkv, bias, L, C, ptid);
+      }
+      tw_cta_sync();                                   // (B) P written
+      tw_cta_sync();                                   // (C) O read: tiles and TMEM are free
     }
-    w_fence_before();
-    __syncthreads();
-    // ---- O_p = [P_A ; P_B] . V_p  (3xTF32) --------------------------------------------------------------------------
-    if (tid == 0) {
-      w_fence_after();
-      constexpr uint32_t ido = w_idesc_tf32(128, 32, false, true);
+  } else {
+    uint32_t phase = 0;
+    int buf = 0;
+    const int row = tid, rp = row >> 6, ri = row & 63;
+    for (int duo = blockIdx.x; duo * 2 < num_pairs; duo += gridDim.x, buf ^= 1) {
+      const TwMeta& m = ms.meta[buf];
+      tw_cta_sync();                                   // (A)
+      // ---- S_p = [Q_A ; Q_B] . K_p^T  (3xTF32) ----------------------------------------------------------------------
+      if (tid == 0) {
+        w_fence_after();
+        constexpr uint32_t ids = w_idesc_tf32(128, 64, false, false);
+        const uint64_t qhi = w_desc_kmajor(sbase + W_QHI), qlo = w_desc_kmajor(sbase + W_QLO);
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const uint64_t vhi = w_desc_mnmajor(sbase + W_VHI + p * 8192, 8192), vlo = w_desc_mnmajor(sbase + W_VLO + p * 8192, 8192);
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t phi = w_desc_kmajor(sbase + W_PHI + kb * 16384), plo = w_desc_kmajor(sbase + W_PLO + kb * 16384);
+        for (int p = 0; p < 2; ++p) {
+          const uint64_t khi = w_desc_kmajor(sbase + W_KHI + p * 8192), klo = w_desc_kmajor(sbase + W_KLO + p * 8192);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint32_t ks = 64u * (uint32_t)(kb * 4 + k);       // 8 keys = two 512-byte atoms of the MN-major V tile
-            w_mma_tf32(tmem + 128 + p * 32, phi + 2 * k, vhi + ks, ido, (kb | k) != 0);
-            w_mma_tf32(tmem + 128 + p * 32, plo + 2 * k, vhi + ks, ido, 1u);
-            w_mma_tf32(tmem + 128 + p * 32, phi + 2 * k, vlo + ks, ido, 1u);
+            w_mma_tf32(tmem + p * 64, qhi + 2 * k, khi + 2 * k, ids, k != 0);
+            w_mma_tf32(tmem + p * 64, qlo + 2 * k, khi + 2 * k, ids, 1u);
+            w_mma_tf32(tmem + p * 64, qhi + 2 * k, klo + 2 * k, ids, 1u);
           }
         }
+        w_commit(&ms.bar_s);
       }
-      w_commit(&ms.bar_o);
-    }
-    if (warp < 4) {
+      __syncwarp();
+      // ---- softmax: thread = accumulator row (warps 0..3 own TMEM lane quadrants 0..3) ------------------------------
+      w_mbar_wait(&ms.bar_s, phase);
+      w_fence_after();
+      {
+        float s[64];
+        w_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(rp * 64), (uint32_t*)s);
+        w_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(rp * 64 + 32), (uint32_t*)(s + 32));
+        const bool live = ri < TW_N && m.pair_valid[rp];
+        float inv = 0.f;
+        if (live) {
+          const int yi = ri / TW_WS, xi = ri - yi * TW_WS, li = m.lab[rp][ri];
+          const float* tb = m.tab[rp];
+          const bool masked = g.shift > 0;
+          float mx = -3.0e38f;
+#pragma unroll
+          for (int j = 0; j < TW_N; ++j) {
+            const int yj = j / TW_WS, xj = j - yj * TW_WS;
+            float x = s[j] + tb[(yi - yj + 6) * 13 + (xi - xj + 6)];
+            if (masked && m.lab[rp][j] != li) x += -100.0f;
+            s[j] = x;
+            mx = fmaxf(mx, x);
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < TW_N; ++j) { s[j] = exp2f((s[j] - mx) * 1.4426950408889634f); sum += s[j]; }
+          inv = 1.f / sum;
+        }
+        // P row -> K-major operand tiles (2 K-blocks of 32 keys), hi + lo; padding rows / keys are zero
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          float4 x;
+          x.x = (live && 4 * c + 0 < TW_N) ? s[4 * c + 0] * inv : 0.f;
+          x.y = (live && 4 * c + 1 < TW_N) ? s[4 * c + 1] * inv : 0.f;
+          x.z = (live && 4 * c + 2 < TW_N) ? s[4 * c + 2] * inv : 0.f;
+          x.w = (live && 4 * c + 3 < TW_N) ? s[4 * c + 3] * inv : 0.f;
+          const uint32_t o = (c >> 3) * 16384 + w_kmaj_chunk(row, c & 7);
+          *(float4*)(smem + W_PHI + o) = x; *(float4*)(smem + W_PLO + o) = w_lo4(x);
+        }
+      }
+      w_fence_async();
+      w_fence_before();
+      tw_cta_sync();                                   // (B)
+      // ---- O_p = [P_A ; P_B] . V_p  (3xTF32) ------------------------------------------------------------------------
+      if (tid == 0) {
+        w_fence_after();
+        constexpr uint32_t ido = w_idesc_tf32(128, 32, false, true);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const uint64_t vhi = w_desc_mnmajor(sbase + W_VHI + p * 8192, 8192), vlo = w_desc_mnmajor(sbase + W_VLO + p * 8192, 8192);
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t phi = w_desc_kmajor(sbase + W_PHI + kb * 16384), plo = w_desc_kmajor(sbase + W_PLO + kb * 16384);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t ks = 64u * (uint32_t)(kb * 4 + k);       // 8 keys = two 512-byte atoms of the MN-major V tile
+              w_mma_tf32(tmem + 128 + p * 32, phi + 2 * k, vhi + ks, ido, (kb | k) != 0);
+              w_mma_tf32(tmem + 128 + p * 32, plo + 2 * k, vhi + ks, ido, 1u);
+              w_mma_tf32(tmem + 128 + p * 32, phi + 2 * k, vlo + ks, ido, 1u);
+            }
+          }
+        }
+        w_commit(&ms.bar_o);
+      }
+      __syncwarp();
       w_mbar_wait(&ms.bar_o, phase);
       w_fence_after();
-      float o[32];
-      w_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(128 + rp * 32), (uint32_t*)o);
-      const int tok = ms.tok[rp][ri];
-      if (tok >= 0) {                                            // padded rows are cropped away (:354-355)
-        float4* dst = (float4*)(ctx + ((int64_t)ms.pair_b[rp] * L + tok) * C + ms.pair_head[rp] * TW_HD);
+      {
+        float o[32];
+        w_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(128 + rp * 32), (uint32_t*)o);
+        const int tok = m.tok[rp][ri];
+        if (tok >= 0) {                                            // padded rows are cropped away (:354-355)
+          float4* dst = (float4*)(ctx + ((int64_t)m.pair_b[rp] * L + tok) * C + m.pair_head[rp] * TW_HD);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+          for (int c = 0; c < 8; ++c) dst[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+        }
       }
+      phase ^= 1;
+      w_fence_before();
+      tw_cta_sync();                                   // (C) TMEM and the operand tiles are free for the next work item
+      w_fence_after();
     }
-    phase ^= 1;
-    w_fence_before();
-    __syncthreads();          // TMEM and the operand tiles are free for the next duo
-    w_fence_after();
   }
   w_fence_before();
   __syncthreads();
