@@ -642,19 +642,23 @@ def ground_embed_probe(c, pk, Bn, H, W):
             out["ge_adaptive_fwd_inference"] = dict(bytes_per_px=24, us=t * 1e6, achieved=24.0 * px / t / 1e9)
             t = timeit(lambda: kernels.ground_plane_into(img, (-1.578, -1.464e-5, -1.386e-3, 0.2589)), reps)
             out["ground_plane"] = dict(bytes_per_px=8, us=t * 1e6, achieved=8.0 * px / t / 1e9)
-        with torch.enable_grad():
-            yh.requires_grad_(True)
-            lh.requires_grad_(True)
-            t = timeit(lambda: kernels.ge_adaptive(img, yh, lh, 1.65, 200.0), reps)
-            out["ge_adaptive_fwd_train"] = dict(bytes_per_px=68, us=t * 1e6, achieved=68.0 * px / t / 1e9)
-            y, pm = kernels.ge_vanilla(img, yh)
-            gy, gpm = torch.randn_like(y), torch.randn_like(pm)
-            t = timeit(lambda: torch.autograd.grad((y, pm), yh, (gy, gpm), retain_graph=True), reps)
-            out["ge_vanilla_bwd"] = dict(bytes_per_px=13, us=t * 1e6, achieved=13.0 * px / t / 1e9)
-            y, pm, lf = kernels.ge_adaptive(img, yh, lh, 1.65, 200.0)
-            gy, gpm, glf = torch.randn_like(y), torch.randn_like(pm), torch.randn_like(lf)
-            t = timeit(lambda: torch.autograd.grad((y, pm, lf), (yh, lh), (gy, gpm, glf), retain_graph=True), reps)
-            out["ge_adaptive_bwd"] = dict(bytes_per_px=59 + 12.0 / 4, us=t * 1e6, achieved=(59.0 + 3.0) * px / t / 1e9)
+        # training-mode forward (full-resolution logits written) and the two backward kernels, straight through the C ABI
+        # on preallocated tensors (through autograd the host-side launch overhead would be timed, not the kernel)
+        from gedepth_b200.kernels import _call, _p, _stream
+        y, pm = torch.empty(Bx, 1, Hx, Wx, device=c.dev), torch.empty(Bx, 1, Hx, Wx, device=c.dev)
+        lf = torch.empty(Bx, 11, Hx, Wx, device=c.dev)
+        gy, gpm, glf = torch.randn_like(y), torch.randn_like(pm), torch.randn_like(lf)
+        g_yh, g_lh = torch.empty_like(yh), torch.empty_like(lh)
+        h2, w2, bs = Hx // 2, Wx // 2, 5 * Hx * Wx
+        t = timeit(lambda: _call("ged_ge_adaptive_fwd", _p(img[:, 4]), bs, _p(yh), _p(lh), None, 1.65, 200.0, _p(y), _p(pm), _p(lf),
+                                 Bx, Hx, Wx, h2, w2, _stream()), reps)
+        out["ge_adaptive_fwd_train"] = dict(bytes_per_px=68, us=t * 1e6, achieved=68.0 * px / t / 1e9)
+        t = timeit(lambda: _call("ged_ge_vanilla_bwd", _p(img[:, 3]), bs, _p(gy), _p(gpm), _p(g_yh), Bx, Hx, Wx, h2, w2, _stream()), reps)
+        out["ge_vanilla_bwd"] = dict(bytes_per_px=13, us=t * 1e6, achieved=13.0 * px / t / 1e9)
+        t = timeit(lambda: _call("ged_ge_adaptive_bwd", _p(img[:, 4]), bs, _p(yh), _p(lh), None, 1.65, 200.0, _p(gy), _p(gpm), _p(glf),
+                                 _p(g_yh), _p(g_lh), Bx, Hx, Wx, h2, w2, _stream()), reps)
+        out["ge_adaptive_bwd"] = dict(bytes_per_px=62.0, us=t * 1e6, achieved=62.0 * px / t / 1e9,
+                                      note="12 B/px of g_y, g_pe_mask, pe + 44 B/px of g_logits + 3 + 3 B/px of half-resolution operands / outputs")
         for v in out.values():
             v["frac"] = v["achieved"] / pk["hbm"]
         return out

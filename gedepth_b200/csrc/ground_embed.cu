@@ -148,6 +148,82 @@ __global__ void __launch_bounds__(TX * TILE_H) ge_vanilla_bwd_kernel(
                            false, sw);
 }
 
+// a14 backward when the full-resolution map is EXACTLY twice the half-resolution one (every GE config: 352 x 1120 over
+// 176 x 560, 384 x 640 over 192 x 320).  align_corners=False x2 upsampling has the closed form
+//     out[2j] = 0.25 in[j-1] + 0.75 in[j],  out[2j+1] = 0.75 in[j] + 0.25 in[j+1]   (edges: out[0] = in[0], out[2n-1] = in[n-1])
+// so its adjoint is a 4 x 4 GATHER per half-resolution pixel with weights (0.25, 0.75, 0.75, 0.25) per axis - no
+// search over candidate taps, no atomics, no zero-fill.  A thread produces two neighbouring half-resolution pixels of
+// one row from 4 rows x (one aligned float4 + the two columns beside it) of each operand.
+__device__ __forceinline__ void x2_weights(int j, int n, float (&w)[4]) {
+  w[0] = j >= 1 ? 0.25f : 0.f;
+  w[1] = j >= 1 ? 0.75f : 1.f;
+  w[2] = j <= n - 2 ? 0.75f : 1.f;
+  w[3] = j <= n - 2 ? 0.25f : 0.f;
+}
+// Separable: a CTA owns X2_H half-resolution rows x 128 columns.  Pass 1: every full-resolution row of the footprint is
+// read ONCE with aligned float4 loads (a lane's left / right neighbour columns come from its neighbours by warp
+// shuffle), G = g_y + g_pe_mask * pe * 200 is formed and contracted along x into shared memory; pass 2 contracts along y.
+constexpr int X2_H = 8;
+__global__ void __launch_bounds__(256) ge_vanilla_bwd_x2_kernel(
+    const float* __restrict__ pe_norm, int64_t pe_bstride, const float* __restrict__ g_y,
+    const float* __restrict__ g_pe_mask, float* __restrict__ g_y_half, int H, int W, int h2, int w2) {
+  __shared__ float2 s_t[2 * X2_H + 2][64];
+  const int tx = threadIdx.x, ty = threadIdx.y, lane = tx & 31;
+  const int t = blockIdx.x * 64 + tx;                    // pair of half-resolution columns 2t, 2t+1
+  const int jy0 = blockIdx.y * X2_H, b = blockIdx.z;
+  const int64_t HW = (int64_t)H * W;
+  const int c0 = 4 * t;
+  const bool col_ok = c0 < W;
+  float wxa[4], wxb[4];
+  x2_weights(2 * t, w2, wxa);
+  x2_weights(2 * t + 1, w2, wxb);
+  for (int r = ty; r < 2 * X2_H + 2; r += 4) {
+    const int oy = 2 * jy0 - 1 + r;
+    float2 acc = make_float2(0.f, 0.f);
+    const bool row_ok = oy >= 0 && oy < H;                // warp-uniform
+    float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t row = (int64_t)oy * W;
+    const float* pp = pe_norm + (int64_t)b * pe_bstride + row;
+    const float* gy = g_y ? g_y + b * HW + row : nullptr;
+    const float* gm = g_pe_mask ? g_pe_mask + b * HW + row : nullptr;
+    if (row_ok && col_ok) {
+      const float4 p4 = __ldg((const float4*)(pp + c0));
+      const float4 y4 = gy ? ldg_stream((const float4*)(gy + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 m4 = gm ? ldg_stream((const float4*)(gm + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      G = make_float4(y4.x + m4.x * p4.x * 200.f, y4.y + m4.y * p4.y * 200.f, y4.z + m4.z * p4.z * 200.f,
+                      y4.w + m4.w * p4.w * 200.f);
+    }
+    float left = __shfl_up_sync(0xffffffffu, G.w, 1), right = __shfl_down_sync(0xffffffffu, G.x, 1);
+    if (row_ok && col_ok) {
+      if (lane == 0) left = c0 >= 1 ? (gy ? __ldg(gy + c0 - 1) : 0.f) + (gm ? __ldg(gm + c0 - 1) * __ldg(pp + c0 - 1) * 200.f : 0.f) : 0.f;
+      if (lane == 31) right = c0 + 4 < W ? (gy ? __ldg(gy + c0 + 4) : 0.f) + (gm ? __ldg(gm + c0 + 4) * __ldg(pp + c0 + 4) * 200.f : 0.f) : 0.f;
+      if (c0 + 4 >= W) right = 0.f;
+      acc.x = wxa[0] * left + wxa[1] * G.x + wxa[2] * G.y + wxa[3] * G.z;
+      acc.y = wxb[0] * G.y + wxb[1] * G.z + wxb[2] * G.w + wxb[3] * right;
+    }
+    s_t[r][tx] = acc;
+  }
+  __syncthreads();
+  if (2 * t >= w2) return;
+  const bool has_b = 2 * t + 1 < w2;
+#pragma unroll
+  for (int k = 0; k < X2_H / 4; ++k) {
+    const int jl = ty + 4 * k, jy = jy0 + jl;
+    if (jy >= h2) break;
+    float wy[4];
+    x2_weights(jy, h2, wy);
+    float2 o = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const float2 v = s_t[2 * jl + a][tx];
+      o.x += wy[a] * v.x; o.y += wy[a] * v.y;
+    }
+    float* dst = g_y_half + ((int64_t)b * h2 + jy) * w2 + 2 * t;
+    if (has_b && ((((uintptr_t)dst) & 7) == 0)) *(float2*)dst = o;
+    else { dst[0] = o.x; if (has_b) dst[1] = o.y; }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // a15: Adaptive.  Per pixel: L = up(logits_half) (11 bins), theta = sum softmax(L) * (c-5),
 // k = tan(theta deg), a = -h/(pe+1e-8), off = -h/((a-k)+1e-8), m = [0 < off <= depth_scale],
@@ -498,6 +574,14 @@ GED_API int ged_ge_vanilla_bwd(const float* pe_norm, int64_t pe_batch_stride, co
   if (!pe_norm || !g_y_half || B <= 0) return GED_ERR_ARG;
   if (!half_shape_ok(H, W, h2, w2)) return GED_ERR_SHAPE;
   const float sy = resize_scale(h2, H, false), sx = resize_scale(w2, W, false);
+  if (H == 2 * h2 && W == 2 * w2 && (W % 4 == 0) && (pe_batch_stride % 4 == 0) && aligned16(pe_norm) &&
+      (!g_y || aligned16(g_y)) && (!g_pe_mask || aligned16(g_pe_mask))) {
+    // exact x2: closed-form gather (every GE config)
+    dim3 block(64, 4), grid(cdiv(cdiv(w2, 2), 64), cdiv(h2, X2_H), B);
+    ge_vanilla_bwd_x2_kernel<<<grid, block, 0, stream>>>(pe_norm, pe_batch_stride, g_y, g_pe_mask, g_y_half, H, W, h2, w2);
+    GED_CHECK_LAUNCH();
+    return GED_OK;
+  }
   if (cudaMemsetAsync(g_y_half, 0, sizeof(float) * (size_t)B * h2 * w2, stream) != cudaSuccess) return GED_ERR_LAUNCH;
   dim3 block(TX, TILE_H), grid(cdiv(W, TILE_W), cdiv(H, TILE_H), B);
   ge_vanilla_bwd_kernel<<<grid, block, 0, stream>>>(pe_norm, pe_batch_stride, g_y, g_pe_mask, g_y_half, H, W, h2, w2, sy, sx);

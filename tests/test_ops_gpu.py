@@ -103,7 +103,7 @@ def _ge_inputs(B, H, W, adaptive, seed=0):
     return torch.from_numpy(b["img"]), y_half, logits_half
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 64, 160), (1, 70, 166), (3, 35, 83), (2, 352, 1120)])
+@pytest.mark.parametrize("B,H,W", [(2, 64, 160), (1, 70, 166), (3, 35, 83), (2, 352, 1120), (1, 4, 8), (2, 6, 12), (1, 384, 640)])
 def test_ge_vanilla_fwd_bwd(B, H, W):
     from gedepth_b200 import kernels as K
     from tests import ops_lib as L
