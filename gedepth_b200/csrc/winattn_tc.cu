@@ -179,8 +179,9 @@ __device__ __forceinline__ void tw_store(const float4 (&v)[TW_ITERS], uint8_t* s
     }
   }
 }
-__device__ __forceinline__ void tw_producer_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-__device__ __forceinline__ void tw_cta_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+// named barriers (non-.aligned form: producer and consumer warps reach them from different program points)
+__device__ __forceinline__ void tw_producer_sync() { __syncwarp(); asm volatile("barrier.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void tw_cta_sync() { __syncwarp(); asm volatile("barrier.sync 2, 256;" ::: "memory"); }
 
 // Warp-specialised: warps 4..7 are PRODUCERS (tables, global loads of the NEXT work item into registers while the current
 // one is in the softmax, then registers -> operand tiles), warps 0..3 CONSUMERS (one accumulator row per thread: softmax

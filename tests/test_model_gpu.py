@@ -72,6 +72,45 @@ def test_train_step_matches_reference(name):
     assert all(ops.native_table()[k] for k in ("ge_vanilla", "ge_adaptive", "fuse_head", "silog", "linear", "conv2d"))
 
 
+@pytest.mark.parametrize("name", ["vanilla_train", "adaptive_train"])
+def test_fp32_accurate_backward_matches_reference_gradients(name, monkeypatch):
+    """GEDEPTH_BWD_GEMM_PASSES=3: dX / dW GEMMs in 3xTF32 and the fp32 deformable-attention backward.  Every gradient norm
+    must then agree with the reference's to 2e-3 (measured: <= 1.3e-3; the default one-pass TF32 backward is held to 2e-2 in
+    test_train_step_matches_reference), the head-side full gradients to 1e-3 of their largest entry (measured 5e-5).
+    Gradients that pass through the deformable-attention sampling LOCATIONS (offsets, reference points, level embedding,
+    everything upstream of the queries) are differences of neighbouring value rows: the 2^-21 relative error of the
+    3xTF32 value_proj is amplified by |v| / |v01 - v00| there, which bounds them at ~5e-3 of the largest entry."""
+    from gedepth_b200 import kernels
+    monkeypatch.setattr(kernels, "BACKWARD_PASSES", 3)
+    case, g, b = load_case(name)
+    model, _ = build_host_model(case, DEV)
+    model.train()
+    data = dict(img=torch.from_numpy(b["img"]).to(DEV), img_metas=metas_for(case),
+                depth_gt=torch.from_numpy(b["depth_gt"]).to(DEV))
+    if "pe_k_gt" in b:
+        data["pe_k_gt"] = torch.from_numpy(b["pe_k_gt"]).to(DEV)
+    out = model.train_step(data, None)
+    out["loss"].backward()
+    params = dict(model.named_parameters())
+    worst = {}
+    for k in g.files:
+        if k.startswith("grad."):
+            got = params[k[5:]].grad.cpu().numpy()
+            worst[k[5:]] = float(np.abs(got - g[k]).max() / np.abs(g[k]).max())
+    print(name, {k: f"{v:.1e}" for k, v in worst.items()})
+    for k, v in worst.items():
+        # reference_points.weight sums d(bilinear sample)/d(location) over 10^7 samples; fp32 location differences at cell
+        # borders (a piecewise-constant derivative) are not a GEMM-precision effect
+        assert v < (1e-3 if k.startswith(("decode_head", "pe_mask_neck")) else 1e-2), (k, v)
+    gn = dict(zip(g["grad_names"].tolist(), g["grad_norms"].tolist()))
+    top = max(gn.values())
+    for n, p in params.items():
+        if n in ZERO_GRAD_KEYS:
+            continue
+        err = abs(float(p.grad.double().norm()) - gn[n]) / (gn[n] + 1e-3 * top)
+        assert err < 2e-3, (n, err)
+
+
 @pytest.mark.parametrize("name", ["vanilla_eval_ragged", "adaptive_eval", "vanilla_eval_k8"])
 def test_inference_matches_reference(name):
     from oracle import ground as og
