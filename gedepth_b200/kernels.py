@@ -465,7 +465,7 @@ _STD_INDEX = {}
 def _standard_rel_index(index: torch.Tensor) -> bool:
     """True when `index` is Swin's relative-position index (dy + 6) * 13 + (dx + 6) (depthformer_swin.py:168-172), which the
     tensor-core kernel evaluates in closed form.  Checked once per buffer (device -> host copy on first use)."""
-    key = (index.data_ptr(), index._version)
+    key = index.data_ptr()          # a registered buffer filled once at construction (depthformer_swin.py:168-172)
     if key not in _STD_INDEX:
         c = torch.arange(7)
         yy, xx = torch.meshgrid(c, c, indexing="ij")

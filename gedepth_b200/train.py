@@ -35,11 +35,30 @@ def cosine_warmup_lr(step: int, base_lr: float = 1e-4, max_iters: int = 1600 * 4
     return lr
 
 
+def completion_group(name: str) -> int:
+    """Order in which the gradients of the path's parameters become FINAL during the backward (it runs head -> PE necks
+    -> neck -> Swin stage 3 -> 2 -> 1 -> 0 / patch embedding / stem): 0 decode head + PE necks, 1 HAHI neck, 2..4 Swin
+    stages 3..1 (with their output LayerNorms), 5 the rest of the backbone.  The arena keeps each group contiguous so
+    that a group can be all-reduced as soon as the backward has passed it."""
+    parts = name.split(".")
+    if parts[0] == "neck":
+        return 1
+    if parts[0] == "backbone":
+        if parts[1] == "stages" and parts[2].isdigit() and int(parts[2]) in (1, 2, 3):
+            return 2 + (3 - int(parts[2]))
+        if parts[1].startswith("norm") and parts[1][4:].isdigit() and int(parts[1][4:]) in (1, 2, 3):
+            return 2 + (3 - int(parts[1][4:]))
+        return 5
+    return 0
+
+
 class FlatArena:
-    """All parameters (and their gradients) of a model as views into two contiguous fp32 buffers."""
+    """All parameters (and their gradients) of a model as views into two contiguous fp32 buffers, laid out group by
+    group in the order their gradients complete (``completion_group``); ``group_ranges`` lists (group, start, end)."""
 
     def __init__(self, model: torch.nn.Module):
         params = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        params = [np_ for _, np_ in sorted(enumerate(params), key=lambda t: (completion_group(t[1][0]), t[0]))]
         self.names = [n for n, _ in params]
         self.params = [p for _, p in params]
         dev = self.params[0].device
@@ -49,7 +68,13 @@ class FlatArena:
         self.flat_g = torch.zeros(self.total, dtype=torch.float32, device=dev)
         self.wd_mask = torch.ones(self.total, dtype=torch.uint8, device=dev)
         off = 0
+        self.group_ranges = []
         for (n, p), sz in zip(params, sizes):
+            gidx = completion_group(n)
+            if self.group_ranges and self.group_ranges[-1][0] == gidx:
+                self.group_ranges[-1][2] = off + sz
+            else:
+                self.group_ranges.append([gidx, off, off + sz])
             view = self._segment(self.flat_p, off, p)
             view.copy_(p.data)
             p.data = view
@@ -76,7 +101,7 @@ class FlatArena:
 
 class Trainer:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_norm=35.0,
-                 native_optimizer: bool = True, lr_schedule=None):
+                 native_optimizer: bool = True, lr_schedule=None, overlap_allreduce: bool = True):
         """lr_schedule: None (constant lr) or a callable step -> lr (e.g. ``cosine_warmup_lr``).  The step's learning
         rate lives in a device scalar that is refreshed before every step, eager or replayed, so a captured CUDA graph
         follows the schedule (and ``trainer.lr = x`` takes effect on the next step)."""
@@ -99,9 +124,68 @@ class Trainer:
         if os.environ.get("GEDEPTH_DW_STREAM", "0") == "1" and self.arena.flat_p.is_cuda:
             self._dw_side = dict(stream=torch.cuda.Stream(), keep=[])
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        # gradient all-reduce sliced by completion group and launched from autograd hooks while the backward is still
+        # running (replaces the bucketed overlap of MMDistributedDataParallel, depth/apis/train.py:58-67)
+        self.overlap = bool(overlap_allreduce) and self.world > 1 and os.environ.get("GEDEPTH_OVERLAP_ALLREDUCE", "1") != "0"
+        self._works, self._launched = [], set()
+        if self.overlap:
+            self._install_overlap_hooks()
         self._graph = None
         self._static = None
         self._static_loss = None
+
+    # ---- overlapped all-reduce ---------------------------------------------------------------------------------------
+    def _reduce_group(self, gidx: int):
+        """All-reduce the arena slice of one completion group on NCCL's stream (async): everything the backward has
+        launched so far is ordered before it; the optimizer waits for all slices."""
+        if gidx in self._launched:
+            return
+        self._launched.add(gidx)
+        for g, s_, e_ in self.arena.group_ranges:
+            if g == gidx:
+                self._works.append(dist.all_reduce(self.arena.flat_g[s_:e_], async_op=True))
+
+    def _watch(self, tensors, gidx: int):
+        """When every tensor of `tensors` has received its gradient, the groups up to `gidx` are final."""
+        if not (self.overlap and torch.is_grad_enabled()):
+            return
+        ts = [t for t in tensors if torch.is_tensor(t) and t.requires_grad]
+        if not ts:
+            return
+        state = {"left": len(ts)}
+
+        def hook(grad):
+            state["left"] -= 1
+            if state["left"] == 0:
+                for g in range(gidx + 1):
+                    self._reduce_group(g)
+            return None
+        for t in ts:
+            t.register_hook(hook)
+
+    def _install_overlap_hooks(self):
+        m = self.model
+        if not (hasattr(m, "neck") and hasattr(m, "backbone")):
+            self.overlap = False
+            return
+        m.neck.register_forward_hook(lambda mod, inp, out: self._watch(out, 0))            # head + PE necks done
+        m.backbone.register_forward_hook(lambda mod, inp, out: self._watch(out, 1))        # + neck done
+        stages = getattr(m.backbone, "stages", None)
+        if stages is not None and len(stages) == 4:
+            for i in (3, 2, 1):                                                            # + Swin stage i done
+                stages[i].register_forward_pre_hook(lambda mod, inp, i=i: self._watch(inp[:1], 2 + (3 - i)))
+
+    def _finish_allreduce(self):
+        if self.world <= 1:
+            return
+        if not self.overlap:
+            dist.all_reduce(self.arena.flat_g)            # ONE collective per step, NCCL over NVLink
+            return
+        for g in sorted({r[0] for r in self.arena.group_ranges}):
+            self._reduce_group(g)                          # whatever the hooks have not launched yet (at least group 5)
+        for w in self._works:
+            w.wait()
+        self._works, self._launched = [], set()
 
     def _refresh_lr(self):
         """Host -> device copy of this step's learning rate (a memcpy on the current stream, never captured)."""
@@ -117,6 +201,7 @@ class Trainer:
         if not torch.cuda.is_current_stream_capturing() if self.arena.flat_p.is_cuda else True:
             self._refresh_lr()
         self.arena.zero_grad()
+        self._works, self._launched = [], set()
         losses = self.model(**data_batch)
         loss, log_vars = self.model._parse_losses(losses, sync=sync_logs)
         kernels.DW_SIDE = self._dw_side
@@ -127,8 +212,8 @@ class Trainer:
         if self._dw_side is not None:               # join: every dW has landed in the arena before it is reduced / read
             torch.cuda.current_stream().wait_stream(self._dw_side["stream"])
             self._dw_side["keep"].clear()
-        if self.world > 1:
-            dist.all_reduce(self.arena.flat_g)            # ONE collective per step, NCCL over NVLink
+        self.early_groups = sorted(self._launched)      # groups whose all-reduce was launched from inside the backward
+        self._finish_allreduce()
         self.step_idx += 1
         self.step_dev.add_(1)
         kernels.sumsq(self.arena.flat_g, self.sumsq)

@@ -47,7 +47,9 @@ def test_arena_decay_mask_follows_custom_keys():
     m = _model()
     arena = FlatArena(m)
     off = 0
-    for n, p in m.named_parameters():
+    byname = dict(m.named_parameters())
+    for n in arena.names:                       # arena order: completion groups, registration order inside a group
+        p = byname[n]
         sz = (p.numel() + 3) // 4 * 4
         want = 0 if any(k in n for k in NO_DECAY_KEYS) else 1
         assert int(arena.wd_mask[off]) == want and int(arena.wd_mask[off + p.numel() - 1]) == want, n
@@ -58,3 +60,11 @@ def test_arena_decay_mask_follows_custom_keys():
     # LayerNorms and relative-position tables are exempt; BatchNorm parameters are decayed
     idx = {n: i for i, n in enumerate(arena.names)}
     assert idx  # names recorded in arena order
+    # completion groups are contiguous and ordered: head + PE necks, neck, Swin stages 3, 2, 1, rest of the backbone
+    groups = [g for g, _, _ in arena.group_ranges]
+    assert groups == sorted(groups) and groups[0] == 0 and groups[-1] == 5 and len(set(groups)) == len(groups)
+    assert arena.group_ranges[0][1] == 0 and arena.group_ranges[-1][2] == arena.total
+    from gedepth_b200.train import completion_group
+    assert completion_group("decode_head.conv_depth.weight") == 0 and completion_group("neck.level_embed") == 1
+    assert completion_group("backbone.stages.3.blocks.0.norm1.weight") == 2 and completion_group("backbone.norm2.bias") == 3
+    assert completion_group("backbone.stages.0.blocks.0.norm1.weight") == 5 and completion_group("backbone.bn1.weight") == 5

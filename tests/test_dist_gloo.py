@@ -33,7 +33,7 @@ def _inject_cpu_ops():
         out.copy_(flat_g.double().pow(2).sum().reshape(1))
         return out
 
-    def adamw_step(p, g, m, v, wd_mask, ss, max_norm, grad_scale, lr, b1, b2, eps, wd, step, step_dev=None):
+    def adamw_step(p, g, m, v, wd_mask, ss, max_norm, grad_scale, lr, b1, b2, eps, wd, step, step_dev=None, lr_dev=None):
         coef = grad_scale * min(max_norm / (float(ss.sqrt()) * grad_scale + 1e-6), 1.0)
         gi = g * coef
         p.mul_(torch.where(wd_mask.bool(), 1 - lr * wd, 1.0))
@@ -81,6 +81,7 @@ def _worker(rank, world, port, out):
         out["loss_logged"] = logs["loss"]
         out["loss_local"] = float(loss)
         out["wd_frac"] = float(tr.arena.wd_mask.float().mean())
+        out["early_groups"] = list(tr.early_groups)
     dist.destroy_process_group()
 
 
@@ -91,6 +92,9 @@ def test_two_rank_step_equals_averaged_gradients():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert out["same_params"], "ranks diverged after the all-reduced step"
+    # the all-reduce is sliced by completion group and launched from autograd hooks: head + PE necks, neck and the Swin
+    # stages 3..1 were already in flight when the backward returned (group 5 = rest of the backbone goes last)
+    assert out["early_groups"] == [0, 1, 2, 3, 4], out["early_groups"]
     assert 0.9 < out["wd_frac"] < 1.0        # LayerNorm / rel-pos-bias tensors are exempt from decay
     # single-process reference: average the two shards' gradients, same update.  Same CPU thread count as
     # the workers: with B=1 the train-mode BatchNorms see <= 10 values per channel at the deepest level, so
