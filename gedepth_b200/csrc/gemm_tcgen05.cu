@@ -810,7 +810,8 @@ static int dispatch(int bn, const CUtensorMap& ma, const CUtensorMap& mb, GemmPa
 }
 
 
-static int g_pair = 1;        // 1 = use the CTA-pair kernel for large problems, 0 = never
+static int g_pair = 2;        // 2 = CTA-pair kernel for large problems in both arithmetic modes (measured: one-pass dX GEMMs
+                              // 45.4 -> 38.1 ms in config 3), 1 = for 3xTF32 only, 0 = never
 
 template <int BN, int STAGES, bool SPLIT>
 static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
@@ -838,7 +839,7 @@ static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams
 // the operand bytes each SM stages and re-reads); no gain for single-pass TF32 (already ~600 TFLOP/s on the wide
 // single-CTA tiles), for 64-column outputs (the A operand dominates) or for problems with fewer tiles than SM pairs.
 static int pick_bn_pair(int M, int N) {
-  if (!g_pair || g_precision != 3 || N < 128) return 0;
+  if (!g_pair || (g_precision != 3 && g_pair != 2) || N < 128) return 0;     // g_pair == 2: also for one-pass TF32 (A/B switch)
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
   const int cands[3] = {256, 192, 128};
   for (int i = 0; i < 3; ++i) {
@@ -922,10 +923,11 @@ GED_API int ged_set_gemm_precision(int passes) {
   return prev;
 }
 
-// 1 = CTA-pair (cta_group::2) kernel for large forward / dX problems (default), 0 = single-CTA kernels only.
+// 2 = CTA-pair (cta_group::2) kernel for large forward / dX problems in both arithmetic modes (default), 1 = for the
+// 3xTF32 arithmetic only, 0 = single-CTA kernels only.
 GED_API int ged_set_gemm_pair(int on) {
   const int prev = g_pair;
-  g_pair = on ? 1 : 0;
+  g_pair = on == 2 ? 2 : (on ? 1 : 0);
   return prev;
 }
 

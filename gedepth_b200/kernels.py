@@ -565,9 +565,10 @@ def gemm(a2d: torch.Tensor, w: torch.Tensor, bias=None, act=None, slope=0.01, re
 DW_MODE = int(os.environ.get("GEDEPTH_DW_MODE", "1"))
 
 
-def set_gemm_pair(on: bool) -> int:
-    """CTA-pair (cta_group::2) GEMM kernel for large problems on/off; returns the previous setting."""
-    return load().ged_set_gemm_pair(int(bool(on)))
+def set_gemm_pair(on) -> int:
+    """CTA-pair (cta_group::2) GEMM kernel for large problems: 2 = both arithmetic modes (default), 1 = 3xTF32 only,
+    0 = off; returns the previous setting."""
+    return load().ged_set_gemm_pair(int(on))
 
 
 def set_gemm_wide_tiles(on: bool) -> int:
