@@ -229,38 +229,7 @@ __global__ void __launch_bounds__(256) ge_vanilla_bwd_x2_kernel(
 // k = tan(theta deg), a = -h/(pe+1e-8), off = -h/((a-k)+1e-8), m = [0 < off <= depth_scale],
 // pe_mask = off*m*y.
 // ---------------------------------------------------------------------------------------------
-struct SlopeEval {
-  float p[NSLOPE];
-  float theta, k, den, off, m;
-};
-
-__device__ __forceinline__ void slope_eval(const float* L, float pe, float h, float depth_scale,
-                                           SlopeEval& e) {
-  float mx = L[0];
-#pragma unroll
-  for (int c = 1; c < NSLOPE; ++c) mx = fmaxf(mx, L[c]);
-  float sum = 0.f;
-#pragma unroll
-  for (int c = 0; c < NSLOPE; ++c) { e.p[c] = __expf(L[c] - mx); sum += e.p[c]; }
-  const float inv = 1.f / sum;
-  float th = 0.f;
-#pragma unroll
-  for (int c = 0; c < NSLOPE; ++c) { e.p[c] *= inv; th += e.p[c] * (float)(c - 5); }
-  e.theta = th;
-  // |theta| <= 5 degrees (a convex combination of the bins): tan by its series, exact to fp32 for |x| <= 0.0873
-  const float xr = th * 0.017453292519943295f, x2 = xr * xr;
-  e.k = xr * (1.f + x2 * (0.33333333333f + x2 * (0.13333333333f + x2 * 0.05396825397f)));
-  const float a = -h / (pe + 1e-8f);
-  e.den = (a - e.k) + 1e-8f;
-  e.off = -h / e.den;
-  // in-place thresholds of encoder_decoder.py:97-100: <0 -> 0, >depth_scale -> 0, >0 -> 1
-  // (a NaN offset survives all three and poisons the pixel exactly as in the reference)
-  float mm = e.off;
-  if (mm < 0.f) mm = 0.f;
-  if (mm > depth_scale) mm = 0.f;
-  if (mm > 0.f) mm = 1.f;
-  e.m = mm;
-}
+// SlopeEval / slope_eval: tile.cuh (shared with ge_adaptive_x2.cu)
 
 // LOGITS: also write the 11 full-resolution logits (training: CE loss input).  A thread takes 4 pixels of one row
 // spaced TX apart, so a warp covers 32 CONSECUTIVE pixels: every global access is one coalesced 128-byte segment
@@ -518,7 +487,18 @@ __global__ void __launch_bounds__(256) find_k_kernel(const float* __restrict__ g
 
 }  // namespace ged
 
+namespace ged {
+// ge_adaptive_x2.cu: exact x2 kernels; 0 = launched, 1 = not eligible (generic kernels below), < 0 = error
+int launch_ge_adaptive_fwd_x2(const float*, int64_t, const float*, const float*, const float*, float, float, float*, float*,
+                              float*, int, int, int, int, int, cudaStream_t);
+int launch_ge_adaptive_bwd_x2(const float*, int64_t, const float*, const float*, const float*, float, float, const float*,
+                              const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
+}  // namespace ged
+
 using namespace ged;
+
+static int g_ge_x2 = 1;      // 1 = closed-form x2 kernels whenever the shape allows (default), 0 = generic kernels only (A/B, tests)
+GED_API int ged_set_ge_x2(int on) { const int prev = g_ge_x2; g_ge_x2 = on ? 1 : 0; return prev; }
 
 // ============================================================================================
 // C-ABI (include/gedepth.h)
@@ -574,7 +554,7 @@ GED_API int ged_ge_vanilla_bwd(const float* pe_norm, int64_t pe_batch_stride, co
   if (!pe_norm || !g_y_half || B <= 0) return GED_ERR_ARG;
   if (!half_shape_ok(H, W, h2, w2)) return GED_ERR_SHAPE;
   const float sy = resize_scale(h2, H, false), sx = resize_scale(w2, W, false);
-  if (H == 2 * h2 && W == 2 * w2 && (W % 4 == 0) && (pe_batch_stride % 4 == 0) && aligned16(pe_norm) &&
+  if (g_ge_x2 && H == 2 * h2 && W == 2 * w2 && (W % 4 == 0) && (pe_batch_stride % 4 == 0) && aligned16(pe_norm) &&
       (!g_y || aligned16(g_y)) && (!g_pe_mask || aligned16(g_pe_mask))) {
     // exact x2: closed-form gather (every GE config)
     dim3 block(64, 4), grid(cdiv(cdiv(w2, 2), 64), cdiv(h2, X2_H), B);
@@ -596,6 +576,11 @@ GED_API int ged_ge_adaptive_fwd(const float* pe_raw, int64_t pe_batch_stride, co
   if (!pe_raw || !y_half || !logits_half || !y || !pe_mask || B <= 0) return GED_ERR_ARG;
   if (!half_shape_ok(H, W, h2, w2)) return GED_ERR_SHAPE;
   if ((W % 4 == 0) && !(aligned16(y) && aligned16(pe_mask) && (!logits_full || aligned16(logits_full)))) return GED_ERR_ALIGN;
+  if (g_ge_x2) {
+    const int rc = launch_ge_adaptive_fwd_x2(pe_raw, pe_batch_stride, y_half, logits_half, height, height_scalar, depth_scale, y,
+                                             pe_mask, logits_full, B, H, W, h2, w2, stream);
+    if (rc <= 0) return rc;
+  }
   const float sy = resize_scale(h2, H, false), sx = resize_scale(w2, W, false);
   dim3 block(TX, TILE_H), grid(cdiv(W, TILE_W), cdiv(H, TILE_H), B);
   if (logits_full)
@@ -614,12 +599,14 @@ GED_API int ged_ge_adaptive_bwd(const float* pe_raw, int64_t pe_batch_stride, co
   if (!pe_raw || !y_half || !logits_half || !g_y_half || !g_logits_half || B <= 0) return GED_ERR_ARG;
   if (!half_shape_ok(H, W, h2, w2)) return GED_ERR_SHAPE;
   const float sy = resize_scale(h2, H, false), sx = resize_scale(w2, W, false);
-  const size_t smem = sizeof(float) * ((NSLOPE + 1) * TILE_H * (TILE_W + 1) + ST_H * ST_W + NSLOPE * ST_H * ST_W);
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(ge_adaptive_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return GED_ERR_LAUNCH;
-    attr_set = true;
+  if (g_ge_x2) {
+    const int rc = launch_ge_adaptive_bwd_x2(pe_raw, pe_batch_stride, y_half, logits_half, height, height_scalar, depth_scale, g_y,
+                                             g_pe_mask, g_logits_full, g_y_half, g_logits_half, B, H, W, h2, w2, stream);
+    if (rc <= 0) return rc;
   }
+  const size_t smem = sizeof(float) * ((NSLOPE + 1) * TILE_H * (TILE_W + 1) + ST_H * ST_W + NSLOPE * ST_H * ST_W);
+  // the attribute is per device: set it on every call (cheap), not once per process
+  if (cudaFuncSetAttribute(ge_adaptive_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return GED_ERR_LAUNCH;
   if (cudaMemsetAsync(g_y_half, 0, sizeof(float) * (size_t)B * h2 * w2, stream) != cudaSuccess) return GED_ERR_LAUNCH;
   if (cudaMemsetAsync(g_logits_half, 0, sizeof(float) * (size_t)B * NSLOPE * h2 * w2, stream) != cudaSuccess) return GED_ERR_LAUNCH;
   dim3 block(TX, TILE_H), grid(cdiv(W, TILE_W), cdiv(H, TILE_H), B);

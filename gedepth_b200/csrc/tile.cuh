@@ -83,4 +83,40 @@ __device__ __forceinline__ void tile_adjoint_upsample(
 }
 
 
+// a15 per-pixel evaluation (encoder_decoder.py:84-100): softmax over the 11 slope bins, expected slope, tan,
+// inverse-depth shift, range mask.
+struct SlopeEval {
+  float p[NSLOPE];
+  float theta, k, den, off, m;
+};
+
+__device__ __forceinline__ void slope_eval(const float* L, float pe, float h, float depth_scale,
+                                           SlopeEval& e) {
+  float mx = L[0];
+#pragma unroll
+  for (int c = 1; c < NSLOPE; ++c) mx = fmaxf(mx, L[c]);
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < NSLOPE; ++c) { e.p[c] = __expf(L[c] - mx); sum += e.p[c]; }
+  const float inv = 1.f / sum;
+  float th = 0.f;
+#pragma unroll
+  for (int c = 0; c < NSLOPE; ++c) { e.p[c] *= inv; th += e.p[c] * (float)(c - 5); }
+  e.theta = th;
+  // |theta| <= 5 degrees (a convex combination of the bins): tan by its series, exact to fp32 for |x| <= 0.0873
+  const float xr = th * 0.017453292519943295f, x2 = xr * xr;
+  e.k = xr * (1.f + x2 * (0.33333333333f + x2 * (0.13333333333f + x2 * 0.05396825397f)));
+  const float a = -h / (pe + 1e-8f);
+  e.den = (a - e.k) + 1e-8f;
+  e.off = -h / e.den;
+  // in-place thresholds of encoder_decoder.py:97-100: <0 -> 0, >depth_scale -> 0, >0 -> 1
+  // (a NaN offset survives all three and poisons the pixel exactly as in the reference)
+  float mm = e.off;
+  if (mm < 0.f) mm = 0.f;
+  if (mm > depth_scale) mm = 0.f;
+  if (mm > 0.f) mm = 1.f;
+  e.m = mm;
+}
+
+
 }  // namespace ged

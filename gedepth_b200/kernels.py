@@ -71,6 +71,7 @@ SIGNATURES = {
     "ged_set_gemm_precision": [_I],
     "ged_set_gemm_wide_tiles": [_I],
     "ged_set_gemm_pair": [_I],
+    "ged_set_ge_x2": [_I],
     "ged_set_msda_variant": [_I],
     "ged_gemm_dw_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I64, _I64, _I, _P, _I, _P],
     "ged_depth_metrics": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P],
@@ -563,6 +564,11 @@ def gemm(a2d: torch.Tensor, w: torch.Tensor, bias=None, act=None, slope=0.01, re
 # Weight gradients: 1 = tcgen05 on the operands as stored (MN-major UMMA descriptors, split-K partials accumulated
 # with vector atomics), 0 = library (cuBLAS / cuDNN wgrad; kept as an A/B switch for the tests).
 DW_MODE = int(os.environ.get("GEDEPTH_DW_MODE", "1"))
+
+
+def set_ge_x2(on: bool) -> int:
+    """Closed-form x2 ground-embedding kernels (default on) vs the generic bilinear ones; returns the previous setting."""
+    return load().ged_set_ge_x2(int(bool(on)))
 
 
 def set_gemm_pair(on) -> int:

@@ -63,6 +63,9 @@ int ged_ge_adaptive_bwd(const float* pe_raw, int64_t pe_batch_stride, const floa
                         float depth_scale, const float* g_y, const float* g_pe_mask,
                         const float* g_logits_full, float* g_y_half, float* g_logits_half, int B, int H,
                         int W, int h2, int w2, cudaStream_t stream);
+/* 1 (default): when H == 2*h2 and W == 2*w2 (every GE config) the Vanilla backward and both Adaptive kernels run their
+ * closed-form x2 versions (csrc/ge_adaptive_x2.cu); 0: generic bilinear kernels only.  Returns the previous setting. */
+int ged_set_ge_x2(int on);
 
 /* depth/models/decode_heads/decode_head.py:489-508.  d = relu(conv_depth(feat)) (B,1,h2,w2);
  * out = d*(1-y_h) + pe_h + min_depth with y_h, pe_h = bilinear(align_corners=True) of y, pe_mask. */

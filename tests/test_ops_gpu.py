@@ -124,7 +124,9 @@ def test_ge_vanilla_fwd_bwd(B, H, W):
     _close(yh1.grad, yh2.grad, 1e-4, 1e-4 * float(yh2.grad.abs().max()), "g_y_half")
 
 
-@pytest.mark.parametrize("B,H,W,per_sample_h", [(2, 64, 160, False), (1, 70, 166, True), (2, 352, 1120, False)])
+@pytest.mark.parametrize("B,H,W,per_sample_h", [(2, 64, 160, False), (1, 70, 166, True), (2, 352, 1120, False), (1, 4, 8, False),
+                                                 (2, 6, 12, True), (3, 36, 84, True), (1, 14, 520, False), (1, 384, 640, True),
+                                                 (2, 30, 244, False)])
 def test_ge_adaptive_fwd_bwd(B, H, W, per_sample_h):
     from gedepth_b200 import kernels as K
     from tests import ops_lib as L
@@ -152,6 +154,50 @@ def test_ge_adaptive_fwd_bwd(B, H, W, per_sample_h):
         d = (p.grad - q.grad).abs()
         tol = 2e-3 * float(q.grad.abs().max()) + 1e-3 * q.grad.abs()
         assert float((d > tol).float().mean()) < 1e-4, (n, float(d.max()), float(q.grad.abs().max()))
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 160), (1, 352, 1120), (2, 30, 244)])
+def test_ge_adaptive_x2_equals_generic(B, H, W):
+    """The closed-form x2 kernels (csrc/ge_adaptive_x2.cu) against the generic bilinear ones on the same inputs, including
+    logits whose neighbours differ by hundreds (the forward's bound on the softmax maximum underflows there and the exact
+    per-pixel path takes over) and camera-plane values at / beyond the thresholds (0, inf, negative)."""
+    from gedepth_b200 import kernels as K
+    img, y_half, logits_half = _ge_inputs(B, H, W, True, seed=3)
+    g = torch.Generator().manual_seed(11)
+    logits_half[:, :, : H // 4] *= 150.0                       # wild logits in the upper half
+    img[:, 4, :, : W // 8] = 0.0
+    img[:, 4, :, W // 8: W // 4] = float("inf")
+    img[:, 4, :, W // 4: W // 3] *= -1.0
+    img_d = img.to(DEV)
+    outs = {}
+    for x2 in (1, 0):
+        prev = K.set_ge_x2(x2)
+        try:
+            a = [t.to(DEV).requires_grad_(True) for t in (y_half, logits_half)]
+            y, pm, lf = K.ge_adaptive(img_d, a[0], a[1], 1.65, 200.0)
+            gy, gpm, glf = (torch.randn(y.shape, generator=g).to(DEV), torch.randn(pm.shape, generator=g).to(DEV) * 0.1,
+                            torch.randn(lf.shape, generator=g).to(DEV) * 0.01)
+            g.manual_seed(11)
+            ((y * gy).sum() + (pm * gpm).sum() + (lf * glf).sum()).backward()
+            with torch.no_grad():
+                y_i, pm_i, _ = K.ge_adaptive(img_d, a[0], a[1], 1.65, 200.0, want_logits=False)
+            outs[x2] = (y, pm, lf, a[0].grad, a[1].grad, y_i, pm_i)
+        finally:
+            K.set_ge_x2(prev)
+    y1, pm1, lf1, gy1, gl1, yi1, pmi1 = outs[1]
+    y0, pm0, lf0, gy0, gl0, yi0, pmi0 = outs[0]
+    assert torch.equal(y1, yi1) and torch.equal(torch.nan_to_num(pm1, 7.0), torch.nan_to_num(pmi1, 7.0))   # LOGITS on / off
+    _close(y1, y0, 1e-6, 1e-6, "y")
+    _close(lf1, lf0, 1e-5, 1e-4, "logits")
+    assert torch.equal(torch.isnan(pm1), torch.isnan(pm0))
+    bad = ((pm1 - pm0).abs() > 2e-3 + 2e-4 * pm0.abs()) & ~torch.isnan(pm0)
+    assert float(bad.float().mean()) < 2e-5, float(bad.float().mean())      # hard range mask: threshold pixels may flip
+    for n, p, q in (("g_y_half", gy1, gy0), ("g_logits_half", gl1, gl0)):
+        fin = torch.isfinite(q) & torch.isfinite(p)
+        assert float((torch.isfinite(q) != torch.isfinite(p)).float().mean()) < 1e-4
+        d = (p - q).abs()[fin]
+        tol = 2e-3 * float(q[fin].abs().max()) + 1e-3 * q[fin].abs()
+        assert float((d > tol).float().mean()) < 1e-4, (n, float(d.max()), float(q[fin].abs().max()))
 
 
 @pytest.mark.parametrize("B,H,W", [(2, 64, 160), (1, 70, 166), (2, 352, 1120)])
