@@ -17,6 +17,8 @@
 //             full-resolution row segment and contracts them along x (neighbour columns by warp shuffle) into shared
 //             memory; phase 2 contracts along y.  A CTA is one warp wide (32 four-pixel slots, the outer two are halo
 //             slots that are evaluated but not emitted), so no contraction crosses a warp.
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include "common.cuh"
 #include "tile.cuh"
 
@@ -77,22 +79,35 @@ __device__ __forceinline__ void x2w(int j, int n, float (&w)[4]) {
 // forward
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int AX_HW = 128;               // half-resolution columns per CTA (256 full-resolution columns)
-constexpr int AX_HH = 8;                 // half-resolution rows per CTA (16 full-resolution rows)
-constexpr int AX_PITCH = AX_HW + 4;      // staged columns k0-2 .. k0+129 (pairs stay 8-byte aligned)
-constexpr int AX_ROWS = AX_HH + 2;       // staged rows jy0-1 .. jy0+8
-constexpr int AX_CH = NSLOPE + 2;        // 11 logits, y, -log2(e) * channel maximum
-constexpr int AX_TILE = AX_CH * AX_ROWS * AX_PITCH;          // floats
-constexpr int AX_SMEM = (AX_TILE + 2 * AX_HH * 2 * AX_HW) * 4;   // + the camera-plane tile (16 x 256 full-resolution pixels)
+constexpr int AX_HH = 4;                 // half-resolution rows per CTA (8 full-resolution rows): 4 CTAs of 128 threads per SM, so
+                                         // one tile is always in flight while others compute
+constexpr int AX_THREADS = 32 * AX_HH;   // 64 x AX_HH/2 threads, 16 pixels each
+constexpr int AX_PITCH = AX_HW + 8;      // staged columns k0-4 .. k0+131 (rows are whole 16-byte units: one TMA box)
+constexpr int AX_ROWS = AX_HH + 2;       // staged rows jy0-1 .. jy0+AX_HH
+constexpr int AX_CHF = AX_ROWS * AX_PITCH;                   // floats per staged channel
+// shared-memory map (bytes; every TMA destination 128-byte aligned)
+constexpr int AX_OFF_Y = ((NSLOPE * AX_CHF * 4 + 127) / 128) * 128;
+constexpr int AX_OFF_M = AX_OFF_Y + ((AX_CHF * 4 + 127) / 128) * 128;
+constexpr int AX_OFF_PE = AX_OFF_M + ((AX_CHF * 4 + 127) / 128) * 128;
+constexpr int AX_OFF_BAR = AX_OFF_PE + 2 * AX_HH * 2 * AX_HW * 4;
+constexpr int AX_SMEM = AX_OFF_BAR + 16;
+
+struct AxMaps { CUtensorMap logits, yh, pe; };     // {w2, h2, B*11} / {w2, h2, B} / {W, H, B}
+
+__device__ __forceinline__ void ax_tma3(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               :: "r"(dst), "l"((uint64_t)map), "r"(bar), "r"(x), "r"(y), "r"(z) : "memory");
+}
 
 // off * m of one pixel with the exact softmax maximum, from the staged tile (rare path of the forward kernel)
 __device__ __noinline__ float exact_pixel(const float* smem, int oy, int ox, int jy0, int k0, int h2, int w2, float pe, float h,
                                           float depth_scale) {
   const Tap tyy = tap(oy, 0.5f, false, h2), txx = tap(ox, 0.5f, false, w2);
-  const int r0 = tyy.i0 - (jy0 - 1), r1 = tyy.i1 - (jy0 - 1), c0 = txx.i0 - (k0 - 2), c1 = txx.i1 - (k0 - 2);
+  const int r0 = tyy.i0 - (jy0 - 1), r1 = tyy.i1 - (jy0 - 1), c0 = txx.i0 - (k0 - 4), c1 = txx.i1 - (k0 - 4);
   float Lx[NSLOPE];
 #pragma unroll
   for (int ch = 0; ch < NSLOPE; ++ch) {
-    const float* sp = smem + ch * (AX_ROWS * AX_PITCH);
+    const float* sp = smem + ch * AX_CHF;
     Lx[ch] = tyy.l0 * (txx.l0 * sp[r0 * AX_PITCH + c0] + txx.l1 * sp[r0 * AX_PITCH + c1]) +
              tyy.l1 * (txx.l0 * sp[r1 * AX_PITCH + c0] + txx.l1 * sp[r1 * AX_PITCH + c1]);
   }
@@ -101,26 +116,52 @@ __device__ __noinline__ float exact_pixel(const float* smem, int oy, int ox, int
   return e.off * e.m;
 }
 
-template <bool LOGITS>
-__global__ void __launch_bounds__(256, 2) ge_adaptive_fwd_x2_kernel(
-    const float* __restrict__ pe_raw, int64_t pe_bstride, const float* __restrict__ y_half,
+// TMA: the three tiles (11 logit planes, y, camera plane) arrive as three bulk tensor copies issued by one thread (rows of
+// the half-resolution maps must be 16-byte multiples: W % 8 == 0); otherwise 8 / 16-byte asynchronous copies by all threads.
+// NAT: pixel pairs in memory order (0,1)(2,3) - needed where the interpolated logits are stored; otherwise the pairs are
+// (0,3)(1,2), which lets the horizontal pass run two columns per instruction as well.
+template <bool LOGITS, bool TMA>
+__global__ void __launch_bounds__(AX_THREADS, 512 / AX_THREADS) ge_adaptive_fwd_x2_kernel(
+    const __grid_constant__ AxMaps maps, const float* __restrict__ pe_raw, int64_t pe_bstride, const float* __restrict__ y_half,
     const float* __restrict__ logits_half, const float* __restrict__ height, float height_scalar, float depth_scale,
     float* __restrict__ y, float* __restrict__ pe_mask, float* __restrict__ logits_full, int H, int W, int h2, int w2) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* smem = (float*)smem_raw;
+  float* s_y = (float*)(smem_raw + AX_OFF_Y);
+  float* s_m = (float*)(smem_raw + AX_OFF_M);
+  float* s_pe = (float*)(smem_raw + AX_OFF_PE);                // [2 AX_HH][2 AX_HW]
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 64 + tx;
   const int b = blockIdx.z, jy0 = blockIdx.y * AX_HH, k0 = blockIdx.x * AX_HW;
-  const int64_t hw2 = (int64_t)h2 * w2, HW = (int64_t)H * W;
+  const int hw2 = h2 * w2;
+  const int64_t HW = (int64_t)H * W;
 
-  // stage the half-resolution tile (+1 row / +2 columns of halo) pair by pair and the camera-plane tile, asynchronously;
-  // out-of-range pairs are zero-filled and only ever meet a zero weight.
-  float* s_pe = smem + AX_TILE;                              // [2 AX_HH][2 AX_HW]
-  {
+  if (TMA) {
+    const uint32_t bar = smem_u32(smem_raw + AX_OFF_BAR);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                   :: "r"(bar), "r"((NSLOPE + 1) * AX_CHF * 4 + 2 * AX_HH * 2 * AX_HW * 4) : "memory");
+      ax_tma3(smem_u32(smem), &maps.logits, bar, k0 - 4, jy0 - 1, b * NSLOPE);
+      ax_tma3(smem_u32(s_y), &maps.yh, bar, k0 - 4, jy0 - 1, b);
+      ax_tma3(smem_u32(s_pe), &maps.pe, bar, 2 * k0, 2 * jy0, b);
+    }
+    __syncthreads();                                           // the barrier is initialised before anyone polls it
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "AXW_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra AXD_%=;\n\t"
+        "bra AXW_%=;\n\t"
+        "AXD_%=:\n\t}" :: "r"(bar) : "memory");
+  } else {
+    // out-of-range pairs are zero-filled and only ever meet a zero weight
     const uint32_t s0 = smem_u32(smem);
     const float* lsrc = logits_half + (int64_t)b * NSLOPE * hw2;
-    const float* ysrc = y_half + b * hw2;
-    for (int i = tid; i < AX_ROWS * (AX_PITCH / 2); i += 256) {
+    const float* ysrc = y_half + (int64_t)b * hw2;
+    for (int i = tid; i < AX_ROWS * (AX_PITCH / 2); i += AX_THREADS) {
       const int r = i / (AX_PITCH / 2), pr = i - r * (AX_PITCH / 2);
-      const int j = jy0 - 1 + r, k = k0 - 2 + 2 * pr;
+      const int j = jy0 - 1 + r, k = k0 - 4 + 2 * pr;
       const bool ok = j >= 0 && j < h2 && k >= 0 && k < w2;
       const int so = ok ? j * w2 + k : 0;
       const int nb = ok ? 8 : 0;
@@ -129,12 +170,12 @@ __global__ void __launch_bounds__(256, 2) ge_adaptive_fwd_x2_kernel(
 #pragma unroll
       for (int ch = 0; ch < NSLOPE; ++ch) {
         cp_async8(dst, src, nb);
-        dst += AX_ROWS * AX_PITCH * 4; src += hw2;
+        dst += AX_CHF * 4; src += hw2;
       }
-      cp_async8(dst, ysrc + so, nb);
+      cp_async8(smem_u32(s_y) + (r * AX_PITCH + 2 * pr) * 4, ysrc + so, nb);
     }
     const float* psrc = pe_raw + (int64_t)b * pe_bstride;
-    for (int i = tid; i < 2 * AX_HH * (2 * AX_HW / 4); i += 256) {
+    for (int i = tid; i < 2 * AX_HH * (2 * AX_HW / 4); i += AX_THREADS) {
       const int r = i >> 6, c4 = i & 63;
       const int oy = 2 * jy0 + r, ox = 2 * k0 + 4 * c4;
       const bool ok = oy < H && ox < W;
@@ -142,19 +183,26 @@ __global__ void __launch_bounds__(256, 2) ge_adaptive_fwd_x2_kernel(
     }
     cp_async_commit();
     cp_async_wait<0>();
+    __syncthreads();
   }
-  __syncthreads();
-  // the per-pixel channel maximum becomes a 13th channel (scaled by -log2 e)
-  for (int i = tid; i < AX_ROWS * (AX_PITCH / 2); i += 256) {
-    const int r = i / (AX_PITCH / 2), pr = i - r * (AX_PITCH / 2);
-    const float* sp = smem + r * AX_PITCH + 2 * pr;
-    float2 mx = *(const float2*)sp;
+  // per half-resolution pixel: -log2(e) * (maximum over the 11 channels); +inf outside the map (never the minimum below)
+  for (int i = tid; i < AX_ROWS * (AX_PITCH / 4); i += AX_THREADS) {
+    const int r = i / (AX_PITCH / 4), q = i - r * (AX_PITCH / 4);
+    const int j = jy0 - 1 + r, k = k0 - 4 + 4 * q;
+    const float* sp = smem + r * AX_PITCH + 4 * q;
+    float4 mx = *(const float4*)sp;
 #pragma unroll
     for (int ch = 1; ch < NSLOPE; ++ch) {
-      const float2 v = *(const float2*)(sp + ch * (AX_ROWS * AX_PITCH));
-      mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y);
+      const float4 v = *(const float4*)(sp + ch * AX_CHF);
+      mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
     }
-    *(float2*)(smem + (NSLOPE + 1) * (AX_ROWS * AX_PITCH) + r * AX_PITCH + 2 * pr) = make_float2(-kLog2e * mx.x, -kLog2e * mx.y);
+    const bool rok = j >= 0 && j < h2;
+    float4 o;
+    o.x = rok && k >= 0 && k < w2 ? -kLog2e * mx.x : INFINITY;
+    o.y = rok && k + 1 >= 0 && k + 1 < w2 ? -kLog2e * mx.y : INFINITY;
+    o.z = rok && k + 2 >= 0 && k + 2 < w2 ? -kLog2e * mx.z : INFINITY;
+    o.w = rok && k + 3 >= 0 && k + 3 < w2 ? -kLog2e * mx.w : INFINITY;
+    *(float4*)(s_m + r * AX_PITCH + 4 * q) = o;
   }
   __syncthreads();
 
@@ -162,44 +210,59 @@ __global__ void __launch_bounds__(256, 2) ge_adaptive_fwd_x2_kernel(
   const int t = blockIdx.x * 64 + tx;                  // half-resolution columns 2t, 2t+1 -> full-resolution columns 4t .. 4t+3
   if (ja >= h2 || 4 * t >= W) return;
   const bool two = ja + 1 < h2;                        // rows 2, 3 exist
-  // vertical weights of output row r over staged rows (r+1)/2 and (r+1)/2 + 1, as packed pairs
-  u64 wv[4][2];
+  // vertical weights of output row r over staged rows (r+1)/2 and (r+1)/2 + 1 (the packed operations broadcast them)
+  float wv[4][2];
   {
     const bool top = ja > 0, mid = ja < h2 - 1, bot = ja + 1 < h2 - 1;
-    const float w00 = top ? 0.25f : 0.f, w01 = top ? 0.75f : 1.f;
-    const float w10 = mid ? 0.75f : 1.f, w11 = mid ? 0.25f : 0.f;
-    const float w30 = bot ? 0.75f : 1.f, w31 = bot ? 0.25f : 0.f;
-    wv[0][0] = pk2(w00, w00); wv[0][1] = pk2(w01, w01);
-    wv[1][0] = pk2(w10, w10); wv[1][1] = pk2(w11, w11);
-    wv[2][0] = pk2(0.25f, 0.25f); wv[2][1] = pk2(0.75f, 0.75f);
-    wv[3][0] = pk2(w30, w30); wv[3][1] = pk2(w31, w31);
+    wv[0][0] = top ? 0.25f : 0.f; wv[0][1] = top ? 0.75f : 1.f;
+    wv[1][0] = mid ? 0.75f : 1.f; wv[1][1] = mid ? 0.25f : 0.f;
+    wv[2][0] = 0.25f; wv[2][1] = 0.75f;
+    wv[3][0] = bot ? 0.75f : 1.f; wv[3][1] = bot ? 0.25f : 0.f;
   }
   const float a0 = t > 0 ? 0.25f : 0.f, a1 = t > 0 ? 0.75f : 1.f;                  // column 4t   over (2t-1, 2t)
   const float b0 = 2 * t + 1 < w2 - 1 ? 0.75f : 1.f, b1 = 2 * t + 1 < w2 - 1 ? 0.25f : 0.f;   // column 4t+3 over (2t+1, 2t+2)
-  const float* sbase = smem + (2 * ty) * AX_PITCH + 2 * tx + 2;
+  const u64 c7525 = pk2(0.75f, 0.25f), c2575 = pk2(0.25f, 0.75f), wo = pk2(a0, b1), wi = pk2(a1, b0);
+  const int soff = (2 * ty) * AX_PITCH + 2 * tx + 4;
 
-  // o[r][q]: output row r, column pair q of one channel
-  auto interp = [&](int ch, u64 (&o)[4][2]) {
-    const float* sp = sbase + ch * (AX_ROWS * AX_PITCH);
+  // o[r][q]: output row r, pixel pair q of one channel; pairs are (0,1)(2,3) when LOGITS, else (0,3)(1,2)
+  auto interp = [&](const float* chan, u64 (&o)[4][2]) {
+    const float* sp = chan + soff;
     u64 hz[4][2];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const float2 v = *(const float2*)(sp + r * AX_PITCH);
       const float vl = sp[r * AX_PITCH - 1], vr = sp[r * AX_PITCH + 2];
-      hz[r][0] = pk2(a0 * vl + a1 * v.x, 0.75f * v.x + 0.25f * v.y);
-      hz[r][1] = pk2(0.25f * v.x + 0.75f * v.y, b0 * v.y + b1 * vr);
+      if (LOGITS) {
+        hz[r][0] = pk2(a0 * vl + a1 * v.x, 0.75f * v.x + 0.25f * v.y);
+        hz[r][1] = pk2(0.25f * v.x + 0.75f * v.y, b0 * v.y + b1 * vr);
+      } else {
+        hz[r][0] = fma2(wi, pk2(v.x, v.y), mul2(wo, pk2(vl, vr)));                       // columns 0, 3
+        hz[r][1] = fma2(pk2(v.y, v.y), c2575, mul2(pk2(v.x, v.x), c7525));               // columns 1, 2
+      }
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      o[0][q] = fma2(wv[0][1], hz[1][q], mul2(wv[0][0], hz[0][q]));
-      o[1][q] = fma2(wv[1][1], hz[2][q], mul2(wv[1][0], hz[1][q]));
-      o[2][q] = fma2(wv[2][1], hz[2][q], mul2(wv[2][0], hz[1][q]));
-      o[3][q] = fma2(wv[3][1], hz[3][q], mul2(wv[3][0], hz[2][q]));
+      o[0][q] = fma2(pk2(wv[0][1], wv[0][1]), hz[1][q], mul2(pk2(wv[0][0], wv[0][0]), hz[0][q]));
+      o[1][q] = fma2(pk2(wv[1][1], wv[1][1]), hz[2][q], mul2(pk2(wv[1][0], wv[1][0]), hz[1][q]));
+      o[2][q] = fma2(pk2(wv[2][1], wv[2][1]), hz[2][q], mul2(pk2(wv[2][0], wv[2][0]), hz[1][q]));
+      o[3][q] = fma2(pk2(wv[3][1], wv[3][1]), hz[3][q], mul2(pk2(wv[3][0], wv[3][0]), hz[2][q]));
     }
   };
 
-  u64 negm[4][2], s[4][2], tt[4][2];
-  interp(NSLOPE + 1, negm);
+  // bound on -log2(e) * max_c L_c over the thread's 16 pixels: the minimum over its 4 x 4 half-resolution neighbourhood
+  // (an interpolated logit never exceeds the largest of its taps)
+  float negm;
+  {
+    const float* sp = s_m + soff;
+    negm = INFINITY;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float2 v = *(const float2*)(sp + r * AX_PITCH);
+      negm = fminf(negm, fminf(fminf(v.x, v.y), fminf(sp[r * AX_PITCH - 1], sp[r * AX_PITCH + 2])));
+    }
+  }
+  const u64 negm2 = pk2(negm, negm);
+  u64 s[4][2], tt[4][2];
 #pragma unroll
   for (int r = 0; r < 4; ++r) { s[r][0] = s[r][1] = tt[r][0] = tt[r][1] = 0ull; }
   const u64 l2e = pk2(kLog2e, kLog2e);
@@ -207,7 +270,7 @@ __global__ void __launch_bounds__(256, 2) ge_adaptive_fwd_x2_kernel(
 #pragma unroll
   for (int ch = 0; ch < NSLOPE; ++ch) {
     u64 L[4][2];
-    interp(ch, L);
+    interp(smem + ch * AX_CHF, L);
     if (LOGITS) {
       float* lp = logits_full + ((int64_t)b * NSLOPE + ch) * HW + pix0;
 #pragma unroll
@@ -226,7 +289,7 @@ __global__ void __launch_bounds__(256, 2) ge_adaptive_fwd_x2_kernel(
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         float x0, x1;
-        upk2(fma2(L[r][q], l2e, negm[r][q]), x0, x1);
+        upk2(fma2(L[r][q], l2e, negm2), x0, x1);
         const u64 e = pk2(ex2_fast(x0), ex2_fast(x1));
         s[r][q] = add2(s[r][q], e);
         tt[r][q] = fma2(e, cw2, tt[r][q]);
@@ -234,31 +297,52 @@ __global__ void __launch_bounds__(256, 2) ge_adaptive_fwd_x2_kernel(
     }
   }
   u64 yv2[4][2];
-  interp(NSLOPE, yv2);
+  interp(s_y, yv2);
   const float h = height ? __ldg(height + b) : height_scalar;
+  const u64 nh2 = pk2(-h, -h), eps2 = pk2(1e-8f, 1e-8f), deg2 = pk2(kDeg, kDeg);
   const float* pp = s_pe + (4 * ty) * (2 * AX_HW) + 4 * tx;
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     if (r >= 2 && !two) break;
     const float4 pe4 = *(const float4*)(pp + r * (2 * AX_HW));
+    // pixel order of pair q: LOGITS (0,1)(2,3), else (0,3)(1,2)
+    const int px[2][2] = {{0, LOGITS ? 1 : 3}, {LOGITS ? 2 : 1, LOGITS ? 3 : 2}};
     const float pe[4] = {pe4.x, pe4.y, pe4.z, pe4.w};
-    float sv[4], tv[4], yv[4], pm[4];
-    upk2(s[r][0], sv[0], sv[1]); upk2(s[r][1], sv[2], sv[3]);
-    upk2(tt[r][0], tv[0], tv[1]); upk2(tt[r][1], tv[2], tv[3]);
-    upk2(yv2[r][0], yv[0], yv[1]); upk2(yv2[r][1], yv[2], yv[3]);
+    float yo[4], pm[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float den, m;
-      if (sv[i] > 1e-30f) {
-        const float th = tv[i] * rcp_fast(sv[i]);
-        pm[i] = shift_and_mask(tan_deg_small(th), pe[i], h, depth_scale, den, m) * yv[i];
-      } else {
-        // the bound on the maximum was too loose (or a logit is not finite): exact evaluation from the staged tile
-        pm[i] = exact_pixel(smem, 2 * ja + r, 4 * t + i, jy0, k0, h2, w2, pe[i], h, depth_scale) * yv[i];
+    for (int q = 0; q < 2; ++q) {
+      float s0, s1;
+      upk2(s[r][q], s0, s1);
+      // expected slope, tan, inverse-depth shift: two pixels per instruction (shift_and_mask / tan_deg_small, packed)
+      const u64 th = mul2(tt[r][q], pk2(rcp_fast(s0), rcp_fast(s1)));
+      const u64 xr = mul2(th, deg2), x2 = mul2(xr, xr);
+      u64 pl = fma2(x2, pk2(0.05396825397f, 0.05396825397f), pk2(0.13333333333f, 0.13333333333f));
+      pl = fma2(x2, pl, pk2(0.33333333333f, 0.33333333333f));
+      pl = fma2(x2, pl, pk2(1.f, 1.f));
+      const u64 k2 = mul2(xr, pl);
+      float d0, d1;
+      upk2(add2(pk2(pe[px[q][0]], pe[px[q][1]]), eps2), d0, d1);
+      const u64 a2 = mul2(nh2, pk2(rcp_fast(d0), rcp_fast(d1)));
+      upk2(add2(fma2(k2, pk2(-1.f, -1.f), a2), eps2), d0, d1);
+      float off[2], yy[2];
+      upk2(mul2(nh2, pk2(rcp_fast(d0), rcp_fast(d1))), off[0], off[1]);
+      upk2(yv2[r][q], yy[0], yy[1]);
+      const float ss[2] = {s0, s1};
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float mm = off[i];
+        if (mm < 0.f) mm = 0.f;
+        if (mm > depth_scale) mm = 0.f;
+        if (mm > 0.f) mm = 1.f;
+        float v = (off[i] * mm) * yy[i];
+        if (!(ss[i] > 1e-30f))   // the bound on the maximum was too loose (or a logit is not finite): exact evaluation
+          v = exact_pixel(smem, 2 * ja + r, 4 * t + px[q][i], jy0, k0, h2, w2, pe[px[q][i]], h, depth_scale) * yy[i];
+        pm[px[q][i]] = v;
+        yo[px[q][i]] = yy[i];
       }
     }
     const int64_t o = (int64_t)b * HW + pix0 + (int64_t)r * W;
-    stg_stream((float4*)(y + o), make_float4(yv[0], yv[1], yv[2], yv[3]));
+    stg_stream((float4*)(y + o), make_float4(yo[0], yo[1], yo[2], yo[3]));
     stg_stream((float4*)(pe_mask + o), make_float4(pm[0], pm[1], pm[2], pm[3]));
   }
 }
@@ -272,7 +356,7 @@ constexpr int BX_EMIT = 30;                // four-pixel slots emitted per CTA (
 constexpr int BX_TROWS = BX_HH + 2;        // staged half-resolution rows jy0-1 .. jy0+7
 constexpr int BX_TP = 68;                  // staged half-resolution columns 60 bx - 4 .. 60 bx + 63
 constexpr int BX_CH = NSLOPE + 1;          // 11 logits + y
-constexpr int BX_RING = 6;                 // g_logits_full channels in flight per warp
+constexpr int BX_RING = 8;                 // g_logits_full channels in flight per warp
 constexpr int BX_TILE = BX_CH * BX_TROWS * BX_TP;                       // floats
 constexpr int BX_ST = BX_CH * BX_FR * 32 * 2;                           // floats (float2 per slot)
 constexpr int BX_SMEM = (BX_TILE + BX_ST + 8 * BX_RING * 32 * 4) * 4;
@@ -325,6 +409,10 @@ __global__ void __launch_bounds__(256, 2) ge_adaptive_bwd_x2_kernel(
   x2w(2 * t, w2, wxa);
   x2w(2 * t + 1, w2, wxb);
   const u64 l2e = pk2(kLog2e, kLog2e);
+  const u64 c7525 = pk2(0.75f, 0.25f), c2575 = pk2(0.25f, 0.75f), wo = pk2(a0, b1), wi = pk2(a1, b0);
+  // x contraction of a slot's four gradients g0..g3 and its neighbours' (left, right), as pairs (acc.x, acc.y):
+  // (wxa0, wxb3) (left, right) + (wxa1, wxb2) (g0, g3) + (wxa2, wxb0) g1 + (wxa3, wxb1) g2
+  const u64 xw_out = pk2(wxa[0], wxb[3]), xw_03 = pk2(wxa[1], wxb[2]), xw_1 = pk2(wxa[2], wxb[0]), xw_2 = pk2(wxa[3], wxb[1]);
   const uint32_t ring0 = smem_u32(s_ring);
 
   // phase 1: per-pixel gradients of one full-resolution row segment, contracted along x.  G[ch][q]: pixel pair q of channel ch.
@@ -337,6 +425,26 @@ __global__ void __launch_bounds__(256, 2) ge_adaptive_bwd_x2_kernel(
     // the 11 rows of g_logits_full stream through a per-warp ring of asynchronous copies: BX_RING channels are in flight
     // while the softmax of this row segment is evaluated, one more is issued per channel consumed
     const float* glsrc = g_logits_full ? g_logits_full + (int64_t)b * NSLOPE * HW + po : nullptr;
+    {
+      // L2 prefetch of everything the NEXT row segment of this thread streams (and of this segment's channels beyond the ring)
+      const int oyn = oy + 8;
+      const bool nxt = r + 8 < BX_FR && oyn < H && col_ok;
+      const int64_t pn = (int64_t)oyn * W + c0;
+      if (g_logits_full) {
+        const float* q = g_logits_full + (int64_t)b * NSLOPE * HW;
+#pragma unroll
+        for (int c = 0; c < NSLOPE; ++c) {
+          if (nxt) asm volatile("prefetch.global.L2 [%0];" :: "l"(q + pn));
+          if (c >= BX_RING && act) asm volatile("prefetch.global.L2 [%0];" :: "l"(q + po));
+          q += HW;
+        }
+      }
+      if (nxt) {
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(pe_raw + (int64_t)b * pe_bstride + pn));
+        if (g_y) asm volatile("prefetch.global.L2 [%0];" :: "l"(g_y + b * HW + pn));
+        if (g_pe_mask) asm volatile("prefetch.global.L2 [%0];" :: "l"(g_pe_mask + b * HW + pn));
+      }
+    }
     if (g_logits_full) {
 #pragma unroll
       for (int c = 0; c < BX_RING; ++c) {
@@ -363,11 +471,12 @@ __global__ void __launch_bounds__(256, 2) ge_adaptive_bwd_x2_kernel(
       for (int ch = 0; ch < BX_CH; ++ch) {
         const float* sp = sp0 + ch * (BX_TROWS * BX_TP);
         const float2 u = *(const float2*)sp, v = *(const float2*)(sp + BX_TP);
-        float wl, wr, w0, w1;
-        upk2(fma2(wy1p, pk2(v.x, v.y), mul2(wy0p, pk2(u.x, u.y))), w0, w1);
-        upk2(fma2(wy1p, pk2(sp[BX_TP - 1], sp[BX_TP + 2]), mul2(wy0p, pk2(sp[-1], sp[2]))), wl, wr);
-        G[ch][0] = pk2(a0 * wl + a1 * w0, 0.75f * w0 + 0.25f * w1);
-        G[ch][1] = pk2(0.25f * w0 + 0.75f * w1, b0 * w1 + b1 * wr);
+        float w0, w1;
+        const u64 wmid = fma2(wy1p, pk2(v.x, v.y), mul2(wy0p, pk2(u.x, u.y)));
+        const u64 wout = fma2(wy1p, pk2(sp[BX_TP - 1], sp[BX_TP + 2]), mul2(wy0p, pk2(sp[-1], sp[2])));
+        upk2(wmid, w0, w1);
+        G[ch][0] = fma2(wi, wmid, mul2(wo, wout));                                   // pixels 0, 3
+        G[ch][1] = fma2(pk2(w1, w1), c2575, mul2(pk2(w0, w0), c7525));               // pixels 1, 2
       }
       // softmax (exact maximum) and expected slope, two pixels per instruction; G[ch] <- exp2 terms
       u64 nm[2], sum[2], tsum[2];
@@ -398,10 +507,10 @@ __global__ void __launch_bounds__(256, 2) ge_adaptive_bwd_x2_kernel(
           tsum[q] = fma2(e, cw2, tsum[q]);
         }
       }
-      float sv[4], tv[4], yv[4];
-      upk2(sum[0], sv[0], sv[1]); upk2(sum[1], sv[2], sv[3]);
-      upk2(tsum[0], tv[0], tv[1]); upk2(tsum[1], tv[2], tv[3]);
-      upk2(G[NSLOPE][0], yv[0], yv[1]); upk2(G[NSLOPE][1], yv[2], yv[3]);
+      float sv[4], tv[4], yv[4];                 // pixel order from here on
+      upk2(sum[0], sv[0], sv[3]); upk2(sum[1], sv[1], sv[2]);
+      upk2(tsum[0], tv[0], tv[3]); upk2(tsum[1], tv[1], tv[2]);
+      upk2(G[NSLOPE][0], yv[0], yv[3]); upk2(G[NSLOPE][1], yv[1], yv[2]);
       const float pe[4] = {pe4.x, pe4.y, pe4.z, pe4.w}, gyv[4] = {gy4.x, gy4.y, gy4.z, gy4.w}, gmv[4] = {gm4.x, gm4.y, gm4.z, gm4.w};
       float gyo[4];
 #pragma unroll
@@ -420,35 +529,40 @@ __global__ void __launch_bounds__(256, 2) ge_adaptive_bwd_x2_kernel(
         Gs[i] = act ? g * inv : 0.f;             // folds the softmax normalisation; inactive lanes contribute nothing
         nth[i] = -th;
       }
-      G[NSLOPE][0] = act ? pk2(gyo[0], gyo[1]) : 0ull;
-      G[NSLOPE][1] = act ? pk2(gyo[2], gyo[3]) : 0ull;
+      G[NSLOPE][0] = act ? pk2(gyo[0], gyo[3]) : 0ull;
+      G[NSLOPE][1] = act ? pk2(gyo[1], gyo[2]) : 0ull;
     }
-    const u64 Gs2[2] = {pk2(Gs[0], Gs[1]), pk2(Gs[2], Gs[3])}, nth2[2] = {pk2(nth[0], nth[1]), pk2(nth[2], nth[3])};
+    const u64 Gs2[2] = {pk2(Gs[0], Gs[3]), pk2(Gs[1], Gs[2])}, nth2[2] = {pk2(nth[0], nth[3]), pk2(nth[1], nth[2])};
+    const float* glnext = glsrc ? glsrc + (int64_t)BX_RING * HW : nullptr;
     float2* st = s_t + r * 32 + lane;
 #pragma unroll
     for (int ch = 0; ch < BX_CH; ++ch) {
-      float g0, g1, g2, g3;
+      u64 g03, g12;
       if (ch < NSLOPE) {
         const float cw = (float)(ch - 5);
         const u64 cw2 = pk2(cw, cw);
-        u64 gl0 = 0ull, gl1 = 0ull;
+        u64 gl03 = 0ull, gl12 = 0ull;
         if (g_logits_full) {
           cp_async_wait<BX_RING - 1>();
           const float4 gl = s_ring[(ch % BX_RING) * 32];
-          gl0 = pk2(gl.x, gl.y); gl1 = pk2(gl.z, gl.w);
-          if (ch + BX_RING < NSLOPE) cp_async16(ring0 + (ch % BX_RING) * 512, glsrc + (int64_t)(ch + BX_RING) * HW, act ? 16 : 0);
+          gl03 = pk2(gl.x, gl.w); gl12 = pk2(gl.y, gl.z);
+          if (ch + BX_RING < NSLOPE) { cp_async16(ring0 + (ch % BX_RING) * 512, glnext, act ? 16 : 0); glnext += HW; }
           cp_async_commit();
         }
-        upk2(fma2(mul2(Gs2[0], G[ch][0]), add2(cw2, nth2[0]), gl0), g0, g1);
-        upk2(fma2(mul2(Gs2[1], G[ch][1]), add2(cw2, nth2[1]), gl1), g2, g3);
+        g03 = fma2(mul2(Gs2[0], G[ch][0]), add2(cw2, nth2[0]), gl03);
+        g12 = fma2(mul2(Gs2[1], G[ch][1]), add2(cw2, nth2[1]), gl12);
       } else {
-        upk2(G[ch][0], g0, g1); upk2(G[ch][1], g2, g3);
+        g03 = G[ch][0]; g12 = G[ch][1];
       }
+      float g0, g1, g2, g3;
+      upk2(g03, g0, g3); upk2(g12, g1, g2);
       const float left = __shfl_up_sync(0xffffffffu, g3, 1), right = __shfl_down_sync(0xffffffffu, g0, 1);
-      float2 acc;
-      acc.x = wxa[0] * left + wxa[1] * g0 + wxa[2] * g1 + wxa[3] * g2;
-      acc.y = wxb[0] * g1 + wxb[1] * g2 + wxb[2] * g3 + wxb[3] * right;
-      st[ch * (BX_FR * 32)] = acc;
+      u64 acc = fma2(xw_03, g03, mul2(xw_out, pk2(left, right)));
+      acc = fma2(xw_1, pk2(g1, g1), acc);
+      acc = fma2(xw_2, pk2(g2, g2), acc);
+      float2 a2;
+      upk2(acc, a2.x, a2.y);
+      st[ch * (BX_FR * 32)] = a2;
     }
   }
   cp_async_wait<0>();
@@ -463,17 +577,56 @@ __global__ void __launch_bounds__(256, 2) ge_adaptive_bwd_x2_kernel(
   float* dst = g_logits_half + (int64_t)b * NSLOPE * hw2 + jy * w2 + 2 * t;
 #pragma unroll
   for (int ch = 0; ch < BX_CH; ++ch) {
-    float2 o = make_float2(0.f, 0.f);
+    u64 o2 = 0ull;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       const float2 v = sp[ch * (BX_FR * 32) + a * 32];
-      o.x = fmaf(wy[a], v.x, o.x); o.y = fmaf(wy[a], v.y, o.y);
+      o2 = fma2(pk2(wy[a], wy[a]), pk2(v.x, v.y), o2);
     }
+    float2 o;
+    upk2(o2, o.x, o.y);
     if (ch == NSLOPE) dst = g_y_half + (int64_t)b * hw2 + jy * w2 + 2 * t;
     *(float2*)dst = o;
     dst += hw2;
   }
 }
+
+static PFN_cuTensorMapEncodeTiled_v12000 ax_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+  if (!enc) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      enc = (PFN_cuTensorMapEncodeTiled_v12000)ptr;
+  }
+  return enc;
+}
+// 3-D fp32 map {w, h, n} with plane stride `plane` elements, box {bw, bh, bd}; out-of-range elements read 0
+static bool ax_map3(CUtensorMap* m, const float* base, int w, int h, int n, int64_t plane, int bw, int bh, int bd) {
+  auto enc = ax_encode();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[2] = {(cuuint64_t)w * 4, (cuuint64_t)plane * 4};
+  cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <bool LOGITS, bool TMA>
+static int ax_launch(const AxMaps& maps, const float* pe_raw, int64_t pe_bstride, const float* y_half, const float* logits_half,
+                     const float* height, float height_scalar, float depth_scale, float* y, float* pe_mask, float* logits_full,
+                     int B, int H, int W, int h2, int w2, cudaStream_t stream) {
+  if (cudaFuncSetAttribute(ge_adaptive_fwd_x2_kernel<LOGITS, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, AX_SMEM) != cudaSuccess)
+    return GED_ERR_LAUNCH;
+  dim3 block(64, AX_HH / 2), grid(cdiv(w2, AX_HW), cdiv(h2, AX_HH), B);
+  ge_adaptive_fwd_x2_kernel<LOGITS, TMA><<<grid, block, AX_SMEM, stream>>>(maps, pe_raw, pe_bstride, y_half, logits_half, height,
+                                                                         height_scalar, depth_scale, y, pe_mask, logits_full, H, W, h2, w2);
+  return cudaGetLastError() == cudaSuccess ? 0 : GED_ERR_LAUNCH;
+}
+
+static int g_ax_tma = 1;     // 0: asynchronous-copy staging even where TMA is possible (A/B, tests)
+void set_ge_x2_tma(int on) { g_ax_tma = on; }
 
 // host side: 0 = launched, 1 = shape / alignment not eligible (caller uses the generic kernels), < 0 = error
 int launch_ge_adaptive_fwd_x2(const float* pe_raw, int64_t pe_bstride, const float* y_half, const float* logits_half,
@@ -481,15 +634,17 @@ int launch_ge_adaptive_fwd_x2(const float* pe_raw, int64_t pe_bstride, const flo
                               float* logits_full, int B, int H, int W, int h2, int w2, cudaStream_t stream) {
   if (H != 2 * h2 || W != 2 * w2 || (W % 4) || (pe_bstride % 4) || !aligned16(pe_raw) || !aligned16(y) || !aligned16(pe_mask) ||
       (logits_full && !aligned16(logits_full)) || ((uintptr_t)y_half & 7) || ((uintptr_t)logits_half & 7)) return 1;
-  if (cudaFuncSetAttribute(ge_adaptive_fwd_x2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AX_SMEM) != cudaSuccess ||
-      cudaFuncSetAttribute(ge_adaptive_fwd_x2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AX_SMEM) != cudaSuccess)
-    return GED_ERR_LAUNCH;
-  dim3 block(64, 4), grid(cdiv(w2, AX_HW), cdiv(h2, AX_HH), B);
-  if (logits_full)
-    ge_adaptive_fwd_x2_kernel<true><<<grid, block, AX_SMEM, stream>>>(pe_raw, pe_bstride, y_half, logits_half, height, height_scalar, depth_scale, y, pe_mask, logits_full, H, W, h2, w2);
-  else
-    ge_adaptive_fwd_x2_kernel<false><<<grid, block, AX_SMEM, stream>>>(pe_raw, pe_bstride, y_half, logits_half, height, height_scalar, depth_scale, y, pe_mask, logits_full, H, W, h2, w2);
-  return cudaGetLastError() == cudaSuccess ? 0 : GED_ERR_LAUNCH;
+  AxMaps maps;
+  bool tma = g_ax_tma && (w2 % 4 == 0) && aligned16(y_half) && aligned16(logits_half) && (int64_t)B * NSLOPE < (1ll << 31);
+  if (tma)
+    tma = ax_map3(&maps.logits, logits_half, w2, h2, B * NSLOPE, (int64_t)h2 * w2, AX_PITCH, AX_ROWS, NSLOPE) &&
+          ax_map3(&maps.yh, y_half, w2, h2, B, (int64_t)h2 * w2, AX_PITCH, AX_ROWS, 1) &&
+          ax_map3(&maps.pe, pe_raw, W, H, B, pe_bstride, 2 * AX_HW, 2 * AX_HH, 1);
+#define AX_GO(L, T) ax_launch<L, T>(maps, pe_raw, pe_bstride, y_half, logits_half, height, height_scalar, depth_scale, y, pe_mask, \
+                                    logits_full, B, H, W, h2, w2, stream)
+  if (logits_full) return tma ? AX_GO(true, true) : AX_GO(true, false);
+  return tma ? AX_GO(false, true) : AX_GO(false, false);
+#undef AX_GO
 }
 
 int launch_ge_adaptive_bwd_x2(const float* pe_raw, int64_t pe_bstride, const float* y_half, const float* logits_half,

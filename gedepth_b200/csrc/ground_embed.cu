@@ -160,6 +160,8 @@ __device__ __forceinline__ void x2_weights(int j, int n, float (&w)[4]) {
   w[2] = j <= n - 2 ? 0.75f : 1.f;
   w[3] = j <= n - 2 ? 0.25f : 0.f;
 }
+// (Tried: issuing the loads of all 4-5 rows of a thread before the first use - 96 registers, 2 CTAs per SM: 0.565 -> 0.38 of
+// the HBM peak; capped at 80 registers with spills: 0.50.  The 48-register loop below with 5 CTAs per SM stays.)
 // Separable: a CTA owns X2_H half-resolution rows x 128 columns.  Pass 1: every full-resolution row of the footprint is
 // read ONCE with aligned float4 loads (a lane's left / right neighbour columns come from its neighbours by warp
 // shuffle), G = g_y + g_pe_mask * pe * 200 is formed and contracted along x into shared memory; pass 2 contracts along y.
@@ -493,12 +495,20 @@ int launch_ge_adaptive_fwd_x2(const float*, int64_t, const float*, const float*,
                               float*, int, int, int, int, int, cudaStream_t);
 int launch_ge_adaptive_bwd_x2(const float*, int64_t, const float*, const float*, const float*, float, float, const float*,
                               const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
+void set_ge_x2_tma(int on);
 }  // namespace ged
 
 using namespace ged;
 
-static int g_ge_x2 = 1;      // 1 = closed-form x2 kernels whenever the shape allows (default), 0 = generic kernels only (A/B, tests)
-GED_API int ged_set_ge_x2(int on) { const int prev = g_ge_x2; g_ge_x2 = on ? 1 : 0; return prev; }
+// 1 = closed-form x2 kernels whenever the shape allows, staged by TMA where the rows allow (default); 2 = x2 kernels staged
+// by per-thread asynchronous copies only; 0 = generic bilinear kernels only (A/B, tests)
+static int g_ge_x2 = 1;
+GED_API int ged_set_ge_x2(int on) {
+  const int prev = g_ge_x2;
+  g_ge_x2 = on == 2 ? 2 : (on ? 1 : 0);
+  set_ge_x2_tma(g_ge_x2 == 1);
+  return prev;
+}
 
 // ============================================================================================
 // C-ABI (include/gedepth.h)

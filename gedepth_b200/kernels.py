@@ -566,9 +566,10 @@ def gemm(a2d: torch.Tensor, w: torch.Tensor, bias=None, act=None, slope=0.01, re
 DW_MODE = int(os.environ.get("GEDEPTH_DW_MODE", "1"))
 
 
-def set_ge_x2(on: bool) -> int:
-    """Closed-form x2 ground-embedding kernels (default on) vs the generic bilinear ones; returns the previous setting."""
-    return load().ged_set_ge_x2(int(bool(on)))
+def set_ge_x2(on) -> int:
+    """Closed-form x2 ground-embedding kernels: 1 = on, TMA-staged forward where W % 8 == 0 (default), 2 = on with per-thread
+    asynchronous copies only, 0 = generic bilinear kernels; returns the previous setting."""
+    return load().ged_set_ge_x2(int(on))
 
 
 def set_gemm_pair(on) -> int:

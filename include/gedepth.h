@@ -64,7 +64,8 @@ int ged_ge_adaptive_bwd(const float* pe_raw, int64_t pe_batch_stride, const floa
                         const float* g_logits_full, float* g_y_half, float* g_logits_half, int B, int H,
                         int W, int h2, int w2, cudaStream_t stream);
 /* 1 (default): when H == 2*h2 and W == 2*w2 (every GE config) the Vanilla backward and both Adaptive kernels run their
- * closed-form x2 versions (csrc/ge_adaptive_x2.cu); 0: generic bilinear kernels only.  Returns the previous setting. */
+ * closed-form x2 versions (csrc/ge_adaptive_x2.cu), the forward staged by TMA when W % 8 == 0; 2: the same kernels staged by
+ * per-thread asynchronous copies only; 0: generic bilinear kernels only.  Returns the previous setting. */
 int ged_set_ge_x2(int on);
 
 /* depth/models/decode_heads/decode_head.py:489-508.  d = relu(conv_depth(feat)) (B,1,h2,w2);

@@ -170,7 +170,7 @@ def test_ge_adaptive_x2_equals_generic(B, H, W):
     img[:, 4, :, W // 4: W // 3] *= -1.0
     img_d = img.to(DEV)
     outs = {}
-    for x2 in (1, 0):
+    for x2 in (1, 2, 0):
         prev = K.set_ge_x2(x2)
         try:
             a = [t.to(DEV).requires_grad_(True) for t in (y_half, logits_half)]
@@ -186,7 +186,13 @@ def test_ge_adaptive_x2_equals_generic(B, H, W):
             K.set_ge_x2(prev)
     y1, pm1, lf1, gy1, gl1, yi1, pmi1 = outs[1]
     y0, pm0, lf0, gy0, gl0, yi0, pmi0 = outs[0]
-    assert torch.equal(y1, yi1) and torch.equal(torch.nan_to_num(pm1, 7.0), torch.nan_to_num(pmi1, 7.0))   # LOGITS on / off
+    # TMA staging vs per-thread asynchronous copies: the same arithmetic on the same staged values
+    for a_, b_ in zip(outs[1], outs[2]):
+        assert torch.equal(torch.nan_to_num(a_, 7.0), torch.nan_to_num(b_, 7.0))
+    # inference variant (no logits written; column pairs (0,3)(1,2)) vs training variant: y identical, pe_mask to rounding
+    _close(y1, yi1, 1e-6, 1e-6, "y, inference variant")
+    badi = ((pm1 - pmi1).abs() > 2e-3 + 2e-4 * pm1.abs()) & ~torch.isnan(pm1)
+    assert torch.equal(torch.isnan(pm1), torch.isnan(pmi1)) and float(badi.float().mean()) < 2e-5
     _close(y1, y0, 1e-6, 1e-6, "y")
     _close(lf1, lf0, 1e-5, 1e-4, "logits")
     assert torch.equal(torch.isnan(pm1), torch.isnan(pm0))
