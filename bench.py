@@ -416,7 +416,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip other_configs / gpu_library_baseline / probes (N = 1 only anyway)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
-    ap.add_argument("--passes", type=int, default=3, choices=[1, 3], help="forward GEMM arithmetic: 3 = 3xTF32 (fp32-accurate), 1 = TF32")
+    ap.add_argument("--passes", type=int, default=3, choices=[1, 2, 3], help="forward GEMM arithmetic: 3 = 3xTF32 (fp32-accurate), 2 = bf16 hi/lo split (3 kind::f16 products), 1 = TF32")
     ap.add_argument("--ncu-step", action="store_true",
                     help="for `ncu --profile-from-start off`: warm up, bracket ONE eager step with cudaProfilerStart/Stop, exit")
     args = ap.parse_args()

@@ -23,6 +23,7 @@
 // Epilogue (fused, in order): + bias[n] -> activation -> dropout -> * row_scale[batch(m)] -> + residual[m,n].
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace ged {
@@ -113,6 +114,13 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -155,6 +163,34 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128_32b(uint32_t smem_ad
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, bool a_mn = false, bool b_mn = false) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// kind::f16 with bf16 operands (a/b format 1), fp32 accumulate; both operands K-major
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// SPLIT == 2 (bf16 hi/lo split): the fp32 tile TMA wrote ([rows][32 floats], 128B-swizzled) becomes a tile of the same
+// size and swizzle whose rows are [32 bf16 hi | 32 bf16 lo], hi = bf16(x), lo = bf16(x - hi): x = hi + lo to 2^-17 |x|.
+// Each k-block then issues hi*hi + lo*hi + hi*lo as kind::f16 MMAs (K = 16 per instruction, half the tensor-pipe time
+// of the three kind::tf32 passes); the dropped lo*lo term and the residual of the split are 2^-16 relative per product,
+// 32x finer than the single-pass TF32 (2^-11) the reference's PyTorch runs on Ampere+.
+__device__ __forceinline__ void split_bf16_tile(const uint8_t* src, uint8_t* dst, int bytes, int st) {
+  for (int i = st; i < bytes / 32; i += 128) {
+    const int r = i >> 2, cp = i & 3;
+    const uint32_t row = (uint32_t)r * 128u, sw = (uint32_t)r & 7u;
+    const float4 x0 = *(const float4*)(src + row + (((2u * cp) ^ sw) << 4));
+    const float4 x1 = *(const float4*)(src + row + (((2u * cp + 1u) ^ sw) << 4));
+    const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    uint32_t hv[4], lv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+      const __nv_bfloat162 l = __floats2bfloat162_rn(x[2 * e] - __low2float(h), x[2 * e + 1] - __high2float(h));
+      hv[e] = *reinterpret_cast<const uint32_t*>(&h);
+      lv[e] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    *(uint4*)(dst + row + (((uint32_t)cp ^ sw) << 4)) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+    *(uint4*)(dst + row + (((4u + cp) ^ sw) << 4)) = make_uint4(lv[0], lv[1], lv[2], lv[3]);
+  }
 }
 __device__ __forceinline__ Unit decode_unit(const GemmParams& p, int u, int BN_) {
   const int tiles = p.num_m_tiles * p.num_n_tiles, per = tiles * p.out_taps;
@@ -279,7 +315,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* tile_s
 // SPLIT = error-compensated "3xTF32": every fp32 operand x is used as hi = tf32(x) (the tensor core's own
 // truncation) plus lo = x - hi (exact in fp32), and each k-step issues hi*hi + lo*hi + hi*lo.  The dropped
 // lo*lo term is 2^-22 relative: the product is fp32-accurate while still running on tcgen05.
-template <int BN, int STAGES, bool SPLIT>
+template <int BN, int STAGES, int SPLIT>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 4;       // 16 KB
   static constexpr int B_BYTES = BN * BK * 4;
@@ -291,7 +327,7 @@ struct GemmSmem {
   static constexpr int THREADS = 128 + EPI_WARPS * 32 + (SPLIT ? SPLIT_WARPS * 32 : 0);
 };
 
-template <int BN, int STAGES, bool SPLIT>
+template <int BN, int STAGES, int SPLIT>
 __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_tf32_kernel(
     const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
     const GemmParams p) {
@@ -385,6 +421,17 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
           const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
           const uint64_t adesc = a_mn ? umma_desc_mnmajor_sw128_32b(sa, BK * 128) : umma_desc_kmajor_sw128(sa);
           const uint64_t bdesc = b_mn ? umma_desc_mnmajor_sw128_32b(sa + S::A_BYTES, BK * 128) : umma_desc_kmajor_sw128(sa + S::A_BYTES);
+          if (SPLIT == 2) {
+            // bf16 hi/lo rows (K-major only): k-steps 0, 1 of a row are hi, 2, 3 are lo (32 bytes = 16 bf16 each)
+            const uint64_t as = adesc + (S::HI_BYTES >> 4), bs = bdesc + (S::HI_BYTES >> 4);
+            constexpr uint32_t idb = umma_idesc_bf16(BM, BN);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              tc_mma_bf16(tmem_d, as + 2 * k, bs + 2 * k, idb, ((kb - u.kb0) | k) != 0);   // hi(A) * hi(B)
+              tc_mma_bf16(tmem_d, as + 2 * (k + 2), bs + 2 * k, idb, 1u);                    // lo(A) * hi(B)
+              tc_mma_bf16(tmem_d, as + 2 * k, bs + 2 * (k + 2), idb, 1u);                    // hi(A) * lo(B)
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             tc_mma_tf32(tmem_d, adesc + kstep_a * k, bdesc + kstep_b * k, idesc, ((kb - u.kb0) | k) != 0);
@@ -393,6 +440,7 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
               tc_mma_tf32(tmem_d, alo + kstep_a * k, bdesc + kstep_b * k, idesc, 1u);   // lo(A) * hi(B)
               tc_mma_tf32(tmem_d, adesc + kstep_a * k, blo + kstep_b * k, idesc, 1u);   // hi(A) * lo(B)
             }
+          }
           }
           tc_commit(empty_bar + stage);          // frees the smem slot when these MMAs retire
           if (kb == u.kb1 - 1) tc_commit(tmem_full + acc);
@@ -426,6 +474,9 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
         mbar_wait(full_bar + stage, phase);
         const float4* hi = (const float4*)(stage_base + stage * S::STAGE_BYTES);
         float4* lo = (float4*)(stage_base + stage * S::STAGE_BYTES + S::HI_BYTES);
+        if (SPLIT == 2) {
+          split_bf16_tile((const uint8_t*)hi, (uint8_t*)lo, S::HI_BYTES, st);
+        } else {
 #pragma unroll 4
         for (int i = st; i < S::HI_BYTES / 16; i += SPLIT_WARPS * 32) {
           const float4 x = hi[i];
@@ -435,6 +486,7 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
           l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
           l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
           lo[i] = l;
+        }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
         __syncwarp();
@@ -500,6 +552,13 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {      // arrives 
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -510,7 +569,7 @@ __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc
 
 constexpr int BM2 = 256;   // rows per CTA-pair tile
 
-template <int BN, int STAGES, bool SPLIT>
+template <int BN, int STAGES, int SPLIT>
 struct Gemm2Smem {
   static constexpr int A_BYTES = BM * BK * 4;              // this CTA's 128 rows
   static constexpr int B_BYTES = (BN / 2) * BK * 4;        // this CTA's half of the B tile
@@ -532,7 +591,7 @@ __device__ __forceinline__ Unit decode_unit2(const GemmParams& p, int u, int BN_
   return t;
 }
 
-template <int BN, int STAGES, bool SPLIT>
+template <int BN, int STAGES, int SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES, SPLIT>::THREADS, 1) gemm2_tf32_kernel(
     const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmParams p) {
   using S = Gemm2Smem<BN, STAGES, SPLIT>;
@@ -617,6 +676,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
           const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
           const uint64_t adesc = umma_desc_kmajor_sw128(sa);
           const uint64_t bdesc = b_mn ? umma_desc_mnmajor_sw128_32b(sa + S::A_BYTES, BK * 128) : umma_desc_kmajor_sw128(sa + S::A_BYTES);
+          if (SPLIT == 2) {
+            const uint64_t as = adesc + (S::HI_BYTES >> 4), bs = bdesc + (S::HI_BYTES >> 4);
+            constexpr uint32_t idb = umma_idesc_bf16(BM2, BN);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              tc_mma_bf16_pair(tmem_d, as + 2 * k, bs + 2 * k, idb, ((kb - u.kb0) | k) != 0);
+              tc_mma_bf16_pair(tmem_d, as + 2 * (k + 2), bs + 2 * k, idb, 1u);
+              tc_mma_bf16_pair(tmem_d, as + 2 * k, bs + 2 * (k + 2), idb, 1u);
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             tc_mma_tf32_pair(tmem_d, adesc + 2 * k, bdesc + kstep_b * k, idesc, ((kb - u.kb0) | k) != 0);
@@ -625,6 +694,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
               tc_mma_tf32_pair(tmem_d, alo + 2 * k, bdesc + kstep_b * k, idesc, 1u);
               tc_mma_tf32_pair(tmem_d, adesc + 2 * k, blo + kstep_b * k, idesc, 1u);
             }
+          }
           }
           tc_commit_pair(empty_bar + stage);
           if (kb == u.kb1 - 1) tc_commit_pair(tmem_full + acc);
@@ -668,6 +738,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
         mbar_wait(full_bar + stage, phase);
         const float4* hi = (const float4*)(stage_base + stage * S::STAGE_BYTES);
         float4* lo = (float4*)(stage_base + stage * S::STAGE_BYTES + S::HI_BYTES);
+        if (SPLIT == 2) {
+          split_bf16_tile((const uint8_t*)hi, (uint8_t*)lo, S::HI_BYTES, st);
+        } else {
 #pragma unroll 4
         for (int i = st; i < S::HI_BYTES / 16; i += SPLIT_WARPS * 32) {
           const float4 x = hi[i];
@@ -677,6 +750,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
           l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
           l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
           lo[i] = l;
+        }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -726,7 +800,7 @@ static int g_num_sms = 0;
 static int g_wide_tiles = 1;   // allow BN = 192 / 256 (fewer re-reads of the A operand through L2)
 static int g_precision = 3;   // 1 = single-pass TF32, 3 = error-compensated 3xTF32 (fp32-accurate)
 
-template <int BN, int STAGES, bool SPLIT>
+template <int BN, int STAGES, int SPLIT>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES, SPLIT>;
   static_assert(S::TOTAL <= 232448, "shared memory budget (227 KB)");
@@ -789,23 +863,33 @@ static int pick_bn(int M, int N, bool split) {
 }
 
 static int dispatch(int bn, const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
-  if (g_precision == 3) {
+  if (g_precision == 2 && p.mode == 0 && !p.b_mn) {      // bf16 hi/lo split: K-major operands only
     switch (bn) {
-      case 32: return launch_gemm<32, 4, true>(ma, mb, p, stream);
-      case 64: return launch_gemm<64, 4, true>(ma, mb, p, stream);
-      case 96: return launch_gemm<96, 3, true>(ma, mb, p, stream);
-      case 192: return launch_gemm<192, 2, true>(ma, mb, p, stream);
-      case 256: return launch_gemm<256, 2, true>(ma, mb, p, stream);
-      default: return launch_gemm<128, 3, true>(ma, mb, p, stream);
+      case 32: return launch_gemm<32, 4, 2>(ma, mb, p, stream);
+      case 64: return launch_gemm<64, 4, 2>(ma, mb, p, stream);
+      case 96: return launch_gemm<96, 3, 2>(ma, mb, p, stream);
+      case 192: return launch_gemm<192, 2, 2>(ma, mb, p, stream);
+      case 256: return launch_gemm<256, 2, 2>(ma, mb, p, stream);
+      default: return launch_gemm<128, 3, 2>(ma, mb, p, stream);
+    }
+  }
+  if (g_precision >= 2) {
+    switch (bn) {
+      case 32: return launch_gemm<32, 4, 1>(ma, mb, p, stream);
+      case 64: return launch_gemm<64, 4, 1>(ma, mb, p, stream);
+      case 96: return launch_gemm<96, 3, 1>(ma, mb, p, stream);
+      case 192: return launch_gemm<192, 2, 1>(ma, mb, p, stream);
+      case 256: return launch_gemm<256, 2, 1>(ma, mb, p, stream);
+      default: return launch_gemm<128, 3, 1>(ma, mb, p, stream);
     }
   }
   switch (bn) {
-    case 32: return launch_gemm<32, 8, false>(ma, mb, p, stream);
-    case 64: return launch_gemm<64, 6, false>(ma, mb, p, stream);
-    case 96: return launch_gemm<96, 6, false>(ma, mb, p, stream);
-    case 192: return launch_gemm<192, 5, false>(ma, mb, p, stream);
-    case 256: return launch_gemm<256, 4, false>(ma, mb, p, stream);
-    default: return launch_gemm<128, 5, false>(ma, mb, p, stream);
+    case 32: return launch_gemm<32, 8, 0>(ma, mb, p, stream);
+    case 64: return launch_gemm<64, 6, 0>(ma, mb, p, stream);
+    case 96: return launch_gemm<96, 6, 0>(ma, mb, p, stream);
+    case 192: return launch_gemm<192, 5, 0>(ma, mb, p, stream);
+    case 256: return launch_gemm<256, 4, 0>(ma, mb, p, stream);
+    default: return launch_gemm<128, 5, 0>(ma, mb, p, stream);
   }
 }
 
@@ -813,7 +897,7 @@ static int dispatch(int bn, const CUtensorMap& ma, const CUtensorMap& mb, GemmPa
 static int g_pair = 2;        // 2 = CTA-pair kernel for large problems in both arithmetic modes (measured: one-pass dX GEMMs
                               // 45.4 -> 38.1 ms in config 3), 1 = for 3xTF32 only, 0 = never
 
-template <int BN, int STAGES, bool SPLIT>
+template <int BN, int STAGES, int SPLIT>
 static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
   using S = Gemm2Smem<BN, STAGES, SPLIT>;
   static_assert(S::TOTAL <= 232448, "shared memory budget (227 KB)");
@@ -839,7 +923,7 @@ static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams
 // the operand bytes each SM stages and re-reads); no gain for single-pass TF32 (already ~600 TFLOP/s on the wide
 // single-CTA tiles), for 64-column outputs (the A operand dominates) or for problems with fewer tiles than SM pairs.
 static int pick_bn_pair(int M, int N) {
-  if (!g_pair || (g_precision != 3 && g_pair != 2) || N < 128) return 0;     // g_pair == 2: also for one-pass TF32 (A/B switch)
+  if (!g_pair || (g_precision < 2 && g_pair != 2) || N < 128) return 0;     // g_pair == 2: also for one-pass TF32 (A/B switch)
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
   const int cands[3] = {256, 192, 128};
   for (int i = 0; i < 3; ++i) {
@@ -853,19 +937,27 @@ static int pick_bn_pair(int M, int N) {
 }
 
 static int dispatch2(int bn, const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
-  if (g_precision == 3) {
+  if (g_precision == 2 && !p.b_mn) {
     switch (bn) {
-      case 64: return launch_gemm2<64, 4, true>(ma, mb, p, stream);
-      case 128: return launch_gemm2<128, 4, true>(ma, mb, p, stream);
-      case 192: return launch_gemm2<192, 3, true>(ma, mb, p, stream);
-      default: return launch_gemm2<256, 3, true>(ma, mb, p, stream);
+      case 64: return launch_gemm2<64, 4, 2>(ma, mb, p, stream);
+      case 128: return launch_gemm2<128, 4, 2>(ma, mb, p, stream);
+      case 192: return launch_gemm2<192, 3, 2>(ma, mb, p, stream);
+      default: return launch_gemm2<256, 3, 2>(ma, mb, p, stream);
+    }
+  }
+  if (g_precision >= 2) {
+    switch (bn) {
+      case 64: return launch_gemm2<64, 4, 1>(ma, mb, p, stream);
+      case 128: return launch_gemm2<128, 4, 1>(ma, mb, p, stream);
+      case 192: return launch_gemm2<192, 3, 1>(ma, mb, p, stream);
+      default: return launch_gemm2<256, 3, 1>(ma, mb, p, stream);
     }
   }
   switch (bn) {
-    case 64: return launch_gemm2<64, 8, false>(ma, mb, p, stream);
-    case 128: return launch_gemm2<128, 8, false>(ma, mb, p, stream);
-    case 192: return launch_gemm2<192, 7, false>(ma, mb, p, stream);
-    default: return launch_gemm2<256, 6, false>(ma, mb, p, stream);
+    case 64: return launch_gemm2<64, 8, 0>(ma, mb, p, stream);
+    case 128: return launch_gemm2<128, 8, 0>(ma, mb, p, stream);
+    case 192: return launch_gemm2<192, 7, 0>(ma, mb, p, stream);
+    default: return launch_gemm2<256, 6, 0>(ma, mb, p, stream);
   }
 }
 
@@ -877,7 +969,7 @@ static int run(const float* A, int64_t a_rows, int lda, const float* Bw, int ldb
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int bn2 = pick_bn_pair(p.M, p.N);
-  const int bn = bn2 ? bn2 : pick_bn(p.M, p.N, g_precision == 3);
+  const int bn = bn2 ? bn2 : pick_bn(p.M, p.N, g_precision >= 2);
   CUtensorMap ma, mb;
   const int Kt = p.K / p.ntaps;
   if (int e = make_map_2d(&ma, A, a_rows, Kt, lda, BM)) return e;
@@ -915,11 +1007,12 @@ static int run_dw(const float* G, int ldg, const float* X, int ldx, int64_t P, i
 }  // namespace ged
 using namespace ged;
 
-// precision: 1 = TF32 (10-bit mantissa products), 3 = 3xTF32 split (fp32-accurate; default).  Returns the
-// previous setting.  Process-wide; not a per-call argument so call sites stay those of F.linear / conv2d.
+// precision: 1 = TF32 (10-bit mantissa products), 3 = 3xTF32 split (fp32-accurate; default), 2 = bf16 hi/lo split
+// (three kind::f16 products per k-step, 2^-16 relative per product; K-major operands only - MN-major ones use 3xTF32).
+// Returns the previous setting.  Process-wide; not a per-call argument so call sites stay those of F.linear / conv2d.
 GED_API int ged_set_gemm_precision(int passes) {
   const int prev = g_precision;
-  if (passes == 1 || passes == 3) g_precision = passes;
+  if (passes == 1 || passes == 2 || passes == 3) g_precision = passes;
   return prev;
 }
 

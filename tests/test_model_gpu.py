@@ -73,7 +73,7 @@ def test_train_step_matches_reference(name):
 
 
 @pytest.mark.parametrize("name", ["vanilla_train", "adaptive_train"])
-def test_fp32_accurate_backward_matches_reference_gradients(name, monkeypatch):
+def test_fp32_accurate_backward_matches_reference_gradients(name, monkeypatch, request):
     """GEDEPTH_BWD_GEMM_PASSES=3: dX / dW GEMMs in 3xTF32 and the fp32 deformable-attention backward.  Every gradient norm
     must then agree with the reference's to 2e-3 (measured: <= 1.3e-3; the default one-pass TF32 backward is held to 2e-2 in
     test_train_step_matches_reference), the head-side full gradients to 1e-3 of their largest entry (measured 5e-5).
@@ -82,6 +82,8 @@ def test_fp32_accurate_backward_matches_reference_gradients(name, monkeypatch):
     3xTF32 value_proj is amplified by |v| / |v01 - v00| there, which bounds them at ~5e-3 of the largest entry."""
     from gedepth_b200 import kernels
     monkeypatch.setattr(kernels, "BACKWARD_PASSES", 3)
+    prev = kernels.set_gemm_precision(3)               # forward in 3xTF32 as well: the activations the gradients multiply
+    request.addfinalizer(lambda: kernels.set_gemm_precision(prev))
     case, g, b = load_case(name)
     model, _ = build_host_model(case, DEV)
     model.train()

@@ -318,9 +318,10 @@ def test_window_attention_fwd_bwd(B, H, W, nH, shift, core, monkeypatch):
 # ------------------------------------------------------------------------------------------------
 # tcgen05 GEMM / conv (TF32: 10-bit mantissa products, fp32 accumulate)
 # ------------------------------------------------------------------------------------------------
-@pytest.fixture(params=[3, 1], ids=["3xtf32", "tf32"])
+@pytest.fixture(params=[3, 2, 1], ids=["3xtf32", "bf16x3", "tf32"])
 def passes(request, monkeypatch):
-    """GEMM arithmetic: 3 = error-compensated 3xTF32 (default, fp32-accurate), 1 = single-pass TF32.
+    """GEMM arithmetic: 3 = error-compensated 3xTF32 (fp32-accurate), 2 = bf16 hi/lo split (three kind::f16 products,
+    2^-16 per product; MN-major operands fall back to 3xTF32), 1 = single-pass TF32.
     The backward (dX) kernels follow the same setting in these tests."""
     from gedepth_b200 import kernels as Kn
     prev = Kn.set_gemm_precision(request.param)
@@ -333,7 +334,8 @@ def _gemm_tol(ref, passes, K=512):
     # 1 pass: tcgen05 kind::tf32 drops the low 13 mantissa bits of both operands -> ~1e-3 of the output scale.
     # 3 passes: hi*hi + lo*hi + hi*lo; what remains is the 2^-22 lo*lo term and the tensor core's fp32
     # accumulation (truncating alignment), which grows with the contraction length K.
-    return (1.5e-3 if passes == 1 else 1e-5 + 8e-9 * K) * float(ref.abs().max()) + 1e-6
+    # bf16 split: x = hi + lo to 2^-17, lo*lo dropped: ~2^-16 per product, random-sign accumulation
+    return (1.5e-3 if passes == 1 else (6e-5 if passes == 2 else 1e-5 + 8e-9 * K)) * float(ref.abs().max()) + 1e-6
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 96, 96), (1000, 288, 96), (24640, 384, 96), (777, 512, 512),

@@ -1,6 +1,7 @@
 """BASELINE config 5: ground-embedding kernel HBM-bandwidth sweep (256x512 -> 1024x2048, batch 1-64) on one GPU.
 CUDA-event timing, L2 flushed (256 MB write) before every launch; algorithmic bytes per SURVEY.md §8(d):
-Vanilla fwd 13 B/px, Vanilla bwd 13 B/px, Adaptive fwd 24 B/px (inference) / 68 B/px (training), ground_plane 8 B/px.
+Vanilla fwd 13 B/px, Vanilla bwd 13 B/px, Adaptive fwd 24 B/px (inference) / 68 B/px (training), Adaptive bwd 62 B/px,
+ground_plane 8 B/px.
 Writes CSV to stdout:  kernel,B,H,W,MB,us,GBs,frac_of_peak,l2_resident
 """
 import json, os, sys, torch
@@ -63,4 +64,15 @@ for (H, W) in [(256, 512), (352, 1120), (384, 640), (512, 1024), (768, 1536), (1
         us = timed(bwd)
         mb = 13 * px / 1e6
         print(f"ge_vanilla_bwd,{B},{H},{W},{mb:.1f},{us:.1f},{mb / us * 1e3:.0f},{mb / us * 1e3 / peak:.3f},{int(mb < 126)}", flush=True)
-        del img, yh, lh, gy, gp, g_half
+        # backward of the adaptive kernel through the C ABI (62 B/px: g_y, g_pe_mask, pe + 44 B/px g_logits + half-res in / out)
+        glf = torch.randn(B, 11, H, W, device=DEV)
+        g_lh = torch.empty(B, 11, H // 2, W // 2, device=DEV)
+        pe4 = img[:, 4]
+
+        def abwd():
+            K._call("ged_ge_adaptive_bwd", K._p(pe4), img.stride(0), K._p(yh), K._p(lh), None, 1.65, 200.0, K._p(gy), K._p(gp),
+                    K._p(glf), K._p(g_half), K._p(g_lh), B, H, W, H // 2, W // 2, K._stream())
+        us = timed(abwd)
+        mb = 62 * px / 1e6
+        print(f"ge_adaptive_bwd,{B},{H},{W},{mb:.1f},{us:.1f},{mb / us * 1e3:.0f},{mb / us * 1e3 / peak:.3f},{int(mb < 126)}", flush=True)
+        del img, yh, lh, gy, gp, g_half, glf, g_lh
