@@ -173,23 +173,40 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 // Each k-block then issues hi*hi + lo*hi + hi*lo as kind::f16 MMAs (K = 16 per instruction, half the tensor-pipe time
 // of the three kind::tf32 passes); the dropped lo*lo term and the residual of the split are 2^-16 relative per product,
 // 32x finer than the single-pass TF32 (2^-11) the reference's PyTorch runs on Ampere+.
-__device__ __forceinline__ void split_bf16_tile(const uint8_t* src, uint8_t* dst, int bytes, int st) {
-  for (int i = st; i < bytes / 32; i += 128) {
-    const int r = i >> 2, cp = i & 3;
-    const uint32_t row = (uint32_t)r * 128u, sw = (uint32_t)r & 7u;
-    const float4 x0 = *(const float4*)(src + row + (((2u * cp) ^ sw) << 4));
-    const float4 x1 = *(const float4*)(src + row + (((2u * cp + 1u) ^ sw) << 4));
-    const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-    uint32_t hv[4], lv[4];
+template <int BYTES>
+__device__ __forceinline__ void split_bf16_tile(const uint8_t* src, uint8_t* dst, int st) {
+  // every shared-memory load of the thread's items is issued before the first conversion (the loop is latency-bound
+  // otherwise: 4 splitter warps, one per scheduler)
+  constexpr int ITEMS = (BYTES / 32 + 127) / 128;
+  float4 x0[ITEMS], x1[ITEMS];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-      const __nv_bfloat162 l = __floats2bfloat162_rn(x[2 * e] - __low2float(h), x[2 * e + 1] - __high2float(h));
-      hv[e] = *reinterpret_cast<const uint32_t*>(&h);
-      lv[e] = *reinterpret_cast<const uint32_t*>(&l);
+  for (int it = 0; it < ITEMS; ++it) {
+    const int i = st + it * 128;
+    if (i < BYTES / 32) {
+      const int r = i >> 2, cp = i & 3;
+      const uint32_t row = (uint32_t)r * 128u, sw = (uint32_t)r & 7u;
+      x0[it] = *(const float4*)(src + row + (((2u * cp) ^ sw) << 4));
+      x1[it] = *(const float4*)(src + row + (((2u * cp + 1u) ^ sw) << 4));
     }
-    *(uint4*)(dst + row + (((uint32_t)cp ^ sw) << 4)) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
-    *(uint4*)(dst + row + (((4u + cp) ^ sw) << 4)) = make_uint4(lv[0], lv[1], lv[2], lv[3]);
+  }
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int i = st + it * 128;
+    if (i < BYTES / 32) {
+      const int r = i >> 2, cp = i & 3;
+      const uint32_t row = (uint32_t)r * 128u, sw = (uint32_t)r & 7u;
+      const float x[8] = {x0[it].x, x0[it].y, x0[it].z, x0[it].w, x1[it].x, x1[it].y, x1[it].z, x1[it].w};
+      uint32_t hv[4], lv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(x[2 * e] - __low2float(h), x[2 * e + 1] - __high2float(h));
+        hv[e] = *reinterpret_cast<const uint32_t*>(&h);
+        lv[e] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      *(uint4*)(dst + row + (((uint32_t)cp ^ sw) << 4)) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+      *(uint4*)(dst + row + (((4u + cp) ^ sw) << 4)) = make_uint4(lv[0], lv[1], lv[2], lv[3]);
+    }
   }
 }
 __device__ __forceinline__ Unit decode_unit(const GemmParams& p, int u, int BN_) {
@@ -475,7 +492,7 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
         const float4* hi = (const float4*)(stage_base + stage * S::STAGE_BYTES);
         float4* lo = (float4*)(stage_base + stage * S::STAGE_BYTES + S::HI_BYTES);
         if (SPLIT == 2) {
-          split_bf16_tile((const uint8_t*)hi, (uint8_t*)lo, S::HI_BYTES, st);
+          split_bf16_tile<S::HI_BYTES>((const uint8_t*)hi, (uint8_t*)lo, st);
         } else {
 #pragma unroll 4
         for (int i = st; i < S::HI_BYTES / 16; i += SPLIT_WARPS * 32) {
@@ -739,7 +756,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
         const float4* hi = (const float4*)(stage_base + stage * S::STAGE_BYTES);
         float4* lo = (float4*)(stage_base + stage * S::STAGE_BYTES + S::HI_BYTES);
         if (SPLIT == 2) {
-          split_bf16_tile((const uint8_t*)hi, (uint8_t*)lo, S::HI_BYTES, st);
+          split_bf16_tile<S::HI_BYTES>((const uint8_t*)hi, (uint8_t*)lo, st);
         } else {
 #pragma unroll 4
         for (int i = st; i < S::HI_BYTES / 16; i += SPLIT_WARPS * 32) {
@@ -804,10 +821,12 @@ template <int BN, int STAGES, int SPLIT>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES, SPLIT>;
   static_assert(S::TOTAL <= 232448, "shared memory budget (227 KB)");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};                 // the attribute is per device
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  if (!attr_set[dev_id & 63]) {
     if (cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return GED_ERR_LAUNCH;
-    attr_set = true;
+    attr_set[dev_id & 63] = true;
   }
   if (!g_num_sms) {
     int dev = 0;
@@ -901,10 +920,12 @@ template <int BN, int STAGES, int SPLIT>
 static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
   using S = Gemm2Smem<BN, STAGES, SPLIT>;
   static_assert(S::TOTAL <= 232448, "shared memory budget (227 KB)");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};                 // the attribute is per device
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  if (!attr_set[dev_id & 63]) {
     if (cudaFuncSetAttribute(gemm2_tf32_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess) return GED_ERR_LAUNCH;
-    attr_set = true;
+    attr_set[dev_id & 63] = true;
   }
   p.num_m_tiles = cdiv(p.M, BM2);
   p.num_n_tiles = cdiv(p.N, BN);

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ l
     const float t = __ldg(target + b * HW + i);
     if (t == ignore_index) continue;
     const int lab = (int)t;     // .long() truncation (decode_head.py:525)
+    if (lab < 0 || lab >= C) { s += (double)NAN; continue; }   // torch's CrossEntropyLoss asserts on such a label: fail loudly (NaN loss)
     float L[C], mx = -INFINITY;
 #pragma unroll
     for (int c = 0; c < C; ++c) { L[c] = __ldg(logits + ((int64_t)b * C + c) * HW + i); mx = fmaxf(mx, L[c]); }

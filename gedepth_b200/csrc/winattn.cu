@@ -238,8 +238,8 @@ GED_API int ged_winattn_bwd(const float* qkv, const float* qkv_bias, const float
   WinGeom g;
   if (int e = make_geom(H, W, shift, g)) return e;
   dim3 grid((g.Hp / WS) * g.nWx, nH, B);
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(winattn_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100); attr_set = true; }
+  // per device, so set on every call (cheap); a failure only costs occupancy, the launch below still reports errors
+  if (cudaFuncSetAttribute(winattn_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) (void)cudaGetLastError();
   winattn_bwd_kernel<<<grid, WA_THREADS, 0, stream>>>(qkv, qkv_bias, table, index, g_ctx, g_qkv, g_bias, g_table, g, C, nH, scale);
   GED_CHECK_LAUNCH();
   return GED_OK;

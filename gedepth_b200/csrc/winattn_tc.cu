@@ -350,6 +350,277 @@ __global__ void __launch_bounds__(TW_THREADS, 2) winattn_tc_fwd_kernel(
   }
 }
 
+
+// =====================================================================================================================
+// Backward on tcgen05 (one pass TF32, like every other backward GEMM; GEDEPTH_BWD_GEMM_PASSES=3 keeps the fp32 SIMT kernel).
+// Same duo work items and stacked M = 128 accumulators as the forward.  Per pair p (rows of the other pair: don't-care):
+//     S_p  [128 x 64] = [Q_A ; Q_B] . K_p^T          dP_p [128 x 64] = [dO_A ; dO_B] . V_p^T            (K-major operands)
+//     P = softmax(S + bias + mask),  dS = P o (dP - rowsum(P o dP))        one accumulator row per thread, from TMEM
+//     dV_p [128 x 32] = [P_A^T ; P_B^T] . dO_p       dK_p = [dS_A^T ; dS_B^T] . Q_p     (A MN-major: rows = query index)
+//     dQ_p [128 x 32] = [dS_A ; dS_B] . K_p                                              (A K-major, B MN-major)
+// Q, K, dO are staged twice (K-major for the products that contract over the head dimension, MN-major for the ones that
+// contract over tokens); the thread that owns row (p, i) writes P and dS back as operand tiles.  TMEM: S, dP in columns
+// 0..255; dV / dQ / dK re-use columns 64..255 once every row has been read.  220 KB of shared memory: one CTA per SM.
+// =====================================================================================================================
+constexpr int WB_QK = 0;            // [128][32]      K-major  (q * scale)
+constexpr int WB_KK = 16384;        // 2 x [64][32]   K-major
+constexpr int WB_VK = 32768;        // 2 x [64][32]   K-major
+constexpr int WB_GK = 49152;        // [128][32]      K-major  (dO)
+constexpr int WB_QM = 65536;        // 2 x [64][32]   MN-major (q * scale)
+constexpr int WB_KM = 81920;        // 2 x [64][32]   MN-major
+constexpr int WB_GM = 98304;        // 2 x [64][32]   MN-major (dO)
+constexpr int WB_PM = 114688;       // P^T operand:  4 panels (pair, 32 keys) x [64 query rows][128 B], MN-major   32 KB
+constexpr int WB_SM = 147456;       // dS^T operand, same layout                                                   32 KB
+constexpr int WB_SK = 180224;       // dS operand: 2 K-blocks (32 keys) x [128 rows][32], K-major                   32 KB
+constexpr int WB_MISC = 212992;
+constexpr int WB_OPERANDS = WB_MISC;
+constexpr int WB_TOTAL = WB_MISC + 8192 + 1024;
+
+struct TbMisc {
+  uint64_t bar_s, bar_o;
+  uint32_t tmem;
+  float gtab[2][176];               // rel-pos-bias gradient of the duo's two heads, by (dy + 6) * 13 + (dx + 6)
+  TwMeta meta[2];
+};
+static_assert(sizeof(TbMisc) <= 8192, "misc area");
+constexpr int TB_ITEMS = 2 * TW_N * 4 * 8;                    // 16-byte chunks of Q, K, V, dO of both pairs
+constexpr int TB_ITERS = (TB_ITEMS + TW_PROD - 1) / TW_PROD;  // 25 chunks per producer thread
+
+__device__ __forceinline__ void tb_load(float4 (&v)[TB_ITERS], const TwMeta& m, const float* __restrict__ qkv,
+                                        const float* __restrict__ bias, const float* __restrict__ g_ctx, int64_t L, int C, int ptid) {
+#pragma unroll
+  for (int it = 0; it < TB_ITERS; ++it) {
+    const int i = ptid + it * TW_PROD;
+    v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < TB_ITEMS) {
+      const int ck = i & 7, which = (i >> 3) & 3, r = i >> 5;
+      const int p = r / TW_N, n = r - p * TW_N;
+      if (m.pair_valid[p]) {
+        const int tok = m.tok[p][n];
+        if (which < 3) {
+          const int col = which * C + m.pair_head[p] * TW_HD + ck * 4;
+          if (tok >= 0) v[it] = __ldg((const float4*)(qkv + ((int64_t)m.pair_b[p] * L + tok) * 3 * C + col));
+          else if (bias) v[it] = __ldg((const float4*)(bias + col));       // zero-padded token: q = k = v = bias
+        } else if (tok >= 0) {                                             // cropped (padded) rows carry no gradient
+          v[it] = __ldg((const float4*)(g_ctx + ((int64_t)m.pair_b[p] * L + tok) * C + m.pair_head[p] * TW_HD + ck * 4));
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void tb_store(const float4 (&v)[TB_ITERS], uint8_t* smem, float scale, int ptid) {
+#pragma unroll
+  for (int it = 0; it < TB_ITERS; ++it) {
+    const int i = ptid + it * TW_PROD;
+    if (i >= TB_ITEMS) continue;
+    const int ck = i & 7, which = (i >> 3) & 3, r = i >> 5;
+    const int p = r / TW_N, n = r - p * TW_N;
+    float4 x = v[it];
+    const uint32_t ok = w_kmaj_chunk(n, ck), om = p * 8192 + w_mnmaj_chunk(n, ck);
+    if (which == 0) {
+      x.x *= scale; x.y *= scale; x.z *= scale; x.w *= scale;
+      *(float4*)(smem + WB_QK + w_kmaj_chunk(p * 64 + n, ck)) = x; *(float4*)(smem + WB_QM + om) = x;
+    } else if (which == 1) {
+      *(float4*)(smem + WB_KK + p * 8192 + ok) = x; *(float4*)(smem + WB_KM + om) = x;
+    } else if (which == 2) {
+      *(float4*)(smem + WB_VK + p * 8192 + ok) = x;
+    } else {
+      *(float4*)(smem + WB_GK + w_kmaj_chunk(p * 64 + n, ck)) = x; *(float4*)(smem + WB_GM + om) = x;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TW_THREADS, 1) winattn_tc_bwd_kernel(
+    const float* __restrict__ qkv, const float* __restrict__ bias, const float* __restrict__ table,
+    const float* __restrict__ g_ctx, float* __restrict__ g_qkv, float* __restrict__ g_bias, float* __restrict__ g_table,
+    TwGeom g, int B, int C, int nH, float scale, int num_pairs) {
+  extern __shared__ uint8_t w_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)w_smem_raw + 1023) & ~(uintptr_t)1023);
+  TbMisc& ms = *reinterpret_cast<TbMisc*>(smem + WB_MISC);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool producer = warp >= 4;
+  const int ptid = tid - 128;
+  const int64_t L = (int64_t)g.H * g.W;
+
+  if (tid == 0) {
+    w_mbar_init(&ms.bar_s, 1); w_mbar_init(&ms.bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(w_smem_u32(&ms.tmem)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // every operand byte starts finite: padding rows / keys are never written again and only meet zero probabilities
+  for (int i = tid; i < WB_OPERANDS / 16; i += TW_THREADS) *(float4*)(smem + i * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < 2 * 176; i += TW_THREADS) (&ms.gtab[0][0])[i] = 0.f;
+  w_fence_before();
+  __syncthreads();
+  w_fence_after();
+  const uint32_t tmem = ms.tmem;
+  const uint32_t sbase = w_smem_u32(smem);
+
+  if (producer) {
+    float4 v[TB_ITERS];
+    tw_prepare(ms.meta[0], g, table, blockIdx.x, num_pairs, nH, ptid);
+    tw_producer_sync();
+    tb_load(v, ms.meta[0], qkv, bias, g_ctx, L, C, ptid);
+    int buf = 0;
+    for (int duo = blockIdx.x; duo * 2 < num_pairs; duo += gridDim.x, buf ^= 1) {
+      tb_store(v, smem, scale, ptid);
+      w_fence_async();
+      tw_cta_sync();                                   // (A) operand tiles complete
+      const int nxt = duo + gridDim.x;
+      if (nxt * 2 < num_pairs) {                        // next work item: tables, then every global load in flight
+        tw_prepare(ms.meta[buf ^ 1], g, table, nxt, num_pairs, nH, ptid);
+        tw_producer_sync();
+        tb_load(v, ms.meta[buf ^ 1], qkv, bias, g_ctx, L, C, ptid);
+      }
+      tw_cta_sync();                                   // (B) P / dS written
+      tw_cta_sync();                                   // (C) gradients read: tiles and TMEM are free
+    }
+  } else {
+    uint32_t phase = 0;
+    int buf = 0;
+    const int row = tid, rp = row >> 6, ri = row & 63;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int duo = blockIdx.x; duo * 2 < num_pairs; duo += gridDim.x, buf ^= 1) {
+      const TwMeta& m = ms.meta[buf];
+      tw_cta_sync();                                   // (A)
+      if (tid == 0) {
+        w_fence_after();
+        constexpr uint32_t ids = w_idesc_tf32(128, 64, false, false);
+        const uint64_t qk = w_desc_kmajor(sbase + WB_QK), gk = w_desc_kmajor(sbase + WB_GK);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const uint64_t kk = w_desc_kmajor(sbase + WB_KK + p * 8192), vk = w_desc_kmajor(sbase + WB_VK + p * 8192);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) w_mma_tf32(tmem + p * 64, qk + 2 * k, kk + 2 * k, ids, k != 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) w_mma_tf32(tmem + 128 + p * 64, gk + 2 * k, vk + 2 * k, ids, k != 0);
+        }
+        w_commit(&ms.bar_s);
+      }
+      __syncwarp();
+      w_mbar_wait(&ms.bar_s, phase);
+      w_fence_after();
+      {
+        float s[64], dp[64];
+        w_ld32(lane_base + (uint32_t)(rp * 64), (uint32_t*)s);
+        w_ld32(lane_base + (uint32_t)(rp * 64 + 32), (uint32_t*)(s + 32));
+        w_ld32(lane_base + (uint32_t)(128 + rp * 64), (uint32_t*)dp);
+        w_ld32(lane_base + (uint32_t)(128 + rp * 64 + 32), (uint32_t*)(dp + 32));
+        const bool live = ri < TW_N && m.pair_valid[rp];
+        if (live) {
+          const int yi = ri / TW_WS, xi = ri - yi * TW_WS, li = m.lab[rp][ri];
+          const float* tb = m.tab[rp];
+          const bool masked = g.shift > 0;
+          float mx = -3.0e38f;
+#pragma unroll
+          for (int j = 0; j < TW_N; ++j) {
+            const int yj = j / TW_WS, xj = j - yj * TW_WS;
+            float x = s[j] + tb[(yi - yj + 6) * 13 + (xi - xj + 6)];
+            if (masked && m.lab[rp][j] != li) x += -100.0f;
+            s[j] = x;
+            mx = fmaxf(mx, x);
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < TW_N; ++j) { s[j] = exp2f((s[j] - mx) * 1.4426950408889634f); sum += s[j]; }
+          const float inv = 1.f / sum;
+          float dot = 0.f;
+#pragma unroll
+          for (int j = 0; j < TW_N; ++j) { s[j] *= inv; dot = fmaf(s[j], dp[j], dot); }
+          float* gt = ms.gtab[rp];
+#pragma unroll
+          for (int j = 0; j < TW_N; ++j) {
+            const int yj = j / TW_WS, xj = j - yj * TW_WS;
+            dp[j] = s[j] * (dp[j] - dot);                                   // dS
+            atomicAdd(gt + (yi - yj + 6) * 13 + (xi - xj + 6), dp[j]);
+          }
+          // P and dS rows -> operand tiles; keys 49..51 share the last written chunk and are zero, chunks beyond stay zero
+#pragma unroll
+          for (int c = 0; c < 13; ++c) {
+            float4 pv, dv;
+            pv.x = 4 * c + 0 < TW_N ? s[4 * c + 0] : 0.f; dv.x = 4 * c + 0 < TW_N ? dp[4 * c + 0] : 0.f;
+            pv.y = 4 * c + 1 < TW_N ? s[4 * c + 1] : 0.f; dv.y = 4 * c + 1 < TW_N ? dp[4 * c + 1] : 0.f;
+            pv.z = 4 * c + 2 < TW_N ? s[4 * c + 2] : 0.f; dv.z = 4 * c + 2 < TW_N ? dp[4 * c + 2] : 0.f;
+            pv.w = 4 * c + 3 < TW_N ? s[4 * c + 3] : 0.f; dv.w = 4 * c + 3 < TW_N ? dp[4 * c + 3] : 0.f;
+            const uint32_t om = (uint32_t)(rp * 2 + (c >> 3)) * 8192u + w_mnmaj_chunk(ri, c & 7);
+            *(float4*)(smem + WB_PM + om) = pv;
+            *(float4*)(smem + WB_SM + om) = dv;
+            *(float4*)(smem + WB_SK + (c >> 3) * 16384 + w_kmaj_chunk(row, c & 7)) = dv;
+          }
+        }
+      }
+      w_fence_async();
+      w_fence_before();
+      tw_cta_sync();                                   // (B)
+      if (tid == 0) {
+        w_fence_after();
+        constexpr uint32_t id_mm = w_idesc_tf32(128, 32, true, true), id_km = w_idesc_tf32(128, 32, false, true);
+        const uint64_t pm = w_desc_mnmajor(sbase + WB_PM, 8192), sm = w_desc_mnmajor(sbase + WB_SM, 8192);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const uint64_t gm = w_desc_mnmajor(sbase + WB_GM + p * 8192, 8192), km = w_desc_mnmajor(sbase + WB_KM + p * 8192, 8192),
+                         qm = w_desc_mnmajor(sbase + WB_QM + p * 8192, 8192);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) w_mma_tf32(tmem + 64 + p * 32, pm + 64u * k, gm + 64u * k, id_mm, k != 0);       // dV
+#pragma unroll
+          for (int k = 0; k < 8; ++k)                                                                             // dQ
+            w_mma_tf32(tmem + 128 + p * 32, w_desc_kmajor(sbase + WB_SK + (k >> 2) * 16384) + 2 * (k & 3), km + 64u * k, id_km, k != 0);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) w_mma_tf32(tmem + 192 + p * 32, sm + 64u * k, qm + 64u * k, id_mm, k != 0);      // dK
+        }
+        w_commit(&ms.bar_o);
+      }
+      __syncwarp();
+      // rel-pos-bias gradient of the two heads: every consumer passed (B), so the table is complete; flush and clear
+      for (int i = tid; i < 2 * 169; i += 128) {
+        const int p = i / 169, e = i - p * 169;
+        const float vsum = ms.gtab[p][e];
+        if (vsum != 0.f) { atomicAdd(g_table + (int64_t)e * nH + m.pair_head[p], vsum); ms.gtab[p][e] = 0.f; }
+      }
+      w_mbar_wait(&ms.bar_o, phase);
+      w_fence_after();
+      {
+        const int tok = m.tok[rp][ri];
+        const bool wr = tok != -2 && m.pair_valid[rp];
+        const int col = m.pair_head[rp] * TW_HD;
+        float* gp = tok >= 0 ? g_qkv + ((int64_t)m.pair_b[rp] * L + tok) * 3 * C + col : nullptr;
+#pragma unroll
+        for (int which = 0; which < 3; ++which) {             // dQ (cols 128), dK (cols 192), dV (cols 64)
+          float o[32];
+          const uint32_t cbase = which == 0 ? 128u : (which == 1 ? 192u : 64u);
+          w_ld32(lane_base + cbase + (uint32_t)(rp * 32), (uint32_t*)o);      // warp-collective: every lane takes part
+          if (wr && tok >= 0) {
+            float4* dst = (float4*)(gp + which * C);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float4 x = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+              if (which == 0) { x.x *= scale; x.y *= scale; x.z *= scale; x.w *= scale; }
+              dst[c] = x;
+            }
+          } else if (wr && g_bias && which > 0) {            // zero-padded token: its k = v = bias (its output row is cropped: dq = 0)
+#pragma unroll
+            for (int d = 0; d < 32; ++d) atomicAdd(g_bias + which * C + col + d, o[d]);
+          }
+        }
+      }
+      phase ^= 1;
+      w_fence_before();
+      tw_cta_sync();                                   // (C) TMEM and the operand tiles are free for the next work item
+      w_fence_after();
+    }
+  }
+  w_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    w_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256) : "memory");
+  }
+}
+
 }  // namespace ged
 using namespace ged;
 
@@ -369,6 +640,29 @@ GED_API int ged_winattn_tc_fwd(const float* qkv, const float* qkv_bias, const fl
   const int duos = (int)((pairs + 1) / 2);
   const int grid = duos < 148 * 2 * 4 ? duos : 148 * 2 * 4;       // 2 CTAs per SM, a few duos each
   winattn_tc_fwd_kernel<<<grid, TW_THREADS, W_TOTAL, stream>>>(qkv, qkv_bias, table, ctx, g, B, C, nH, scale, (int)pairs);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+// Same contract as ged_winattn_bwd (g_qkv fully overwritten, g_bias / g_table accumulated into), one pass TF32 on tcgen05.
+GED_API int ged_winattn_tc_bwd(const float* qkv, const float* qkv_bias, const float* table, const float* g_ctx, float* g_qkv,
+                               float* g_bias, float* g_table, int B, int H, int W, int C, int nH, int window, int shift,
+                               float scale, cudaStream_t stream) {
+  if (!qkv || !table || !g_ctx || !g_qkv || !g_table || B <= 0) return GED_ERR_ARG;
+  if (window != TW_WS || C != nH * TW_HD || H <= 0 || W <= 0 || shift < 0 || shift >= TW_WS) return GED_ERR_SHAPE;
+  if (!aligned16(qkv) || !aligned16(g_ctx) || !aligned16(g_qkv) || (qkv_bias && !aligned16(qkv_bias))) return GED_ERR_ALIGN;
+  TwGeom g;
+  g.H = H; g.W = W; g.shift = shift;
+  g.Hp = cdiv(H, TW_WS) * TW_WS; g.Wp = cdiv(W, TW_WS) * TW_WS; g.nWx = g.Wp / TW_WS; g.nWin = (g.Hp / TW_WS) * g.nWx;
+  const int64_t pairs = (int64_t)B * g.nWin * nH;
+  if (pairs > 0x7fffffff) return GED_ERR_SHAPE;
+  if (cudaFuncSetAttribute(winattn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WB_TOTAL) != cudaSuccess) return GED_ERR_LAUNCH;
+  const int duos = (int)((pairs + 1) / 2);
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = duos < sms ? duos : sms;                        // one CTA per SM, persistent over the duos
+  winattn_tc_bwd_kernel<<<grid, TW_THREADS, WB_TOTAL, stream>>>(qkv, qkv_bias, table, g_ctx, g_qkv, g_bias, g_table, g, B, C, nH,
+                                                               scale, (int)pairs);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }

@@ -39,6 +39,7 @@ SIGNATURES = {
     "ged_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P],
     "ged_winattn_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "ged_winattn_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    "ged_winattn_tc_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "ged_winattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "ged_gemm_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _I, _P, _F, C.c_uint, _P, _P],
     "ged_dropout_bwd": [_P, _I64, _P, _P, _I64, _I, _F, C.c_uint, _P, _P],
@@ -457,9 +458,14 @@ def layer_norm_fork(x, w, b, eps):
     return _LayerNorm.apply(x, w, b, eps, _sink(w), _sink(b), True)
 
 
-# Forward of the 49 x 49 core on tcgen05 (csrc/winattn_tc.cu, 3xTF32) unless GEDEPTH_WINATTN_TC=0; the backward is the
-# SIMT kernel of csrc/winattn.cu (it recomputes P in fp32).
+# Forward of the 49 x 49 core on tcgen05 (csrc/winattn_tc.cu, 3xTF32) unless GEDEPTH_WINATTN_TC=0.  The backward has a
+# tcgen05 implementation too (one pass TF32 like the other backward GEMMs; GEDEPTH_WINATTN_TC_BWD=1), parity-tested but
+# NOT the default: measured at Swin-L / B = 16 / 352 x 1120 it takes 59.8 ms per step against 38.3 ms for the fp32 SIMT
+# kernel of csrc/winattn.cu (tools/ab_winattn_bwd.py) - its 220 KB of operand tiles and 255 registers allow one CTA per SM
+# and the serial stage -> MMA -> softmax/dS -> MMA -> store chain of a work item leaves the SM 91 % idle (ncu:
+# profiles/r02_ncu_winattn_tc_bwd.csv).
 WINATTN_TC = os.environ.get("GEDEPTH_WINATTN_TC", "1") != "0"
+WINATTN_TC_BWD = os.environ.get("GEDEPTH_WINATTN_TC_BWD", "0") != "0"
 _STD_INDEX = {}
 
 
@@ -495,6 +501,7 @@ class _WinAttn(Function):
         ctx.save_for_backward(qkv, qkv_bias if qkv_bias is not None else torch.empty(0, device=qkv.device),
                               table_c, idx)
         ctx.cfg = (B, H, W, Cc, nH, ws, shift, float(scale), qkv_bias is not None)
+        ctx.std_index = _standard_rel_index(index)
         return ctx_out
 
     @staticmethod
@@ -508,8 +515,12 @@ class _WinAttn(Function):
         g_bias = None
         if has_bias:
             g_bias = bias_sink if bias_sink is not None else torch.zeros(3 * Cc, dtype=torch.float32, device=qkv.device)
-        _call("ged_winattn_bwd", _p(qkv), _p(bias if has_bias else None), _p(table), _p(idx), _p(g), _p(g_qkv),
-              _p(g_bias), _p(g_table), B, H, W, Cc, nH, ws, shift, scale, _stream())
+        if WINATTN_TC and WINATTN_TC_BWD and BACKWARD_PASSES == 1 and ctx.std_index:
+            _call("ged_winattn_tc_bwd", _p(qkv), _p(bias if has_bias else None), _p(table), _p(g), _p(g_qkv),
+                  _p(g_bias), _p(g_table), B, H, W, Cc, nH, ws, shift, scale, _stream())
+        else:
+            _call("ged_winattn_bwd", _p(qkv), _p(bias if has_bias else None), _p(table), _p(idx), _p(g), _p(g_qkv),
+                  _p(g_bias), _p(g_table), B, H, W, Cc, nH, ws, shift, scale, _stream())
         return (g_qkv, None if bias_sink is not None else g_bias, None if table_sink is not None else g_table,
                 None, None, None, None, None, None, None, None, None)
 
