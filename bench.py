@@ -545,10 +545,11 @@ def main():
             hbm_kernels[k] = dict(ms=round(kern[k]["ms"], 3), calls=kern[k]["calls"], achieved_gbs=round(gb, 1),
                                   frac=round(gb / pk["hbm"], 3))
 
-    ge = swin_attn = cpu = None
+    ge = swin_attn = cpu = aug = None
     if extras:
         ge = ground_embed_probe(c, pk, Bn, H, W)
         swin_attn = swin_attention_probe(c, pk, spec, Bn, H, W, args.passes)
+        aug = train_augment_probe(c, pk)
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
@@ -568,11 +569,14 @@ def main():
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype=("f32 (fp32 storage and accumulation; forward GEMMs/convs error-compensated 3xTF32 on tcgen05, backward GEMMs "
                        "single-pass TF32 = what the reference's PyTorch 1.8 runs on Ampere+)") if args.passes == 3
+                else ("f32 storage and accumulation; forward GEMMs/convs bf16 hi/lo split (hi*hi + lo*hi + hi*lo as kind::f16, 2^-16 per "
+                      "product) on tcgen05, backward GEMMs single-pass TF32") if args.passes == 2
                 else "tf32 (single-pass TF32 forward and backward, fp32 storage and accumulation)", data="synthetic",
                 config=cfg,
                 e2e=dict(value=e2e_val, unit="frames/s", h2d_bytes_per_step=main_res["h2d"], d2h_bytes_per_step=4, ms_per_step=ms_e2e),
                 gpu_launches=main_res["launches"], clocks=main_res["clocks"], roofline=roof, roofline_tensor=roof_tensor,
-                msda_kernels=msda, ground_embed=ge, swin_window_attention=swin_attn, roofline_hbm_kernels=hbm_kernels,
+                msda_kernels=msda, ground_embed=ge, swin_window_attention=swin_attn, train_augment=aug,
+                roofline_hbm_kernels=hbm_kernels,
                 cpu_baseline=cpu, other_configs=others or None, gpu_library_baseline=lib,
                 vs_library_gpu=(value / lib["frames_s"]) if lib and "frames_s" in lib else None,
                 native_ops=ops.native_table(),
@@ -670,6 +674,50 @@ def ground_embed_probe(c, pk, Bn, H, W):
     del flush
     torch.cuda.empty_cache()
     return res
+
+
+def train_augment_probe(c, pk, frames=8):
+    """the KITTI train-time augmentation of the 5-channel input on the device (csrc/augment.cu) next to the
+    same chain through cv2 / numpy on the host (what the reference's data-loader workers run), same drawn parameters."""
+    import random
+    import numpy as np
+    torch = c.torch
+    from gedepth_b200 import augment as ga
+    from gedepth_b200.synth import synth_raw_frame
+    aug = ga.TrainAugmenter(c.dev)
+    np.random.seed(7)
+    random.seed(7)
+    img5, depth, lab = synth_raw_frame(7)
+    bgr = torch.from_numpy(np.ascontiguousarray(img5[:, :, 0:3].astype(np.uint8))).to(c.dev)
+    f = aug.frame_planes(bgr, torch.from_numpy(np.ascontiguousarray(img5[:, :, 3])).to(c.dev),
+                         torch.from_numpy(np.ascontiguousarray(img5[:, :, 4])).to(c.dev))
+    d, l = torch.from_numpy(depth).to(c.dev), torch.from_numpy(lab).to(c.dev)
+    params = [ga.draw_params() for _ in range(frames)]
+    run = lambda: aug([f] * frames, [d] * frames, [l] * frames, params)
+    for _ in range(3):
+        run()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    s.record()
+    for _ in range(reps):
+        run()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / reps
+    # algorithmic bytes per frame: KB window read (7 planes), canvas written and read back (7 planes), 7 output planes
+    by = sum(4.0 * 7 * (352 * 1216 + 2 * p["canvas_w"] * p["canvas_h"] + 352 * 704) for p in params)
+    out = dict(frames=frames, ms=round(ms, 3), frames_s=round(frames / ms * 1e3, 1), achieved_gbs=round(by / ms / 1e6, 1),
+               frac_of_hbm_peak=round(by / ms / 1e6 / pk["hbm"], 3),
+               note="resize + pad + rotate + flip + crop + ColorAug + Normalize, two kernels per frame launched per frame from the host "
+                    "(launch-bound at this size); bit-identical to the reference transforms for the same drawn parameters")
+    try:
+        from oracle import augment as oa           # CPU baseline leg: the same chain through cv2 / numpy on the host
+        t = sum(oa.cv2_reference_seconds(img5, depth, lab, p, reps=2) for p in params[:4]) / 4
+        out["cpu_cv2"] = dict(frames_s=round(1.0 / t, 1), cores=1, kind="port",
+                              sample="4 frames through cv2.resize / cv2.warpAffine / numpy as the reference's loader workers run them, one thread")
+    except Exception as ex:      # cv2 missing on the box
+        out["cpu_cv2"] = dict(unavailable=str(ex)[:80])
+    return out
 
 
 def swin_attention_probe(c, pk, spec, Bn, H, W, passes):

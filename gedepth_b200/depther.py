@@ -52,7 +52,9 @@ class GroundEmbedding(nn.Module):
             y, pe_mask = ops.ge_vanilla(img, y_half)
             return y, pe_mask, None
         h = self.cam_height if height is None else height
-        return ops.ge_adaptive(img, y_half, logits_half, h, self.depth_scale)
+        # the full-resolution logits feed the CE loss of forward_train: keyed on training mode, not on autograd's grad mode
+        # (forward_train under torch.no_grad() still reports loss_dynamic_pe)
+        return ops.ge_adaptive(img, y_half, logits_half, h, self.depth_scale, want_logits=self.training or torch.is_grad_enabled())
 
 
 class BaseDepther(BaseModule):

@@ -110,3 +110,24 @@ def synth_batch(B: int, H: int, W: int, seed: int = 1234, depth_scale: float = 2
         k = rng.integers(0, 11, (B, H, W)).astype(np.float32)
         out["pe_k_gt"] = np.where(gt[:, 0] > 0, k, 255).astype(np.float32)
     return out
+
+
+def synth_raw_frame(seed: int, h: int = 375, w: int = 1242):
+    """Un-augmented KITTI-shaped frame as the train loader stacks it (loading.py:362,388-403,524-527): (h, w, 5) float32 =
+    BGR image as float, the clamped ground-plane map, the raw one; sparse depth (h, w); slope labels (h, w) in {0..10} with
+    255 where there is no LiDAR return.  Input of the device augmentation (augment.py) in bench.py and the tests."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    base = np.stack([127 + 90 * np.sin(xx / (37.0 + 5 * c) + c) * np.cos(yy / (23.0 + 3 * c)) for c in range(3)], -1)
+    bgr = np.clip(base + rng.normal(0, 12, (h, w, 3)), 0, 255).astype(np.uint8)
+    num, cu, cv, c1 = kitti_plane_coef()
+    with np.errstate(divide="ignore"):
+        pe = (num / (cu * np.arange(w, dtype=np.float64)[None, :] + cv * np.arange(h, dtype=np.float64)[:, None] + c1)).astype(np.float32)
+    pe_c = pe.copy()
+    pe_c[pe_c > 200] = 0
+    pe_c[pe_c < 0] = 0
+    img5 = np.concatenate([bgr.astype(np.float32), pe_c[:, :, None], pe[:, :, None]], -1).astype(np.float32)
+    keep = rng.random((h, w)) < 0.06
+    depth = np.where(keep, rng.uniform(2, 80, (h, w)), 0).astype(np.float32)
+    lab = np.where(keep, rng.integers(0, 11, (h, w)), 255).astype(np.float32)
+    return img5, depth, lab

@@ -307,6 +307,25 @@ int ged_adamw_step(float* p, const float* g, float* m, float* v, const uint8_t* 
                    float beta2, float eps, float weight_decay, int step, const int* step_dev,
                    const float* lr_dev /* NULL, or the step's learning rate in device memory */, cudaStream_t stream);
 
+/* ---- train-time augmentation of the 5-channel input on the device (csrc/augment.cu) -------------------
+ * Replaces the CPU data-loader transforms of configs/depthformer/depthformer_v.py:13-33 - KBCrop, Resize, Padding,
+ * RandomRotate, RandomFlip, RandomCrop, ColorAug, Normalize (depth/datasets/pipelines/transforms.py:149-205, 484-732, 64-109,
+ * 208-296, 299-353, 356-417, 420-481, 12-61) - which run through mmcv into cv2.resize / cv2.warpAffine on float32 H x W x 5
+ * images.  Bit-identical to the reference for the same drawn parameters (OpenCV's own fixed-point / fp32 arithmetic). */
+/* planes 0..2 of a (5, H, W) float32 frame <- uint8 BGR (H, W, 3) */
+int ged_aug_u8_to_planes(const unsigned char* bgr, float* planes, int H, int W, cudaStream_t stream);
+/* KB window (top, left, sh x sw) of src5 (5 planes [H0][W0]) / depth / label -> resized to nw x nh (bilinear / nearest) ->
+ * placed at (pad_x, pad_y) on the cw x ch canvas (background 0 / 0 / 255) */
+int ged_aug_resize_pad(const float* src5, const float* depth, const float* label, int H0, int W0, int top, int left, int sh,
+                       int sw, int nw, int nh, int pad_x, int pad_y, int cw, int ch, float* canvas5, float* canvas_d,
+                       float* canvas_l, cudaStream_t stream);
+/* canvas -> rotate (minv6: inverted 2x3 matrix, double, host) -> flip -> crop -> ColorAug (colors3: float64 BGR factors, host)
+ * -> Normalize -> img (5, out_h, out_w), depth (out_h, out_w), label (out_h, out_w); mean3 / std3 in RGB order (host) */
+int ged_aug_warp_crop_norm(const float* canvas5, const float* canvas_d, const float* canvas_l, int cw, int ch,
+                           const double* minv6, int rotate, int flip, int crop_x, int crop_y, int out_w, int out_h, int color,
+                           float gamma, float brightness, const double* colors3, const float* mean3, const float* std3,
+                           float depth_scale, float* img, float* depth, float* label, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,12 +3,14 @@ four Swin stage shapes of 352 x 1120 (Swin-L and Swin-T head counts), L2 flushed
 import sys, torch
 sys.path.insert(0, '.')
 from gedepth_b200 import kernels as K
-from oracle import model as om
 DEV = 'cuda:0'
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 ONLY = sys.argv[2] if len(sys.argv) > 2 else ""
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
-index = om.relative_position_index(7).to(DEV)
+_c = torch.arange(7)
+_yy, _xx = torch.meshgrid(_c, _c, indexing="ij")
+_y, _x = _yy.reshape(-1), _xx.reshape(-1)
+index = ((_y[:, None] - _y[None, :] + 6) * 13 + (_x[:, None] - _x[None, :] + 6)).to(DEV)     # depthformer_swin.py:168-172
 
 
 def t_ms(fn, reps=5):
