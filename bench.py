@@ -676,7 +676,7 @@ def ground_embed_probe(c, pk, Bn, H, W):
     return res
 
 
-def train_augment_probe(c, pk, frames=8):
+def train_augment_probe(c, pk, frames=16):
     """the KITTI train-time augmentation of the 5-channel input on the device (csrc/augment.cu) next to the
     same chain through cv2 / numpy on the host (what the reference's data-loader workers run), same drawn parameters."""
     import random
@@ -708,8 +708,8 @@ def train_augment_probe(c, pk, frames=8):
     by = sum(4.0 * 7 * (352 * 1216 + 2 * p["canvas_w"] * p["canvas_h"] + 352 * 704) for p in params)
     out = dict(frames=frames, ms=round(ms, 3), frames_s=round(frames / ms * 1e3, 1), achieved_gbs=round(by / ms / 1e6, 1),
                frac_of_hbm_peak=round(by / ms / 1e6 / pk["hbm"], 3),
-               note="resize + pad + rotate + flip + crop + ColorAug + Normalize, two kernels per frame launched per frame from the host "
-                    "(launch-bound at this size); bit-identical to the reference transforms for the same drawn parameters")
+               note="resize + pad + rotate + flip + crop + ColorAug + Normalize: one descriptor copy + two kernels per BATCH; "
+                    "bit-identical to the reference transforms for the same drawn parameters")
     try:
         from oracle import augment as oa           # CPU baseline leg: the same chain through cv2 / numpy on the host
         t = sum(oa.cv2_reference_seconds(img5, depth, lab, p, reps=2) for p in params[:4]) / 4

@@ -86,10 +86,12 @@ class TrainAugmenter:
         self.crop_hw, self.kb_hw = tuple(crop_hw), tuple(kb_hw)
         self.depth_scale = float(depth_scale)
         mh, mw = int(kb_hw[0] * max_ratio) + 2, int(kb_hw[1] * max_ratio) + 2
-        self.canvas = torch.empty(7, mh * mw, dtype=torch.float32, device=self.device)      # 5 image planes, depth, labels
+        self._slot = 7 * mh * mw                                                            # 5 image planes, depth, labels
+        self.canvas = torch.empty(self._slot, dtype=torch.float32, device=self.device)      # grows to one slot per frame
         self._mean = (C.c_float * 3)(*mean)
         self._std = (C.c_float * 3)(*std)
-        K.load()
+        self._frame_bytes = int(K.load().ged_aug_frame_bytes())
+        self._desc_dev = torch.empty(0, dtype=torch.uint8, device=self.device)
 
     def frame_planes(self, bgr_u8: torch.Tensor, pe_clamped: torch.Tensor, pe_raw: torch.Tensor) -> torch.Tensor:
         """(5, H0, W0) float32 frame as the loader stacks it (loading.py:524-527): BGR as float, the clamped plane map
@@ -112,23 +114,28 @@ class TrainAugmenter:
         dep = torch.empty(B, 1, oh, ow, dtype=torch.float32, device=self.device)
         lab = torch.empty(B, oh, ow, dtype=torch.float32, device=self.device)
         sh, sw = self.kb_hw
+        if self.canvas.numel() < B * self._slot:
+            self.canvas = torch.empty(B * self._slot, dtype=torch.float32, device=self.device)
+        if self._desc_dev.numel() < B * self._frame_bytes:
+            self._desc_dev = torch.empty(B * self._frame_bytes, dtype=torch.uint8, device=self.device)
+        desc = C.create_string_buffer(B * self._frame_bytes)
         for i in range(B):
             f, d, l, p = frames[i], depth_gt[i], pe_k_gt[i], params[i]
             H0, W0 = int(f.shape[1]), int(f.shape[2])
             top, left = int(H0 - sh), int((W0 - sw) / 2)                                             # KBCrop :177-178
             cw, ch = int(p["canvas_w"]), int(p["canvas_h"])
-            if cw * ch > self.canvas.shape[1]:
+            if 7 * cw * ch > self._slot:
                 raise ValueError(f"canvas {cw}x{ch} exceeds the workspace")
-            # 5 image planes, the depth plane and the label plane, cw*ch floats each, packed at the front of the workspace
-            work = self.canvas.view(-1)
-            n = cw * ch
-            K._call("ged_aug_resize_pad", K._p(f), K._p(d), K._p(l), H0, W0, top, left, sh, sw, int(p["new_w"]), int(p["new_h"]),
-                    int(p["pad_x"]), int(p["pad_y"]), cw, ch, K._p(work), K._p(work[5 * n:]), K._p(work[6 * n:]), K._stream())
             minv = (C.c_double * 6)(*(_inverse_rotation(cw, ch, p["degree"]) if p["rotate"] else [0.0] * 6))
             colors = (C.c_double * 3)(*[float(c) for c in p["colors"]])
-            K._call("ged_aug_warp_crop_norm", K._p(work), K._p(work[5 * n:]), K._p(work[6 * n:]), cw, ch,
-                    C.cast(minv, C.c_void_p), int(p["rotate"]), int(p["flip"]), int(p["crop_x"]), int(p["crop_y"]), ow, oh,
-                    int(p["color"]), float(np.float32(p["gamma"])), float(np.float32(p["brightness"])),
-                    C.cast(colors, C.c_void_p), C.cast(self._mean, C.c_void_p), C.cast(self._std, C.c_void_p),
-                    self.depth_scale, K._p(img[i]), K._p(dep[i]), K._p(lab[i]), K._stream())
+            rc = K.load().ged_aug_pack_frame(
+                C.cast(desc, C.c_void_p), i, K._p(f), K._p(d), K._p(l), K._p(self.canvas[i * self._slot:]), K._p(img[i]), K._p(dep[i]),
+                K._p(lab[i]), H0, W0, top, left, sh, sw, int(p["new_w"]), int(p["new_h"]), int(p["pad_x"]), int(p["pad_y"]), cw, ch,
+                C.cast(minv, C.c_void_p), int(p["rotate"]), int(p["flip"]), int(p["crop_x"]), int(p["crop_y"]), ow, oh,
+                int(p["color"]), float(np.float32(p["gamma"])), float(np.float32(p["brightness"])), C.cast(colors, C.c_void_p),
+                C.cast(self._mean, C.c_void_p), C.cast(self._std, C.c_void_p), self.depth_scale)
+            if rc != 0:
+                raise RuntimeError(f"ged_aug_pack_frame failed for frame {i}: {rc}")
+        # cudaMemcpyAsync from pageable memory returns once `desc` has been staged, so the buffer may go out of scope here
+        K._call("ged_aug_train_batch", C.cast(desc, C.c_void_p), B, K._p(self._desc_dev), K._stream())
         return img, dep, lab

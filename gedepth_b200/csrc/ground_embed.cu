@@ -166,7 +166,7 @@ __device__ __forceinline__ void x2_weights(int j, int n, float (&w)[4]) {
 // read ONCE with aligned float4 loads (a lane's left / right neighbour columns come from its neighbours by warp
 // shuffle), G = g_y + g_pe_mask * pe * 200 is formed and contracted along x into shared memory; pass 2 contracts along y.
 constexpr int X2_H = 8;
-__global__ void __launch_bounds__(256) ge_vanilla_bwd_x2_kernel(
+__global__ void __launch_bounds__(256, 4) ge_vanilla_bwd_x2_kernel(
     const float* __restrict__ pe_norm, int64_t pe_bstride, const float* __restrict__ g_y,
     const float* __restrict__ g_pe_mask, float* __restrict__ g_y_half, int H, int W, int h2, int w2) {
   __shared__ float2 s_t[2 * X2_H + 2][64];
@@ -179,31 +179,45 @@ __global__ void __launch_bounds__(256) ge_vanilla_bwd_x2_kernel(
   float wxa[4], wxb[4];
   x2_weights(2 * t, w2, wxa);
   x2_weights(2 * t + 1, w2, wxb);
-  for (int r = ty; r < 2 * X2_H + 2; r += 4) {
+  // One row segment per iteration.  The loads of the NEXT iteration (and the warp's two outer neighbour columns, which only
+  // lanes 0 / 31 need) are issued before the current row is consumed: two rows in flight per warp, no dependent second
+  // round trip for the edge lanes.
+  struct RowLoads { float4 p4, y4, m4; float eL, eR; bool ok; };
+  auto issue = [&](int r) {
+    RowLoads q;
     const int oy = 2 * jy0 - 1 + r;
-    float2 acc = make_float2(0.f, 0.f);
-    const bool row_ok = oy >= 0 && oy < H;                // warp-uniform
-    float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int64_t row = (int64_t)oy * W;
-    const float* pp = pe_norm + (int64_t)b * pe_bstride + row;
-    const float* gy = g_y ? g_y + b * HW + row : nullptr;
-    const float* gm = g_pe_mask ? g_pe_mask + b * HW + row : nullptr;
-    if (row_ok && col_ok) {
-      const float4 p4 = __ldg((const float4*)(pp + c0));
-      const float4 y4 = gy ? ldg_stream((const float4*)(gy + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 m4 = gm ? ldg_stream((const float4*)(gm + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      G = make_float4(y4.x + m4.x * p4.x * 200.f, y4.y + m4.y * p4.y * 200.f, y4.z + m4.z * p4.z * 200.f,
-                      y4.w + m4.w * p4.w * 200.f);
+    q.ok = r < 2 * X2_H + 2 && oy >= 0 && oy < H && col_ok;
+    q.p4 = q.y4 = q.m4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    q.eL = q.eR = 0.f;
+    if (q.ok) {
+      const int64_t row = (int64_t)oy * W;
+      const float* pp = pe_norm + (int64_t)b * pe_bstride + row;
+      const float* gy = g_y ? g_y + b * HW + row : nullptr;
+      const float* gm = g_pe_mask ? g_pe_mask + b * HW + row : nullptr;
+      q.p4 = __ldg((const float4*)(pp + c0));
+      if (gy) q.y4 = ldg_stream((const float4*)(gy + c0));
+      if (gm) q.m4 = ldg_stream((const float4*)(gm + c0));
+      if (lane == 0 && c0 >= 1) q.eL = (gy ? __ldg(gy + c0 - 1) : 0.f) + (gm ? __ldg(gm + c0 - 1) * __ldg(pp + c0 - 1) * 200.f : 0.f);
+      if (lane == 31 && c0 + 4 < W) q.eR = (gy ? __ldg(gy + c0 + 4) : 0.f) + (gm ? __ldg(gm + c0 + 4) * __ldg(pp + c0 + 4) * 200.f : 0.f);
     }
+    return q;
+  };
+  RowLoads cur = issue(ty);
+  for (int r = ty; r < 2 * X2_H + 2; r += 4) {
+    const RowLoads nxt = issue(r + 4);
+    const float4 G = make_float4(cur.y4.x + cur.m4.x * cur.p4.x * 200.f, cur.y4.y + cur.m4.y * cur.p4.y * 200.f,
+                                 cur.y4.z + cur.m4.z * cur.p4.z * 200.f, cur.y4.w + cur.m4.w * cur.p4.w * 200.f);
     float left = __shfl_up_sync(0xffffffffu, G.w, 1), right = __shfl_down_sync(0xffffffffu, G.x, 1);
-    if (row_ok && col_ok) {
-      if (lane == 0) left = c0 >= 1 ? (gy ? __ldg(gy + c0 - 1) : 0.f) + (gm ? __ldg(gm + c0 - 1) * __ldg(pp + c0 - 1) * 200.f : 0.f) : 0.f;
-      if (lane == 31) right = c0 + 4 < W ? (gy ? __ldg(gy + c0 + 4) : 0.f) + (gm ? __ldg(gm + c0 + 4) * __ldg(pp + c0 + 4) * 200.f : 0.f) : 0.f;
+    float2 acc = make_float2(0.f, 0.f);
+    if (cur.ok) {
+      if (lane == 0) left = cur.eL;
+      if (lane == 31) right = cur.eR;
       if (c0 + 4 >= W) right = 0.f;
       acc.x = wxa[0] * left + wxa[1] * G.x + wxa[2] * G.y + wxa[3] * G.z;
       acc.y = wxb[0] * G.y + wxb[1] * G.z + wxb[2] * G.w + wxb[3] * right;
     }
     s_t[r][tx] = acc;
+    cur = nxt;
   }
   __syncthreads();
   if (2 * t >= w2) return;

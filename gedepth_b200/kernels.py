@@ -81,6 +81,10 @@ SIGNATURES = {
     "ged_aug_u8_to_planes": [_P, _P, _I, _I, _P],
     "ged_aug_resize_pad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "ged_aug_warp_crop_norm": [_P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _F, _P, _P, _P, _P],
+    "ged_aug_frame_bytes": [],
+    "ged_aug_pack_frame": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I,
+                           _I, _F, _F, _P, _P, _P, _F],
+    "ged_aug_train_batch": [_P, _I, _P, _P],
     "ged_sumsq": [_P, _I64, _P, _P],
     "ged_adamw_step": [_P, _P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _F, _F, _I, _P, _P, _P],
 }

@@ -325,6 +325,16 @@ int ged_aug_warp_crop_norm(const float* canvas5, const float* canvas_d, const fl
                            const double* minv6, int rotate, int flip, int crop_x, int crop_y, int out_w, int out_h, int color,
                            float gamma, float brightness, const double* colors3, const float* mean3, const float* std3,
                            float depth_scale, float* img, float* depth, float* label, cudaStream_t stream);
+/* Whole batch in two launches: fill frame `index` of a host array of B * ged_aug_frame_bytes() bytes with the union of the
+ * arguments above (`canvas`: 7 * cw * ch floats of workspace private to the frame), then ged_aug_train_batch copies the
+ * descriptors to `frames_dev` (same size) and runs both kernels over grid (blocks, B). */
+int ged_aug_frame_bytes(void);
+int ged_aug_pack_frame(void* frames_host, int index, const float* src5, const float* depth, const float* label, float* canvas,
+                       float* img, float* depth_out, float* label_out, int H0, int W0, int top, int left, int sh, int sw, int nw,
+                       int nh, int pad_x, int pad_y, int cw, int ch, const double* minv6, int rotate, int flip, int crop_x,
+                       int crop_y, int out_w, int out_h, int color, float gamma, float brightness, const double* colors3,
+                       const float* mean3, const float* std3, float depth_scale);
+int ged_aug_train_batch(const void* frames_host, int B, void* frames_dev, cudaStream_t stream);
 
 #ifdef __cplusplus
 }
