@@ -416,7 +416,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip other_configs / gpu_library_baseline / probes (N = 1 only anyway)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
-    ap.add_argument("--passes", type=int, default=3, choices=[1, 2, 3], help="forward GEMM arithmetic: 3 = 3xTF32 (fp32-accurate), 2 = bf16 hi/lo split (3 kind::f16 products), 1 = TF32")
+    ap.add_argument("--passes", type=int, default=3, choices=[1, 2, 3], help="forward GEMM arithmetic: 3 = 3xTF32 (fp32-accurate, default), 2 = bf16 hi/lo split (3 kind::f16 products), 1 = TF32")
     ap.add_argument("--ncu-step", action="store_true",
                     help="for `ncu --profile-from-start off`: warm up, bracket ONE eager step with cudaProfilerStart/Stop, exit")
     args = ap.parse_args()
@@ -498,6 +498,9 @@ def main():
     tensor_names = ("ged_gemm_tf32", "ged_conv3x3_tf32", "ged_gemm_tf32_bt", "ged_conv3x3_dx_tf32", "ged_gemm_dw_tf32")
     fwd_names = ("ged_gemm_tf32", "ged_conv3x3_tf32")
     tf32_peak = pk["bf16_sustained"] / 2.0
+    # tensor-pipe time of one algorithmic pass, in units of a TF32 pass: 3xTF32 issues 3 kind::tf32 MMAs per k-step, the bf16
+    # hi/lo split 3 kind::f16 MMAs at twice the TF32 rate, single-pass TF32 one
+    pipe_passes = {1: 1.0, 2: 1.5, 3: 3.0}
     tkey = f"{dom}@{args.workload}"
     if dom in tensor_names:
         tf = kern[dom]["flops"] / (kern[dom]["ms"] / 1e3) / 1e12
@@ -507,10 +510,11 @@ def main():
                     peak_note=f"TF32 dense = 1/2 of the {pk['src']} sustained bf16 cuBLAS figure ({pk['bf16_sustained']})",
                     calls_per_step=kern[dom]["calls"], avg_launch_ms=kern[dom]["ms"] / kern[dom]["calls"],
                     share_of_step=kern[dom]["ms"] / main_res["step_ms_profiled"], mma_passes=passes,
-                    issued_mma_frac=tf * passes / tf32_peak,
+                    issued_mma_frac=tf * pipe_passes[passes] / tf32_peak,
                     note="achieved counts ALGORITHMIC flops (2MNK) of all launches of this kernel in one step over their "
-                         "summed device time (CUDA events on the launching stream); the 3xTF32 forward issues 3 tcgen05.mma "
-                         "per k-step (issued_mma_frac)")
+                         "summed device time (CUDA events on the launching stream); issued_mma_frac = tensor-pipe time of the "
+                         "MMAs actually issued: mma_passes 3 = 3xTF32 (3 kind::tf32 MMAs per k-step), 2 = bf16 hi/lo split (3 "
+                         "kind::f16 MMAs at twice the TF32 rate = 1.5 TF32 passes), 1 = single-pass TF32")
     else:
         gbs = kern[dom]["flops"] / (kern[dom]["ms"] / 1e3) / 1e9 if kern[dom]["flops"] else None
         roof = dict(kernel=dom, bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s",
@@ -529,7 +533,7 @@ def main():
             return None
         alg = sum(t["flops"] for t in ks) / (ms / 1e3) / 1e12
         return dict(kernels=[k for k in names if k in kern], ms=round(ms, 3), algorithmic_tflops=alg, mma_passes=passes,
-                    issued_mma_tflops=alg * passes, tensor_pipe_frac=alg * passes / tf32_peak)
+                    issued_mma_tflops=alg * pipe_passes[passes], tensor_pipe_frac=alg * pipe_passes[passes] / tf32_peak)
     roof_tensor = dict(kernels=list(tensor_names), bound="tensor", achieved=tens_tf, peak=tf32_peak, unit="TFLOP/s",
                        frac=(tens_tf / tf32_peak) if tens_tf else None, share_of_step=tens_ms / main_res["step_ms_profiled"],
                        forward=group(fwd_names, args.passes),
@@ -757,7 +761,9 @@ def swin_attention_probe(c, pk, spec, Bn, H, W, passes):
         f_core = 2.0 * nW * nH * 49 * 49 * 32 * 2
         core_tc = kernels.WINATTN_TC if hasattr(kernels, "WINATTN_TC") else False
         ms = sum(t)
-        issued = passes * f_gemm + (passes * f_core if core_tc else 0.0)
+        # tensor-pipe time in TF32 passes: GEMMs per the forward arithmetic (3xTF32 = 3, bf16 split = 1.5, TF32 = 1); the core is
+        # always 3xTF32 when it runs on the tensor cores
+        issued = {1: 1.0, 2: 1.5, 3: 3.0}[passes] * f_gemm + (3.0 * f_core if core_tc else 0.0)
         return dict(shape=dict(tokens=[Bx, hh, ww], C=Cc, heads=nH, shift=shift), ms=dict(qkv=t[0], core=t[1], proj=t[2]),
                     algorithmic_tflops=(f_gemm + f_core) / ms / 1e9, issued_mma_tflops=issued / ms / 1e9,
                     tensor_pipe_frac=issued / ms / 1e9 / (pk["bf16_sustained"] / 2.0), core_on_tensor_cores=bool(core_tc))

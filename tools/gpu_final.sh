@@ -12,12 +12,12 @@ if [ "$NG" -ge 2 ]; then
   echo "rc=$?" >> gpurun_out/bench_n2.log
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/bench_ref_n2.log 2>&1
 fi
-timeout 900 python bench.py --backbone swin_l --variant a --batch 16 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_swinl_a.log 2>&1
-timeout 900 python bench.py --backbone swin_l --variant a --dataset ddad --batch 4 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_swinl_a_ddad.log 2>&1
+timeout 900 python bench.py --workload config2 --steps 5 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_config2.log 2>&1
+timeout 900 python bench.py --passes 2 --steps 5 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_p2.log 2>&1
 tail -n 4 gpurun_out/t_gpu.log; tail -n 2 gpurun_out/smoke.log
 python - <<'PY'
 import json
-for f in ['bench','bench_ref','bench_n2','bench_ref_n2','bench_swinl_a','bench_swinl_a_ddad']:
+for f in ['bench','bench_ref','bench_n2','bench_ref_n2','bench_config2','bench_p2']:
     try:
         txt=open(f'gpurun_out/{f}.log').read()
     except Exception as e:
