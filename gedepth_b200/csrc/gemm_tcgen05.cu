@@ -599,12 +599,16 @@ struct Gemm2Smem {
 };
 
 __device__ __forceinline__ Unit decode_unit2(const GemmParams& p, int u, int BN_) {
+  // same unit order as decode_unit (split-major, then output tap, then tile) with 256-row tiles
+  const int tiles = p.num_m_tiles * p.num_n_tiles, per = tiles * p.out_taps;
+  const int split = u / per, r = u - split * per;
   Unit t;
-  t.tap = 0;
-  t.m0 = (u / p.num_n_tiles) * BM2;
-  t.n0 = (u % p.num_n_tiles) * BN_;
-  t.kb0 = 0;
-  t.kb1 = p.total_kb;
+  t.tap = r / tiles;
+  const int tile = r - t.tap * tiles;
+  t.m0 = (tile / p.num_n_tiles) * BM2;
+  t.n0 = (tile % p.num_n_tiles) * BN_;
+  t.kb0 = split * p.kb_per_split;
+  t.kb1 = min(t.kb0 + p.kb_per_split, p.total_kb);
   return t;
 }
 
@@ -628,7 +632,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  const int num_units = p.num_m_tiles * p.num_n_tiles;
+  const int num_units = p.num_m_tiles * p.num_n_tiles * p.out_taps * p.splits;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&map_a) : "memory");
@@ -660,15 +664,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = stage_base + stage * S::STAGE_BYTES;
           mbar_expect_tx(full_bar + stage, S::HI_BYTES);
-          const int t = kb / p.kblocks_per_tap, kc = kb - t * p.kblocks_per_tap;
-          tma_load_2d(sa, &map_a, full_bar + stage, kc * BK, m0 + p.tap_off[t]);
-          if (!p.b_mn) {
-            tma_load_2d(sa + S::A_BYTES, &map_b, full_bar + stage, t * p.Kt + kc * BK, n0);
+          if (p.mode == 0) {
+            const int t = kb / p.kblocks_per_tap, kc = kb - t * p.kblocks_per_tap;
+            tma_load_2d(sa, &map_a, full_bar + stage, kc * BK, m0 + p.tap_off[t]);
+            if (!p.b_mn) {
+              tma_load_2d(sa + S::A_BYTES, &map_b, full_bar + stage, t * p.Kt + kc * BK, n0);
+            } else {
+#pragma unroll
+              for (int pnl = 0; pnl < BN / 64; ++pnl)
+                tma_load_2d(sa + S::A_BYTES + pnl * (BK * 128), &map_b, full_bar + stage,
+                            t * p.b_tap_cols + n0 + 32 * pnl, kc * BK);
+            }
           } else {
+            // weight gradient: operands as stored (rows = pixels), this CTA's 128 of the 256 M features and its half of the N panels
+#pragma unroll
+            for (int pnl = 0; pnl < BM / 32; ++pnl)
+              tma_load_2d(sa + pnl * (BK * 128), &map_a, full_bar + stage, m0 + 32 * pnl, kb * BK);
 #pragma unroll
             for (int pnl = 0; pnl < BN / 64; ++pnl)
-              tma_load_2d(sa + S::A_BYTES + pnl * (BK * 128), &map_b, full_bar + stage,
-                          t * p.b_tap_cols + n0 + 32 * pnl, kc * BK);
+              tma_load_2d(sa + S::A_BYTES + pnl * (BK * 128), &map_b, full_bar + stage, n0 + 32 * pnl, kb * BK + p.tap_off[u.tap]);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -677,9 +691,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
   } else if (warp == 1) {
     // ===== MMA issuer: one thread of the leader CTA =====
     if (lane == 0 && rank == 0) {
-      const bool b_mn = p.b_mn != 0;
-      const uint32_t idesc = umma_idesc_tf32(BM2, BN, false, b_mn);
-      const uint32_t kstep_b = b_mn ? 64u : 2u;
+      const bool a_mn = p.mode == 1, b_mn = p.mode == 1 || p.b_mn != 0;
+      const uint32_t idesc = umma_idesc_tf32(BM2, BN, a_mn, b_mn);
+      const uint32_t kstep_a = a_mn ? 64u : 2u, kstep_b = b_mn ? 64u : 2u;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
@@ -691,7 +705,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
           mbar_wait_cluster(ready_bar + stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
-          const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+          const uint64_t adesc = a_mn ? umma_desc_mnmajor_sw128_32b(sa, BK * 128) : umma_desc_kmajor_sw128(sa);
           const uint64_t bdesc = b_mn ? umma_desc_mnmajor_sw128_32b(sa + S::A_BYTES, BK * 128) : umma_desc_kmajor_sw128(sa + S::A_BYTES);
           if (SPLIT == 2) {
             const uint64_t as = adesc + (S::HI_BYTES >> 4), bs = bdesc + (S::HI_BYTES >> 4);
@@ -705,11 +719,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
           } else {
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
-            tc_mma_tf32_pair(tmem_d, adesc + 2 * k, bdesc + kstep_b * k, idesc, ((kb - u.kb0) | k) != 0);
+            tc_mma_tf32_pair(tmem_d, adesc + kstep_a * k, bdesc + kstep_b * k, idesc, ((kb - u.kb0) | k) != 0);
             if (SPLIT) {
               const uint64_t alo = adesc + (S::HI_BYTES >> 4), blo = bdesc + (S::HI_BYTES >> 4);
-              tc_mma_tf32_pair(tmem_d, alo + 2 * k, bdesc + kstep_b * k, idesc, 1u);
-              tc_mma_tf32_pair(tmem_d, adesc + 2 * k, blo + kstep_b * k, idesc, 1u);
+              tc_mma_tf32_pair(tmem_d, alo + kstep_a * k, bdesc + kstep_b * k, idesc, 1u);
+              tc_mma_tf32_pair(tmem_d, adesc + kstep_a * k, blo + kstep_b * k, idesc, 1u);
             }
           }
           }
@@ -725,7 +739,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
     if (!SPLIT && lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
-        for (int kb = 0; kb < p.total_kb; ++kb) {
+        const Unit u = decode_unit2(p, unit, BN);
+        for (int kb = u.kb0; kb < u.kb1; ++kb) {
           mbar_wait(full_bar + stage, phase);
           mbar_arrive_remote(mapa_rank(ready_bar + stage, 0));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -740,7 +755,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
     for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
       const Unit u = decode_unit2(p, unit, BN);
       epilogue_tile<BN>(p, tile_s, tmem_base + (uint32_t)(acc * BN), tmem_full + acc, acc_phase, u.m0 + (int)rank * BM, u.n0,
-                        p.D, q, half, lane);
+                        p.D + (int64_t)u.tap * p.tap_dstride, q, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(mapa_rank(tmem_empty + acc, 0));
@@ -751,7 +766,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
     const int st = threadIdx.x - (4 + EPI_WARPS) * 32;
     int stage = 0; uint32_t phase = 0;
     for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
-      for (int kb = 0; kb < p.total_kb; ++kb) {
+      const Unit u = decode_unit2(p, unit, BN);
+      for (int kb = u.kb0; kb < u.kb1; ++kb) {
         mbar_wait(full_bar + stage, phase);
         const float4* hi = (const float4*)(stage_base + stage * S::STAGE_BYTES);
         float4* lo = (float4*)(stage_base + stage * S::STAGE_BYTES + S::HI_BYTES);
@@ -916,6 +932,8 @@ static int dispatch(int bn, const CUtensorMap& ma, const CUtensorMap& mb, GemmPa
 static int g_pair = 2;        // 2 = CTA-pair kernel for large problems in both arithmetic modes (measured: one-pass dX GEMMs
                               // 45.4 -> 38.1 ms in config 3), 1 = for 3xTF32 only, 0 = never
 
+static int g_pair_dw = 1;     // weight-gradient GEMMs on the CTA-pair kernel where the output has >= 256 rows
+
 template <int BN, int STAGES, int SPLIT>
 static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
   using S = Gemm2Smem<BN, STAGES, SPLIT>;
@@ -929,10 +947,21 @@ static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams
   }
   p.num_m_tiles = cdiv(p.M, BM2);
   p.num_n_tiles = cdiv(p.N, BN);
-  p.out_taps = 1; p.tap_dstride = 0; p.splits = 1;
-  p.total_kb = p.ntaps * p.kblocks_per_tap; p.kb_per_split = p.total_kb;
-  const int units = p.num_m_tiles * p.num_n_tiles;
   const int max_clusters = g_num_sms / 2;
+  if (p.mode == 0) {
+    p.out_taps = 1; p.tap_dstride = 0; p.splits = 1;
+    p.total_kb = p.ntaps * p.kblocks_per_tap; p.kb_per_split = p.total_kb;
+  } else {
+    // split the contraction so that every SM pair gets ~2 units, but keep >= 8 k-blocks (256 pixel rows) per unit
+    const int base_units = p.num_m_tiles * p.num_n_tiles * p.out_taps;
+    int splits = cdiv(2 * max_clusters, base_units);
+    const int max_splits = p.total_kb / 8 > 0 ? p.total_kb / 8 : 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.kb_per_split = cdiv(p.total_kb, splits);
+    p.splits = cdiv(p.total_kb, p.kb_per_split);
+  }
+  const int units = p.num_m_tiles * p.num_n_tiles * p.out_taps * p.splits;
   const int clusters = units < max_clusters ? units : max_clusters;
   gemm2_tf32_kernel<BN, STAGES, SPLIT><<<2 * clusters, S::THREADS, S::TOTAL, stream>>>(ma, mb, p);
   GED_CHECK_LAUNCH();
@@ -958,7 +987,7 @@ static int pick_bn_pair(int M, int N) {
 }
 
 static int dispatch2(int bn, const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
-  if (g_precision == 2 && !p.b_mn) {
+  if (g_precision == 2 && p.mode == 0 && !p.b_mn) {
     switch (bn) {
       case 64: return launch_gemm2<64, 4, 2>(ma, mb, p, stream);
       case 128: return launch_gemm2<128, 4, 2>(ma, mb, p, stream);
@@ -1022,6 +1051,9 @@ static int run_dw(const float* G, int ldg, const float* X, int ldx, int64_t P, i
   if (int e = make_map_2d(&ma, G, P, p.M, ldg, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
   if (int e = make_map_2d(&mb, X, Px, p.N, ldx, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
   p.ntaps = 1; p.Kt = (int)P; p.kblocks_per_tap = cdiv((int)P, BK); p.total_kb = p.kblocks_per_tap;
+  // CTA-pair tiles (256 output features x bn): the X operand is re-read once per 256 instead of per 128 output features
+  if (g_pair_dw && g_precision == 1 && p.M >= 256 && (p.M % 256 == 0 || p.M >= 1024) && bn >= 64 && (bn % 64) == 0)
+    return dispatch2(bn, ma, mb, p, stream);
   return dispatch(bn, ma, mb, p, stream);
 }
 
@@ -1042,6 +1074,13 @@ GED_API int ged_set_gemm_precision(int passes) {
 GED_API int ged_set_gemm_pair(int on) {
   const int prev = g_pair;
   g_pair = on == 2 ? 2 : (on ? 1 : 0);
+  return prev;
+}
+
+// 1 = weight-gradient GEMMs use the CTA-pair kernel where the output has >= 256 rows (default), 0 = single-CTA kernels.
+GED_API int ged_set_gemm_pair_dw(int on) {
+  const int prev = g_pair_dw;
+  g_pair_dw = on ? 1 : 0;
   return prev;
 }
 

@@ -72,6 +72,7 @@ SIGNATURES = {
     "ged_set_gemm_precision": [_I],
     "ged_set_gemm_wide_tiles": [_I],
     "ged_set_gemm_pair": [_I],
+    "ged_set_gemm_pair_dw": [_I],
     "ged_set_ge_x2": [_I],
     "ged_set_msda_variant": [_I],
     "ged_gemm_dw_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I64, _I64, _I, _P, _I, _P],
@@ -594,6 +595,11 @@ def set_gemm_pair(on) -> int:
     """CTA-pair (cta_group::2) GEMM kernel for large problems: 2 = both arithmetic modes (default), 1 = 3xTF32 only,
     0 = off; returns the previous setting."""
     return load().ged_set_gemm_pair(int(on))
+
+
+def set_gemm_pair_dw(on: bool) -> int:
+    """Weight-gradient GEMMs on the CTA-pair kernel where the output has >= 256 rows (default on); returns the previous setting."""
+    return load().ged_set_gemm_pair_dw(int(bool(on)))
 
 
 def set_gemm_wide_tiles(on: bool) -> int:

@@ -167,6 +167,8 @@ int ged_set_gemm_precision(int passes);
 /* 1 (default) = large forward / dX problems run on CTA pairs (tcgen05 cta_group::2: a 256 x BN tile per two SMs,
  * each staging half of the operands), 0 = single-CTA kernels only.  Returns the previous value. */
 int ged_set_gemm_pair(int on);
+/* 1 (default): weight-gradient GEMMs with >= 256 output rows run on the CTA-pair kernel; 0: single-CTA kernels only */
+int ged_set_gemm_pair_dw(int on);
 /* 1 (default) = allow 192/256-column output tiles, 0 = at most 128.  Returns the previous value. */
 int ged_set_gemm_wide_tiles(int on);
 /* Weight gradients (autograd of every nn.Linear / Conv2d on the path; the reference gets them from cuBLAS /

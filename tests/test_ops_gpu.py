@@ -357,7 +357,8 @@ def test_gemm_plain(M, N, K, passes):
 
 
 @pytest.mark.parametrize("P,N,K", [(64, 32, 32), (600, 384, 96), (1000, 96, 288), (5000, 128, 128), (20011, 512, 64),
-                                   (70000, 64, 256), (3000, 1536, 384), (777, 16, 2304)])
+                                   (70000, 64, 256), (3000, 1536, 384), (777, 16, 2304), (24640, 2304, 768), (9000, 768, 192),
+                                   (4100, 1024, 100)])
 def test_gemm_dw(P, N, K, passes):
     """dW[n,k] = sum_p G[p,n] X[p,k] on tcgen05 with MN-major operands as stored; contraction split across SMs
     with atomic accumulation."""
@@ -368,12 +369,19 @@ def test_gemm_dw(P, N, K, passes):
     out = Kn.gemm_dw(G, X)
     ref = (G.double().t() @ X.double()).float()
     _close(out, ref, 0, _gemm_tol(ref, passes, P), f"dW {P}x{N}x{K}")
+    prev = Kn.set_gemm_pair_dw(False)                      # single-CTA kernel (the pair kernel serves N >= 256 in one-pass TF32)
+    try:
+        out1 = Kn.gemm_dw(G, X)
+    finally:
+        Kn.set_gemm_pair_dw(prev)
+    _close(out1, ref, 0, _gemm_tol(ref, passes, P), f"dW single-CTA {P}x{N}x{K}")
     # accumulation into a running gradient
     out2 = Kn.gemm_dw(G, X, out=ref.clone())
     _close(out2, 2 * ref, 0, 2 * _gemm_tol(ref, passes, P), "dW accumulate")
 
 
-@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 11, 35, 64, 64), (1, 22, 70, 576, 192), (3, 9, 12, 96, 32)])
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 11, 35, 64, 64), (1, 22, 70, 576, 192), (3, 9, 12, 96, 32), (2, 11, 35, 64, 512),
+                                            (1, 22, 70, 192, 768)])
 def test_conv3x3_dw_taps(B, H, W, Cin, Cout, passes):
     """3x3 weight gradient as nine row-shifted contractions over the zero-bordered NHWC operands."""
     from gedepth_b200 import kernels as Kn
