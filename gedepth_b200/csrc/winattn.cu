@@ -204,6 +204,232 @@ __global__ void __launch_bounds__(WA_THREADS, 4) winattn_bwd_kernel(
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward with the five 49 x 49 x 32 products on the tensor cores through warp-level mma.sync (m16n8k8, TF32 operands by
+// truncation, fp32 accumulate) - the arithmetic of every other backward GEMM (one pass TF32); GEDEPTH_BWD_GEMM_PASSES=3 keeps
+// the fp32 SIMT kernel above.  Same CTA-per-(window, head) structure (3 CTAs per SM hide the gather latency): the tiles
+// are far below the 128-row tcgen05 shape - the tcgen05 version (winattn_tc.cu) needs 220 KB of operand tiles per pair of
+// windows and leaves the SM 91 % idle - while the SIMT kernel is bound by shared-memory loads (6 wavefronts per 384 FMAs).
+// Here a warp owns a 16-row block of each product and feeds fragments straight from the padded (64-row) tiles.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int MR = 64;            // padded token count (rows 49..63 are zero)
+constexpr int MP = 36;            // pitch of the 32-float q / k / v / dO rows: fragment loads [row g][col t] hit 32 distinct banks
+constexpr int MS = 68;            // pitch of the 64 x 64 P / dS tiles
+constexpr int WM_SMEM = (4 * MR * MP + 2 * MR * MS) * 4;
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// A fragment (16 x 8) of a row-major tile: element (m, k) at t[m * pitch + k]
+__device__ __forceinline__ void frag_a_rm(uint32_t (&a)[4], const float* t, int pitch, int m0, int k0, int g, int tq) {
+  a[0] = __float_as_uint(t[(m0 + g) * pitch + k0 + tq]);
+  a[1] = __float_as_uint(t[(m0 + g + 8) * pitch + k0 + tq]);
+  a[2] = __float_as_uint(t[(m0 + g) * pitch + k0 + tq + 4]);
+  a[3] = __float_as_uint(t[(m0 + g + 8) * pitch + k0 + tq + 4]);
+}
+// A fragment of the TRANSPOSE of a row-major tile: element (m, k) at t[k * pitch + m]
+__device__ __forceinline__ void frag_a_tr(uint32_t (&a)[4], const float* t, int pitch, int m0, int k0, int g, int tq) {
+  a[0] = __float_as_uint(t[(k0 + tq) * pitch + m0 + g]);
+  a[1] = __float_as_uint(t[(k0 + tq) * pitch + m0 + g + 8]);
+  a[2] = __float_as_uint(t[(k0 + tq + 4) * pitch + m0 + g]);
+  a[3] = __float_as_uint(t[(k0 + tq + 4) * pitch + m0 + g + 8]);
+}
+// B fragment (8 x 8): element (k, n) at t[n * pitch + k] ("col": the operand stored as [n][k]) or at t[k * pitch + n]
+__device__ __forceinline__ void frag_b_nk(uint32_t (&b)[2], const float* t, int pitch, int k0, int n0, int g, int tq) {
+  b[0] = __float_as_uint(t[(n0 + g) * pitch + k0 + tq]);
+  b[1] = __float_as_uint(t[(n0 + g) * pitch + k0 + tq + 4]);
+}
+__device__ __forceinline__ void frag_b_kn(uint32_t (&b)[2], const float* t, int pitch, int k0, int n0, int g, int tq) {
+  b[0] = __float_as_uint(t[(k0 + tq) * pitch + n0 + g]);
+  b[1] = __float_as_uint(t[(k0 + tq + 4) * pitch + n0 + g]);
+}
+
+// relative-position index of (query i, key j): the reference's buffer (depthformer_swin.py:168-172), or its closed form
+// (dy + 6) * 13 + (dx + 6) when the host has verified that the buffer is the standard one (STD: no global lookups)
+template <bool STD>
+__device__ __forceinline__ int rel_index(const long long* __restrict__ index, int i, int j) {
+  if (STD) {
+    const int yi = i / WS, xi = i - yi * WS, yj = j / WS, xj = j - yj * WS;
+    return (yi - yj + WS - 1) * (2 * WS - 1) + (xi - xj + WS - 1);
+  }
+  return (int)__ldg(index + i * WN + j);
+}
+
+template <bool STD>
+__global__ void __launch_bounds__(WA_THREADS, 3) winattn_bwd_mma_kernel(
+    const float* __restrict__ qkv, const float* __restrict__ bias, const float* __restrict__ table,
+    const long long* __restrict__ index, const float* __restrict__ g_ctx, float* __restrict__ g_qkv,
+    float* __restrict__ g_bias, float* __restrict__ g_table, WinGeom g, int C, int nH, float scale) {
+  extern __shared__ __align__(16) float wm_smem[];
+  float* s_q = wm_smem;                     // [MR][MP]  q * scale
+  float* s_k = s_q + MR * MP;
+  float* s_v = s_k + MR * MP;
+  float* s_o = s_v + MR * MP;               // dO
+  float* s_s = s_o + MR * MP;               // [MR][MS]  S -> P
+  float* s_d = s_s + MR * MS;               // [MR][MS]  dP -> dS
+  __shared__ float s_tab[(2 * WS - 1) * (2 * WS - 1)], s_bias[(2 * WS - 1) * (2 * WS - 1)];
+  __shared__ int s_tok[WN], s_lab[WN];
+  const int win = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int wy = win / g.nWx, wx = win - wy * g.nWx;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  if (tid < WN) { int lab; s_tok[tid] = token_index(g, wy, wx, tid, lab); s_lab[tid] = lab; }
+  for (int i = tid; i < (2 * WS - 1) * (2 * WS - 1); i += WA_THREADS) { s_tab[i] = 0.f; s_bias[i] = __ldg(table + (int64_t)i * nH + head); }
+  // padding: rows 49..63 of q / k / v / dO (the gather writes every element of rows 0..48) and the whole P / dS tiles
+  for (int i = tid; i < 4 * (MR - WN) * MP / 4; i += WA_THREADS) {
+    const int tIdx = i / ((MR - WN) * MP / 4), r = i - tIdx * ((MR - WN) * MP / 4);
+    ((float4*)(wm_smem + tIdx * MR * MP + WN * MP))[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int i = tid; i < 2 * MR * MS / 4; i += WA_THREADS) ((float4*)s_s)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  const int64_t L = (int64_t)g.H * g.W, boff = (int64_t)b * L * 3 * C;
+  // gather q (scaled), k, v, dO: 49 tokens x 4 x 8 float4 chunks
+  for (int i = tid; i < WN * 32; i += WA_THREADS) {
+    const int n = i >> 5, which = (i >> 3) & 3, c4 = i & 7, t = s_tok[n];
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (which < 3) {
+      const int col = which * C + head * HD + c4 * 4;
+      if (t >= 0) x = __ldg((const float4*)(qkv + boff + (int64_t)t * 3 * C + col));
+      else if (bias) x = __ldg((const float4*)(bias + col));
+      if (which == 0) { x.x *= scale; x.y *= scale; x.z *= scale; x.w *= scale; }
+    } else if (t >= 0) {
+      x = __ldg((const float4*)(g_ctx + ((int64_t)b * L + t) * C + head * HD + c4 * 4));
+    }
+    float* dst = (which == 0 ? s_q : which == 1 ? s_k : which == 2 ? s_v : s_o) + n * MP + c4 * 4;
+    *(float4*)dst = x;
+  }
+  __syncthreads();
+  // ---- S = q k^T (+ bias, mask) and dP = dO v^T: warp = 16 rows x 32 columns of both ---------------------------------
+  {
+    const int m0 = (warp >> 1) * 16, nb = (warp & 1) * 32;
+    float accS[4][4], accP[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { accS[n][e] = 0.f; accP[n][e] = 0.f; }
+#pragma unroll
+    for (int k0 = 0; k0 < HD; k0 += 8) {
+      uint32_t aq[4], ao[4];
+      frag_a_rm(aq, s_q, MP, m0, k0, gq, tq);
+      frag_a_rm(ao, s_o, MP, m0, k0, gq, tq);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        uint32_t bk[2], bv[2];
+        frag_b_nk(bk, s_k, MP, k0, nb + 8 * n, gq, tq);
+        frag_b_nk(bv, s_v, MP, k0, nb + 8 * n, gq, tq);
+        mma_tf32_16x8x8(accS[n], aq, bk);
+        mma_tf32_16x8x8(accP[n], ao, bv);
+      }
+    }
+    const bool masked = g.shift > 0;
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = m0 + gq + (e >> 1) * 8, j = nb + 8 * n + 2 * tq + (e & 1);
+        if (i < WN && j < WN) {
+          float x = accS[n][e] + s_bias[rel_index<STD>(index, i, j)];
+          if (masked && s_lab[i] != s_lab[j]) x += -100.0f;
+          s_s[i * MS + j] = x;
+          s_d[i * MS + j] = accP[n][e];
+        }
+      }
+  }
+  __syncthreads();
+  // ---- softmax rows, dS = P o (dP - sum_j dP P), bias-table gradient: a warp takes TWO rows at a time so that the three
+  // shuffle reductions of one row overlap those of the other -----------------------------------------------------------
+  for (int i0 = 2 * warp; i0 < WN; i0 += 2 * (WA_THREADS / 32)) {
+    float a[2], b2[2], da[2], dbv[2];
+    const bool hi = lane + 32 < WN;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i = min(i0 + r, WN - 1);
+      a[r] = s_s[i * MS + lane]; b2[r] = hi ? s_s[i * MS + lane + 32] : -INFINITY;
+      da[r] = s_d[i * MS + lane]; dbv[r] = hi ? s_d[i * MS + lane + 32] : 0.f;
+    }
+    float mx[2] = {fmaxf(a[0], b2[0]), fmaxf(a[1], b2[1])};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mx[0] = fmaxf(mx[0], __shfl_xor_sync(0xffffffffu, mx[0], o)); mx[1] = fmaxf(mx[1], __shfl_xor_sync(0xffffffffu, mx[1], o)); }
+    float ea[2], eb[2], sum[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) { ea[r] = expf(a[r] - mx[r]); eb[r] = hi ? expf(b2[r] - mx[r]) : 0.f; sum[r] = ea[r] + eb[r]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], o); sum[1] += __shfl_xor_sync(0xffffffffu, sum[1], o); }
+    float pa[2], pb[2], dot[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) { const float inv = 1.f / sum[r]; pa[r] = ea[r] * inv; pb[r] = eb[r] * inv; dot[r] = pa[r] * da[r] + pb[r] * dbv[r]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { dot[0] += __shfl_xor_sync(0xffffffffu, dot[0], o); dot[1] += __shfl_xor_sync(0xffffffffu, dot[1], o); }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i = i0 + r;
+      if (i >= WN) break;
+      const float sa = pa[r] * (da[r] - dot[r]), sb = pb[r] * (dbv[r] - dot[r]);
+      s_s[i * MS + lane] = pa[r];
+      s_d[i * MS + lane] = sa;
+      atomicAdd(&s_tab[rel_index<STD>(index, i, lane)], sa);
+      if (hi) {
+        s_s[i * MS + lane + 32] = pb[r];
+        s_d[i * MS + lane + 32] = sb;
+        atomicAdd(&s_tab[rel_index<STD>(index, i, lane + 32)], sb);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < (2 * WS - 1) * (2 * WS - 1); i += WA_THREADS)
+    if (s_tab[i] != 0.f) atomicAdd(g_table + (int64_t)i * nH + head, s_tab[i]);
+  // ---- dV = P^T dO, dQ = dS k, dK = dS^T q: warp = 16 output rows x 16 channels of all three ---------------------------
+  {
+    const int m0 = (warp >> 1) * 16, nb = (warp & 1) * 16;
+    float accV[2][4], accQ[2][4], accK[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { accV[n][e] = 0.f; accQ[n][e] = 0.f; accK[n][e] = 0.f; }
+#pragma unroll 2
+    for (int k0 = 0; k0 < 56; k0 += 8) {          // contraction over the 49 (-> 56) tokens; rows beyond are zero
+      uint32_t apt[4], asr[4], ast[4];
+      frag_a_tr(apt, s_s, MS, m0, k0, gq, tq);    // P^T
+      frag_a_rm(asr, s_d, MS, m0, k0, gq, tq);    // dS
+      frag_a_tr(ast, s_d, MS, m0, k0, gq, tq);    // dS^T
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        uint32_t bo[2], bk[2], bq[2];
+        frag_b_kn(bo, s_o, MP, k0, nb + 8 * n, gq, tq);
+        frag_b_kn(bk, s_k, MP, k0, nb + 8 * n, gq, tq);
+        frag_b_kn(bq, s_q, MP, k0, nb + 8 * n, gq, tq);
+        mma_tf32_16x8x8(accV[n], apt, bo);
+        mma_tf32_16x8x8(accQ[n], asr, bk);
+        mma_tf32_16x8x8(accK[n], ast, bq);
+      }
+    }
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int r = m0 + gq + 8 * h2;
+      if (r >= WN) continue;
+      const int t = s_tok[r];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const int col = head * HD + nb + 8 * n + 2 * tq;
+        const float2 dq = make_float2(accQ[n][2 * h2] * scale, accQ[n][2 * h2 + 1] * scale);
+        const float2 dk = make_float2(accK[n][2 * h2], accK[n][2 * h2 + 1]);
+        const float2 dv = make_float2(accV[n][2 * h2], accV[n][2 * h2 + 1]);
+        if (t >= 0) {
+          float* gp = g_qkv + boff + (int64_t)t * 3 * C + col;
+          *(float2*)gp = dq;
+          *(float2*)(gp + C) = dk;
+          *(float2*)(gp + 2 * C) = dv;
+        } else if (g_bias) {
+          atomicAdd(g_bias + C + col, dk.x); atomicAdd(g_bias + C + col + 1, dk.y);
+          atomicAdd(g_bias + 2 * C + col, dv.x); atomicAdd(g_bias + 2 * C + col + 1, dv.y);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace ged
 using namespace ged;
 
@@ -241,6 +467,30 @@ GED_API int ged_winattn_bwd(const float* qkv, const float* qkv_bias, const float
   // per device, so set on every call (cheap); a failure only costs occupancy, the launch below still reports errors
   if (cudaFuncSetAttribute(winattn_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) (void)cudaGetLastError();
   winattn_bwd_kernel<<<grid, WA_THREADS, 0, stream>>>(qkv, qkv_bias, table, index, g_ctx, g_qkv, g_bias, g_table, g, C, nH, scale);
+  GED_CHECK_LAUNCH();
+  return GED_OK;
+}
+
+// ged_winattn_bwd with the five products on the tensor cores through warp-level mma.sync (one pass TF32, the arithmetic of
+// the other backward GEMMs); same contract.
+// std_index != 0: `index` has been verified (host) to be Swin's standard relative-position index; it is then evaluated in
+// closed form instead of being read.
+GED_API int ged_winattn_bwd_mma(const float* qkv, const float* qkv_bias, const float* table, const long long* index,
+                                const float* g_ctx, float* g_qkv, float* g_bias, float* g_table, int B, int H, int W, int C,
+                                int nH, int window, int shift, float scale, int std_index, cudaStream_t stream) {
+  if (!qkv || !table || !index || !g_ctx || !g_qkv || !g_table || B <= 0) return GED_ERR_ARG;
+  if (window != WS || C != nH * HD) return GED_ERR_SHAPE;
+  if (!aligned16(qkv) || !aligned16(g_ctx) || !aligned16(g_qkv) || (qkv_bias && !aligned16(qkv_bias))) return GED_ERR_ALIGN;
+  WinGeom g;
+  if (int e = make_geom(H, W, shift, g)) return e;
+  dim3 grid((g.Hp / WS) * g.nWx, nH, B);
+  if (cudaFuncSetAttribute(winattn_bwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WM_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(winattn_bwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WM_SMEM) != cudaSuccess)
+    return GED_ERR_LAUNCH;
+  if (std_index)
+    winattn_bwd_mma_kernel<true><<<grid, WA_THREADS, WM_SMEM, stream>>>(qkv, qkv_bias, table, index, g_ctx, g_qkv, g_bias, g_table, g, C, nH, scale);
+  else
+    winattn_bwd_mma_kernel<false><<<grid, WA_THREADS, WM_SMEM, stream>>>(qkv, qkv_bias, table, index, g_ctx, g_qkv, g_bias, g_table, g, C, nH, scale);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }

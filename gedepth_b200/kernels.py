@@ -40,6 +40,7 @@ SIGNATURES = {
     "ged_winattn_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "ged_winattn_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "ged_winattn_tc_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    "ged_winattn_bwd_mma": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P],
     "ged_winattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "ged_gemm_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _I, _P, _F, C.c_uint, _P, _P],
     "ged_dropout_bwd": [_P, _I64, _P, _P, _I64, _I, _F, C.c_uint, _P, _P],
@@ -474,20 +475,31 @@ def layer_norm_fork(x, w, b, eps):
 # profiles/r02_ncu_winattn_tc_bwd.csv).
 WINATTN_TC = os.environ.get("GEDEPTH_WINATTN_TC", "1") != "0"
 WINATTN_TC_BWD = os.environ.get("GEDEPTH_WINATTN_TC_BWD", "0") != "0"
-_STD_INDEX = {}
+# Default backward (one-pass TF32 arithmetic): the SIMT kernel's CTA-per-(window, head) structure with its five products on
+# warp-level mma.sync (csrc/winattn.cu::winattn_bwd_mma_kernel): 19.8 ms per step against 38.3 (SIMT) and 53-60 (tcgen05);
+# GEDEPTH_WINATTN_BWD_MMA=0 or GEDEPTH_BWD_GEMM_PASSES=3 select the fp32 SIMT kernel.
+WINATTN_BWD_MMA = os.environ.get("GEDEPTH_WINATTN_BWD_MMA", "1") != "0"
 
 
 def _standard_rel_index(index: torch.Tensor) -> bool:
     """True when `index` is Swin's relative-position index (dy + 6) * 13 + (dx + 6) (depthformer_swin.py:168-172), which the
     tensor-core kernel evaluates in closed form.  Checked once per buffer (device -> host copy on first use)."""
-    key = index.data_ptr()          # a registered buffer filled once at construction (depthformer_swin.py:168-172)
-    if key not in _STD_INDEX:
-        c = torch.arange(7)
-        yy, xx = torch.meshgrid(c, c, indexing="ij")
-        y, x = yy.reshape(-1), xx.reshape(-1)
-        want = (y[:, None] - y[None, :] + 6) * 13 + (x[:, None] - x[None, :] + 6)
-        _STD_INDEX[key] = tuple(index.shape) == (49, 49) and bool(torch.equal(index.detach().cpu().long(), want))
-    return _STD_INDEX[key]
+    # cached on the tensor object itself (never keyed by address: freed addresses are reused).  The buffer is filled once at
+    # construction (depthformer_swin.py:168-172); in-place copies of the same content (state_dict loads, Trainer.capture()'s
+    # snapshot restore) bump its version, so the version is deliberately not part of the key.
+    cached = getattr(index, "_ged_std_index", None)
+    if cached is not None:
+        return cached[1]
+    c = torch.arange(7)
+    yy, xx = torch.meshgrid(c, c, indexing="ij")
+    y, x = yy.reshape(-1), xx.reshape(-1)
+    want = (y[:, None] - y[None, :] + 6) * 13 + (x[:, None] - x[None, :] + 6)
+    std = tuple(index.shape) == (49, 49) and bool(torch.equal(index.detach().cpu().long(), want))
+    try:
+        index._ged_std_index = (index._version, std)
+    except Exception:
+        pass
+    return std
 
 
 class _WinAttn(Function):
@@ -526,6 +538,9 @@ class _WinAttn(Function):
         if WINATTN_TC and WINATTN_TC_BWD and BACKWARD_PASSES == 1 and ctx.std_index:
             _call("ged_winattn_tc_bwd", _p(qkv), _p(bias if has_bias else None), _p(table), _p(g), _p(g_qkv),
                   _p(g_bias), _p(g_table), B, H, W, Cc, nH, ws, shift, scale, _stream())
+        elif WINATTN_BWD_MMA and BACKWARD_PASSES == 1:
+            _call("ged_winattn_bwd_mma", _p(qkv), _p(bias if has_bias else None), _p(table), _p(idx), _p(g), _p(g_qkv),
+                  _p(g_bias), _p(g_table), B, H, W, Cc, nH, ws, shift, scale, int(ctx.std_index), _stream())
         else:
             _call("ged_winattn_bwd", _p(qkv), _p(bias if has_bias else None), _p(table), _p(idx), _p(g), _p(g_qkv),
                   _p(g_bias), _p(g_table), B, H, W, Cc, nH, ws, shift, scale, _stream())

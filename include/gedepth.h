@@ -116,6 +116,12 @@ int ged_winattn_fwd(const float* qkv, const float* qkv_bias, const float* table,
  * Swin's closed form (dy + 6) * 13 + (dx + 6) (depthformer_swin.py:168-172). */
 int ged_winattn_tc_fwd(const float* qkv, const float* qkv_bias, const float* table, float* ctx, int B, int H, int W, int C,
                        int nH, int window, int shift, float scale, cudaStream_t stream);
+/* ged_winattn_bwd with the five 49 x 49 x 32 products on the tensor cores through warp-level mma.sync (m16n8k8 TF32, one
+ * pass like the other backward GEMMs): the default backward of the path (csrc/winattn.cu). */
+int ged_winattn_bwd_mma(const float* qkv, const float* qkv_bias, const float* table, const long long* index,
+                        const float* g_ctx, float* g_qkv, float* g_bias, float* g_table, int B, int H, int W, int C, int nH,
+                        int window, int shift, float scale, int std_index /* index verified standard: closed form */,
+                        cudaStream_t stream);
 /* ged_winattn_bwd on the tensor cores (csrc/winattn_tc.cu): S, dP, dV, dQ, dK as tcgen05.mma (one pass TF32, like the
  * other backward GEMMs), softmax / dS one TMEM row per thread.  Standard Swin relative-position index only. */
 int ged_winattn_tc_bwd(const float* qkv, const float* qkv_bias, const float* table, const float* g_ctx, float* g_qkv,

@@ -284,13 +284,13 @@ def test_layernorm_fwd_bwd(rows, C):
         _close(p.grad, q.grad, 1e-4, 2e-5 * float(q.grad.abs().max()), n)
 
 
-@pytest.mark.parametrize("core", ["tcgen05", "tcgen05_fwd", "simt"])
+@pytest.mark.parametrize("core", ["path", "tcgen05", "tcgen05_fwd", "simt"])
 @pytest.mark.parametrize("B,H,W,nH,shift", [(2, 16, 40, 3, 0), (2, 16, 40, 3, 3), (1, 9, 21, 6, 3), (2, 7, 7, 12, 0), (1, 18, 42, 3, 3),
                                             (2, 11, 35, 24, 3), (1, 11, 35, 48, 0), (3, 12, 20, 3, 3), (1, 88, 280, 3, 3)])
 def test_window_attention_fwd_bwd(B, H, W, nH, shift, core, monkeypatch):
-    """`tcgen05`: forward (3xTF32) AND backward (one pass TF32, like every other backward GEMM) of the 49 x 49 core on the
-    tensor cores (csrc/winattn_tc.cu) - what the path runs; `tcgen05_fwd`: that forward with the fp32 SIMT backward (what
-    GEDEPTH_BWD_GEMM_PASSES=3 selects); `simt`: both directions SIMT fp32 (csrc/winattn.cu).  11 x 35 (stage 3 at
+    """`path`: what the step runs - tcgen05 forward (3xTF32, csrc/winattn_tc.cu) and the mma.sync backward (one pass TF32 like
+    every other backward GEMM, csrc/winattn.cu); `tcgen05`: forward AND backward on tcgen05 (optional, slower); `tcgen05_fwd`:
+    tcgen05 forward with the fp32 SIMT backward (what GEDEPTH_BWD_GEMM_PASSES=3 selects); `simt`: both directions SIMT fp32.  11 x 35 (stage 3 at
     352 x 1120, padded to 14 x 35) and 12 x 20 maps exercise padding tokens whose q = k = v = the qkv bias; odd pair
     counts exercise the half-empty last work item."""
     from gedepth_b200 import kernels as K
@@ -298,6 +298,7 @@ def test_window_attention_fwd_bwd(B, H, W, nH, shift, core, monkeypatch):
     from oracle import model as om
     monkeypatch.setattr(K, "WINATTN_TC", core != "simt")
     monkeypatch.setattr(K, "WINATTN_TC_BWD", core == "tcgen05")
+    monkeypatch.setattr(K, "WINATTN_BWD_MMA", core == "path")
     C = nH * 32
     g = torch.Generator().manual_seed(8)
     qkv0 = torch.randn(B, H * W, 3 * C, generator=g)
@@ -315,8 +316,36 @@ def test_window_attention_fwd_bwd(B, H, W, nH, shift, core, monkeypatch):
     for n, p, q in zip(("g_qkv", "g_bias", "g_table"), a1, a2):
         qg = q.grad if q.grad is not None else torch.zeros_like(q)      # no padded tokens -> bias unused
         # one pass TF32 (10-bit mantissa operands) through five chained products: ~2e-3 of the gradient's scale
-        atol = (3e-3 if core == "tcgen05" else 2e-5) * float(qg.abs().max()) + 1e-6
+        atol = (3e-3 if core in ("tcgen05", "path") else 2e-5) * float(qg.abs().max()) + 1e-6
         _close(p.grad, qg, 1e-3, atol, n)
+
+
+def test_window_attention_nonstandard_index():
+    """A relative-position index that is NOT Swin's standard one: the path must read the buffer (SIMT forward, mma.sync
+    backward with index lookups) instead of the closed form."""
+    from gedepth_b200 import kernels as K
+    from tests import ops_lib as L
+    from oracle import model as om
+    B, H, W, nH, shift = 2, 14, 21, 3, 3
+    C = nH * 32
+    g = torch.Generator().manual_seed(18)
+    qkv0 = torch.randn(B, H * W, 3 * C, generator=g)
+    bias0 = torch.randn(3 * C, generator=g) * 0.5
+    table0 = torch.randn(169, nH, generator=g) * 0.5
+    index = om.relative_position_index(7)
+    index = index[torch.randperm(49, generator=g)].contiguous().to(DEV)          # rows permuted: valid entries, not the closed form
+    assert not K._standard_rel_index(index)
+    a1 = [t.to(DEV).requires_grad_(True) for t in (qkv0, bias0, table0)]
+    a2 = [t.to(DEV).requires_grad_(True) for t in (qkv0, bias0, table0)]
+    o1 = K.window_attention(a1[0], a1[1], a1[2], index, (H, W), nH, 7, shift, 32 ** -0.5)
+    o2 = L.window_attention(a2[0], a2[1], a2[2], index, (H, W), nH, 7, shift, 32 ** -0.5)
+    _close(o1, o2, 1e-4, 1e-5, "context")
+    go = torch.randn_like(o1)
+    (o1 * go).sum().backward()
+    (o2 * go).sum().backward()
+    for n, p, q in zip(("g_qkv", "g_bias", "g_table"), a1, a2):
+        qg = q.grad if q.grad is not None else torch.zeros_like(q)
+        _close(p.grad, qg, 1e-3, 3e-3 * float(qg.abs().max()) + 1e-6, n)
 
 
 # ------------------------------------------------------------------------------------------------

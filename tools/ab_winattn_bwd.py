@@ -43,8 +43,11 @@ for st, (hh, ww) in enumerate(((88, 280), (44, 140), (22, 70), (11, 35))):
                          B, hh, ww, C, nH, 7, 3, 32 ** -0.5, _stream())
     tc = lambda: _call("ged_winattn_tc_bwd", _p(qkv), _p(bias), _p(table), _p(g), _p(g_qkv), _p(g_bias), _p(g_table),
                        B, hh, ww, C, nH, 7, 3, 32 ** -0.5, _stream())
-    a, b = t_ms(simt), t_ms(tc)
-    tot["simt"] += a * blocks; tot["tcgen05"] += b * blocks
+    mma = lambda: _call("ged_winattn_bwd_mma", _p(qkv), _p(bias), _p(table), _p(index), _p(g), _p(g_qkv), _p(g_bias), _p(g_table),
+                        B, hh, ww, C, nH, 7, 3, 32 ** -0.5, 1, _stream())
+    a, b, m = t_ms(simt), t_ms(tc), t_ms(mma)
+    tot["simt"] += a * blocks; tot["tcgen05"] += b * blocks; tot["mma"] = tot.get("mma", 0.0) + m * blocks
+    print(f"   mma.sync {m:.3f} ms")
     pairs = (-(-hh // 7)) * (-(-ww // 7)) * B * nH
     print(f"stage {st} B={B} {hh}x{ww} heads {nH}: simt {a:.3f} ms, tcgen05 {b:.3f} ms ({b * 1e3 / (pairs / 2) * 148:.2f} us per duo per SM)", flush=True)
-print(f"swin_l backward cores per step (blocks weighted): simt {tot['simt']:.2f} ms, tcgen05 {tot['tcgen05']:.2f} ms")
+print(f"swin_l backward cores per step (blocks weighted): simt {tot['simt']:.2f} ms, tcgen05 {tot['tcgen05']:.2f} ms, mma.sync {tot.get('mma', 0):.2f} ms")
