@@ -114,6 +114,27 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (128 lanes = rows, one 32-bit column per tf32 element of K), B from shared memory
+__device__ __forceinline__ void tc_mma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 consecutive columns of this thread's TMEM lane <- 32 registers
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+         "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+         "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -337,7 +358,9 @@ struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 4;       // 16 KB
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int HI_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGE_BYTES = HI_BYTES * (SPLIT ? 2 : 1);
+  // SPLIT == 3: 3xTF32 with the A operand (hi and lo) in tensor memory - only B keeps a lo tile in shared memory
+  static constexpr int STAGE_BYTES = SPLIT == 3 ? HI_BYTES + B_BYTES : HI_BYTES * (SPLIT ? 2 : 1);
+  static constexpr int A_TMEM_COLS = SPLIT == 3 ? STAGES * 2 * BK : 0;          // hi | lo, BK columns each, per stage
   static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
   static constexpr int BAR_BYTES = (3 * STAGES + 4) * 8 + 16;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
@@ -349,7 +372,9 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
     const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
     const GemmParams p) {
   using S = GemmSmem<BN, STAGES, SPLIT>;
-  constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr int TMEM_NEED = 2 * BN + S::A_TMEM_COLS;
+  static_assert(TMEM_NEED <= 512, "tensor memory budget");
+  constexpr int TMEM_COLS = (TMEM_NEED <= 32) ? 32 : (TMEM_NEED <= 64) ? 64 : (TMEM_NEED <= 128) ? 128 : (TMEM_NEED <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024B alignment
   uint8_t* stage_base = smem;
@@ -438,7 +463,17 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
           const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
           const uint64_t adesc = a_mn ? umma_desc_mnmajor_sw128_32b(sa, BK * 128) : umma_desc_kmajor_sw128(sa);
           const uint64_t bdesc = b_mn ? umma_desc_mnmajor_sw128_32b(sa + S::A_BYTES, BK * 128) : umma_desc_kmajor_sw128(sa + S::A_BYTES);
-          if (SPLIT == 2) {
+          if (SPLIT == 3) {
+            // A hi / lo in tensor memory (columns 2 BN + stage * 64 .. +31 / +32 .. +63), B hi = the fp32 tile, B lo behind it
+            const uint32_t ta = tmem_base + (uint32_t)(2 * BN + stage * 2 * BK);
+            const uint64_t blo = bdesc + (S::B_BYTES >> 4);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              tc_mma_tf32_ta(tmem_d, ta + UK * k, bdesc + 2 * k, idesc, ((kb - u.kb0) | k) != 0);      // hi(A) * hi(B)
+              tc_mma_tf32_ta(tmem_d, ta + BK + UK * k, bdesc + 2 * k, idesc, 1u);                       // lo(A) * hi(B)
+              tc_mma_tf32_ta(tmem_d, ta + UK * k, blo + 2 * k, idesc, 1u);                              // hi(A) * lo(B)
+            }
+          } else if (SPLIT == 2) {
             // bf16 hi/lo rows (K-major only): k-steps 0, 1 of a row are hi, 2, 3 are lo (32 bytes = 16 bf16 each)
             const uint64_t as = adesc + (S::HI_BYTES >> 4), bs = bdesc + (S::HI_BYTES >> 4);
             constexpr uint32_t idb = umma_idesc_bf16(BM, BN);
@@ -491,7 +526,40 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
         mbar_wait(full_bar + stage, phase);
         const float4* hi = (const float4*)(stage_base + stage * S::STAGE_BYTES);
         float4* lo = (float4*)(stage_base + stage * S::STAGE_BYTES + S::HI_BYTES);
-        if (SPLIT == 2) {
+        if (SPLIT == 3) {
+          // this thread's row of the A tile (row st = TMEM lane st; splitter warp w owns lane quadrant w % 4): 8 swizzled
+          // 16-byte chunks -> hi (the values as they are: the tensor core truncates) and lo = x - tf32(x) -> tensor memory
+          const uint8_t* arow = (const uint8_t*)hi + st * 128;
+          uint32_t vh[32], vl[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 x = *(const float4*)(arow + ((c ^ (st & 7)) << 4));
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              vh[4 * c + e] = __float_as_uint(xs[e]);
+              vl[4 * c + e] = __float_as_uint(xs[e] - __uint_as_float(__float_as_uint(xs[e]) & 0xFFFFE000u));
+            }
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)((st >> 5) * 32) << 16) + (uint32_t)(2 * BN + stage * 2 * BK);
+          tc_st32(ta, vh);
+          tc_st32(ta + BK, vl);
+          // B: lo tile behind the fp32 tile, in shared memory as before
+          const float4* bh = (const float4*)((const uint8_t*)hi + S::A_BYTES);
+          float4* bl = (float4*)((uint8_t*)hi + S::HI_BYTES);
+#pragma unroll 4
+          for (int i = st; i < S::B_BYTES / 16; i += SPLIT_WARPS * 32) {
+            const float4 x = bh[i];
+            float4 l;
+            l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+            l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+            l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+            l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+            bl[i] = l;
+          }
+          tc_wait_st();
+          tc_fence_before();
+        } else if (SPLIT == 2) {
           split_bf16_tile<S::HI_BYTES>((const uint8_t*)hi, (uint8_t*)lo, st);
         } else {
 #pragma unroll 4
@@ -832,6 +900,12 @@ static int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_
 static int g_num_sms = 0;
 static int g_wide_tiles = 1;   // allow BN = 192 / 256 (fewer re-reads of the A operand through L2)
 static int g_precision = 3;   // 1 = single-pass TF32, 3 = error-compensated 3xTF32 (fp32-accurate)
+// 1: the 3xTF32 single-CTA kernels (tiles <= 128 wide) keep the A operand's hi / lo in tensor memory (tcgen05.st by the
+// splitter, tcgen05.mma with a TMEM A operand).  Measured on the 64-wide 3x3 convs at 176 x 560: 3.82 vs 3.87 ms - their time
+// per k-block (~1160 clk against ~600 for one-pass TF32) also does not move with the splitter's width (4 / 8 warps, two
+// alternating groups), the ring depth (3 / 4 / 5 stages), the MMA count (a probe that skipped a third of them) or CTA
+// pairing (slower): tools/ab_gemm_narrow.py.  Off by default.
+static int g_a_tmem = 0;
 
 template <int BN, int STAGES, int SPLIT>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
@@ -906,6 +980,14 @@ static int dispatch(int bn, const CUtensorMap& ma, const CUtensorMap& mb, GemmPa
       case 192: return launch_gemm<192, 2, 2>(ma, mb, p, stream);
       case 256: return launch_gemm<256, 2, 2>(ma, mb, p, stream);
       default: return launch_gemm<128, 3, 2>(ma, mb, p, stream);
+    }
+  }
+  if (g_precision == 3 && g_a_tmem && p.mode == 0 && !p.b_mn && bn <= 128) {   // 3xTF32 with A hi / lo in tensor memory
+    switch (bn) {
+      case 32: return launch_gemm<32, 6, 3>(ma, mb, p, stream);
+      case 64: return launch_gemm<64, 5, 3>(ma, mb, p, stream);
+      case 96: return launch_gemm<96, 4, 3>(ma, mb, p, stream);
+      default: return launch_gemm<128, 3, 3>(ma, mb, p, stream);
     }
   }
   if (g_precision >= 2) {
@@ -1074,6 +1156,13 @@ GED_API int ged_set_gemm_precision(int passes) {
 GED_API int ged_set_gemm_pair(int on) {
   const int prev = g_pair;
   g_pair = on == 2 ? 2 : (on ? 1 : 0);
+  return prev;
+}
+
+// 1 = the 3xTF32 single-CTA kernels feed the A operand (hi and lo) from tensor memory, 0 (default) = from shared memory.
+GED_API int ged_set_gemm_a_tmem(int on) {
+  const int prev = g_a_tmem;
+  g_a_tmem = on ? 1 : 0;
   return prev;
 }
 

@@ -74,6 +74,7 @@ SIGNATURES = {
     "ged_set_gemm_wide_tiles": [_I],
     "ged_set_gemm_pair": [_I],
     "ged_set_gemm_pair_dw": [_I],
+    "ged_set_gemm_a_tmem": [_I],
     "ged_set_ge_x2": [_I],
     "ged_set_msda_variant": [_I],
     "ged_gemm_dw_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I64, _I64, _I, _P, _I, _P],
@@ -610,6 +611,12 @@ def set_gemm_pair(on) -> int:
     """CTA-pair (cta_group::2) GEMM kernel for large problems: 2 = both arithmetic modes (default), 1 = 3xTF32 only,
     0 = off; returns the previous setting."""
     return load().ged_set_gemm_pair(int(on))
+
+
+def set_gemm_a_tmem(on: bool) -> int:
+    """3xTF32 single-CTA kernels with the A operand's hi / lo in tensor memory (default off: measured neutral); returns the
+    previous setting."""
+    return load().ged_set_gemm_a_tmem(int(bool(on)))
 
 
 def set_gemm_pair_dw(on: bool) -> int:

@@ -385,6 +385,32 @@ def test_gemm_plain(M, N, K, passes):
     _close(out, ref, 0, _gemm_tol(ref, passes, K), f"gemm {M}x{N}x{K}")
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (1000, 64, 96), (24640, 96, 384), (777, 32, 512), (50000, 64, 2304), (3000, 128, 100)])
+def test_gemm_a_operand_from_tensor_memory(M, N, K):
+    """3xTF32 with the A operand's hi / lo parts written to tensor memory by the splitter warps (tcgen05.st) and read by
+    tcgen05.mma from there, against the shared-memory-operand kernel and fp64."""
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(77)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    prev_p = Kn.set_gemm_precision(3)
+    outs = {}
+    try:
+        for on in (1, 0):
+            prev = Kn.set_gemm_a_tmem(on)
+            try:
+                outs[on] = Kn.gemm(a, w, bias, "gelu")
+            finally:
+                Kn.set_gemm_a_tmem(prev)
+    finally:
+        Kn.set_gemm_precision(prev_p)
+    from tests import ops_lib as L
+    ref = L._act((a.double() @ w.double().t() + bias.double()).float(), "gelu")
+    _close(outs[1], ref, 0, _gemm_tol(ref, 3, K), "A from TMEM vs fp64")
+    _close(outs[1], outs[0], 0, 2e-6 * float(ref.abs().max()) + 1e-6, "A from TMEM vs A from shared memory")
+
+
 @pytest.mark.parametrize("P,N,K", [(64, 32, 32), (600, 384, 96), (1000, 96, 288), (5000, 128, 128), (20011, 512, 64),
                                    (70000, 64, 256), (3000, 1536, 384), (777, 16, 2304), (24640, 2304, 768), (9000, 768, 192),
                                    (4100, 1024, 100)])

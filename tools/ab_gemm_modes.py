@@ -19,7 +19,7 @@ def t_ms(fn, reps=5):
 
 
 for (M, N, Kd) in [(T0, 576, 192), (T0, 768, 192), (T0, 192, 768), (T0 // 4, 1536, 384), (T0 // 16, 2304, 768), (T0 // 16, 3072, 768),
-                   (T0 // 16, 768, 3072), (B * 98560 // 2, 512, 512), (T0, 64, 192)]:
+                   (T0 // 16, 768, 3072), (B * 98560 // 2, 512, 512), (T0, 64, 192), (T0, 96, 192), (T0 // 4, 128, 384)]:
     a, w = torch.randn(M, Kd, device=DEV), torch.randn(N, Kd, device=DEV) / Kd ** .5
     out = torch.empty(M, N, device=DEV)
     row = []
@@ -27,6 +27,11 @@ for (M, N, Kd) in [(T0, 576, 192), (T0, 768, 192), (T0, 192, 768), (T0 // 4, 153
         K.set_gemm_precision(passes)
         ms = t_ms(lambda: K.gemm(a, w, out=out))
         row.append(f"p{passes}: {ms:.3f} ms {2 * M * N * Kd / ms / 1e9:.0f} TF")
+        if passes == 3:
+            prev = K.set_gemm_a_tmem(1)
+            ms = t_ms(lambda: K.gemm(a, w, out=out))
+            K.set_gemm_a_tmem(prev)
+            row.append(f"p3 (A in TMEM): {ms:.3f} ms")
     print("gemm", M, N, Kd, " | ".join(row), flush=True)
     del a, w, out
 for (Bc, H, W, Ci, Co) in [(B, 176, 560, 256, 64), (B, 22, 70, 2304, 768), (B, 88, 280, 576, 192), (B, 44, 140, 1152, 384)]:
@@ -37,5 +42,10 @@ for (Bc, H, W, Ci, Co) in [(B, 176, 560, 256, 64), (B, 22, 70, 2304, 768), (B, 8
         K.set_gemm_precision(passes)
         ms = t_ms(lambda: K.conv3x3_padded(xp, wk, None, 'leaky_relu', 0.01))
         row.append(f"p{passes}: {ms:.3f} ms {2 * Bc * H * W * Ci * Co * 9 / ms / 1e9:.0f} TF")
+        if passes == 3:
+            prev = K.set_gemm_a_tmem(1)
+            ms = t_ms(lambda: K.conv3x3_padded(xp, wk, None, 'leaky_relu', 0.01))
+            K.set_gemm_a_tmem(prev)
+            row.append(f"p3 (A in TMEM): {ms:.3f} ms")
     print("conv3x3", Bc, H, W, Ci, Co, " | ".join(row), flush=True)
 K.set_gemm_precision(3)
