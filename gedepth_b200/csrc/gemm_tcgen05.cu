@@ -903,8 +903,11 @@ static int g_precision = 3;   // 1 = single-pass TF32, 3 = error-compensated 3xT
 // 1: the 3xTF32 single-CTA kernels (tiles <= 128 wide) keep the A operand's hi / lo in tensor memory (tcgen05.st by the
 // splitter, tcgen05.mma with a TMEM A operand).  Measured on the 64-wide 3x3 convs at 176 x 560: 3.82 vs 3.87 ms - their time
 // per k-block (~1160 clk against ~600 for one-pass TF32) also does not move with the splitter's width (4 / 8 warps, two
-// alternating groups), the ring depth (3 / 4 / 5 stages), the MMA count (a probe that skipped a third of them) or CTA
-// pairing (slower): tools/ab_gemm_narrow.py.  Off by default.
+// alternating groups), the ring depth (3 / 4 / 5 stages), the proxy fence, the polling style or CTA pairing (slower):
+// tools/ab_gemm_narrow.py.  Timing probes (no-op splitter, hi*hi MMAs only) leave the 3xTF32 kernel at 3.76 ms against
+// 1.94 ms for the one-pass kernel, and a single extra branch in the issuing loops costs the one-pass kernel 20 %: the
+// narrow tile is bound by the instruction stream of the ONE thread that issues tcgen05.mma (12 MMAs of 43 tensor-clocks
+// each per k-block), not by data movement.  Off by default.
 static int g_a_tmem = 0;
 
 template <int BN, int STAGES, int SPLIT>
