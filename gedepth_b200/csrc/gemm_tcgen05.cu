@@ -97,6 +97,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE_%=:\n\t}"
       :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// One lane of a CONVERGED warp.  The MMA issuer runs its loop with all 32 lanes and issues under this predicate: inside a
+// divergent `if (lane == 0)` the compiler cannot prove the descriptor / TMEM-address operands of tcgen05.mma uniform and wraps
+// every UTCHMMA in an elect-and-broadcast loop (PLOP3 / ELECT / R2UR.BROADCAST / BRA.U.ANY, ~8 instructions and a branch per
+// MMA), which paces the narrow tiles.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -443,8 +456,8 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop, one elected lane issues =====
+    {
       const bool a_mn = p.mode == 1, b_mn = p.mode == 1 || p.b_mn;
       const uint32_t idesc = umma_idesc_tf32(BM, BN, a_mn, b_mn);
       // K-major: 8 tf32 = 32 bytes inside the 128B swizzle row, +2 in the (addr>>4) field per k-step;
@@ -463,6 +476,7 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
           const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
           const uint64_t adesc = a_mn ? umma_desc_mnmajor_sw128_32b(sa, BK * 128) : umma_desc_kmajor_sw128(sa);
           const uint64_t bdesc = b_mn ? umma_desc_mnmajor_sw128_32b(sa + S::A_BYTES, BK * 128) : umma_desc_kmajor_sw128(sa + S::A_BYTES);
+          if (elect_one()) {
           if (SPLIT == 3) {
             // A hi / lo in tensor memory (columns 2 BN + stage * 64 .. +31 / +32 .. +63), B hi = the fp32 tile, B lo behind it
             const uint32_t ta = tmem_base + (uint32_t)(2 * BN + stage * 2 * BK);
@@ -496,6 +510,8 @@ __global__ void __launch_bounds__(GemmSmem<BN, STAGES, SPLIT>::THREADS, 1) gemm_
           }
           tc_commit(empty_bar + stage);          // frees the smem slot when these MMAs retire
           if (kb == u.kb1 - 1) tc_commit(tmem_full + acc);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -757,8 +773,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: one thread of the leader CTA =====
-    if (lane == 0 && rank == 0) {
+    // ===== MMA issuer: warp 1 of the leader CTA runs the loop, one elected lane issues =====
+    if (rank == 0) {
       const bool a_mn = p.mode == 1, b_mn = p.mode == 1 || p.b_mn != 0;
       const uint32_t idesc = umma_idesc_tf32(BM2, BN, a_mn, b_mn);
       const uint32_t kstep_a = a_mn ? 64u : 2u, kstep_b = b_mn ? 64u : 2u;
@@ -775,6 +791,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
           const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
           const uint64_t adesc = a_mn ? umma_desc_mnmajor_sw128_32b(sa, BK * 128) : umma_desc_kmajor_sw128(sa);
           const uint64_t bdesc = b_mn ? umma_desc_mnmajor_sw128_32b(sa + S::A_BYTES, BK * 128) : umma_desc_kmajor_sw128(sa + S::A_BYTES);
+          if (elect_one()) {
           if (SPLIT == 2) {
             const uint64_t as = adesc + (S::HI_BYTES >> 4), bs = bdesc + (S::HI_BYTES >> 4);
             constexpr uint32_t idb = umma_idesc_bf16(BM2, BN);
@@ -797,6 +814,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Smem<BN, STAGES
           }
           tc_commit_pair(empty_bar + stage);
           if (kb == u.kb1 - 1) tc_commit_pair(tmem_full + acc);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -900,15 +919,13 @@ static int make_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_
 static int g_num_sms = 0;
 static int g_wide_tiles = 1;   // allow BN = 192 / 256 (fewer re-reads of the A operand through L2)
 static int g_precision = 3;   // 1 = single-pass TF32, 3 = error-compensated 3xTF32 (fp32-accurate)
-// 1: the 3xTF32 single-CTA kernels (tiles <= 128 wide) keep the A operand's hi / lo in tensor memory (tcgen05.st by the
-// splitter, tcgen05.mma with a TMEM A operand).  Measured on the 64-wide 3x3 convs at 176 x 560: 3.82 vs 3.87 ms - their time
-// per k-block (~1160 clk against ~600 for one-pass TF32) also does not move with the splitter's width (4 / 8 warps, two
-// alternating groups), the ring depth (3 / 4 / 5 stages), the proxy fence, the polling style or CTA pairing (slower):
-// tools/ab_gemm_narrow.py.  Timing probes (no-op splitter, hi*hi MMAs only) leave the 3xTF32 kernel at 3.76 ms against
-// 1.94 ms for the one-pass kernel, and a single extra branch in the issuing loops costs the one-pass kernel 20 %: the
-// narrow tile is bound by the instruction stream of the ONE thread that issues tcgen05.mma (12 MMAs of 43 tensor-clocks
-// each per k-block), not by data movement.  Off by default.
-static int g_a_tmem = 0;
+// 1 (default): the 3xTF32 single-CTA kernels (tiles <= 128 wide) keep the A operand's hi / lo in tensor memory (tcgen05.st by
+// the splitter, tcgen05.mma with a TMEM A operand): the MMAs then read only B from shared memory.  Narrow tiles spend 43
+// tensor-clocks per MMA, so they were first paced by the ISSUING THREAD (probes: no-op splitter, a third of the MMAs skipped,
+// 3 / 4 / 5 ring stages, 4 / 8 splitter warps, CTA pairing all left the 64-wide 3x3 conv at 3.8-4.2 ms against 1.94 ms for
+// the one-pass kernel); with the issue loop fixed (elect_one above) shared-memory traffic is what is left, and the TMEM
+// operand takes the 256 -> 64 conv at 16 x 176 x 560 from 3.5-4.0 to 2.4 ms (tools/ab_gemm_narrow.py).
+static int g_a_tmem = 1;
 
 template <int BN, int STAGES, int SPLIT>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, cudaStream_t stream) {
@@ -1162,7 +1179,7 @@ GED_API int ged_set_gemm_pair(int on) {
   return prev;
 }
 
-// 1 = the 3xTF32 single-CTA kernels feed the A operand (hi and lo) from tensor memory, 0 (default) = from shared memory.
+// 1 (default) = the 3xTF32 single-CTA kernels feed the A operand (hi and lo) from tensor memory, 0 = from shared memory.
 GED_API int ged_set_gemm_a_tmem(int on) {
   const int prev = g_a_tmem;
   g_a_tmem = on ? 1 : 0;

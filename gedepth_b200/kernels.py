@@ -614,7 +614,7 @@ def set_gemm_pair(on) -> int:
 
 
 def set_gemm_a_tmem(on: bool) -> int:
-    """3xTF32 single-CTA kernels with the A operand's hi / lo in tensor memory (default off: measured neutral); returns the
+    """3xTF32 single-CTA kernels with the A operand's hi / lo in tensor memory (default on); returns the
     previous setting."""
     return load().ged_set_gemm_a_tmem(int(bool(on)))
 

@@ -175,7 +175,7 @@ int ged_set_gemm_precision(int passes);
 int ged_set_gemm_pair(int on);
 /* 1 (default): weight-gradient GEMMs with >= 256 output rows run on the CTA-pair kernel; 0: single-CTA kernels only */
 int ged_set_gemm_pair_dw(int on);
-/* 1: the 3xTF32 single-CTA kernels (tiles <= 128 wide) keep the A operand (hi and lo) in tensor memory; 0 (default): shared memory */
+/* 1 (default): the 3xTF32 single-CTA kernels (tiles <= 128 wide) keep the A operand (hi and lo) in tensor memory; 0: shared memory */
 int ged_set_gemm_a_tmem(int on);
 /* 1 (default) = allow 192/256-column output tiles, 0 = at most 128.  Returns the previous value. */
 int ged_set_gemm_wide_tiles(int on);

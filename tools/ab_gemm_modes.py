@@ -28,10 +28,10 @@ for (M, N, Kd) in [(T0, 576, 192), (T0, 768, 192), (T0, 192, 768), (T0 // 4, 153
         ms = t_ms(lambda: K.gemm(a, w, out=out))
         row.append(f"p{passes}: {ms:.3f} ms {2 * M * N * Kd / ms / 1e9:.0f} TF")
         if passes == 3:
-            prev = K.set_gemm_a_tmem(1)
+            prev = K.set_gemm_a_tmem(0)
             ms = t_ms(lambda: K.gemm(a, w, out=out))
             K.set_gemm_a_tmem(prev)
-            row.append(f"p3 (A in TMEM): {ms:.3f} ms")
+            row.append(f"p3 (A in smem): {ms:.3f} ms")
     print("gemm", M, N, Kd, " | ".join(row), flush=True)
     del a, w, out
 for (Bc, H, W, Ci, Co) in [(B, 176, 560, 256, 64), (B, 22, 70, 2304, 768), (B, 88, 280, 576, 192), (B, 44, 140, 1152, 384)]:
@@ -43,9 +43,9 @@ for (Bc, H, W, Ci, Co) in [(B, 176, 560, 256, 64), (B, 22, 70, 2304, 768), (B, 8
         ms = t_ms(lambda: K.conv3x3_padded(xp, wk, None, 'leaky_relu', 0.01))
         row.append(f"p{passes}: {ms:.3f} ms {2 * Bc * H * W * Ci * Co * 9 / ms / 1e9:.0f} TF")
         if passes == 3:
-            prev = K.set_gemm_a_tmem(1)
+            prev = K.set_gemm_a_tmem(0)
             ms = t_ms(lambda: K.conv3x3_padded(xp, wk, None, 'leaky_relu', 0.01))
             K.set_gemm_a_tmem(prev)
-            row.append(f"p3 (A in TMEM): {ms:.3f} ms")
+            row.append(f"p3 (A in smem): {ms:.3f} ms")
     print("conv3x3", Bc, H, W, Ci, Co, " | ".join(row), flush=True)
 K.set_gemm_precision(3)
