@@ -62,6 +62,17 @@ __device__ __forceinline__ void c_fence_async() { asm volatile("fence.proxy.asyn
 __device__ __forceinline__ void c_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(c_smem_u32(bar)) : "memory");
 }
+// one lane of a CONVERGED warp: tcgen05.mma issued under it needs no per-instruction elect-and-broadcast loop (see
+// gemm_tcgen05.cu::elect_one)
+__device__ __forceinline__ bool c_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void c_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -317,7 +328,7 @@ __global__ void __launch_bounds__(CTHREADS, 3) msda_tc_bwd_kernel(
     c_fence_async();
     __syncthreads();
     // ---- TMA: V_l window; tensor cores: dV_l = A_l^T . G (cols 0..63), D_l^T = V_l . G^T (cols 64..95) -----------
-    if (tid == 0) {
+    if (warp == 0 && c_elect_one()) {
       c_mbar_expect_tx(tma_bar, 2 * WIN_BYTES);
       c_tma_window(smem + B_V, &maps.m[l], tma_bar, h * CHD, wx0, wy0, b);
       c_tma_window(smem + B_V + 16384, &maps.m[l], tma_bar, h * CHD + 32, wx0, wy0, b);
@@ -544,7 +555,7 @@ __global__ void __launch_bounds__(CTHREADS, 2) msda_tc_fwd_kernel(
     }
     c_fence_async();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && c_elect_one()) {
       c_mbar_wait(tma_bar, l & 1);
       c_fence_after();
       const uint32_t base = c_smem_u32(smem);

@@ -42,6 +42,17 @@ __device__ __forceinline__ void w_fence_async() { asm volatile("fence.proxy.asyn
 __device__ __forceinline__ void w_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(w_smem_u32(bar)) : "memory");
 }
+// one lane of a CONVERGED warp: tcgen05.mma issued under it needs no per-instruction elect-and-broadcast loop (see
+// gemm_tcgen05.cu::elect_one)
+__device__ __forceinline__ bool w_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void w_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(TW_THREADS, 2) winattn_tc_fwd_kernel(
       const TwMeta& m = ms.meta[buf];
       tw_cta_sync();                                   // (A)
       // ---- S_p = [Q_A ; Q_B] . K_p^T  (3xTF32) ----------------------------------------------------------------------
-      if (tid == 0) {
+      if (warp == 0 && w_elect_one()) {
         w_fence_after();
         constexpr uint32_t ids = w_idesc_tf32(128, 64, false, false);
         const uint64_t qhi = w_desc_kmajor(sbase + W_QHI), qlo = w_desc_kmajor(sbase + W_QLO);
@@ -303,7 +314,7 @@ __global__ void __launch_bounds__(TW_THREADS, 2) winattn_tc_fwd_kernel(
       w_fence_before();
       tw_cta_sync();                                   // (B)
       // ---- O_p = [P_A ; P_B] . V_p  (3xTF32) ------------------------------------------------------------------------
-      if (tid == 0) {
+      if (warp == 0 && w_elect_one()) {
         w_fence_after();
         constexpr uint32_t ido = w_idesc_tf32(128, 32, false, true);
 #pragma unroll
@@ -487,7 +498,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) winattn_tc_bwd_kernel(
     for (int duo = blockIdx.x; duo * 2 < num_pairs; duo += gridDim.x, buf ^= 1) {
       const TwMeta& m = ms.meta[buf];
       tw_cta_sync();                                   // (A)
-      if (tid == 0) {
+      if (warp == 0 && w_elect_one()) {
         w_fence_after();
         constexpr uint32_t ids = w_idesc_tf32(128, 64, false, false);
         const uint64_t qk = w_desc_kmajor(sbase + WB_QK), gk = w_desc_kmajor(sbase + WB_GK);
@@ -556,7 +567,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) winattn_tc_bwd_kernel(
       w_fence_async();
       w_fence_before();
       tw_cta_sync();                                   // (B)
-      if (tid == 0) {
+      if (warp == 0 && w_elect_one()) {
         w_fence_after();
         constexpr uint32_t id_mm = w_idesc_tf32(128, 32, true, true), id_km = w_idesc_tf32(128, 32, false, true);
         const uint64_t pm = w_desc_mnmajor(sbase + WB_PM, 8192), sm = w_desc_mnmajor(sbase + WB_SM, 8192);
