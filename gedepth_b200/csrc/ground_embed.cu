@@ -162,6 +162,7 @@ __device__ __forceinline__ void x2_weights(int j, int n, float (&w)[4]) {
 }
 // (Tried: issuing the loads of all 4-5 rows of a thread before the first use - 96 registers, 2 CTAs per SM: 0.565 -> 0.38 of
 // the HBM peak; capped at 80 registers with spills: 0.50.  The 48-register loop below with 5 CTAs per SM stays.)
+// Kept as the A/B partner of the streaming kernel below (ged_set_ge_x2(2)).
 // Separable: a CTA owns X2_H half-resolution rows x 128 columns.  Pass 1: every full-resolution row of the footprint is
 // read ONCE with aligned float4 loads (a lane's left / right neighbour columns come from its neighbours by warp
 // shuffle), G = g_y + g_pe_mask * pe * 200 is formed and contracted along x into shared memory; pass 2 contracts along y.
@@ -182,13 +183,15 @@ __global__ void __launch_bounds__(256, 4) ge_vanilla_bwd_x2_kernel(
   // One row segment per iteration.  The loads of the NEXT iteration (and the warp's two outer neighbour columns, which only
   // lanes 0 / 31 need) are issued before the current row is consumed: two rows in flight per warp, no dependent second
   // round trip for the edge lanes.
-  struct RowLoads { float4 p4, y4, m4; float eL, eR; bool ok; };
+  struct RowLoads { float4 p4, y4, m4; float ep, ey, em; bool ok; };
+  const int ce = lane == 0 ? c0 - 1 : c0 + 4;
+  const bool edge_ok = (lane == 0 || lane == 31) && ce >= 0 && ce < W;
   auto issue = [&](int r) {
     RowLoads q;
     const int oy = 2 * jy0 - 1 + r;
     q.ok = r < 2 * X2_H + 2 && oy >= 0 && oy < H && col_ok;
     q.p4 = q.y4 = q.m4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    q.eL = q.eR = 0.f;
+    q.ep = q.ey = q.em = 0.f;
     if (q.ok) {
       const int64_t row = (int64_t)oy * W;
       const float* pp = pe_norm + (int64_t)b * pe_bstride + row;
@@ -197,8 +200,11 @@ __global__ void __launch_bounds__(256, 4) ge_vanilla_bwd_x2_kernel(
       q.p4 = __ldg((const float4*)(pp + c0));
       if (gy) q.y4 = ldg_stream((const float4*)(gy + c0));
       if (gm) q.m4 = ldg_stream((const float4*)(gm + c0));
-      if (lane == 0 && c0 >= 1) q.eL = (gy ? __ldg(gy + c0 - 1) : 0.f) + (gm ? __ldg(gm + c0 - 1) * __ldg(pp + c0 - 1) * 200.f : 0.f);
-      if (lane == 31 && c0 + 4 < W) q.eR = (gy ? __ldg(gy + c0 + 4) : 0.f) + (gm ? __ldg(gm + c0 + 4) * __ldg(pp + c0 + 4) * 200.f : 0.f);
+      if (edge_ok) {      // raw operands only; combined when the row is consumed (no wait on the loads just issued)
+        q.ep = __ldg(pp + ce);
+        if (gy) q.ey = __ldg(gy + ce);
+        if (gm) q.em = __ldg(gm + ce);
+      }
     }
     return q;
   };
@@ -210,8 +216,9 @@ __global__ void __launch_bounds__(256, 4) ge_vanilla_bwd_x2_kernel(
     float left = __shfl_up_sync(0xffffffffu, G.w, 1), right = __shfl_down_sync(0xffffffffu, G.x, 1);
     float2 acc = make_float2(0.f, 0.f);
     if (cur.ok) {
-      if (lane == 0) left = cur.eL;
-      if (lane == 31) right = cur.eR;
+      const float Ge = cur.ey + cur.em * cur.ep * 200.f;
+      if (lane == 0) left = Ge;
+      if (lane == 31) right = Ge;
       if (c0 + 4 >= W) right = 0.f;
       acc.x = wxa[0] * left + wxa[1] * G.x + wxa[2] * G.y + wxa[3] * G.z;
       acc.y = wxb[0] * G.y + wxb[1] * G.z + wxb[2] * G.w + wxb[3] * right;
@@ -237,6 +244,94 @@ __global__ void __launch_bounds__(256, 4) ge_vanilla_bwd_x2_kernel(
     float* dst = g_y_half + ((int64_t)b * h2 + jy) * w2 + 2 * t;
     if (has_b && ((((uintptr_t)dst) & 7) == 0)) *(float2*)dst = o;
     else { dst[0] = o.x; if (has_b) dst[1] = o.y; }
+  }
+}
+
+// Streaming form of the same adjoint (default).  A WARP owns a strip of 128 full-resolution columns and walks VB_CH
+// half-resolution rows down it: the x-contracted values of the two previous full-resolution rows stay in registers, the two
+// new rows of iteration j+1 are in flight while iteration j is contracted along y and stored (4 rows x 3 operands x 512 B =
+// 6 KB per warp in flight), no shared memory, no barrier; the halo is 2 rows per 2 VB_CH.
+// What held BOTH forms at 0.52-0.57 of the HBM peak was not the tiling but the strip's outer columns: lanes 0 / 31 loaded
+// their neighbour column's three operands and combined them at once (LDG, LDG, LDG, FMUL in the SASS), so the whole warp
+// waited a full memory latency right after issuing every row.  With the raw operands carried to the point of use:
+// tiled 0.575 -> 0.756 / 0.80, streaming 0.52 -> 0.844 / 0.91 at 32 / 64 x 1024 x 2048 (tools/ab_ge_vbwd.py).
+struct VbRow { float4 p4, y4, m4; float ep, ey, em; };
+template <int VB_CH, int MINB, int UNR>
+__global__ void __launch_bounds__(128, MINB) ge_vanilla_bwd_x2s_kernel(
+    const float* __restrict__ pe_norm, int64_t pe_bstride, const float* __restrict__ g_y,
+    const float* __restrict__ g_pe_mask, float* __restrict__ g_y_half, int H, int W, int h2, int w2) {
+  const int lane = threadIdx.x, strip = blockIdx.x * 4 + threadIdx.y;
+  if (strip * 128 >= W) return;                          // warp-uniform
+  const int t = strip * 32 + lane;                       // half-resolution columns 2t, 2t+1 <- full-resolution 4t-1 .. 4t+4
+  const int c0 = 4 * t, b = blockIdx.z;
+  const int jy0 = blockIdx.y * VB_CH, jy1 = min(jy0 + VB_CH, h2);
+  const bool col_ok = c0 < W;
+  const int64_t HW = (int64_t)H * W;
+  const float* pp0 = pe_norm + (int64_t)b * pe_bstride;
+  const float* gy0 = g_y ? g_y + b * HW : nullptr;
+  const float* gm0 = g_pe_mask ? g_pe_mask + b * HW : nullptr;
+  float wxa[4], wxb[4];
+  x2_weights(2 * t, w2, wxa);
+  x2_weights(2 * t + 1, w2, wxb);
+  // the column just outside the warp's strip: lane 0 needs 4t-1, lane 31 needs 4t+4 (the others get theirs by shuffle).
+  // The three raw operands are only LOADED here and combined in contract(), one iteration later: combining them at once
+  // made the whole warp wait a full memory latency on every row (the first version of this kernel, and the tiled one).
+  const int ce = lane == 0 ? c0 - 1 : c0 + 4;
+  const bool edge_ok = (lane == 0 || lane == 31) && ce >= 0 && ce < W && col_ok;
+  auto issue = [&](int oy) {
+    VbRow q;
+    q.p4 = q.y4 = q.m4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    q.ep = q.ey = q.em = 0.f;
+    if (oy >= 0 && oy < H && col_ok) {
+      const int64_t row = (int64_t)oy * W;
+      const float* pp = pp0 + row;
+      q.p4 = ldg_stream((const float4*)(pp + c0));
+      if (gy0) q.y4 = ldg_stream((const float4*)(gy0 + row + c0));
+      if (gm0) q.m4 = ldg_stream((const float4*)(gm0 + row + c0));
+      if (edge_ok) {
+        q.ep = __ldg(pp + ce);
+        if (gy0) q.ey = __ldg(gy0 + row + ce);
+        if (gm0) q.em = __ldg(gm0 + row + ce);
+      }
+    }
+    return q;
+  };
+  // rows outside the map and slots right of it were never loaded: their G is 0 and so is everything contracted from it
+  auto contract = [&](const VbRow& q) {
+    const float4 G = make_float4(q.y4.x + q.m4.x * q.p4.x * 200.f, q.y4.y + q.m4.y * q.p4.y * 200.f,
+                                 q.y4.z + q.m4.z * q.p4.z * 200.f, q.y4.w + q.m4.w * q.p4.w * 200.f);
+    const float Ge = q.ey + q.em * q.ep * 200.f;
+    float left = __shfl_up_sync(0xffffffffu, G.w, 1), right = __shfl_down_sync(0xffffffffu, G.x, 1);
+    if (lane == 0) left = Ge;
+    if (lane == 31) right = Ge;
+    return make_float2(wxa[0] * left + wxa[1] * G.x + wxa[2] * G.y + wxa[3] * G.z,
+                       wxb[0] * G.y + wxb[1] * G.z + wxb[2] * G.w + wxb[3] * right);
+  };
+  VbRow a0 = issue(2 * jy0 - 1), a1 = issue(2 * jy0);
+  VbRow n0 = issue(2 * jy0 + 1), n1 = issue(2 * jy0 + 2);
+  float2 tm1 = contract(a0), t0 = contract(a1);
+  const bool emit = 2 * t < w2;
+  const bool has_b = 2 * t + 1 < w2;
+  float* dst = g_y_half + ((int64_t)b * h2 + jy0) * w2 + 2 * t;
+  const bool dst8 = has_b && ((((uintptr_t)dst) & 7) == 0) && ((w2 & 1) == 0);
+#pragma unroll UNR
+  for (int jy = jy0; jy < jy1; ++jy) {
+    const VbRow c0r = n0, c1r = n1;
+    if (jy + 1 < jy1) { n0 = issue(2 * jy + 3); n1 = issue(2 * jy + 4); }
+    const float2 t1 = contract(c0r), t2 = contract(c1r);
+    float wy[4];
+    x2_weights(jy, h2, wy);
+    float2 o = make_float2(0.f, 0.f);
+    o.x += wy[0] * tm1.x; o.y += wy[0] * tm1.y;
+    o.x += wy[1] * t0.x; o.y += wy[1] * t0.y;
+    o.x += wy[2] * t1.x; o.y += wy[2] * t1.y;
+    o.x += wy[3] * t2.x; o.y += wy[3] * t2.y;
+    if (emit) {
+      if (dst8) *(float2*)dst = o;
+      else { dst[0] = o.x; if (has_b) dst[1] = o.y; }
+    }
+    dst += w2;
+    tm1 = t1; t0 = t2;
   }
 }
 
@@ -580,9 +675,15 @@ GED_API int ged_ge_vanilla_bwd(const float* pe_norm, int64_t pe_batch_stride, co
   const float sy = resize_scale(h2, H, false), sx = resize_scale(w2, W, false);
   if (g_ge_x2 && H == 2 * h2 && W == 2 * w2 && (W % 4 == 0) && (pe_batch_stride % 4 == 0) && aligned16(pe_norm) &&
       (!g_y || aligned16(g_y)) && (!g_pe_mask || aligned16(g_pe_mask))) {
-    // exact x2: closed-form gather (every GE config)
-    dim3 block(64, 4), grid(cdiv(cdiv(w2, 2), 64), cdiv(h2, X2_H), B);
-    ge_vanilla_bwd_x2_kernel<<<grid, block, 0, stream>>>(pe_norm, pe_batch_stride, g_y, g_pe_mask, g_y_half, H, W, h2, w2);
+    // exact x2: closed-form gather (every GE config); ged_set_ge_x2(2) keeps the tiled round-2a kernel for A/B
+    if (g_ge_x2 == 1) {
+      // 16 half-resolution rows per warp, 6 CTAs of 4 warps per SM (measured against 8 / 32 rows and 4 / 5 CTAs)
+      dim3 block(32, 4), grid(cdiv(W, 512), cdiv(h2, 16), B);
+      ge_vanilla_bwd_x2s_kernel<16, 6, 1><<<grid, block, 0, stream>>>(pe_norm, pe_batch_stride, g_y, g_pe_mask, g_y_half, H, W, h2, w2);
+    } else {
+      dim3 block(64, 4), grid(cdiv(cdiv(w2, 2), 64), cdiv(h2, X2_H), B);
+      ge_vanilla_bwd_x2_kernel<<<grid, block, 0, stream>>>(pe_norm, pe_batch_stride, g_y, g_pe_mask, g_y_half, H, W, h2, w2);
+    }
     GED_CHECK_LAUNCH();
     return GED_OK;
   }
