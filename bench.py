@@ -193,8 +193,9 @@ def algorithmic(name, a):
         return 4.0 * a[10] * a[11] * (2 * (3 if a[2] is not None else 2) + 1)
     if name == "ged_layernorm_fwd":
         return 4.0 * a[6] * a[7] * 2
-    if name == "ged_layernorm_bwd":           # dx pass (g, x [, g_add] -> dx) + weight/bias pass (g, x)
-        return 4.0 * a[9] * a[10] * (5 + int(a[5] is not None))
+    if name == "ged_layernorm_bwd":           # g, x [, g_add] read once, dx written (dw / db come out of the same pass for
+        # rows of <= 768 channels; wider rows take a second pass over g and x)
+        return 4.0 * a[9] * a[10] * (3 + int(a[5] is not None) + (2 if a[10] > 768 else 0))
     if name == "ged_prep_conv_input":         # sources once, bordered tensor written
         C0, h0, w0, C1, Bq, Hq, Wq = a[1], a[2], a[3], a[5], a[7], a[8], a[9]
         return 4.0 * Bq * (h0 * w0 * C0 + Hq * Wq * C1 + (Hq + 2) * (Wq + 2) * (C0 + C1))

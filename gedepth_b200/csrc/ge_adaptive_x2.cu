@@ -395,9 +395,10 @@ __global__ void __launch_bounds__(256, 2) ge_adaptive_bwd_x2_kernel(
       cp_async8(dst, ysrc + so, nb);
     }
     cp_async_commit();
-    cp_async_wait<0>();
+    // NOT awaited here: the first row segment's own loads (ring, pe, g_y, g_pe_mask) are issued first, so that the staging
+    // latency and theirs overlap instead of adding up (a CTA lives for two row segments per warp: one exposed latency less
+    // out of three)
   }
-  __syncthreads();
 
   const int t = blockIdx.x * BX_EMIT - 1 + lane;         // four-pixel slot: full-resolution columns 4t .. 4t+3
   const int c0 = 4 * t;
@@ -458,6 +459,10 @@ __global__ void __launch_bounds__(256, 2) ge_adaptive_bwd_x2_kernel(
       pe4 = ldg_stream((const float4*)(pe_raw + (int64_t)b * pe_bstride + po));
       if (g_y) gy4 = ldg_stream((const float4*)(g_y + b * HW + po));
       if (g_pe_mask) gm4 = ldg_stream((const float4*)(g_pe_mask + b * HW + po));
+    }
+    if (r == ty) {                 // first segment of every warp (ty < BX_FR): the staged tile must have landed
+      if (g_logits_full) cp_async_wait<BX_RING>(); else cp_async_wait<0>();
+      __syncthreads();
     }
     float Gs[4], nth[4];
     {

@@ -80,11 +80,23 @@ __global__ void __launch_bounds__(TX * 4) ge_vanilla_fwd_kernel(
   const int oy_last = min(oy0 + VT_H, H) - 1, ox_last = min(ox0 + TILE_W, W) - 1;
   const int sy0 = tap(oy0, sy, false, h2).i0, sx0 = tap(ox0, sx, false, w2).i0;
   const int sh = tap(oy_last, sy, false, h2).i1 - sy0 + 1, sw_ = tap(ox_last, sx, false, w2).i1 - sx0 + 1;
+  const int ox = ox0 + threadIdx.x * 4;
+  // all of the thread's pe rows are requested before the first one is used: the streaming loads / stores are volatile
+  // asm, so a load written inside the row loop could not be moved above the previous row's stores and every row paid a
+  // full memory latency (SASS: LDG, LDS.., STG, STG, LDG, ..).  Issued ahead of the staging so that they overlap it too.
+  float4 pe4[VT_H / 4];
+  if (VEC && ox < W) {
+#pragma unroll
+    for (int k = 0; k < VT_H / 4; ++k) {
+      const int oy = oy0 + threadIdx.y + 4 * k;
+      pe4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (oy < H) pe4[k] = ldg_stream((const float4*)(pe_norm + (int64_t)b * pe_bstride + (int64_t)oy * W + ox));
+    }
+  }
   const float* yh = y_half + (int64_t)b * h2 * w2;
   for (int r = threadIdx.y; r < sh; r += 4)
     for (int c = threadIdx.x; c < sw_; c += TX) s_y[r][c] = __ldg(yh + (int64_t)(sy0 + r) * w2 + sx0 + c);
   __syncthreads();
-  const int ox = ox0 + threadIdx.x * 4;
   if (ox >= W) return;
   const int n = min(4, W - ox);
   int c0[4], c1[4];
@@ -104,7 +116,7 @@ __global__ void __launch_bounds__(TX * 4) ge_vanilla_fwd_kernel(
     const int64_t o = ((int64_t)b * H + oy) * W + ox;
     const float* pp = pe_norm + (int64_t)b * pe_bstride + (int64_t)oy * W + ox;
     float pe[4], yo[4], mo[4];
-    if (VEC) { float4 t = ldg_stream((const float4*)pp); pe[0] = t.x; pe[1] = t.y; pe[2] = t.z; pe[3] = t.w; }
+    if (VEC) { pe[0] = pe4[k].x; pe[1] = pe4[k].y; pe[2] = pe4[k].z; pe[3] = pe4[k].w; }
     else { for (int i = 0; i < n; ++i) pe[i] = __ldg(pp + i); }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -118,6 +130,81 @@ __global__ void __launch_bounds__(TX * 4) ge_vanilla_fwd_kernel(
     } else {
       for (int i = 0; i < n; ++i) { y[o + i] = yo[i]; pe_mask[o + i] = mo[i]; }
     }
+  }
+}
+
+// a14 forward when the full-resolution map is exactly twice the half-resolution one (every GE config), streaming form: a
+// WARP owns a strip of 128 full-resolution columns and walks VF_FR rows down it.  The x-interpolated half-resolution row
+// (out[2k] = 1/4 in[k-1] + 3/4 in[k], out[2k+1] = 3/4 in[k] + 1/4 in[k+1], clamped at the map's edges) is formed once per
+// half-resolution row from one float2 per lane + two shuffles and kept in registers; every full-resolution row is a
+// vertical blend of two such rows.  The pe rows and the half-resolution row of the NEXT iteration are requested before the
+// current one is blended and stored; no shared memory, no barrier.
+struct VfHalf { float2 v; float e; };
+template <int VF_FR>
+__global__ void __launch_bounds__(128) ge_vanilla_fwd_x2s_kernel(
+    const float* __restrict__ pe_norm, int64_t pe_bstride, const float* __restrict__ y_half,
+    float* __restrict__ y, float* __restrict__ pe_mask, int H, int W, int h2, int w2) {
+  const int lane = threadIdx.x, strip = blockIdx.x * 4 + threadIdx.y;
+  if (strip * 128 >= W) return;                          // warp-uniform
+  const int t = strip * 32 + lane, c0 = 4 * t, b = blockIdx.z;
+  const bool col_ok = c0 < W;
+  const float* pp0 = pe_norm + (int64_t)b * pe_bstride;
+  const float* yh = y_half + (int64_t)b * h2 * w2;
+  // half-resolution column just outside the lane's pair: lane 0 needs 2t-1, lane 31 needs 2t+2 (the others: shuffle)
+  const int ce = lane == 0 ? 2 * t - 1 : 2 * t + 2;
+  const bool edge_ok = (lane == 0 || lane == 31) && ce >= 0 && ce < w2 && col_ok;
+  const float a0 = t > 0 ? 0.25f : 0.f, a1 = t > 0 ? 0.75f : 1.f;
+  const float b0 = 2 * t + 2 < w2 ? 0.75f : 1.f, b1 = 2 * t + 2 < w2 ? 0.25f : 0.f;
+  auto pload = [&](int oy) {
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (oy >= 0 && oy < H && col_ok) p = ldg_stream((const float4*)(pp0 + (int64_t)oy * W + c0));
+    return p;
+  };
+  auto hload = [&](int j) {
+    const int jc = min(max(j, 0), h2 - 1);
+    VfHalf q;
+    q.v = make_float2(0.f, 0.f); q.e = 0.f;
+    if (col_ok) {
+      q.v = __ldg((const float2*)(yh + (int64_t)jc * w2 + 2 * t));
+      if (edge_ok) q.e = __ldg(yh + (int64_t)jc * w2 + ce);
+    }
+    return q;
+  };
+  auto hrow = [&](const VfHalf& q) {
+    float left = __shfl_up_sync(0xffffffffu, q.v.y, 1), right = __shfl_down_sync(0xffffffffu, q.v.x, 1);
+    if (lane == 0) left = q.e;
+    if (lane == 31) right = q.e;
+    return make_float4(a0 * left + a1 * q.v.x, 0.75f * q.v.x + 0.25f * q.v.y, 0.25f * q.v.x + 0.75f * q.v.y,
+                       b0 * q.v.y + b1 * right);
+  };
+  // iteration k emits rows 2k+1 and 2k+2 from half-resolution rows k, k+1; the chunk owns rows [r0, r1)
+  const int r0 = blockIdx.y * VF_FR, r1 = min(r0 + VF_FR, H);
+  const int k_first = r0 == 0 ? -1 : (r0 - 1) >> 1;     // r0 even: rows r0-1 (not ours), r0
+  const int k_last = (r1 - 2) >> 1;                      // last row r1-1 = 2 k_last + 1 or + 2
+  VfHalf hn = hload(k_first + 1);
+  float4 hk = hrow(hload(k_first));
+  float4 pA = pload(2 * k_first + 1), pB = pload(2 * k_first + 2);
+  for (int k = k_first; k <= k_last; ++k) {
+    VfHalf hnn = hn;
+    float4 pAn = pA, pBn = pB;
+    if (k < k_last) { hnn = hload(k + 2); pAn = pload(2 * k + 3); pBn = pload(2 * k + 4); }
+    const float4 hk1 = hrow(hn);
+    const int oyA = 2 * k + 1, oyB = 2 * k + 2;
+    if (oyA >= r0 && oyA < r1 && col_ok) {
+      const float wl = k < h2 - 1 ? 0.75f : 1.f, wh = k < h2 - 1 ? 0.25f : 0.f;
+      const float4 yo = make_float4(wl * hk.x + wh * hk1.x, wl * hk.y + wh * hk1.y, wl * hk.z + wh * hk1.z, wl * hk.w + wh * hk1.w);
+      const int64_t o = ((int64_t)b * H + oyA) * W + c0;
+      stg_stream((float4*)(y + o), yo);
+      stg_stream((float4*)(pe_mask + o), make_float4(pA.x * yo.x * 200.f, pA.y * yo.y * 200.f, pA.z * yo.z * 200.f, pA.w * yo.w * 200.f));
+    }
+    if (oyB >= r0 && oyB < r1 && col_ok) {
+      const float wl = k + 1 > 0 ? 0.25f : 0.f, wh = k + 1 > 0 ? 0.75f : 1.f;
+      const float4 yo = make_float4(wl * hk.x + wh * hk1.x, wl * hk.y + wh * hk1.y, wl * hk.z + wh * hk1.z, wl * hk.w + wh * hk1.w);
+      const int64_t o = ((int64_t)b * H + oyB) * W + c0;
+      stg_stream((float4*)(y + o), yo);
+      stg_stream((float4*)(pe_mask + o), make_float4(pB.x * yo.x * 200.f, pB.y * yo.y * 200.f, pB.z * yo.z * 200.f, pB.w * yo.w * 200.f));
+    }
+    hk = hk1; hn = hnn; pA = pAn; pB = pBn;
   }
 }
 
@@ -661,6 +748,18 @@ GED_API int ged_ge_vanilla_fwd(const float* pe_norm, int64_t pe_batch_stride, co
   if ((float)(H < VT_H ? H : VT_H) * sy + 3.f > (float)VS_H) return GED_ERR_SHAPE;
   const bool vec = (W % 4 == 0) && aligned16(pe_norm) && aligned16(y) && aligned16(pe_mask) &&
                    (pe_batch_stride % 4 == 0);
+  if (g_ge_x2 == 1 && vec && H == 2 * h2 && W == 2 * w2 && ((((uintptr_t)y_half) & 7) == 0)) {
+    // exact x2 (every GE config): streaming kernel; ged_set_ge_x2(2 / 0) keeps the tiled one for A/B
+    // 32 rows per warp; 8 when that would leave the GPU short of warps (a warp's rows are a serial chain of loads)
+    if ((int64_t)B * cdiv(W, 128) * cdiv(H, 32) >= 148 * 32)
+      ge_vanilla_fwd_x2s_kernel<32><<<dim3(cdiv(W, 512), cdiv(H, 32), B), dim3(32, 4), 0, stream>>>(pe_norm, pe_batch_stride, y_half, y,
+                                                                                                   pe_mask, H, W, h2, w2);
+    else
+      ge_vanilla_fwd_x2s_kernel<8><<<dim3(cdiv(W, 512), cdiv(H, 8), B), dim3(32, 4), 0, stream>>>(pe_norm, pe_batch_stride, y_half, y,
+                                                                                                 pe_mask, H, W, h2, w2);
+    GED_CHECK_LAUNCH();
+    return GED_OK;
+  }
   if (vec) ge_vanilla_fwd_kernel<true><<<grid, block, 0, stream>>>(pe_norm, pe_batch_stride, y_half, y, pe_mask, H, W, h2, w2, sy, sx);
   else ge_vanilla_fwd_kernel<false><<<grid, block, 0, stream>>>(pe_norm, pe_batch_stride, y_half, y, pe_mask, H, W, h2, w2, sy, sx);
   GED_CHECK_LAUNCH();
@@ -677,9 +776,15 @@ GED_API int ged_ge_vanilla_bwd(const float* pe_norm, int64_t pe_batch_stride, co
       (!g_y || aligned16(g_y)) && (!g_pe_mask || aligned16(g_pe_mask))) {
     // exact x2: closed-form gather (every GE config); ged_set_ge_x2(2) keeps the tiled round-2a kernel for A/B
     if (g_ge_x2 == 1) {
-      // 16 half-resolution rows per warp, 6 CTAs of 4 warps per SM (measured against 8 / 32 rows and 4 / 5 CTAs)
-      dim3 block(32, 4), grid(cdiv(W, 512), cdiv(h2, 16), B);
-      ge_vanilla_bwd_x2s_kernel<16, 6, 1><<<grid, block, 0, stream>>>(pe_norm, pe_batch_stride, g_y, g_pe_mask, g_y_half, H, W, h2, w2);
+      // 16 half-resolution rows per warp, 6 CTAs of 4 warps per SM (measured against 8 / 32 rows and 4 / 5 CTAs); 4 rows when
+      // 16 would leave the GPU short of warps
+      dim3 block(32, 4);
+      if ((int64_t)B * cdiv(W, 128) * cdiv(h2, 16) >= 148 * 24)
+        ge_vanilla_bwd_x2s_kernel<16, 6, 1><<<dim3(cdiv(W, 512), cdiv(h2, 16), B), block, 0, stream>>>(pe_norm, pe_batch_stride, g_y, g_pe_mask,
+                                                                                                      g_y_half, H, W, h2, w2);
+      else
+        ge_vanilla_bwd_x2s_kernel<4, 6, 1><<<dim3(cdiv(W, 512), cdiv(h2, 4), B), block, 0, stream>>>(pe_norm, pe_batch_stride, g_y, g_pe_mask,
+                                                                                                    g_y_half, H, W, h2, w2);
     } else {
       dim3 block(64, 4), grid(cdiv(cdiv(w2, 2), 64), cdiv(h2, X2_H), B);
       ge_vanilla_bwd_x2_kernel<<<grid, block, 0, stream>>>(pe_norm, pe_batch_stride, g_y, g_pe_mask, g_y_half, H, W, h2, w2);

@@ -81,6 +81,132 @@ __global__ void __launch_bounds__(256) upsample_nhwc_bwd_kernel(
   }
 }
 
+// Row-structured forms of the two kernels above (default where they apply).  The flat grid-stride kernels decompose a 64-bit
+// element index with five divisions per float4 and - in the adjoint - re-derive the bilinear weights of up to 7 x 7 candidate
+// pixels for EVERY channel quad (~700 instructions per 16 bytes: instruction-bound at 0.6 of the HBM peak and below).  Here a
+// CTA owns one output row of one sample: the row's y taps and, per column, the x taps are evaluated ONCE into shared memory
+// and re-used across all channels; the per-element work is one 32-bit division, the loads and the FMAs, in the same
+// summation order (bit-identical results).
+constexpr int RW_MAXW = 1024;     // widest row the forward's tap table holds (wider maps take the flat kernels)
+constexpr int RW_MAXW0 = 512;     // widest SOURCE row of the adjoint's tables (28 KB; wider maps / > x3.3 ratios: flat kernel)
+constexpr int RW_T = 8;           // non-zero adjoint taps per axis (2 / scale + 1 <= 8 for scale >= 0.3)
+
+__global__ void __launch_bounds__(256) prep_conv_input_rows_kernel(
+    const float* __restrict__ src0, int C0, int h0, int w0, const float* __restrict__ src1, int C1,
+    float* __restrict__ dst, int B, int H, int W, float sy, float sx) {
+  __shared__ int s_i0[RW_MAXW], s_i1[RW_MAXW];
+  __shared__ float s_l1[RW_MAXW];
+  const int yp = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int C = C0 + C1, C4 = C >> 2, Wp = W + 2;
+  float4* drow = (float4*)(dst + (((int64_t)b * (H + 2) + yp) * Wp) * C);
+  const int n = Wp * C4;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (yp == 0 || yp == H + 1) {
+    for (int i = tid; i < n; i += 256) drow[i] = zero4;
+    return;
+  }
+  const int y = yp - 1;
+  const bool resize = !(h0 == H && w0 == W);
+  if (resize) {
+    for (int x = tid; x < W; x += 256) { const Tap tx = tap(x, sx, true, w0); s_i0[x] = tx.i0; s_i1[x] = tx.i1; s_l1[x] = tx.l1; }
+    __syncthreads();
+  }
+  const Tap ty = tap(y, sy, true, h0);
+  const float* r0 = src0 + ((int64_t)b * h0 + ty.i0) * w0 * C0;
+  const float* r1 = src0 + ((int64_t)b * h0 + ty.i1) * w0 * C0;
+  const float* s0row = src0 + ((int64_t)b * H + y) * W * C0;                 // same-size case
+  const float* s1row = src1 ? src1 + ((int64_t)b * H + y) * W * C1 : nullptr;
+  for (int i = tid; i < n; i += 256) {
+    const int xp = i / C4, c = (i - xp * C4) * 4;
+    float4 v = zero4;
+    if (xp > 0 && xp <= W) {
+      const int x = xp - 1;
+      if (c < C0) {
+        if (!resize) {
+          v = __ldg((const float4*)(s0row + (int64_t)x * C0 + c));
+        } else {
+          const int i0 = s_i0[x], i1 = s_i1[x];
+          const float l1 = s_l1[x], l0 = 1.f - l1;
+          const float4 v00 = __ldg((const float4*)(r0 + (int64_t)i0 * C0 + c));
+          const float4 v01 = __ldg((const float4*)(r0 + (int64_t)i1 * C0 + c));
+          const float4 v10 = __ldg((const float4*)(r1 + (int64_t)i0 * C0 + c));
+          const float4 v11 = __ldg((const float4*)(r1 + (int64_t)i1 * C0 + c));
+          v.x = ty.l0 * (l0 * v00.x + l1 * v01.x) + ty.l1 * (l0 * v10.x + l1 * v11.x);
+          v.y = ty.l0 * (l0 * v00.y + l1 * v01.y) + ty.l1 * (l0 * v10.y + l1 * v11.y);
+          v.z = ty.l0 * (l0 * v00.z + l1 * v01.z) + ty.l1 * (l0 * v10.z + l1 * v11.z);
+          v.w = ty.l0 * (l0 * v00.w + l1 * v01.w) + ty.l1 * (l0 * v10.w + l1 * v11.w);
+        }
+      } else {
+        v = __ldg((const float4*)(s1row + (int64_t)x * C1 + (c - C0)));
+      }
+    }
+    drow[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) upsample_nhwc_bwd_rows_kernel(
+    const float* __restrict__ g, int ldg, float* __restrict__ out, int C0, int B, int H, int W, int h0, int w0,
+    float sy, float sx) {
+  __shared__ float s_xw[RW_MAXW0][RW_T];
+  __shared__ short s_xi[RW_MAXW0][RW_T];
+  __shared__ int s_xn[RW_MAXW0];
+  __shared__ float s_yw[RW_T];
+  __shared__ int s_yi[RW_T], s_yn;
+  const int j = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int C4 = C0 >> 2;
+  if (tid == 0) {
+    int ylo, yhi, n = 0;
+    adjoint_range(j, sy, true, h0, H, ylo, yhi);
+    for (int y = ylo; y <= yhi && n < RW_T; ++y) {
+      const Tap ty = tap(y, sy, true, h0);
+      const float wy = (ty.i0 == j ? ty.l0 : 0.f) + (ty.i1 == j ? ty.l1 : 0.f);
+      if (wy != 0.f) { s_yw[n] = wy; s_yi[n] = y; ++n; }
+    }
+    s_yn = n;
+  }
+  for (int k = tid; k < w0; k += 256) {
+    int xlo, xhi, n = 0;
+    adjoint_range(k, sx, true, w0, W, xlo, xhi);
+    for (int x = xlo; x <= xhi && n < RW_T; ++x) {
+      const Tap tx = tap(x, sx, true, w0);
+      const float wx = (tx.i0 == k ? tx.l0 : 0.f) + (tx.i1 == k ? tx.l1 : 0.f);
+      if (wx != 0.f) { s_xw[k][n] = wx; s_xi[k][n] = (short)x; ++n; }
+    }
+    s_xn[k] = n;
+  }
+  __syncthreads();
+  const int ny = s_yn, n = w0 * C4;
+  float4* orow = (float4*)(out + (((int64_t)b * h0 + j) * w0) * C0);
+  for (int i = tid; i < n; i += 256) {
+    const int k = i / C4, c = (i - k * C4) * 4;
+    const int nx = s_xn[k];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // the (<= 5, rarely more) x taps of one y tap are requested together, then accumulated in order: a load consumed right
+    // after its issue inside a loop of dynamic length leaves ONE load in flight per thread
+    constexpr int XC = 5;
+    for (int a = 0; a < ny; ++a) {
+      const float wy = s_yw[a];
+      const float* grow = g + ((int64_t)b * H + s_yi[a]) * W * ldg + c;
+      for (int t0 = 0; t0 < nx; t0 += XC) {
+        float4 v[XC];
+        float wgt[XC];
+#pragma unroll
+        for (int u = 0; u < XC; ++u) {
+          const bool on = t0 + u < nx;
+          wgt[u] = on ? wy * s_xw[k][t0 + u] : 0.f;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (on && wgt[u] != 0.f) v[u] = __ldg((const float4*)(grow + (int64_t)s_xi[k][t0 + u] * ldg));
+        }
+#pragma unroll
+        for (int u = 0; u < XC; ++u) {
+          if (wgt[u] != 0.f) { acc.x += wgt[u] * v[u].x; acc.y += wgt[u] * v[u].y; acc.z += wgt[u] * v[u].z; acc.w += wgt[u] * v[u].w; }
+        }
+      }
+    }
+    orow[i] = acc;
+  }
+}
+
 // out (B,H,W,C) = base + bilinear(t (B,h0,w0,C) -> HxW, align_corners=True); out may alias base (in place)
 __global__ void __launch_bounds__(256) resize_add_nhwc_kernel(
     const float* __restrict__ t, const float* base_in, float* acc, int C, int B, int H, int W, int h0, int w0, float sy,
@@ -108,6 +234,20 @@ __global__ void __launch_bounds__(256) resize_add_nhwc_kernel(
   }
 }
 
+// d/dx [x Phi(x)] = Phi(x) + x phi(x) for the exact (erf) GELU.  Phi through Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 on
+// erf, i.e. 7.5e-8 on Phi - below fp32 round-off of the sum), whose exp(-u^2) with u = |x| / sqrt(2) IS the exp(-x^2 / 2) of
+// the density term: one ex2, one rcp and a degree-5 polynomial instead of erff + expf (the kernel is issue-bound on the
+// GELU layers: ~170 instructions per float4 of a 48-byte-per-float4 stream).
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float E = __expf(-0.5f * x * x);
+  const float u = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(1.f + 0.3275911f * u);
+  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  const float erf_abs = 1.f - poly * E;                       // erf(|x| / sqrt 2)
+  const float Phi = 0.5f * (1.f + copysignf(erf_abs, x));
+  return Phi + x * 0.3989422804014327f * E;
+}
+
 // gz[r, c] = g[r, c] * act'(ref[r, c]) * row_scale[r / rows_per_batch];  db[c] += sum_r gz[r, c]
 // act: 1 relu, 2 leaky (ref = output), 3 gelu (ref = pre-activation), 4 sigmoid (ref = output), 0 none.
 // grid (ceil(N/128), row chunks), block (32, 8): a thread owns 4 consecutive columns.
@@ -125,6 +265,8 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
   const uint32_t dseed = drop ? drop_seed_eff(drop_seed, drop_step) : 0u, dthresh = drop_threshold(drop_p);
   const float dinv = drop ? drop_scale(dthresh) : 1.f;
   if (c < N) {
+    // (Tried: requesting the operands of row r + 8 before row r is evaluated - two rows in flight per thread: 13.3 -> 14.8 ms
+    // per step; the kernel is not short of loads in flight, the extra registers cost occupancy.)
     for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
       float4 v = __ldg((const float4*)(g + r * ldg + c));
       if (drop) {      // the mask the GEMM epilogue drew for this element
@@ -143,7 +285,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
           if (act == 1) d[e] = t > 0.f ? 1.f : 0.f;
           else if (act == 2) d[e] = t > 0.f ? 1.f : slope;
           else if (act == 4) d[e] = t * (1.f - t);
-          else d[e] = 0.5f * (1.f + erff(t * 0.70710678118654752f)) + t * 0.3989422804014327f * __expf(-0.5f * t * t);
+          else d[e] = gelu_grad(t);
         }
         v.x *= d[0]; v.y *= d[1]; v.z *= d[2]; v.w *= d[3];
       }
@@ -209,6 +351,55 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ i
   }
 }
 
+// Row form (default): one CTA per output row (b, oy); the feature index k -> (channel plane offset, ky, kx) table is built
+// once in shared memory, a thread emits four consecutive features as one 128-bit store, all index arithmetic is 32-bit
+// (the flat kernel above spends ~300 instructions on 64-bit divisions per 4-byte element).
+constexpr int IM_MAXK = 1024;
+__global__ void __launch_bounds__(256) im2col_rows_kernel(const float* __restrict__ img, int64_t bstride,
+                                                           float* __restrict__ tok, int Cin, int H, int W, int kh, int kw,
+                                                           int stride, int pad, int Ho, int Wo, int Kp) {
+  __shared__ int s_off[IM_MAXK];
+  __shared__ short s_ky[IM_MAXK], s_kx[IM_MAXK];
+  const int oy = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int K = Cin * kh * kw;
+  for (int k = tid; k < Kp; k += 256) {
+    const int c = k / (kh * kw), r = k - c * kh * kw, ky = r / kw, kx = r - ky * kw;
+    s_off[k] = k < K ? (c * H + ky) * W + kx : -1;
+    s_ky[k] = (short)ky; s_kx[k] = (short)kx;
+  }
+  __syncthreads();
+  const int Kq = Kp >> 2, n4 = Wo * Kq;
+  const int y0 = oy * stride - pad;
+  const float* ib = img + b * bstride;
+  float4* trow = (float4*)(tok + ((int64_t)b * Ho + oy) * Wo * Kp);
+  for (int i = tid; i < n4; i += 256) {
+    const int ox = i / Kq, k0 = (i - ox * Kq) * 4;
+    const int x0 = ox * stride - pad;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = k0 + e, off = s_off[k];
+      const int y = y0 + s_ky[k], x = x0 + s_kx[k];
+      v[e] = (off >= 0 && y >= 0 && y < H && x >= 0 && x < W) ? __ldg(ib + off + y0 * W + x0) : 0.f;
+    }
+    trow[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// merge_patches with one CTA per unmerged row (b, y): 32-bit index arithmetic (same mapping as the flat kernel below)
+__global__ void __launch_bounds__(256) merge_patches_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                  int H, int W, int C, int H2, int W2, int dir) {
+  const int y = blockIdx.x, b = blockIdx.y;
+  const int64_t urow = ((int64_t)b * H + y) * W * C;                                  // unmerged row start
+  const int64_t mrow = ((int64_t)b * H2 + (y >> 1)) * W2 * (4 * (int64_t)C) + (y & 1) * 2;
+  const int n = W * C;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int x = i / C, c = i - x * C;
+    const int64_t m = mrow + (int64_t)(x >> 1) * (4 * C) + c * 4 + (x & 1);
+    if (dir == 0) dst[m] = __ldg(src + urow + i); else dst[urow + i] = __ldg(src + m);
+  }
+}
+
 // x (B, H, W, C) tokens -> (B, ceil(H/2)*ceil(W/2), 4C) in nn.Unfold(2,2) order: feature = c*4 + ky*2 + kx
 // (depthformer_swin.py:86,115; zero padding bottom/right for odd sizes :110-111).  dir=1: backward (scatter = gather).
 __global__ void __launch_bounds__(256) merge_patches_kernel(const float* __restrict__ src, float* __restrict__ dst,
@@ -246,6 +437,9 @@ __global__ void __launch_bounds__(256) clamp_resize_kernel(const float* __restri
 }  // namespace ged
 using namespace ged;
 
+static int g_layout_rows = 1;     // 0: the flat grid-stride forms of prep_conv_input / upsample_nhwc_bwd (A/B, tests)
+GED_API int ged_set_layout_rows(int on) { const int prev = g_layout_rows; g_layout_rows = on ? 1 : 0; return prev; }
+
 static inline unsigned grid_for(int64_t total) {
   const int64_t b = (total + 255) / 256;
   return (unsigned)(b < 148 * 16 ? b : 148 * 16);
@@ -258,8 +452,12 @@ GED_API int ged_prep_conv_input(const float* src0, int C0, int h0, int w0, const
   if ((C0 % 4) || (C1 % 4)) return GED_ERR_SHAPE;
   if (!aligned16(src0) || !aligned16(dst) || (src1 && !aligned16(src1))) return GED_ERR_ALIGN;
   const int64_t total = (int64_t)B * (H + 2) * (W + 2) * ((C0 + C1) / 4);
-  prep_conv_input_kernel<<<grid_for(total), 256, 0, stream>>>(src0, C0, h0, w0, src1, C1, dst, B, H, W,
-                                                             resize_scale(h0, H, true), resize_scale(w0, W, true));
+  if (g_layout_rows && W <= RW_MAXW && B <= 65535 && (int64_t)(W + 2) * ((C0 + C1) / 4) < (1 << 30))
+    prep_conv_input_rows_kernel<<<dim3(H + 2, B), 256, 0, stream>>>(src0, C0, h0, w0, src1, C1, dst, B, H, W,
+                                                                   resize_scale(h0, H, true), resize_scale(w0, W, true));
+  else
+    prep_conv_input_kernel<<<grid_for(total), 256, 0, stream>>>(src0, C0, h0, w0, src1, C1, dst, B, H, W,
+                                                               resize_scale(h0, H, true), resize_scale(w0, W, true));
   GED_CHECK_LAUNCH();
   return GED_OK;
 }
@@ -270,8 +468,11 @@ GED_API int ged_upsample_nhwc_bwd(const float* g, int ldg, float* out, int C0, i
   if ((C0 % 4) || (ldg % 4)) return GED_ERR_SHAPE;
   if (!aligned16(g) || !aligned16(out)) return GED_ERR_ALIGN;
   const int64_t total = (int64_t)B * h0 * w0 * (C0 / 4);
-  upsample_nhwc_bwd_kernel<<<grid_for(total), 256, 0, stream>>>(g, ldg, out, C0, B, H, W, h0, w0,
-                                                               resize_scale(h0, H, true), resize_scale(w0, W, true));
+  const float sy = resize_scale(h0, H, true), sx = resize_scale(w0, W, true);
+  if (g_layout_rows && w0 <= RW_MAXW0 && W <= 32767 && B <= 65535 && sy >= 0.3f && sx >= 0.3f && (int64_t)w0 * (C0 / 4) < (1 << 30))
+    upsample_nhwc_bwd_rows_kernel<<<dim3(h0, B), 256, 0, stream>>>(g, ldg, out, C0, B, H, W, h0, w0, sy, sx);
+  else
+    upsample_nhwc_bwd_kernel<<<grid_for(total), 256, 0, stream>>>(g, ldg, out, C0, B, H, W, h0, w0, sy, sx);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }
@@ -335,7 +536,10 @@ GED_API int ged_im2col(const float* img, int64_t batch_stride, float* tok, int B
   const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
   if (Ho <= 0 || Wo <= 0) return GED_ERR_SHAPE;
   const int64_t total = (int64_t)B * Ho * Wo * Kp;
-  im2col_kernel<<<grid_for(total), 256, 0, stream>>>(img, batch_stride, tok, Cin, H, W, kh, kw, stride, pad, Ho, Wo, Kp, total);
+  if (g_layout_rows && Kp <= IM_MAXK && B <= 65535 && (int64_t)Wo * Kp < (1 << 30) && (int64_t)Cin * H * W < (1 << 30) && aligned16(tok))
+    im2col_rows_kernel<<<dim3(Ho, B), 256, 0, stream>>>(img, batch_stride, tok, Cin, H, W, kh, kw, stride, pad, Ho, Wo, Kp);
+  else
+    im2col_kernel<<<grid_for(total), 256, 0, stream>>>(img, batch_stride, tok, Cin, H, W, kh, kw, stride, pad, Ho, Wo, Kp, total);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }
@@ -348,7 +552,10 @@ GED_API int ged_merge_patches(const float* src, float* dst, int B, int H, int W,
   if (!backward && ((H | W) & 1))
     if (cudaMemsetAsync(dst, 0, sizeof(float) * (size_t)B * H2 * W2 * 4 * C, stream) != cudaSuccess) return GED_ERR_LAUNCH;
   const int64_t total = (int64_t)B * H * W * C;
-  merge_patches_kernel<<<grid_for(total), 256, 0, stream>>>(src, dst, H, W, C, H2, W2, total, backward);
+  if (g_layout_rows && B <= 65535 && (int64_t)W * C < (1 << 30))
+    merge_patches_rows_kernel<<<dim3(H, B), 256, 0, stream>>>(src, dst, H, W, C, H2, W2, backward);
+  else
+    merge_patches_kernel<<<grid_for(total), 256, 0, stream>>>(src, dst, H, W, C, H2, W2, total, backward);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }

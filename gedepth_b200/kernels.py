@@ -76,6 +76,8 @@ SIGNATURES = {
     "ged_set_gemm_pair_dw": [_I],
     "ged_set_gemm_a_tmem": [_I],
     "ged_set_ge_x2": [_I],
+    "ged_set_layernorm_reg": [_I],
+    "ged_set_layout_rows": [_I],
     "ged_set_msda_variant": [_I],
     "ged_gemm_dw_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I64, _I64, _I, _P, _I, _P],
     "ged_depth_metrics": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P],
@@ -605,6 +607,17 @@ def set_ge_x2(on) -> int:
     """Closed-form x2 ground-embedding kernels: 1 = on, TMA-staged forward where W % 8 == 0 (default), 2 = on with per-thread
     asynchronous copies only, 0 = generic bilinear kernels; returns the previous setting."""
     return load().ged_set_ge_x2(int(on))
+
+
+def set_layernorm_reg(on: bool) -> int:
+    """LayerNorm rows of <= 768 channels held in registers, dw / db fused into the dx kernel (default on); returns the
+    previous setting."""
+    return load().ged_set_layernorm_reg(int(bool(on)))
+
+
+def set_layout_rows(on: bool) -> int:
+    """Row-structured prep_conv_input / upsample adjoint kernels (default on); returns the previous setting."""
+    return load().ged_set_layout_rows(int(bool(on)))
 
 
 def set_gemm_pair(on) -> int:

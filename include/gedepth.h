@@ -106,6 +106,9 @@ int ged_layernorm_fwd(const float* x, const float* w, const float* b, float* y, 
  * LayerNorm input and the identity, depthformer_swin.py:461-472). */
 int ged_layernorm_bwd(const float* g, const float* x, const float* w, const float* mean, const float* rstd,
                       const float* g_add, float* dx, float* dw, float* db, int64_t rows, int C, cudaStream_t stream);
+/* 1 (default): rows of C <= 768 channels are held in registers (one global read per operand; the backward's weight / bias
+ * gradients come out of the same kernel); 0: the three-pass forward and the two-kernel backward.  Returns the previous setting. */
+int ged_set_layernorm_reg(int on);
 /* depthformer_swin.py:285-360 + :184-224 minus the two linears.  qkv (B,H*W,3C) image order. */
 int ged_winattn_fwd(const float* qkv, const float* qkv_bias, const float* table, const long long* index,
                     float* ctx, int B, int H, int W, int C, int nH, int window, int shift, float scale,
@@ -195,6 +198,10 @@ int ged_conv3x3_tf32(const float* Xpad, const float* Wk, float* Y, int ldy, int 
                      int Cout, const float* bias, int act, float slope, cudaStream_t stream);
 
 /* ---- data movement around the convs (NHWC fp32) ------------------------------------------------ */
+/* 1 (default): ged_prep_conv_input / ged_upsample_nhwc_bwd run one CTA per output row with the bilinear taps tabulated once
+ * in shared memory; 0: the flat grid-stride kernels (also taken for rows wider than 1024 / source rows wider than 512 / ratios above x3.3).  Returns the
+ * previous setting. */
+int ged_set_layout_rows(int on);
 /* dst [B,H+2,W+2,C0+C1] = zero border | [bilinear(src0 (B,h0,w0,C0) -> HxW, align_corners=True), src1 (B,H,W,C1)]:
  * F.interpolate + torch.cat + padding of densedepth_head.py:24-27 / hahi.py:329-353 in one pass. */
 int ged_prep_conv_input(const float* src0, int C0, int h0, int w0, const float* src1, int C1, float* dst, int B,

@@ -124,6 +124,38 @@ def test_ge_vanilla_fwd_bwd(B, H, W):
     _close(yh1.grad, yh2.grad, 1e-4, 1e-4 * float(yh2.grad.abs().max()), "g_y_half")
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 64, 160), (1, 4, 8), (2, 6, 12), (2, 352, 1120), (1, 384, 640), (1, 66, 516), (3, 34, 1032), (1, 2, 4)])
+def test_ge_vanilla_x2_streaming_equals_tiled(B, H, W):
+    """The streaming (warp per 128-column strip) x2 kernels, forward and backward, against the tiled ones (ged_set_ge_x2(2)) and
+    the generic bilinear ones (0): strips that end inside a warp, maps narrower than one strip, chunks that end inside the map,
+    a missing g_y / g_pe_mask."""
+    from gedepth_b200 import kernels as K
+    img, y_half, _ = _ge_inputs(B, H, W, False)
+    img_d, yh = img.to(DEV), y_half.to(DEV)
+    gy, gp = torch.randn(B, 1, H, W, device=DEV), torch.randn(B, 1, H, W, device=DEV) * 0.1
+    res = {}
+    for mode in (1, 2, 0):
+        prev = K.set_ge_x2(mode)
+        try:
+            with torch.no_grad():
+                y, pm = K.ge_vanilla(img_d, yh)
+            outs = []
+            for a, bb in ((gy, gp), (None, gp), (gy, None)):
+                o = torch.full((B, 1, H // 2, W // 2), 3.0, device=DEV)
+                if mode == 0:
+                    o.zero_()
+                K._call("ged_ge_vanilla_bwd", K._p(img_d[:, 3]), img_d.stride(0), K._p(a), K._p(bb), K._p(o), B, H, W, H // 2, W // 2,
+                        K._stream())
+                outs.append(o)
+            torch.cuda.synchronize()
+        finally:
+            K.set_ge_x2(prev)
+        res[mode] = (y, pm, *outs)
+    for mode in (2, 0):
+        for name, a, bb in zip(("y", "pe_mask", "g_y_half", "g_y_half (no g_y)", "g_y_half (no g_pe_mask)"), res[1], res[mode]):
+            _close(a, bb, 1e-5, 1e-6 * max(1.0, float(bb.abs().max())), f"{name} vs mode {mode}")
+
+
 @pytest.mark.parametrize("B,H,W,per_sample_h", [(2, 64, 160, False), (1, 70, 166, True), (2, 352, 1120, False), (1, 4, 8, False),
                                                  (2, 6, 12, True), (3, 36, 84, True), (1, 14, 520, False), (1, 384, 640, True),
                                                  (2, 30, 244, False)])
@@ -266,20 +298,29 @@ def test_cross_entropy_fwd_bwd():
 # ------------------------------------------------------------------------------------------------
 # Swin pieces
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rows,C", [(640, 96), (333, 384), (70, 1536), (50, 3072)])
-def test_layernorm_fwd_bwd(rows, C):
+@pytest.mark.parametrize("reg", [1, 0])
+@pytest.mark.parametrize("rows,C", [(640, 96), (333, 384), (70, 1536), (50, 3072), (1237, 192), (9001, 768), (77, 512), (65, 640),
+                                     (3, 4), (20011, 192)])
+def test_layernorm_fwd_bwd(rows, C, reg):
+    """reg = 1: rows of <= 768 channels in registers, dw / db out of the dx kernel (default); reg = 0: three-pass forward,
+    two-kernel backward (what wider rows always take).  Also the residual-branch gradient added in the dx pass (g_add)."""
     from gedepth_b200 import kernels as K
     g = torch.Generator().manual_seed(7)
     x0 = torch.randn(2, rows, C, generator=g) * 3 + 1
     w0, b0 = torch.randn(C, generator=g), torch.randn(C, generator=g)
     a1 = [t.to(DEV).requires_grad_(True) for t in (x0, w0, b0)]
     a2 = [t.to(DEV).requires_grad_(True) for t in (x0, w0, b0)]
-    y1 = K.layer_norm(*a1, 1e-5)
-    y2 = F.layer_norm(a2[0], (C,), a2[1], a2[2], 1e-5)
-    _close(y1, y2, 1e-5, 1e-5, "layernorm")
-    go = torch.randn_like(y1)
-    (y1 * go).sum().backward()
-    (y2 * go).sum().backward()
+    prev = K.set_layernorm_reg(reg)
+    try:
+        y1, xid = K.layer_norm_fork(*a1, 1e-5)
+        y2 = F.layer_norm(a2[0], (C,), a2[1], a2[2], 1e-5)
+        _close(y1, y2, 1e-5, 1e-5, "layernorm")
+        go, gi = torch.randn_like(y1), torch.randn_like(y1)
+        ((y1 * go).sum() + (xid * gi).sum()).backward()
+        ((y2 * go).sum() + (a2[0] * gi).sum()).backward()
+        torch.cuda.synchronize()
+    finally:
+        K.set_layernorm_reg(prev)
     for n, p, q in zip(("dx", "dw", "db"), a1, a2):
         _close(p.grad, q.grad, 1e-4, 2e-5 * float(q.grad.abs().max()), n)
 
@@ -840,21 +881,31 @@ def test_adamw_and_clip_match_torch():
 # ------------------------------------------------------------------------------------------------
 # data-movement kernels around the convs
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,h0,w0,H,W,C0,C1", [(2, 11, 35, 22, 70, 64, 32), (1, 9, 12, 9, 12, 32, 96), (2, 22, 70, 44, 139, 96, 0)])
-def test_prep_conv_input_and_adjoint(B, h0, w0, H, W, C0, C1):
+@pytest.mark.parametrize("rows_mode", [1, 0])
+@pytest.mark.parametrize("B,h0,w0,H,W,C0,C1", [(2, 11, 35, 22, 70, 64, 32), (1, 9, 12, 9, 12, 32, 96), (2, 22, 70, 44, 139, 96, 0),
+                                               (1, 88, 280, 176, 560, 192, 64), (2, 5, 7, 16, 22, 8, 4), (1, 3, 4, 11, 15, 4, 0),
+                                               (1, 7, 9, 7, 9, 4, 4)])
+def test_prep_conv_input_and_adjoint(B, h0, w0, H, W, C0, C1, rows_mode):
+    """rows_mode = 1: one CTA per output row, bilinear taps tabulated in shared memory (default); 0: the flat grid-stride
+    kernels.  (1, 3, 4, 11, 15): a x3.6 ratio, which the row form of the adjoint hands to the flat kernel by itself."""
     from gedepth_b200 import kernels as Kn
     g = torch.Generator().manual_seed(20)
     x0 = torch.randn(B, h0, w0, C0, generator=g).to(DEV)
     x1 = torch.randn(B, H, W, C1, generator=g).to(DEV) if C1 else None
-    xp = Kn.prep_conv_input(x0, x1, H, W)
+    prev = Kn.set_layout_rows(rows_mode)
+    try:
+        xp = Kn.prep_conv_input(x0, x1, H, W)
+        gfull = torch.randn(B, H, W, C0 + C1, generator=g).to(DEV)
+        out = torch.empty(B, h0, w0, C0, device=DEV)
+        Kn._call("ged_upsample_nhwc_bwd", Kn._p(gfull), C0 + C1, Kn._p(out), C0, B, H, W, h0, w0, Kn._stream())
+        torch.cuda.synchronize()
+    finally:
+        Kn.set_layout_rows(prev)
     up = F.interpolate(x0.permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True) if (h0, w0) != (H, W) else x0.permute(0, 3, 1, 2)
     ref = torch.cat([up] + ([x1.permute(0, 3, 1, 2)] if C1 else []), 1)
     ref = F.pad(ref, (1, 1, 1, 1)).permute(0, 2, 3, 1)
     _close(xp, ref, 1e-5, 1e-5, "prep")
     # adjoint of the resize on the first C0 channels
-    gfull = torch.randn(B, H, W, C0 + C1, generator=g).to(DEV)
-    out = torch.empty(B, h0, w0, C0, device=DEV)
-    Kn._call("ged_upsample_nhwc_bwd", Kn._p(gfull), C0 + C1, Kn._p(out), C0, B, H, W, h0, w0, Kn._stream())
     x0r = x0.clone().requires_grad_(True)
     upr = F.interpolate(x0r.permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True)
     (upr * gfull[..., :C0].permute(0, 3, 1, 2)).sum().backward()
@@ -866,7 +917,7 @@ def test_act_bwd(act):
     from gedepth_b200 import kernels as Kn
     from tests import ops_lib as L
     g = torch.Generator().manual_seed(21)
-    rows, N, T = 3 * 217, 96, 217
+    rows, N, T = 3 * 217, 96, 217          # 651 rows: five 128-row chunks + a ragged one (the two-row prefetch loop's tail)
     pre = torch.randn(rows, N, generator=g).to(DEV).requires_grad_(True)
     go = torch.randn(rows, N, generator=g).to(DEV)
     rs = torch.tensor([0.0, 1.4, 1.4]).to(DEV)
@@ -937,8 +988,17 @@ def test_patch_embed_as_gemm(H, W, passes):
     _close(b.grad, b2.grad, 1e-4, 1e-3, "db")
 
 
+@pytest.fixture(params=[1, 0], ids=["rows", "flat"])
+def layout_rows(request):
+    """Both forms of the data-movement kernels: one CTA per output row (default) and the flat grid-stride kernels."""
+    from gedepth_b200 import kernels as Kn
+    prev = Kn.set_layout_rows(request.param)
+    yield request.param
+    Kn.set_layout_rows(prev)
+
+
 @pytest.mark.parametrize("H,W", [(64, 160), (35, 83)])
-def test_stem_conv_as_im2col_gemm(H, W, passes):
+def test_stem_conv_as_im2col_gemm(H, W, passes, layout_rows):
     """7x7/s2/p3 stem conv on channels 0-2 of the 5-channel batch (depthformer_swin.py:1032-1039,1152) as
     im2col + tcgen05 GEMM, forward and weight gradient, vs F.conv2d in fp64."""
     from gedepth_b200 import kernels as Kn
@@ -961,7 +1021,7 @@ def test_stem_conv_as_im2col_gemm(H, W, passes):
 
 
 @pytest.mark.parametrize("H,W,C", [(16, 40, 96), (9, 21, 192), (5, 11, 384)])
-def test_merge_patches_fwd_bwd(H, W, C):
+def test_merge_patches_fwd_bwd(H, W, C, layout_rows):
     from gedepth_b200 import kernels as Kn
     from tests import ops_lib as L
     g = torch.Generator().manual_seed(25)
