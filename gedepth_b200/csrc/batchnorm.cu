@@ -51,12 +51,14 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, float* __res
   }
 }
 
+// IT = unsigned when the element count fits 32 bits (a 64-bit modulo per float4 otherwise)
+template <typename IT>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ b, const float* __restrict__ mean,
                                                         const float* __restrict__ rstd, float* __restrict__ y,
-                                                        int64_t total4, int C, int relu) {
-  const int C4 = C >> 2;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+                                                        int64_t total4_, int C, int relu) {
+  const IT C4 = (IT)(C >> 2), total4 = (IT)total4_;
+  for (IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (IT)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * 4;
     const float4 v = __ldg((const float4*)x + i), mu = __ldg((const float4*)(mean + c)), rs = __ldg((const float4*)(rstd + c));
     const float4 ww = __ldg((const float4*)(w + c)), bb = __ldg((const float4*)(b + c));
@@ -105,18 +107,18 @@ __global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float* __restric
 }
 
 // dx = w * rstd * (gz - db/n - xhat * dw/n);  also writes db, dw (float) from the fp64 sums (thread 0..C-1 of block 0)
+template <typename IT>
 __global__ void __launch_bounds__(256) bn_bwd_dx_kernel(const float* __restrict__ g, const float* __restrict__ x,
                                                          const float* __restrict__ y, const float* __restrict__ w,
                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                                          const double* __restrict__ sums, float* __restrict__ dx,
                                                          float* __restrict__ dw, float* __restrict__ db, int64_t rows,
                                                          int C, int relu) {
-  const int C4 = C >> 2;
-  const int64_t total4 = rows * C4;
+  const IT C4 = (IT)(C >> 2), total4 = (IT)rows * C4;
   const float invn = 1.f / (float)rows;
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < C; c += blockDim.x) { db[c] = (float)sums[c]; dw[c] = (float)sums[C + c]; }
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+  for (IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (IT)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * 4;
     float4 gg = __ldg((const float4*)g + i);
     const float4 v = __ldg((const float4*)x + i);
@@ -156,7 +158,11 @@ GED_API int ged_bn_train_fwd(const float* x, const float* w, const float* b, flo
   dim3 grid(cdiv(C, 128), (unsigned)((rows + BN_ROWS_PER_BLOCK - 1) / BN_ROWS_PER_BLOCK));
   bn_stats_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, sums, rows, C);
   bn_finalize_kernel<<<cdiv(C, 128), 128, 0, stream>>>(sums, save_mean, save_rstd, running_mean, running_var, rows, C, eps, momentum);
-  bn_apply_kernel<<<bn_grid(rows * (C / 4)), 256, 0, stream>>>(x, w, b, save_mean, save_rstd, y, rows * (C / 4), C, relu);
+  const int64_t total4 = rows * (C / 4);
+  if (total4 + (int64_t)bn_grid(total4) * 256 < (1ll << 32))
+    bn_apply_kernel<unsigned><<<bn_grid(total4), 256, 0, stream>>>(x, w, b, save_mean, save_rstd, y, total4, C, relu);
+  else
+    bn_apply_kernel<int64_t><<<bn_grid(total4), 256, 0, stream>>>(x, w, b, save_mean, save_rstd, y, total4, C, relu);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }
@@ -171,7 +177,11 @@ GED_API int ged_bn_train_bwd(const float* g, const float* x, const float* y, con
   if (cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, stream) != cudaSuccess) return GED_ERR_LAUNCH;
   dim3 grid(cdiv(C, 128), (unsigned)((rows + BN_ROWS_PER_BLOCK - 1) / BN_ROWS_PER_BLOCK));
   bn_bwd_sums_kernel<<<grid, dim3(32, 8), 0, stream>>>(g, x, y, save_mean, save_rstd, sums, rows, C, relu);
-  bn_bwd_dx_kernel<<<bn_grid(rows * (C / 4)), 256, 0, stream>>>(g, x, y, w, save_mean, save_rstd, sums, dx, dw, db, rows, C, relu);
+  const int64_t total4 = rows * (C / 4);
+  if (total4 + (int64_t)bn_grid(total4) * 256 < (1ll << 32))
+    bn_bwd_dx_kernel<unsigned><<<bn_grid(total4), 256, 0, stream>>>(g, x, y, w, save_mean, save_rstd, sums, dx, dw, db, rows, C, relu);
+  else
+    bn_bwd_dx_kernel<int64_t><<<bn_grid(total4), 256, 0, stream>>>(g, x, y, w, save_mean, save_rstd, sums, dx, dw, db, rows, C, relu);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }

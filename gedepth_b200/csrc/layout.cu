@@ -208,17 +208,19 @@ __global__ void __launch_bounds__(256) upsample_nhwc_bwd_rows_kernel(
 }
 
 // out (B,H,W,C) = base + bilinear(t (B,h0,w0,C) -> HxW, align_corners=True); out may alias base (in place)
+template <typename IT>      // unsigned when the element count fits 32 bits: five divisions per float4
 __global__ void __launch_bounds__(256) resize_add_nhwc_kernel(
     const float* __restrict__ t, const float* base_in, float* acc, int C, int B, int H, int W, int h0, int w0, float sy,
     float sx) {
   const int C4 = C >> 2;
-  const int64_t total = (int64_t)B * H * W * C4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4) * 4;
-    int64_t p = i / C4;
-    const int x = (int)(p % W); p /= W;
-    const int y = (int)(p % H);
-    const int b = (int)(p / H);
+  const IT total = (IT)B * (IT)H * (IT)W * (IT)C4;
+  for (IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IT)gridDim.x * blockDim.x) {
+    IT p = i / (IT)C4;
+    const int c = (int)(i - p * (IT)C4) * 4;
+    const IT p2 = p / (IT)W;
+    const int x = (int)(p - p2 * (IT)W);
+    const int b = (int)(p2 / (IT)H);
+    const int y = (int)(p2 - (IT)b * (IT)H);
     const Tap ty = tap(y, sy, true, h0), tx = tap(x, sx, true, w0);
     const float* base = t + (int64_t)b * h0 * w0 * C + c;
     const float4 v00 = __ldg((const float4*)(base + ((int64_t)ty.i0 * w0 + tx.i0) * C));
@@ -251,6 +253,10 @@ __device__ __forceinline__ float gelu_grad(float x) {
 // gz[r, c] = g[r, c] * act'(ref[r, c]) * row_scale[r / rows_per_batch];  db[c] += sum_r gz[r, c]
 // act: 1 relu, 2 leaky (ref = output), 3 gelu (ref = pre-activation), 4 sigmoid (ref = output), 0 none.
 // grid (ceil(N/128), row chunks), block (32, 8): a thread owns 4 consecutive columns.
+// GELU = true: act == 3 (the ~100-instruction derivative; one row per iteration keeps 40 registers and 6 CTAs per SM - requesting
+// the next row first cost occupancy: 13.3 -> 14.8 ms per step).  GELU = false: every other case is a pure stream (column sums
+// only, DropPath row scale, ReLU-class masks, dropout): two rows in flight per thread.
+template <bool GELU>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ ref,
                                                        float* __restrict__ gz, float* __restrict__ db,
                                                        const float* __restrict__ row_scale, int rows_per_batch,
@@ -264,11 +270,27 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
   const bool drop = drop_p > 0.f;
   const uint32_t dseed = drop ? drop_seed_eff(drop_seed, drop_step) : 0u, dthresh = drop_threshold(drop_p);
   const float dinv = drop ? drop_scale(dthresh) : 1.f;
+  const bool small_rows = rows < (1ll << 31);
   if (c < N) {
-    // (Tried: requesting the operands of row r + 8 before row r is evaluated - two rows in flight per thread: 13.3 -> 14.8 ms
-    // per step; the kernel is not short of loads in flight, the extra registers cost occupancy.)
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
-      float4 v = __ldg((const float4*)(g + r * ldg + c));
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t r = r0 + threadIdx.y;
+    float4 vn = zero4, yn = zero4;
+    if (!GELU && r < r1) {
+      vn = __ldg((const float4*)(g + r * ldg + c));
+      if (act) yn = __ldg((const float4*)(ref + r * N + c));
+    }
+    for (; r < r1; r += 8) {
+      float4 v, y;
+      if (GELU) {
+        v = __ldg((const float4*)(g + r * ldg + c));
+        y = __ldg((const float4*)(ref + r * N + c));
+      } else {
+        v = vn; y = yn;
+        if (r + 8 < r1) {
+          vn = __ldg((const float4*)(g + (r + 8) * ldg + c));
+          if (act) yn = __ldg((const float4*)(ref + (r + 8) * N + c));
+        }
+      }
       if (drop) {      // the mask the GEMM epilogue drew for this element
         const uint32_t keep = drop_keep4(dseed, (uint32_t)(r * N + c), dthresh);
         v.x = (keep & 1u) ? v.x * dinv : 0.f;
@@ -276,21 +298,22 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
         v.z = (keep & 4u) ? v.z * dinv : 0.f;
         v.w = (keep & 8u) ? v.w * dinv : 0.f;
       }
-      if (act) {
-        const float4 y = __ldg((const float4*)(ref + r * N + c));
+      if (GELU) {
+        v.x *= gelu_grad(y.x); v.y *= gelu_grad(y.y); v.z *= gelu_grad(y.z); v.w *= gelu_grad(y.w);
+      } else if (act) {
         float d[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float t = d[e];
           if (act == 1) d[e] = t > 0.f ? 1.f : 0.f;
           else if (act == 2) d[e] = t > 0.f ? 1.f : slope;
-          else if (act == 4) d[e] = t * (1.f - t);
-          else d[e] = gelu_grad(t);
+          else d[e] = t * (1.f - t);
         }
         v.x *= d[0]; v.y *= d[1]; v.z *= d[2]; v.w *= d[3];
       }
       if (row_scale) {
-        const float s = __ldg(row_scale + r / rows_per_batch);
+        const int64_t sb = small_rows ? (int64_t)((unsigned)r / (unsigned)rows_per_batch) : r / rows_per_batch;   // 32-bit division when it fits
+        const float s = __ldg(row_scale + sb);
         v.x *= s; v.y *= s; v.z *= s; v.w *= s;
       }
       if (gz) *(float4*)(gz + r * N + c) = v;
@@ -483,8 +506,12 @@ GED_API int ged_resize_add_nhwc(const float* t, const float* base, float* out, i
   if (C % 4) return GED_ERR_SHAPE;
   if (!aligned16(t) || !aligned16(base) || !aligned16(out)) return GED_ERR_ALIGN;
   const int64_t total = (int64_t)B * H * W * (C / 4);
-  resize_add_nhwc_kernel<<<grid_for(total), 256, 0, stream>>>(t, base, out, C, B, H, W, h0, w0, resize_scale(h0, H, true),
-                                                             resize_scale(w0, W, true));
+  if (total + (int64_t)grid_for(total) * 256 < (1ll << 32))
+    resize_add_nhwc_kernel<unsigned><<<grid_for(total), 256, 0, stream>>>(t, base, out, C, B, H, W, h0, w0, resize_scale(h0, H, true),
+                                                                         resize_scale(w0, W, true));
+  else
+    resize_add_nhwc_kernel<int64_t><<<grid_for(total), 256, 0, stream>>>(t, base, out, C, B, H, W, h0, w0, resize_scale(h0, H, true),
+                                                                        resize_scale(w0, W, true));
   GED_CHECK_LAUNCH();
   return GED_OK;
 }
@@ -497,8 +524,12 @@ GED_API int ged_act_bwd(const float* g, int64_t ldg, const float* ref, float* gz
   if (!aligned16(g) || (gz && !aligned16(gz)) || (ref && !aligned16(ref))) return GED_ERR_ALIGN;
   const int rpb = 128;
   dim3 grid(cdiv(N, 128), (unsigned)((rows + rpb - 1) / rpb));
-  act_bwd_kernel<<<grid, dim3(32, 8), 0, stream>>>(g, ldg, ref, gz, db, row_scale, rows_per_batch > 0 ? rows_per_batch : 1,
-                                                  rows, N, act, slope, rpb, 0.f, 0u, nullptr);
+  if (act == 3)
+    act_bwd_kernel<true><<<grid, dim3(32, 8), 0, stream>>>(g, ldg, ref, gz, db, row_scale, rows_per_batch > 0 ? rows_per_batch : 1,
+                                                          rows, N, act, slope, rpb, 0.f, 0u, nullptr);
+  else
+    act_bwd_kernel<false><<<grid, dim3(32, 8), 0, stream>>>(g, ldg, ref, gz, db, row_scale, rows_per_batch > 0 ? rows_per_batch : 1,
+                                                           rows, N, act, slope, rpb, 0.f, 0u, nullptr);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }
@@ -512,7 +543,7 @@ GED_API int ged_dropout_bwd(const float* g, int64_t ldg, float* gz, float* db, i
   if (!aligned16(g) || !aligned16(gz)) return GED_ERR_ALIGN;
   const int rpb = 128;
   dim3 grid(cdiv(N, 128), (unsigned)((rows + rpb - 1) / rpb));
-  act_bwd_kernel<<<grid, dim3(32, 8), 0, stream>>>(g, ldg, nullptr, gz, db, nullptr, 1, rows, N, 0, 0.f, rpb, drop_p, drop_seed, drop_step);
+  act_bwd_kernel<false><<<grid, dim3(32, 8), 0, stream>>>(g, ldg, nullptr, gz, db, nullptr, 1, rows, N, 0, 0.f, rpb, drop_p, drop_seed, drop_step);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }

@@ -210,13 +210,17 @@ struct LevelStarts {
 __device__ __forceinline__ int level_of(const LevelStarts& ls, int s) { return (s >= ls.start[1]) + (s >= ls.start[2]) + (s >= ls.start[3]); }
 
 // q[b][s][:] = query[b][s][:] + pos[s][:] (+ level_embed[level(s)][:])
+// IT = unsigned when the element count fits 32 bits (always on this path): a 64-bit division costs ~5x a 32-bit one and
+// there are two per float4
+template <typename IT>
 __global__ void __launch_bounds__(256) add_pos_kernel(const float4* __restrict__ query, const float4* __restrict__ pos,
                                                       const float4* __restrict__ level_embed, float4* __restrict__ q, int B, int S,
                                                       int C4, LevelStarts ls) {
-  const int64_t total = (int64_t)B * S * C4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4);
-    const int s = (int)((i / C4) % S);
+  const IT total = (IT)B * (IT)S * (IT)C4;
+  for (IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IT)gridDim.x * blockDim.x) {
+    const IT row = i / (IT)C4;
+    const int c = (int)(i - row * (IT)C4);
+    const int s = (int)(row % (IT)S);
     float4 v = ldg_stream(query + i);
     const float4 pv = __ldg(pos + (int64_t)s * C4 + c);
     v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
@@ -342,8 +346,13 @@ GED_API int ged_add_pos_fwd(const float* query, const float* pos, const float* l
   LevelStarts ls{};
   for (int i = 0; i < 5; ++i) ls.start[i] = level_start ? level_start[i] : (i == 0 ? 0 : S);
   const int64_t total = (int64_t)B * S * (C / 4);
-  add_pos_kernel<<<(int)imin64((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
-      (const float4*)query, (const float4*)pos, (const float4*)level_embed, (float4*)q, B, S, C / 4, ls);
+  const int blocks = (int)imin64((total + 255) / 256, 148 * 16);
+  if (total + (int64_t)blocks * 256 < (1ll << 32))
+    add_pos_kernel<unsigned><<<blocks, 256, 0, stream>>>((const float4*)query, (const float4*)pos, (const float4*)level_embed, (float4*)q,
+                                                       B, S, C / 4, ls);
+  else
+    add_pos_kernel<int64_t><<<blocks, 256, 0, stream>>>((const float4*)query, (const float4*)pos, (const float4*)level_embed, (float4*)q,
+                                                      B, S, C / 4, ls);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }
