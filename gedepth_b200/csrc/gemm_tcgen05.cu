@@ -46,7 +46,8 @@ struct GemmParams {
   int rows_per_batch;       // for row_scale
   float* D;
   float* D_pre;             // optional: pre-activation (x + bias) copy, same pitch as D (saved for GELU')
-  int ldd;                  // row pitch of D / residual in floats
+  int ldd;                  // row pitch of D (and of residual when ldr == 0) in floats
+  int ldr;                  // row pitch of residual in floats; 0 = ldd
   int act;
   float slope;
   // dropout on the activated output, before row scale / residual (0 = off)
@@ -286,7 +287,8 @@ constexpr int SPLIT_WARPS = 4;
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* tile_s, uint32_t tmem_acc, uint64_t* full_bar,
                                           uint32_t full_phase, int m0, int n0, float* Dt, int q, int half, int lane) {
-  const bool vec = ((p.ldd & 3) == 0) && ((p.N & 3) == 0) && aligned16(p.D) && (!p.residual || aligned16(p.residual));
+  const int64_t ldr = p.ldr ? p.ldr : p.ldd;
+  const bool vec = ((p.ldd & 3) == 0) && ((p.N & 3) == 0) && aligned16(p.D) && (!p.residual || (aligned16(p.residual) && (ldr & 3) == 0));
   const int lr = lane >> 2, lc = (lane & 3) * 4;          // store phase: lane -> (row lr + 8 i, 4 columns from lc)
   // the four output rows this lane stores (fixed for the whole tile)
   int64_t orow[4];
@@ -348,14 +350,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* tile_s
           else for (int e = 0; e < 4; ++e) if (col + e < p.N) atomicAdd(dst + e, x[e]);
         } else if (vec) {
           if (p.residual) {
-            const float4 r = __ldg((const float4*)(p.residual + orow[i] * p.ldd + col));
+            const float4 r = __ldg((const float4*)(p.residual + orow[i] * ldr + col));
             x[0] += r.x; x[1] += r.y; x[2] += r.z; x[3] += r.w;
           }
           *(float4*)dst = make_float4(x[0], x[1], x[2], x[3]);
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            if (col + e < p.N) dst[e] = x[e] + (p.residual ? __ldg(p.residual + orow[i] * p.ldd + col + e) : 0.f);
+            if (col + e < p.N) dst[e] = x[e] + (p.residual ? __ldg(p.residual + orow[i] * ldr + col + e) : 0.f);
         }
       }
     }
@@ -1232,15 +1234,15 @@ GED_API int ged_gemm_tf32_bt(const float* A, int lda, const float* Wt, int ldw, 
   return run(A, M, lda, Wt, ldw, p, stream);
 }
 
-// The same plus a residual: D = A @ Wt + R (R with D's row pitch; R == D accumulates in place).  Lets a gradient that
+// The same plus a residual: D = A @ Wt + R (R with row pitch ldr, 0 = D's; R == D accumulates in place).  Lets a gradient that
 // fans in from several consumers be summed inside the GEMM epilogues instead of by separate elementwise passes.
 GED_API int ged_gemm_tf32_bt_acc(const float* A, int lda, const float* Wt, int ldw, float* D, int ldd, int M, int N,
-                                 int K, const float* residual, cudaStream_t stream) {
-  if (!A || !Wt || !D || M <= 0 || N <= 0 || K <= 0) return GED_ERR_ARG;
+                                 int K, const float* residual, int ldr, cudaStream_t stream) {
+  if (!A || !Wt || !D || M <= 0 || N <= 0 || K <= 0 || ldr < 0 || (ldr > 0 && ldr < N)) return GED_ERR_ARG;
   if ((K % 4) || (N % 4)) return GED_ERR_SHAPE;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.ntaps = 1; p.tap_off[0] = 0; p.b_mn = 1; p.b_tap_cols = 0;
-  p.rows_per_batch = 1; p.D = D; p.ldd = ldd; p.residual = residual;
+  p.rows_per_batch = 1; p.D = D; p.ldd = ldd; p.residual = residual; p.ldr = ldr;
   return run(A, M, lda, Wt, ldw, p, stream);
 }
 

@@ -14,7 +14,7 @@ namespace ged {
 
 __global__ void __launch_bounds__(256) prep_conv_input_kernel(
     const float* __restrict__ src0, int C0, int h0, int w0, const float* __restrict__ src1, int C1,
-    float* __restrict__ dst, int B, int H, int W, float sy, float sx) {
+    float* __restrict__ dst, int B, int H, int W, float sy, float sx, int64_t bs0, int64_t bs1) {
   const int C = C0 + C1, C4 = C >> 2;
   const int64_t total = (int64_t)B * (H + 2) * (W + 2) * C4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -28,10 +28,10 @@ __global__ void __launch_bounds__(256) prep_conv_input_kernel(
       const int x = xp - 1, y = yp - 1;
       if (c < C0) {
         if (h0 == H && w0 == W) {
-          v = __ldg((const float4*)(src0 + (((int64_t)b * H + y) * W + x) * C0 + c));
+          v = __ldg((const float4*)(src0 + b * bs0 + ((int64_t)y * W + x) * C0 + c));
         } else {
           const Tap ty = tap(y, sy, true, h0), tx = tap(x, sx, true, w0);
-          const float* base = src0 + (int64_t)b * h0 * w0 * C0 + c;
+          const float* base = src0 + b * bs0 + c;
           const float4 v00 = __ldg((const float4*)(base + ((int64_t)ty.i0 * w0 + tx.i0) * C0));
           const float4 v01 = __ldg((const float4*)(base + ((int64_t)ty.i0 * w0 + tx.i1) * C0));
           const float4 v10 = __ldg((const float4*)(base + ((int64_t)ty.i1 * w0 + tx.i0) * C0));
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) prep_conv_input_kernel(
           v.w = ty.l0 * (tx.l0 * v00.w + tx.l1 * v01.w) + ty.l1 * (tx.l0 * v10.w + tx.l1 * v11.w);
         }
       } else {
-        v = __ldg((const float4*)(src1 + (((int64_t)b * H + y) * W + x) * C1 + (c - C0)));
+        v = __ldg((const float4*)(src1 + b * bs1 + ((int64_t)y * W + x) * C1 + (c - C0)));
       }
     }
     *((float4*)dst + i) = v;
@@ -88,12 +88,12 @@ __global__ void __launch_bounds__(256) upsample_nhwc_bwd_kernel(
 // and re-used across all channels; the per-element work is one 32-bit division, the loads and the FMAs, in the same
 // summation order (bit-identical results).
 constexpr int RW_MAXW = 1024;     // widest row the forward's tap table holds (wider maps take the flat kernels)
-constexpr int RW_MAXW0 = 512;     // widest SOURCE row of the adjoint's tables (28 KB; wider maps / > x3.3 ratios: flat kernel)
-constexpr int RW_T = 8;           // non-zero adjoint taps per axis (2 / scale + 1 <= 8 for scale >= 0.3)
+constexpr int RW_SMEM0 = 40 * 1024; // the adjoint's x-tap tables (w0 x taps x 6 bytes + 4 w0; larger: flat kernel)
+constexpr int RW_T = 24;          // most non-zero adjoint taps per axis (2 / scale + 2: ratios up to x10)
 
 __global__ void __launch_bounds__(256) prep_conv_input_rows_kernel(
     const float* __restrict__ src0, int C0, int h0, int w0, const float* __restrict__ src1, int C1,
-    float* __restrict__ dst, int B, int H, int W, float sy, float sx) {
+    float* __restrict__ dst, int B, int H, int W, float sy, float sx, int64_t bs0, int64_t bs1) {
   __shared__ int s_i0[RW_MAXW], s_i1[RW_MAXW];
   __shared__ float s_l1[RW_MAXW];
   const int yp = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(256) prep_conv_input_rows_kernel(
     __syncthreads();
   }
   const Tap ty = tap(y, sy, true, h0);
-  const float* r0 = src0 + ((int64_t)b * h0 + ty.i0) * w0 * C0;
-  const float* r1 = src0 + ((int64_t)b * h0 + ty.i1) * w0 * C0;
-  const float* s0row = src0 + ((int64_t)b * H + y) * W * C0;                 // same-size case
-  const float* s1row = src1 ? src1 + ((int64_t)b * H + y) * W * C1 : nullptr;
+  const float* r0 = src0 + b * bs0 + (int64_t)ty.i0 * w0 * C0;
+  const float* r1 = src0 + b * bs0 + (int64_t)ty.i1 * w0 * C0;
+  const float* s0row = src0 + b * bs0 + (int64_t)y * W * C0;                 // same-size case
+  const float* s1row = src1 ? src1 + b * bs1 + (int64_t)y * W * C1 : nullptr;
   for (int i = tid; i < n; i += 256) {
     const int xp = i / C4, c = (i - xp * C4) * 4;
     float4 v = zero4;
@@ -146,10 +146,12 @@ __global__ void __launch_bounds__(256) prep_conv_input_rows_kernel(
 
 __global__ void __launch_bounds__(256) upsample_nhwc_bwd_rows_kernel(
     const float* __restrict__ g, int ldg, float* __restrict__ out, int C0, int B, int H, int W, int h0, int w0,
-    float sy, float sx) {
-  __shared__ float s_xw[RW_MAXW0][RW_T];
-  __shared__ short s_xi[RW_MAXW0][RW_T];
-  __shared__ int s_xn[RW_MAXW0];
+    float sy, float sx, int T) {
+  // dynamic shared memory: x-tap weights [w0][T] (float), x-tap columns [w0][T] (short), tap counts [w0] (int)
+  extern __shared__ __align__(16) unsigned char rw_smem[];
+  float* s_xw = (float*)rw_smem;
+  int* s_xn = (int*)(s_xw + (size_t)w0 * T);
+  short* s_xi = (short*)(s_xn + w0);
   __shared__ float s_yw[RW_T];
   __shared__ int s_yi[RW_T], s_yn;
   const int j = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
@@ -167,10 +169,10 @@ __global__ void __launch_bounds__(256) upsample_nhwc_bwd_rows_kernel(
   for (int k = tid; k < w0; k += 256) {
     int xlo, xhi, n = 0;
     adjoint_range(k, sx, true, w0, W, xlo, xhi);
-    for (int x = xlo; x <= xhi && n < RW_T; ++x) {
+    for (int x = xlo; x <= xhi && n < T; ++x) {
       const Tap tx = tap(x, sx, true, w0);
       const float wx = (tx.i0 == k ? tx.l0 : 0.f) + (tx.i1 == k ? tx.l1 : 0.f);
-      if (wx != 0.f) { s_xw[k][n] = wx; s_xi[k][n] = (short)x; ++n; }
+      if (wx != 0.f) { s_xw[k * T + n] = wx; s_xi[k * T + n] = (short)x; ++n; }
     }
     s_xn[k] = n;
   }
@@ -193,9 +195,9 @@ __global__ void __launch_bounds__(256) upsample_nhwc_bwd_rows_kernel(
 #pragma unroll
         for (int u = 0; u < XC; ++u) {
           const bool on = t0 + u < nx;
-          wgt[u] = on ? wy * s_xw[k][t0 + u] : 0.f;
+          wgt[u] = on ? wy * s_xw[k * T + t0 + u] : 0.f;
           v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (on && wgt[u] != 0.f) v[u] = __ldg((const float4*)(grow + (int64_t)s_xi[k][t0 + u] * ldg));
+          if (on && wgt[u] != 0.f) v[u] = __ldg((const float4*)(grow + (int64_t)s_xi[k * T + t0 + u] * ldg));
         }
 #pragma unroll
         for (int u = 0; u < XC; ++u) {
@@ -470,17 +472,19 @@ static inline unsigned grid_for(int64_t total) {
 
 // dst [B,H+2,W+2,C0+C1] <- zero border | [resize(src0 (B,h0,w0,C0)) , src1 (B,H,W,C1)].  src1 may be NULL (C1=0).
 GED_API int ged_prep_conv_input(const float* src0, int C0, int h0, int w0, const float* src1, int C1, float* dst,
-                                int B, int H, int W, cudaStream_t stream) {
+                                int B, int H, int W, int64_t src0_bstride, int64_t src1_bstride, cudaStream_t stream) {
   if (!src0 || !dst || B <= 0 || H <= 0 || W <= 0 || C0 <= 0 || (C1 > 0 && !src1)) return GED_ERR_ARG;
-  if ((C0 % 4) || (C1 % 4)) return GED_ERR_SHAPE;
+  if ((C0 % 4) || (C1 % 4) || (src0_bstride % 4) || (src1_bstride % 4)) return GED_ERR_SHAPE;
   if (!aligned16(src0) || !aligned16(dst) || (src1 && !aligned16(src1))) return GED_ERR_ALIGN;
+  // batch strides in floats (0 = dense): a source may be one level's slice of a (B, S, C) token tensor
+  const int64_t bs0 = src0_bstride ? src0_bstride : (int64_t)h0 * w0 * C0, bs1 = src1_bstride ? src1_bstride : (int64_t)H * W * C1;
   const int64_t total = (int64_t)B * (H + 2) * (W + 2) * ((C0 + C1) / 4);
   if (g_layout_rows && W <= RW_MAXW && B <= 65535 && (int64_t)(W + 2) * ((C0 + C1) / 4) < (1 << 30))
     prep_conv_input_rows_kernel<<<dim3(H + 2, B), 256, 0, stream>>>(src0, C0, h0, w0, src1, C1, dst, B, H, W,
-                                                                   resize_scale(h0, H, true), resize_scale(w0, W, true));
+                                                                   resize_scale(h0, H, true), resize_scale(w0, W, true), bs0, bs1);
   else
     prep_conv_input_kernel<<<grid_for(total), 256, 0, stream>>>(src0, C0, h0, w0, src1, C1, dst, B, H, W,
-                                                               resize_scale(h0, H, true), resize_scale(w0, W, true));
+                                                               resize_scale(h0, H, true), resize_scale(w0, W, true), bs0, bs1);
   GED_CHECK_LAUNCH();
   return GED_OK;
 }
@@ -492,8 +496,10 @@ GED_API int ged_upsample_nhwc_bwd(const float* g, int ldg, float* out, int C0, i
   if (!aligned16(g) || !aligned16(out)) return GED_ERR_ALIGN;
   const int64_t total = (int64_t)B * h0 * w0 * (C0 / 4);
   const float sy = resize_scale(h0, H, true), sx = resize_scale(w0, W, true);
-  if (g_layout_rows && w0 <= RW_MAXW0 && W <= 32767 && B <= 65535 && sy >= 0.3f && sx >= 0.3f && (int64_t)w0 * (C0 / 4) < (1 << 30))
-    upsample_nhwc_bwd_rows_kernel<<<dim3(h0, B), 256, 0, stream>>>(g, ldg, out, C0, B, H, W, h0, w0, sy, sx);
+  const int Tx = sx > 0.f ? (int)ceilf(2.f / sx) + 2 : RW_T + 1, Ty = sy > 0.f ? (int)ceilf(2.f / sy) + 2 : RW_T + 1;
+  const size_t rsmem = (size_t)w0 * Tx * 6 + (size_t)w0 * 4 + 16;
+  if (g_layout_rows && Tx <= RW_T && Ty <= RW_T && rsmem <= RW_SMEM0 && W <= 32767 && B <= 65535 && (int64_t)w0 * (C0 / 4) < (1 << 30))
+    upsample_nhwc_bwd_rows_kernel<<<dim3(h0, B), 256, rsmem, stream>>>(g, ldg, out, C0, B, H, W, h0, w0, sy, sx, Tx);
   else
     upsample_nhwc_bwd_kernel<<<grid_for(total), 256, 0, stream>>>(g, ldg, out, C0, B, H, W, h0, w0, sy, sx);
   GED_CHECK_LAUNCH();

@@ -44,7 +44,7 @@ SIGNATURES = {
     "ged_winattn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "ged_gemm_tf32": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _F, _P, _P, _I, _P, _F, C.c_uint, _P, _P],
     "ged_dropout_bwd": [_P, _I64, _P, _P, _I64, _I, _F, C.c_uint, _P, _P],
-    "ged_prep_conv_input": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P],
+    "ged_prep_conv_input": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I64, _I64, _P],
     "ged_upsample_nhwc_bwd": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "ged_resize_add_nhwc": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ged_act_bwd": [_P, _I64, _P, _P, _P, _P, _I, _I64, _I, _I, _F, _P],
@@ -63,7 +63,7 @@ SIGNATURES = {
     "ged_msda_tc_fwd": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_msda_tc_bwd": [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ged_gemm_tf32_bt": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P],
-    "ged_gemm_tf32_bt_acc": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P],
+    "ged_gemm_tf32_bt_acc": [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P],
     "ged_conv3x3_small_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "ged_linear_small_fwd": [_P, _P, _P, _P, _I64, _I, _I, _I, _P],
     "ged_linear_small_bwd": [_P, _P, _P, _P, _P, _P, _P, _I64, _I, _I, _I, _P],
@@ -683,8 +683,10 @@ def gemm_bt(a2d: torch.Tensor, wt: torch.Tensor, residual: Optional[torch.Tensor
     if residual is None:
         _call("ged_gemm_tf32_bt", _p(a2d), a2d.stride(0), _p(wt), wt.stride(0), _p(out), N, M, N, K, _stream())
     else:
-        assert residual.shape == (M, N) and residual.is_contiguous() and out.is_contiguous()
-        _call("ged_gemm_tf32_bt_acc", _p(a2d), a2d.stride(0), _p(wt), wt.stride(0), _p(out), N, M, N, K, _p(residual), _stream())
+        # the residual may be a channel slice of a wider gradient (its own row pitch); the output is dense
+        assert residual.shape == (M, N) and residual.stride(1) == 1 and residual.stride(0) % 4 == 0 and out.is_contiguous()
+        _call("ged_gemm_tf32_bt_acc", _p(a2d), a2d.stride(0), _p(wt), wt.stride(0), _p(out), N, M, N, K, _p(residual),
+              residual.stride(0), _stream())
     return out
 
 
@@ -828,12 +830,26 @@ def conv2d_supported(x, w, stride, padding) -> bool:
     return kh == 3 and kw == 3 and padding == 1
 
 
+def _batch_dense(x: torch.Tensor) -> bool:
+    """(B, h, w, C) fp32 whose samples are dense NHWC blocks at a uniform, 16-byte aligned batch stride (e.g. one level's
+    slice of the (B, S, C) token tensor): the kernels take the stride, no copy."""
+    if x.dtype != torch.float32 or x.dim() != 4:
+        return False
+    _, h, w, c = x.shape
+    return (x.stride(3) == 1 and x.stride(2) == c and x.stride(1) == w * c and x.stride(0) % 4 == 0 and x.stride(0) >= h * w * c
+            and x.data_ptr() % 16 == 0)
+
+
 def prep_conv_input(x0: torch.Tensor, x1: Optional[torch.Tensor], H: int, W: int) -> torch.Tensor:
     """Zero-bordered NHWC input [B,H+2,W+2,C0+C1] = [bilinear(x0 -> HxW, align_corners=True) | x1] in one pass."""
+    x0 = x0 if _batch_dense(x0) else _f32c(x0)
+    if x1 is not None:
+        x1 = x1 if _batch_dense(x1) else _f32c(x1)
     B, h0, w0, C0 = x0.shape
     C1 = 0 if x1 is None else x1.shape[3]
     xp = torch.empty(B, H + 2, W + 2, C0 + C1, dtype=torch.float32, device=x0.device)
-    _call("ged_prep_conv_input", _p(x0), C0, h0, w0, _p(x1), C1, _p(xp), B, H, W, _stream())
+    _call("ged_prep_conv_input", _p(x0), C0, h0, w0, _p(x1), C1, _p(xp), B, H, W, x0.stride(0), 0 if x1 is None else x1.stride(0),
+          _stream())
     return xp
 
 
@@ -863,8 +879,12 @@ class _Conv(Function):
     def forward(ctx, x0, x1, w, b, act, slope, w_sink=None, b_sink=None):
         ctx.w_sink, ctx.b_sink = w_sink, b_sink
         Cout, Cin, kh, kw = w.shape
-        a0 = _nhwc(x0)
-        a1 = None if x1 is None else _nhwc(x1)
+        if kh == 3:      # the staging kernel takes batch-strided sources (a level's slice of the token tensor): no copy
+            a0 = x0.permute(0, 2, 3, 1) if _batch_dense(x0.permute(0, 2, 3, 1)) else _nhwc(x0)
+            a1 = None if x1 is None else (x1.permute(0, 2, 3, 1) if _batch_dense(x1.permute(0, 2, 3, 1)) else _nhwc(x1))
+        else:
+            a0 = _nhwc(x0)
+            a1 = None if x1 is None else _nhwc(x1)
         B = a0.shape[0]
         H, W = (a0.shape[1], a0.shape[2]) if a1 is None else (a1.shape[1], a1.shape[2])
         if kh == 3:
@@ -1395,7 +1415,9 @@ class _MSDAModule(Function):
         B, S, Q, E = cfg["dims"]
         shapes, nH, P, sinks = cfg["shapes"], cfg["nH"], cfg["P"], cfg["sinks"]
         dev = q.device
-        g2 = _f32c(g).reshape(-1, E)
+        # g may be a channel slice of the fusion conv's dX (row pitch 512 + C1): its consumers below take the pitch, except
+        # the level-embedding adjoint, which wants the dense matrix
+        g2 = _rows(g, E) if not cfg["has_le"] else _f32c(g).reshape(-1, E)
 
         def acc_or_new(name, shape):
             return sinks[name] if sinks.get(name) is not None else torch.zeros(shape, dtype=torch.float32, device=dev)

@@ -161,10 +161,10 @@ int ged_dropout_bwd(const float* g, int64_t ldg, float* gz, float* db, int64_t r
  * as an MN-major UMMA operand (no transposed copy; torch.autograd's grad_output @ weight). */
 int ged_gemm_tf32_bt(const float* A, int lda, const float* Wt, int ldw, float* D, int ldd, int M, int N, int K,
                      cudaStream_t stream);
-/* D = A @ Wt + R: the same GEMM with a residual of D's row pitch (R may be D itself: accumulate in place), so that a
- * gradient fanning in from several consumers is summed in the GEMM epilogues. */
+/* D = A @ Wt + R: the same GEMM with a residual of row pitch ldr (0 = D's; R may be D itself: accumulate in place; R may be
+ * a channel slice of a wider gradient), so that a gradient fanning in from several consumers is summed in the GEMM epilogues. */
 int ged_gemm_tf32_bt_acc(const float* A, int lda, const float* Wt, int ldw, float* D, int ldd, int M, int N, int K,
-                         const float* residual, cudaStream_t stream);
+                         const float* residual, int ldr, cudaStream_t stream);
 /* dX of the 3x3/s1/p1 conv from the zero-bordered dY [B,H+2,W+2,Cout] and the FORWARD weights [Cout][3][3][Cin]
  * read in place (cuDNN dgrad in the reference); DX [B,H,W,*] with channel pitch ldx. */
 int ged_conv3x3_dx_tf32(const float* Gpad, const float* Wk, float* DX, int ldx, int B, int H, int W, int Cin,
@@ -199,13 +199,14 @@ int ged_conv3x3_tf32(const float* Xpad, const float* Wk, float* Y, int ldy, int 
 
 /* ---- data movement around the convs (NHWC fp32) ------------------------------------------------ */
 /* 1 (default): ged_prep_conv_input / ged_upsample_nhwc_bwd run one CTA per output row with the bilinear taps tabulated once
- * in shared memory; 0: the flat grid-stride kernels (also taken for rows wider than 1024 / source rows wider than 512 / ratios above x3.3).  Returns the
+ * in shared memory; 0: the flat grid-stride kernels (also taken for rows wider than 1024, tap tables beyond 40 KB or ratios above x10).  Returns the
  * previous setting. */
 int ged_set_layout_rows(int on);
 /* dst [B,H+2,W+2,C0+C1] = zero border | [bilinear(src0 (B,h0,w0,C0) -> HxW, align_corners=True), src1 (B,H,W,C1)]:
- * F.interpolate + torch.cat + padding of densedepth_head.py:24-27 / hahi.py:329-353 in one pass. */
+ * F.interpolate + torch.cat + padding of densedepth_head.py:24-27 / hahi.py:329-353 in one pass.  src*_bstride: batch stride
+ * in floats, 0 = dense (a source may be one level's slice of the (B, S, C) token tensor: hahi.py:338-353). */
 int ged_prep_conv_input(const float* src0, int C0, int h0, int w0, const float* src1, int C1, float* dst, int B,
-                        int H, int W, cudaStream_t stream);
+                        int H, int W, int64_t src0_bstride, int64_t src1_bstride, cudaStream_t stream);
 /* out (B,h0,w0,C0) = resize^T of channels [0,C0) of g (B,H,W,ldg). */
 int ged_upsample_nhwc_bwd(const float* g, int ldg, float* out, int C0, int B, int H, int W, int h0, int w0,
                           cudaStream_t stream);

@@ -526,6 +526,15 @@ def test_gemm_pair_kernel(M, N, K, passes):
         out = Kn.gemm_bt(a, wt)
         ref2 = (a.double() @ wt.double()).float()
         _close(out, ref2, 0, _gemm_tol(ref2, passes, K), f"gemm_bt {M}x{N}x{K}")
+        # + residual: dense, accumulated in place, and a channel slice of a wider matrix (its own row pitch)
+        wide = torch.randn(M, N + 12, generator=g).to(DEV)
+        out_r = Kn.gemm_bt(a, wt, residual=res)
+        _close(out_r, ref2 + res, 0, _gemm_tol(ref2, passes, K), "gemm_bt + residual")
+        out_s = Kn.gemm_bt(a, wt, residual=wide[:, 4:4 + N])
+        _close(out_s, ref2 + wide[:, 4:4 + N], 0, _gemm_tol(ref2, passes, K), "gemm_bt + strided residual")
+        acc = res.clone()
+        Kn.gemm_bt(a, wt, residual=acc, out=acc)
+        _close(acc, ref2 + res, 0, _gemm_tol(ref2, passes, K), "gemm_bt accumulated in place")
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(4, 64, 160, 64, 64), (2, 44, 140, 96, 192), (2, 88, 280, 128, 32)])
@@ -884,10 +893,12 @@ def test_adamw_and_clip_match_torch():
 @pytest.mark.parametrize("rows_mode", [1, 0])
 @pytest.mark.parametrize("B,h0,w0,H,W,C0,C1", [(2, 11, 35, 22, 70, 64, 32), (1, 9, 12, 9, 12, 32, 96), (2, 22, 70, 44, 139, 96, 0),
                                                (1, 88, 280, 176, 560, 192, 64), (2, 5, 7, 16, 22, 8, 4), (1, 3, 4, 11, 15, 4, 0),
-                                               (1, 7, 9, 7, 9, 4, 4)])
+                                               (1, 7, 9, 7, 9, 4, 4), (1, 4, 9, 32, 72, 8, 0), (2, 11, 35, 44, 140, 64, 0),
+                                               (1, 2, 3, 40, 50, 4, 0)])
 def test_prep_conv_input_and_adjoint(B, h0, w0, H, W, C0, C1, rows_mode):
     """rows_mode = 1: one CTA per output row, bilinear taps tabulated in shared memory (default); 0: the flat grid-stride
-    kernels.  (1, 3, 4, 11, 15): a x3.6 ratio, which the row form of the adjoint hands to the flat kernel by itself."""
+    kernels.  x4 / x8 ratios (the PE necks' resize_add adjoints) use longer tap tables; (1, 2, 3, 40, 50) is a x20+ ratio,
+    which the row form of the adjoint hands to the flat kernel by itself."""
     from gedepth_b200 import kernels as Kn
     g = torch.Generator().manual_seed(20)
     x0 = torch.randn(B, h0, w0, C0, generator=g).to(DEV)
@@ -910,6 +921,24 @@ def test_prep_conv_input_and_adjoint(B, h0, w0, H, W, C0, C1, rows_mode):
     upr = F.interpolate(x0r.permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=True)
     (upr * gfull[..., :C0].permute(0, 3, 1, 2)).sum().backward()
     _close(out, x0r.grad, 1e-4, 1e-5, "resize adjoint")
+
+
+def test_prep_conv_input_batch_strided_sources(layout_rows):
+    """Sources that are one level's slice of a (B, S, C) token tensor (hahi.py:338-353: samples dense, batch stride S * C) are
+    read in place; the result equals the one from dense copies."""
+    from gedepth_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(26)
+    B, H, W, C0, C1, h0, w0 = 3, 12, 20, 32, 16, 6, 10
+    tok0 = torch.randn(B, h0 * w0 + 37, C0, generator=g).to(DEV)
+    tok1 = torch.randn(B, 11 + H * W, C1, generator=g).to(DEV)
+    x0 = tok0[:, 5:5 + h0 * w0].reshape(B, h0, w0, C0)
+    x1 = tok1[:, 11:].reshape(B, H, W, C1)
+    assert not x0.is_contiguous() and Kn._batch_dense(x0) and Kn._batch_dense(x1)
+    got = Kn.prep_conv_input(x0, x1, H, W)
+    ref = Kn.prep_conv_input(x0.contiguous(), x1.contiguous(), H, W)
+    assert torch.equal(got, ref)
+    same = Kn.prep_conv_input(x1, None, H, W)
+    assert torch.equal(same, Kn.prep_conv_input(x1.contiguous(), None, H, W))
 
 
 @pytest.mark.parametrize("act", [None, "relu", "leaky_relu", "gelu", "sigmoid"])
