@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(256) prep_conv_input_rows_kernel(
   }
 }
 
+template <int CG>
 __global__ void __launch_bounds__(256) upsample_nhwc_bwd_rows_kernel(
     const float* __restrict__ g, int ldg, float* __restrict__ out, int C0, int B, int H, int W, int h0, int w0,
     float sy, float sx, int T) {
@@ -177,12 +178,16 @@ __global__ void __launch_bounds__(256) upsample_nhwc_bwd_rows_kernel(
     s_xn[k] = n;
   }
   __syncthreads();
-  const int ny = s_yn, n = w0 * C4;
+  // A thread produces CG channel quads (C4 / CG apart) of one source column: the tap weights / columns / addresses are formed
+  // once per CG float4 loads (they were ~12 instructions per 16-byte load).
+  const int ny = s_yn, Cg = C4 / CG, n = w0 * Cg;
   float4* orow = (float4*)(out + (((int64_t)b * h0 + j) * w0) * C0);
   for (int i = tid; i < n; i += 256) {
-    const int k = i / C4, c = (i - k * C4) * 4;
+    const int k = i / Cg, cq = i - k * Cg, c = cq * 4;      // quads cq, cq + Cg, ..: every load instruction stays fully coalesced
     const int nx = s_xn[k];
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc[CG];
+#pragma unroll
+    for (int q = 0; q < CG; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     // the (<= 5, rarely more) x taps of one y tap are requested together, then accumulated in order: a load consumed right
     // after its issue inside a loop of dynamic length leaves ONE load in flight per thread
     constexpr int XC = 5;
@@ -190,22 +195,32 @@ __global__ void __launch_bounds__(256) upsample_nhwc_bwd_rows_kernel(
       const float wy = s_yw[a];
       const float* grow = g + ((int64_t)b * H + s_yi[a]) * W * ldg + c;
       for (int t0 = 0; t0 < nx; t0 += XC) {
-        float4 v[XC];
+        float4 v[XC][CG];
         float wgt[XC];
 #pragma unroll
         for (int u = 0; u < XC; ++u) {
           const bool on = t0 + u < nx;
           wgt[u] = on ? wy * s_xw[k * T + t0 + u] : 0.f;
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (on && wgt[u] != 0.f) v[u] = __ldg((const float4*)(grow + (int64_t)s_xi[k * T + t0 + u] * ldg));
+          const float4* src = (const float4*)(grow + (int64_t)(on ? s_xi[k * T + t0 + u] : 0) * ldg);
+#pragma unroll
+          for (int q = 0; q < CG; ++q) {
+            v[u][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (on && wgt[u] != 0.f) v[u][q] = __ldg(src + q * Cg);
+          }
         }
 #pragma unroll
         for (int u = 0; u < XC; ++u) {
-          if (wgt[u] != 0.f) { acc.x += wgt[u] * v[u].x; acc.y += wgt[u] * v[u].y; acc.z += wgt[u] * v[u].z; acc.w += wgt[u] * v[u].w; }
+          if (wgt[u] != 0.f) {
+#pragma unroll
+            for (int q = 0; q < CG; ++q) {
+              acc[q].x += wgt[u] * v[u][q].x; acc[q].y += wgt[u] * v[u][q].y; acc[q].z += wgt[u] * v[u][q].z; acc[q].w += wgt[u] * v[u][q].w;
+            }
+          }
         }
       }
     }
-    orow[i] = acc;
+#pragma unroll
+    for (int q = 0; q < CG; ++q) orow[(size_t)k * C4 + cq + q * Cg] = acc[q];
   }
 }
 
@@ -499,7 +514,10 @@ GED_API int ged_upsample_nhwc_bwd(const float* g, int ldg, float* out, int C0, i
   const int Tx = sx > 0.f ? (int)ceilf(2.f / sx) + 2 : RW_T + 1, Ty = sy > 0.f ? (int)ceilf(2.f / sy) + 2 : RW_T + 1;
   const size_t rsmem = (size_t)w0 * Tx * 6 + (size_t)w0 * 4 + 16;
   if (g_layout_rows && Tx <= RW_T && Ty <= RW_T && rsmem <= RW_SMEM0 && W <= 32767 && B <= 65535 && (int64_t)w0 * (C0 / 4) < (1 << 30))
-    upsample_nhwc_bwd_rows_kernel<<<dim3(h0, B), 256, rsmem, stream>>>(g, ldg, out, C0, B, H, W, h0, w0, sy, sx, Tx);
+  {
+    if ((C0 / 4) % 2 == 0) upsample_nhwc_bwd_rows_kernel<2><<<dim3(h0, B), 256, rsmem, stream>>>(g, ldg, out, C0, B, H, W, h0, w0, sy, sx, Tx);
+    else upsample_nhwc_bwd_rows_kernel<1><<<dim3(h0, B), 256, rsmem, stream>>>(g, ldg, out, C0, B, H, W, h0, w0, sy, sx, Tx);
+  }
   else
     upsample_nhwc_bwd_kernel<<<grid_for(total), 256, 0, stream>>>(g, ldg, out, C0, B, H, W, h0, w0, sy, sx);
   GED_CHECK_LAUNCH();
@@ -528,7 +546,9 @@ GED_API int ged_act_bwd(const float* g, int64_t ldg, const float* ref, float* gz
   if (!g || (!gz && !db) || rows <= 0 || N <= 0 || (act && !ref) || ldg < N) return GED_ERR_ARG;
   if ((N % 4) || (ldg % 4)) return GED_ERR_SHAPE;
   if (!aligned16(g) || (gz && !aligned16(gz)) || (ref && !aligned16(ref))) return GED_ERR_ALIGN;
-  const int rpb = 128;
+  // rows per CTA: 128, or 512 where that still leaves >= 8 CTAs per SM (4x fewer column-sum atomics, 64 instead of 16 row
+  // iterations per thread to amortise the fill and the drain of its two-rows-in-flight load pipeline)
+  const int rpb = (rows / 512) * cdiv(N, 128) >= 148 * 8 ? 512 : 128;
   dim3 grid(cdiv(N, 128), (unsigned)((rows + rpb - 1) / rpb));
   if (act == 3)
     act_bwd_kernel<true><<<grid, dim3(32, 8), 0, stream>>>(g, ldg, ref, gz, db, row_scale, rows_per_batch > 0 ? rows_per_batch : 1,
