@@ -90,7 +90,6 @@ __global__ void __launch_bounds__(256) conv3x3_small_dx_kernel(const float* __re
 // accumulators, UNR pixels per iteration: all of their loads are issued before the first product.  (One pixel per
 // iteration with 2 CTAs per SM left 10 dependent-latency loads per warp in flight: 1.3 ms per launch at 16 x 176 x 560 x 64
 // for 0.4 GB of operands.)
-constexpr int DW_SW = 16;       // columns per strip
 template <int CO>
 struct SmallDw {
   static constexpr int UNR = 4;                       // CO = 11: 99 accumulators + 4 x 20 operands, one CTA of 8 warps per SM
@@ -99,14 +98,15 @@ struct SmallDw {
 template <int CO>
 __global__ void __launch_bounds__(256, SmallDw<CO>::MINB) conv3x3_small_dw_kernel(
     const float* __restrict__ gz, const float* __restrict__ xp, float* __restrict__ dw, int B, int H, int W, int CI,
-    int rows_per_block) {
+    int rows_per_block, int sw_log2) {
   constexpr int UNR = SmallDw<CO>::UNR;
+  const int DW_SW = 1 << sw_log2;       // columns per strip
   float acc[CO][9];
 #pragma unroll
   for (int co = 0; co < CO; ++co)
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[co][t] = 0.f;
-  // A CTA owns a strip of DW_SW columns x `rows_per_block` rows of one sample and walks it row by row: the three input
+  // A CTA owns a strip of DW_SW (16 or 64) columns x `rows_per_block` rows of one sample and walks it row by row: the three input
   // rows a pixel row needs are re-used by the next two pixel rows while still in L1 / L2.  (Walking a flat pixel range, all
   // CTAs together kept 3 rows x 144 KB x 444 CTAs = 190 MB live - more than the L2 - and every tap row came from DRAM again:
   // 1.18 GB of DRAM traffic for a 0.41 GB input.)
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256, SmallDw<CO>::MINB) conv3x3_small_dw_kerne
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int pl = pb + u * step;
-      const int yl = pl / DW_SW, xl = pl - yl * DW_SW;
+      const int yl = pl >> sw_log2, xl = pl - (yl << sw_log2);
       const bool ok = pl < n_local && xs + xl < W;
       const int x = ok ? xs + xl : xs, yy = ok ? y0 + yl : y0;      // a valid address; its products are discarded through gv = 0
       const int64_t p = (b * H + yy) * W + x;
@@ -305,14 +305,17 @@ GED_API int ged_conv3x3_small_bwd(const float* g, const float* y, float* gz, con
   }
   if (dw) {
     const int ny = max(1, 256 / Cin);
-    // CTAs = B x strips x row chunks: about three (Cout = 1), two or one (Cout = 11: 248 registers) per SM
-    const int target = 148 * (Cout == 1 ? 3 : (Cout == 2 ? 2 : 1));
-    const int strips = cdiv(W, DW_SW);
+    // CTAs = B x strips x row chunks.  Cout = 11 (248 registers, one CTA per SM, 6336 atomics per CTA at the end): 64-column
+    // strips and about ONE wave of CTAs; Cout <= 2 (three / two CTAs per SM): 16-column strips and about four waves, so that
+    // the last wave's idle SMs cost little.
+    const int sw_log2 = Cout > 2 ? 6 : 4;
+    const int target = Cout > 2 ? 148 : 148 * (Cout == 1 ? 3 : 2) * 4;
+    const int strips = cdiv(W, 1 << sw_log2);
     int ychunks = max(1, min(H, cdiv(target, B * strips)));
     const int rpb = cdiv(H, ychunks);
     ychunks = cdiv(H, rpb);
     const int wblocks = B * strips * ychunks;
-    SMALL_CO_SWITCH(Cout, (conv3x3_small_dw_kernel<C_><<<wblocks, dim3(Cin, ny), 0, stream>>>(gz, xp, dw, B, H, W, Cin, rpb)));
+    SMALL_CO_SWITCH(Cout, (conv3x3_small_dw_kernel<C_><<<wblocks, dim3(Cin, ny), 0, stream>>>(gz, xp, dw, B, H, W, Cin, rpb, sw_log2)));
   }
   GED_CHECK_LAUNCH();
   return GED_OK;
