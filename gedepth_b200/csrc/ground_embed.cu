@@ -13,6 +13,7 @@
 // vanilla bwd 13; adaptive fwd 24 (+44 when the full-resolution logits are written); fuse_head ~9.
 #include "common.cuh"
 #include "tile.cuh"
+#include <cstdlib>
 
 namespace ged {
 
@@ -750,13 +751,15 @@ GED_API int ged_ge_vanilla_fwd(const float* pe_norm, int64_t pe_batch_stride, co
                    (pe_batch_stride % 4 == 0);
   if (g_ge_x2 == 1 && vec && H == 2 * h2 && W == 2 * w2 && ((((uintptr_t)y_half) & 7) == 0)) {
     // exact x2 (every GE config): streaming kernel; ged_set_ge_x2(2 / 0) keeps the tiled one for A/B
-    // 32 rows per warp; 8 when that would leave the GPU short of warps (a warp's rows are a serial chain of loads)
-    if ((int64_t)B * cdiv(W, 128) * cdiv(H, 32) >= 148 * 32)
-      ge_vanilla_fwd_x2s_kernel<32><<<dim3(cdiv(W, 512), cdiv(H, 32), B), dim3(32, 4), 0, stream>>>(pe_norm, pe_batch_stride, y_half, y,
-                                                                                                   pe_mask, H, W, h2, w2);
-    else
-      ge_vanilla_fwd_x2s_kernel<8><<<dim3(cdiv(W, 512), cdiv(H, 8), B), dim3(32, 4), 0, stream>>>(pe_norm, pe_batch_stride, y_half, y,
-                                                                                                 pe_mask, H, W, h2, w2);
+    // rows per warp: 32, or 16 / 8 when that would leave the GPU short of warps (a warp's rows are a serial chain of loads)
+    static const int force_fr = getenv("GEDEPTH_VF_FR") ? atoi(getenv("GEDEPTH_VF_FR")) : 0;
+    const int64_t strips_b = (int64_t)B * cdiv(W, 128);
+    int fr = strips_b * cdiv(H, 32) >= 148 * 32 ? 32 : 8;
+    if (force_fr) fr = force_fr;
+#define VF_LAUNCH(FR) ge_vanilla_fwd_x2s_kernel<FR><<<dim3(cdiv(W, 512), cdiv(H, FR), B), dim3(32, 4), 0, stream>>>(pe_norm, pe_batch_stride, \
+        y_half, y, pe_mask, H, W, h2, w2)
+    if (fr == 32) VF_LAUNCH(32); else if (fr == 16) VF_LAUNCH(16); else VF_LAUNCH(8);
+#undef VF_LAUNCH
     GED_CHECK_LAUNCH();
     return GED_OK;
   }
@@ -779,12 +782,13 @@ GED_API int ged_ge_vanilla_bwd(const float* pe_norm, int64_t pe_batch_stride, co
       // 16 half-resolution rows per warp, 6 CTAs of 4 warps per SM (measured against 8 / 32 rows and 4 / 5 CTAs); 4 rows when
       // 16 would leave the GPU short of warps
       dim3 block(32, 4);
-      if ((int64_t)B * cdiv(W, 128) * cdiv(h2, 16) >= 148 * 24)
-        ge_vanilla_bwd_x2s_kernel<16, 6, 1><<<dim3(cdiv(W, 512), cdiv(h2, 16), B), block, 0, stream>>>(pe_norm, pe_batch_stride, g_y, g_pe_mask,
-                                                                                                      g_y_half, H, W, h2, w2);
-      else
-        ge_vanilla_bwd_x2s_kernel<4, 6, 1><<<dim3(cdiv(W, 512), cdiv(h2, 4), B), block, 0, stream>>>(pe_norm, pe_batch_stride, g_y, g_pe_mask,
-                                                                                                    g_y_half, H, W, h2, w2);
+      static const int force_ch = getenv("GEDEPTH_VB_CH") ? atoi(getenv("GEDEPTH_VB_CH")) : 0;
+      int ch = (int64_t)B * cdiv(W, 128) * cdiv(h2, 16) >= 148 * 24 ? 16 : 4;
+      if (force_ch) ch = force_ch;
+#define VB_LAUNCH(CH) ge_vanilla_bwd_x2s_kernel<CH, 6, 1><<<dim3(cdiv(W, 512), cdiv(h2, CH), B), block, 0, stream>>>(pe_norm, pe_batch_stride, \
+          g_y, g_pe_mask, g_y_half, H, W, h2, w2)
+      if (ch == 16) VB_LAUNCH(16); else if (ch == 8) VB_LAUNCH(8); else VB_LAUNCH(4);
+#undef VB_LAUNCH
     } else {
       dim3 block(64, 4), grid(cdiv(cdiv(w2, 2), 64), cdiv(h2, X2_H), B);
       ge_vanilla_bwd_x2_kernel<<<grid, block, 0, stream>>>(pe_norm, pe_batch_stride, g_y, g_pe_mask, g_y_half, H, W, h2, w2);
