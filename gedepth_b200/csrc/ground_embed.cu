@@ -13,7 +13,6 @@
 // vanilla bwd 13; adaptive fwd 24 (+44 when the full-resolution logits are written); fuse_head ~9.
 #include "common.cuh"
 #include "tile.cuh"
-#include <cstdlib>
 
 namespace ged {
 
@@ -751,14 +750,14 @@ GED_API int ged_ge_vanilla_fwd(const float* pe_norm, int64_t pe_batch_stride, co
                    (pe_batch_stride % 4 == 0);
   if (g_ge_x2 == 1 && vec && H == 2 * h2 && W == 2 * w2 && ((((uintptr_t)y_half) & 7) == 0)) {
     // exact x2 (every GE config): streaming kernel; ged_set_ge_x2(2 / 0) keeps the tiled one for A/B
-    // rows per warp: 32, or 16 / 8 when that would leave the GPU short of warps (a warp's rows are a serial chain of loads)
-    static const int force_fr = getenv("GEDEPTH_VF_FR") ? atoi(getenv("GEDEPTH_VF_FR")) : 0;
+    // rows per warp: 16, or 8 when that leaves less than one wave of warps (a warp's rows are a serial chain of loads).
+    // Measured (fraction of the HBM peak at 32 / 16 / 8 rows per warp): 64x352x1120 0.73 / 0.78 / 0.78,
+    // 64x384x640 0.60 / 0.74 / 0.71, 32x1024x2048 0.85 / 0.89 / 0.88, 64x1024x2048 0.92 / 0.93 / 0.91, 8x352x1120 0.28 / 0.36 / 0.44
     const int64_t strips_b = (int64_t)B * cdiv(W, 128);
-    int fr = strips_b * cdiv(H, 32) >= 148 * 32 ? 32 : 8;
-    if (force_fr) fr = force_fr;
+    const int fr = strips_b * cdiv(H, 16) >= 148 * 36 ? 16 : 8;
 #define VF_LAUNCH(FR) ge_vanilla_fwd_x2s_kernel<FR><<<dim3(cdiv(W, 512), cdiv(H, FR), B), dim3(32, 4), 0, stream>>>(pe_norm, pe_batch_stride, \
         y_half, y, pe_mask, H, W, h2, w2)
-    if (fr == 32) VF_LAUNCH(32); else if (fr == 16) VF_LAUNCH(16); else VF_LAUNCH(8);
+    if (fr == 16) VF_LAUNCH(16); else VF_LAUNCH(8);
 #undef VF_LAUNCH
     GED_CHECK_LAUNCH();
     return GED_OK;
@@ -779,12 +778,12 @@ GED_API int ged_ge_vanilla_bwd(const float* pe_norm, int64_t pe_batch_stride, co
       (!g_y || aligned16(g_y)) && (!g_pe_mask || aligned16(g_pe_mask))) {
     // exact x2: closed-form gather (every GE config); ged_set_ge_x2(2) keeps the tiled round-2a kernel for A/B
     if (g_ge_x2 == 1) {
-      // 16 half-resolution rows per warp, 6 CTAs of 4 warps per SM (measured against 8 / 32 rows and 4 / 5 CTAs); 4 rows when
-      // 16 would leave the GPU short of warps
+      // 6 CTAs of 4 warps per SM (measured against 4 / 5 CTAs)
       dim3 block(32, 4);
-      static const int force_ch = getenv("GEDEPTH_VB_CH") ? atoi(getenv("GEDEPTH_VB_CH")) : 0;
-      int ch = (int64_t)B * cdiv(W, 128) * cdiv(h2, 16) >= 148 * 24 ? 16 : 4;
-      if (force_ch) ch = force_ch;
+      // half-resolution rows per warp: 16 with >= 3 waves of warps, else 8, else 4 (measured at 16 / 8 / 4 rows: 64x1024x2048
+      // 0.92 / 0.90 / 0.84, 32x1024x2048 0.85 / 0.84 / 0.80, 64x352x1120 0.66 / 0.70 / 0.69, 64x384x640 0.61 / 0.66 / 0.63)
+      const int64_t strips_b = (int64_t)B * cdiv(W, 128);
+      const int ch = strips_b * cdiv(h2, 16) >= 148 * 24 * 3 ? 16 : (strips_b * cdiv(h2, 8) >= 148 * 24 ? 8 : 4);
 #define VB_LAUNCH(CH) ge_vanilla_bwd_x2s_kernel<CH, 6, 1><<<dim3(cdiv(W, 512), cdiv(h2, CH), B), block, 0, stream>>>(pe_norm, pe_batch_stride, \
           g_y, g_pe_mask, g_y_half, H, W, h2, w2)
       if (ch == 16) VB_LAUNCH(16); else if (ch == 8) VB_LAUNCH(8); else VB_LAUNCH(4);
