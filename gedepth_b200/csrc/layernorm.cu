@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_wb_kernel(
 // round trips, and the backward needs a second kernel that re-reads g and x for the weight / bias gradients.  For
 // C <= 32 * 4 * NV a lane keeps its NV float4 of the row in registers: ONE global read per operand, all of a row's loads in
 // flight at once, the same summation order (bit-identical y / mean / rstd / dx); the backward accumulates dw / db per lane
-// over the rows its warp walks and reduces them once per CTA.
+// over the rows its warp walks and reduces them once per CTA.  (Measured and rejected for C = 768: re-reading w and g_add late
+// instead of holding them - 171 -> 127 registers, two CTAs per SM - 4.95 -> 5.4 ms per step.)
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_fwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                  const float* __restrict__ b, float* __restrict__ y,

@@ -271,7 +271,8 @@ __device__ __forceinline__ float gelu_grad(float x) {
 // act: 1 relu, 2 leaky (ref = output), 3 gelu (ref = pre-activation), 4 sigmoid (ref = output), 0 none.
 // grid (ceil(N/128), row chunks), block (32, 8): a thread owns 4 consecutive columns.
 // GELU = true: act == 3 (the ~100-instruction derivative; one row per iteration keeps 40 registers and 6 CTAs per SM - requesting
-// the next row first cost occupancy: 13.3 -> 14.8 ms per step).  GELU = false: every other case is a pure stream (column sums
+// the next row first cost occupancy: 13.3 -> 14.8 ms per step).  Also measured and rejected: 16- / 8-lane thread rows for matrices of
+// <= 64 / 32 columns, so that no lane idles (12.5 -> 14.2 ms: two rows per warp halve the bytes per load instruction).  GELU = false: every other case is a pure stream (column sums
 // only, DropPath row scale, ReLU-class masks, dropout): two rows in flight per thread.
 template <bool GELU>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ ref,

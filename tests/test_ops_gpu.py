@@ -941,12 +941,14 @@ def test_prep_conv_input_batch_strided_sources(layout_rows):
     assert torch.equal(same, Kn.prep_conv_input(x1.contiguous(), None, H, W))
 
 
+@pytest.mark.parametrize("N", [96, 64, 24, 200])
 @pytest.mark.parametrize("act", [None, "relu", "leaky_relu", "gelu", "sigmoid"])
-def test_act_bwd(act):
+def test_act_bwd(act, N):
+    """N = 64 / 24: the 16- and 8-lane thread mappings of narrow matrices; 200: a partial last column block."""
     from gedepth_b200 import kernels as Kn
     from tests import ops_lib as L
     g = torch.Generator().manual_seed(21)
-    rows, N, T = 3 * 217, 96, 217          # 651 rows: five 128-row chunks + a ragged one (the two-row prefetch loop's tail)
+    rows, T = 3 * 217, 217          # 651 rows: five 128-row chunks + a ragged one (the two-row prefetch loop's tail)
     pre = torch.randn(rows, N, generator=g).to(DEV).requires_grad_(True)
     go = torch.randn(rows, N, generator=g).to(DEV)
     rs = torch.tensor([0.0, 1.4, 1.4]).to(DEV)
@@ -1092,7 +1094,7 @@ def test_clamp_resize():
         _close(Kn.clamp_resize(x, 1e-3, 80.0, (70, 166)), L.clamp_resize(x, 1e-3, 80.0, (70, 166), True), 1e-5, 1e-5, "clamp_resize")
 
 
-@pytest.mark.parametrize("B,C,H,W,relu", [(2, 64, 32, 80, True), (3, 192, 9, 21, False), (2, 1536, 2, 5, True)])
+@pytest.mark.parametrize("B,C,H,W,relu", [(2, 64, 32, 80, True), (3, 192, 9, 21, False), (2, 1536, 2, 5, True), (2, 24, 16, 20, True), (1, 200, 7, 9, False)])
 def test_batchnorm_train_fwd_bwd(B, C, H, W, relu):
     from gedepth_b200 import kernels as Kn
     g = torch.Generator().manual_seed(27)
