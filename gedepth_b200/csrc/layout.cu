@@ -427,17 +427,37 @@ __global__ void __launch_bounds__(256) im2col_rows_kernel(const float* __restric
   }
 }
 
-// merge_patches with one CTA per unmerged row (b, y): 32-bit index arithmetic (same mapping as the flat kernel below)
+// merge_patches with one CTA per MERGED row (b, y2): a thread owns one (x2, c) and moves the four pixels of its 2 x 2 patch as
+// ONE 128-bit access on the merged side (features c*4 .. c*4+3 = (ky, kx) = (0,0) (0,1) (1,0) (1,1)) and four coalesced 4-byte
+// accesses on the unmerged side; 32-bit index arithmetic.  (One thread per unmerged element wrote the merged side as 4-byte
+// pieces 16 bytes apart: 34 % DRAM utilisation under ncu.)  Pixels beyond an odd H / W read as zero / are not written.
 __global__ void __launch_bounds__(256) merge_patches_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                                   int H, int W, int C, int H2, int W2, int dir) {
-  const int y = blockIdx.x, b = blockIdx.y;
-  const int64_t urow = ((int64_t)b * H + y) * W * C;                                  // unmerged row start
-  const int64_t mrow = ((int64_t)b * H2 + (y >> 1)) * W2 * (4 * (int64_t)C) + (y & 1) * 2;
-  const int n = W * C;
+  const int y2 = blockIdx.x, b = blockIdx.y;
+  const int y0 = 2 * y2, y1 = 2 * y2 + 1;
+  const bool has_y1 = y1 < H;
+  const int64_t urow0 = ((int64_t)b * H + y0) * W * C, urow1 = ((int64_t)b * H + y1) * W * C;   // unmerged row starts
+  const int64_t mrow = ((int64_t)b * H2 + y2) * W2 * (4 * (int64_t)C);
+  const int n = W2 * C;
   for (int i = threadIdx.x; i < n; i += 256) {
-    const int x = i / C, c = i - x * C;
-    const int64_t m = mrow + (int64_t)(x >> 1) * (4 * C) + c * 4 + (x & 1);
-    if (dir == 0) dst[m] = __ldg(src + urow + i); else dst[urow + i] = __ldg(src + m);
+    const int x2 = i / C, c = i - x2 * C;
+    const int xa = 2 * x2, xb = 2 * x2 + 1;
+    const bool has_xb = xb < W;
+    const int64_t m = mrow + (int64_t)x2 * (4 * C) + c * 4;
+    if (dir == 0) {
+      float4 v;
+      v.x = __ldg(src + urow0 + (int64_t)xa * C + c);
+      v.y = has_xb ? __ldg(src + urow0 + (int64_t)xb * C + c) : 0.f;
+      v.z = has_y1 ? __ldg(src + urow1 + (int64_t)xa * C + c) : 0.f;
+      v.w = (has_y1 && has_xb) ? __ldg(src + urow1 + (int64_t)xb * C + c) : 0.f;
+      *(float4*)(dst + m) = v;
+    } else {
+      const float4 v = __ldg((const float4*)(src + m));
+      dst[urow0 + (int64_t)xa * C + c] = v.x;
+      if (has_xb) dst[urow0 + (int64_t)xb * C + c] = v.y;
+      if (has_y1) dst[urow1 + (int64_t)xa * C + c] = v.z;
+      if (has_y1 && has_xb) dst[urow1 + (int64_t)xb * C + c] = v.w;
+    }
   }
 }
 
@@ -610,8 +630,8 @@ GED_API int ged_merge_patches(const float* src, float* dst, int B, int H, int W,
   if (!backward && ((H | W) & 1))
     if (cudaMemsetAsync(dst, 0, sizeof(float) * (size_t)B * H2 * W2 * 4 * C, stream) != cudaSuccess) return GED_ERR_LAUNCH;
   const int64_t total = (int64_t)B * H * W * C;
-  if (g_layout_rows && B <= 65535 && (int64_t)W * C < (1 << 30))
-    merge_patches_rows_kernel<<<dim3(H, B), 256, 0, stream>>>(src, dst, H, W, C, H2, W2, backward);
+  if (g_layout_rows && B <= 65535 && (int64_t)W * C < (1 << 30) && aligned16(backward ? src : dst))
+    merge_patches_rows_kernel<<<dim3(H2, B), 256, 0, stream>>>(src, dst, H, W, C, H2, W2, backward);
   else
     merge_patches_kernel<<<grid_for(total), 256, 0, stream>>>(src, dst, H, W, C, H2, W2, total, backward);
   GED_CHECK_LAUNCH();
